@@ -1,0 +1,105 @@
+"""Pin the CPU oracle (oracle/amep_oracle.py) against outputs of the unmodified
+reference stored in tests/golden/ (made by oracle/make_golden.py)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import amep_oracle as orc
+
+from conftest import GOLDEN
+
+
+def _load(name):
+    return np.load(os.path.join(GOLDEN, name), allow_pickle=False)
+
+
+RDF_CASES = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "rdf_*.npz"))
+                   if "kdtree" not in p)
+
+
+def rdf_kwargs(z):
+    kw = dict(pbc=bool(z["pbc"]))
+    if int(z["nbins"]) >= 0:
+        kw["nbins"] = int(z["nbins"])
+    if not bool(z["rmax_is_default"]):
+        kw["rmax"] = float(z["rmax"])
+    return kw
+
+
+@pytest.mark.parametrize("name", RDF_CASES)
+def test_rdf_counts_and_g_bit_exact(name):
+    z = _load(name)
+    other = z["other"] if "other" in z.files else None
+    kw = rdf_kwargs(z)
+    hist, edges = orc.rdf_counts(z["coords"], z["box"], other, **kw)
+    assert hist.dtype == np.int64
+    assert edges.dtype == z["edges"].dtype
+    np.testing.assert_array_equal(edges, z["edges"])
+    np.testing.assert_array_equal(hist, z["counts"])
+    g, r = orc.rdf(z["coords"], z["box"], other, **kw)
+    assert g.dtype == z["g"].dtype and r.dtype == z["r"].dtype
+    np.testing.assert_array_equal(g, z["g"])
+    np.testing.assert_array_equal(r, z["r"])
+
+
+def test_rdf_image_count():
+    for name in RDF_CASES:
+        z = _load(name)
+        if bool(z["pbc"]):
+            assert len(orc.periodic_images(z["coords"], z["box"])) == int(z["n_images"])
+
+
+def test_rdf_reference_unittest_criterion():
+    """test/test_spatialcor.py:73-102: diff and kdtree agree to 3 decimals."""
+    z = _load("rdf_unittest_2d_f64.npz")
+    gk = _load("rdf_unittest_2d_kdtree.npz")["g"]
+    g, _ = orc.rdf(z["coords"], z["box"], nbins=50, rmax=5.0)
+    assert (g.round(3) == gk.round(3)).all()
+
+
+@pytest.mark.parametrize("name", ["sfiso_2d_f64.npz", "sfiso_2d_f32.npz", "sfiso_3d_f64.npz",
+                                  "sfiso_3d_cross_f32.npz"])
+def test_sfiso_fast_bit_exact(name):
+    z = _load(name)
+    other = z["other"] if "other" in z.files else None
+    s, q = orc.sfiso_fast(z["coords"], z["box"], qmax=float(z["qmax"]), twod=bool(z["twod"]),
+                          num=int(z["num"]), other_coords=other)
+    np.testing.assert_array_equal(q, z["q"])
+    np.testing.assert_array_equal(s, z["S"])
+
+
+@pytest.mark.parametrize("name", ["sf2d_f64_onechunk.npz", "sf2d_f32_chunks.npz", "sf2d_f64_cross.npz"])
+def test_sf2d_std_bit_exact(name):
+    z = _load(name)
+    other = z["other"] if "other" in z.files else None
+    cs = int(z["chunksize"])
+    s, qx, qy = orc.sf2d_std(z["coords"], z["box"], other, qmax=float(z["qmax"]),
+                             chunksize=None if cs < 0 else cs)
+    np.testing.assert_array_equal(qx, z["Qx"])
+    np.testing.assert_array_equal(qy, z["Qy"])
+    assert s.dtype == z["S"].dtype
+    np.testing.assert_array_equal(s, z["S"])
+    # the float64 evaluation of the same formula sits within the reference's
+    # own complex64 noise
+    s64, _, _ = orc.sf2d_f64(z["coords"], z["box"], other, qmax=float(z["qmax"]))
+    assert np.max(np.abs(s64 - s)) < 2e-3 * max(1.0, np.max(np.abs(s64)))
+
+
+def test_evaluate_rdf_matches_reference_average_func():
+    z = _load("evaluate_rdf_f32.npz")
+    stack, box = z["coords"], z["box"]
+    frames = [(stack[i], box) for i in range(len(stack))]
+    res, avg, idx = orc.evaluate(frames, lambda f: orc.rdf(f[0], f[1], nbins=int(z["nbins"])),
+                                 skip=float(z["skip"]), nav=int(z["nav"]))
+    np.testing.assert_array_equal(idx, z["indices"])
+    np.testing.assert_array_equal(res, z["frames"])
+    np.testing.assert_array_equal(avg, z["avg"])
+
+
+def test_frame_indices_rule():
+    np.testing.assert_array_equal(orc.frame_indices(100, 0.0, 100), np.arange(100))
+    np.testing.assert_array_equal(orc.frame_indices(51, 0.9, 2), np.array([46, 50]))
+    assert len(orc.frame_indices(10, 0.5, 50)) == 5
+    assert len(orc.frame_indices(10, 0.0, None)) == 10
