@@ -1,0 +1,250 @@
+"""Array plumbing between NumPy / PyTorch and the C ABI (no arithmetic here)."""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.split(".")[0] == "torch"
+
+
+class Particles:
+    """A batch of coordinate frames ``[F, N, 3]`` in host (NumPy) or device
+    (CUDA tensor) memory, float32 or float64, C-contiguous."""
+
+    def __init__(self, data, name="coords"):
+        self.tensor = None
+        self.array = None
+        if _is_torch(data):
+            import torch
+            t = data
+            if t.dtype not in (torch.float32, torch.float64):
+                # NumPy promotion of the reference: integers behave like float64
+                # in `c - coords` (amep/spatialcor.py:381), halves like float32
+                t = t.to(torch.float32 if t.dtype in (torch.float16, torch.bfloat16) else torch.float64)
+            if t.dim() == 2:
+                t = t.unsqueeze(0)
+            if t.dim() != 3 or t.shape[-1] != 3:
+                raise ValueError(f"coordinates do not have a known shape. {tuple(data.shape)}")
+            t = t.contiguous()
+            if t.is_cuda:
+                self.tensor = t
+                self.dtype = _lib.F32 if t.dtype == torch.float32 else _lib.F64
+                self.shape = tuple(t.shape)
+                return
+            data = t.numpy()
+        a = np.asarray(data)
+        if a.dtype not in (np.float32, np.float64):
+            a = a.astype(np.float32 if a.dtype == np.float16 else np.float64)
+        if a.ndim == 2:
+            a = a[None]
+        if a.ndim != 3 or a.shape[-1] != 3:
+            raise ValueError(f"coordinates do not have a known shape. {np.shape(data)}")
+        self.array = np.ascontiguousarray(a)
+        self.dtype = _lib.F32 if self.array.dtype == np.float32 else _lib.F64
+        self.shape = self.array.shape
+
+    @property
+    def on_device(self) -> bool:
+        return self.tensor is not None
+
+    @property
+    def nframes(self) -> int:
+        return self.shape[0]
+
+    @property
+    def n(self) -> int:
+        return self.shape[1]
+
+    def ptr(self) -> int:
+        if self.tensor is not None:
+            return self.tensor.data_ptr()
+        return self.array.ctypes.data
+
+    def to_device(self, device):
+        import torch
+        if self.tensor is not None:
+            return self
+        out = Particles.__new__(Particles)
+        out.array = None
+        out.tensor = torch.from_numpy(self.array).to(device, non_blocking=False)
+        out.dtype, out.shape = self.dtype, self.shape
+        return out
+
+
+def box_array(box_boundary, nframes):
+    """-> (float64 [F,3,2] contiguous, dtype code of the caller's box)."""
+    if _is_torch(box_boundary):
+        box_boundary = box_boundary.detach().cpu().numpy()
+    b = np.asarray(box_boundary)
+    code = _lib.F32 if b.dtype == np.float32 else _lib.F64
+    if b.ndim == 2:
+        b = np.broadcast_to(b, (nframes, 3, 2))
+    if b.shape != (nframes, 3, 2):
+        raise ValueError(f"box_boundary must have shape (3,2) or ({nframes},3,2), got {b.shape}")
+    return np.ascontiguousarray(b, dtype=np.float64), code
+
+
+def _device_of(p: Particles, device):
+    if p.on_device:
+        return p.tensor.device.index if p.tensor.device.index is not None else 0
+    if device is None:
+        return 0
+    if isinstance(device, int):
+        return device
+    import torch
+    d = torch.device(device)
+    return d.index if d.index is not None else 0
+
+
+def _stream_for(dev_index, on_device):
+    if not on_device:
+        return None
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream(dev_index).cuda_stream)
+
+
+def rdf_histograms(coords, box_boundary, edges, other=None, pbc=True, device=None, out=None):
+    """Integer pair histograms for a batch of frames (amepb_rdf_batch).
+
+    Returns ``(hist, dims)``: ``hist`` int64 ``[F, nbins]`` (a CUDA tensor if the
+    coordinates live on the device, else a NumPy array), ``dims`` int32 ``[F]``.
+    Raises ValueError for frames that are neither 2D nor 3D (as the reference,
+    amep/pbc.py:290-294).
+    """
+    pc = coords if isinstance(coords, Particles) else Particles(coords)
+    po = None
+    if other is not None:
+        po = other if isinstance(other, Particles) else Particles(other, "other_coords")
+        if po.nframes != pc.nframes:
+            raise ValueError("coords and other_coords must have the same number of frames")
+        if pc.on_device != po.on_device:
+            dev = (pc if pc.on_device else po).tensor.device
+            pc, po = pc.to_device(dev), po.to_device(dev)
+    nf = pc.nframes
+    if pc.n == 0 or (po is not None and po.n == 0):
+        raise IndexError("index 0 is out of bounds for axis 0 with size 0")
+    box, box_code = box_array(box_boundary, nf)
+    e = np.ascontiguousarray(np.asarray(edges), dtype=np.float64)
+    if e.ndim == 1:
+        nbins, stride = e.shape[0] - 1, 0
+    elif e.ndim == 2 and e.shape[0] == nf:
+        nbins, stride = e.shape[1] - 1, e.shape[1]
+    else:
+        raise ValueError("edges must have shape (nbins+1,) or (F, nbins+1)")
+    if nbins < 1:
+        raise ValueError("`bins` must be positive, when an integer")
+    dev_index = _device_of(pc, device)
+    ctx = _lib.context(dev_index)
+    dims = np.zeros(nf, dtype=np.int32)
+    if pc.on_device:
+        import torch
+        if out is None:
+            out = torch.empty((nf, nbins), dtype=torch.int64, device=pc.tensor.device)
+        hist_ptr = out.data_ptr()
+        space = _lib.DEVICE
+    else:
+        if out is None:
+            out = np.empty((nf, nbins), dtype=np.int64)
+        hist_ptr = out.ctypes.data
+        space = _lib.HOST
+    rc = ctx.lib.amepb_rdf_batch(
+        ctx.handle,
+        ctypes.c_void_p(pc.ptr()), pc.dtype, pc.n,
+        ctypes.c_void_p(po.ptr()) if po is not None else None,
+        po.dtype if po is not None else 0, po.n if po is not None else 0,
+        space, nf,
+        box.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), box_code,
+        e.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), stride, nbins,
+        1 if pbc else 0,
+        ctypes.c_void_p(hist_ptr), dims.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+        _stream_for(dev_index, pc.on_device))
+    if rc == _lib.E_DIMENSION:
+        raise ValueError(ctx.error())
+    ctx.check(rc, "amepb_rdf_batch")
+    return out, dims
+
+
+def frame_dimensions(coords, device=None):
+    """dimension() of every frame (amep/utils.py:1617-1667) -> int32 ``[F]``."""
+    pc = coords if isinstance(coords, Particles) else Particles(coords)
+    if pc.n == 0:
+        raise IndexError("index 0 is out of bounds for axis 0 with size 0")
+    dev_index = _device_of(pc, device)
+    ctx = _lib.context(dev_index)
+    dims = np.zeros(pc.nframes, dtype=np.int32)
+    rc = ctx.lib.amepb_frame_dimension(
+        ctx.handle, ctypes.c_void_p(pc.ptr()), pc.dtype,
+        _lib.DEVICE if pc.on_device else _lib.HOST, pc.nframes, pc.n,
+        dims.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), _stream_for(dev_index, pc.on_device))
+    ctx.check(rc, "amepb_frame_dimension")
+    return dims
+
+
+def sq_harmonics(coords, kvec, nharm, device=None):
+    """``out[f, d, h] = (sum cos((h+1) k_d.r), sum sin((h+1) k_d.r))`` (amepb_sq_harmonics).
+
+    ``kvec``: float64 ``[ndir, 3]`` (shared) or ``[F, ndir, 3]``."""
+    pc = coords if isinstance(coords, Particles) else Particles(coords)
+    nf = pc.nframes
+    k = np.ascontiguousarray(np.asarray(kvec), dtype=np.float64)
+    if k.ndim == 2:
+        ndir, stride = k.shape[0], 0
+    elif k.ndim == 3 and k.shape[0] == nf:
+        ndir, stride = k.shape[1], k.shape[1] * 3
+    else:
+        raise ValueError("kvec must have shape (ndir,3) or (F,ndir,3)")
+    dev_index = _device_of(pc, device)
+    ctx = _lib.context(dev_index)
+    if pc.on_device:
+        import torch
+        out = torch.empty((nf, ndir, nharm, 2), dtype=torch.float64, device=pc.tensor.device)
+        optr, space = out.data_ptr(), _lib.DEVICE
+    else:
+        out = np.empty((nf, ndir, nharm, 2), dtype=np.float64)
+        optr, space = out.ctypes.data, _lib.HOST
+    rc = ctx.lib.amepb_sq_harmonics(
+        ctx.handle, ctypes.c_void_p(pc.ptr()), pc.dtype, space, nf, pc.n,
+        k.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), stride, ndir, int(nharm),
+        ctypes.c_void_p(optr), _stream_for(dev_index, pc.on_device))
+    ctx.check(rc, "amepb_sq_harmonics")
+    return out
+
+
+def sf2d_modes(coords, qpos, nq, accum="c64", chunksize=0, device=None):
+    """rho(q) on the sf2d grid (amepb_sf2d_modes) -> complex array ``[F, 2nq, 2nq]``.
+
+    ``qpos``: the positive half of the q axis, float64 ``[nq]`` (shared) or ``[F, nq]``."""
+    pc = coords if isinstance(coords, Particles) else Particles(coords)
+    nf = pc.nframes
+    q = np.ascontiguousarray(np.asarray(qpos, dtype=np.float64))
+    if q.ndim == 1 and q.shape[0] == nq:
+        stride = 0
+    elif q.ndim == 2 and q.shape == (nf, nq):
+        stride = nq
+    else:
+        raise ValueError("qpos must have shape (nq,) or (F, nq)")
+    mode = {"c64": _lib.ACCUM_C64_REFERENCE, "f64": _lib.ACCUM_F64}[accum]
+    dev_index = _device_of(pc, device)
+    ctx = _lib.context(dev_index)
+    g = 2 * int(nq)
+    if pc.on_device:
+        import torch
+        out = torch.empty((nf, g, g), dtype=torch.complex64 if accum == "c64" else torch.complex128,
+                          device=pc.tensor.device)
+        optr, space = out.data_ptr(), _lib.DEVICE
+    else:
+        out = np.empty((nf, g, g), dtype=np.complex64 if accum == "c64" else np.complex128)
+        optr, space = out.ctypes.data, _lib.HOST
+    if nq == 0:
+        return out
+    rc = ctx.lib.amepb_sf2d_modes(
+        ctx.handle, ctypes.c_void_p(pc.ptr()), pc.dtype, space, nf, pc.n,
+        q.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), stride, int(nq), mode, int(chunksize),
+        ctypes.c_void_p(optr), _stream_for(dev_index, pc.on_device))
+    ctx.check(rc, "amepb_sf2d_modes")
+    return out

@@ -1,0 +1,84 @@
+// amepb_internal.cuh -- context, workspace and error plumbing shared by the
+// translation units of libamepb.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+
+#include "amepb.h"
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+enum {
+    BUF_STATS = 0,     // stats partials
+    BUF_PLANS,         // FramePlan[]
+    BUF_THR,           // threshold tables
+    BUF_TCOUNT,        // target cell counters
+    BUF_TSTART,        // target cell offsets
+    BUF_QCOUNT,        // query cell counters
+    BUF_QSTART,        // query cell offsets
+    BUF_TSORTED,       // images in cell order
+    BUF_QSORTED,       // queries in cell order
+    BUF_SCAN,          // scan block sums
+    BUF_MISC,          // task counter, candidate counter
+    BUF_STAGE_A,       // host-space staging: coords
+    BUF_STAGE_B,       // host-space staging: other
+    BUF_STAGE_OUT,     // host-space staging: results
+    BUF_SQ_A,          // S(q) workspaces
+    BUF_SQ_B,
+    BUF_COUNT
+};
+
+struct amepb_ctx {
+    int device = 0;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    size_t total_mem = 0;
+    std::string err;
+    int64_t launches = 0;
+    DevBuf bufs[BUF_COUNT];
+    void* pinned = nullptr;  // pinned host scratch (plans, stats read-back)
+    size_t pinned_cap = 0;
+    amepb_rdf_info rdf_info;
+    int rdf_k_override = 0;
+    void* last_stream = nullptr;
+};
+
+namespace amepb {
+
+int fail(amepb_ctx* ctx, int code, const char* fmt, ...);
+int fail_cuda(amepb_ctx* ctx, cudaError_t e, const char* what, const char* file, int line);
+int ensure_device(amepb_ctx* ctx, int which, size_t bytes);
+int ensure_pinned(amepb_ctx* ctx, size_t bytes);
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+}  // namespace amepb
+
+#define AMEPB_CUDA(ctx, call)                                                         \
+    do {                                                                              \
+        cudaError_t e__ = (call);                                                     \
+        if (e__ != cudaSuccess) return amepb::fail_cuda(ctx, e__, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define AMEPB_LAUNCH_CHECK(ctx)                                                       \
+    do {                                                                              \
+        (ctx)->launches++;                                                            \
+        cudaError_t e__ = cudaGetLastError();                                         \
+        if (e__ != cudaSuccess) return amepb::fail_cuda(ctx, e__, "kernel launch", __FILE__, __LINE__); \
+    } while (0)

@@ -1,0 +1,127 @@
+// context.cu -- context life cycle, error text, workspace growth.
+#include <stdarg.h>
+
+#include "amepb_internal.cuh"
+
+namespace {
+thread_local std::string g_create_error;
+}
+
+namespace amepb {
+
+int fail(amepb_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    else g_create_error = buf;
+    return code;
+}
+
+int fail_cuda(amepb_ctx* ctx, cudaError_t e, const char* what, const char* file, int line) {
+    const char* base = file;
+    for (const char* p = file; *p; ++p)
+        if (*p == '/') base = p + 1;
+    fail(ctx, (int)e, "CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), base, line, what);
+    return (int)e > 0 ? (int)e : 1;
+}
+
+int ensure_device(amepb_ctx* ctx, int which, size_t bytes) {
+    DevBuf& b = ctx->bufs[which];
+    if (b.cap >= bytes && b.p) return 0;
+    if (b.p) {
+        AMEPB_CUDA(ctx, cudaFree(b.p));
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        want = bytes;
+        e = cudaMalloc(&b.p, want);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        b.p = nullptr;
+        return fail(ctx, AMEPB_E_NOMEM, "device workspace %d of %zu bytes does not fit", which, bytes);
+    }
+    b.cap = want;
+    return 0;
+}
+
+int ensure_pinned(amepb_ctx* ctx, size_t bytes) {
+    if (ctx->pinned_cap >= bytes && ctx->pinned) return 0;
+    if (ctx->pinned) {
+        AMEPB_CUDA(ctx, cudaFreeHost(ctx->pinned));
+        ctx->pinned = nullptr;
+        ctx->pinned_cap = 0;
+    }
+    size_t want = bytes + bytes / 4 + 4096;
+    AMEPB_CUDA(ctx, cudaMallocHost(&ctx->pinned, want));
+    ctx->pinned_cap = want;
+    return 0;
+}
+
+}  // namespace amepb
+
+extern "C" {
+
+int amepb_abi_version(void) { return AMEPB_ABI_VERSION; }
+
+int amepb_create(int device, amepb_ctx** out) {
+    if (!out) return amepb::fail(nullptr, AMEPB_E_INVAL, "amepb_create: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) {
+        cudaGetLastError();
+        return amepb::fail(nullptr, AMEPB_E_NODEVICE,
+                           "amepb_create: no CUDA device (%s); libamepb has no CPU fallback",
+                           e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    if (device < 0 || device >= count)
+        return amepb::fail(nullptr, AMEPB_E_INVAL, "amepb_create: device %d out of range [0,%d)", device, count);
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return amepb::fail_cuda(nullptr, e, "cudaGetDeviceProperties", __FILE__, __LINE__);
+    if (prop.major < 10)
+        return amepb::fail(nullptr, AMEPB_E_NODEVICE,
+                           "amepb_create: device %d is sm_%d%d; libamepb is built for sm_100a (B200) only",
+                           device, prop.major, prop.minor);
+    amepb_ctx* ctx = new amepb_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    ctx->total_mem = prop.totalGlobalMem;
+    memset(&ctx->rdf_info, 0, sizeof(ctx->rdf_info));
+    *out = ctx;
+    return 0;
+}
+
+void amepb_destroy(amepb_ctx* ctx) {
+    if (!ctx) return;
+    amepb::DeviceGuard guard(ctx->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < BUF_COUNT; ++i)
+        if (ctx->bufs[i].p) cudaFree(ctx->bufs[i].p);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    delete ctx;
+}
+
+const char* amepb_last_error(const amepb_ctx* ctx) {
+    return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+int64_t amepb_kernel_launches(const amepb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int amepb_synchronize(amepb_ctx* ctx, void* stream) {
+    if (!ctx) return AMEPB_E_INVAL;
+    amepb::DeviceGuard guard(ctx->device);
+    AMEPB_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)stream));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,972 @@
+// rdf.cu -- periodic-boundary pair histograms (RDF) on sm_100a.
+//
+// Replaces, for a whole batch of frames at once:
+//   amep/pbc.py:169-350         pbc_points(width=0.5)   -> images generated on the fly
+//   amep/spatialcor.py:348-388  __rdf_diff              -> cell-list pair kernel
+//   amep/spatialcor.py:566-600  chunk fan-out + sum     -> persistent blocks + one merge
+//
+// Pipeline per sub-batch of frames (all on the caller's stream):
+//   stats      min/max/constant-column flags per frame          (HBM bound, 12 B/particle)
+//   plan       host: grid, neighbour rows, tasks                (rdf_plan.h)
+//   count      periodic images -> cell counters                  (HBM bound)
+//   scan       exclusive scan of the cell counters
+//   fill       images / queries written in cell order (float4)   (HBM bound)
+//   pairs      persistent blocks: warp = (query cell, neighbour row); lanes hold
+//              images in registers, queries are broadcast; exact float32 / float64
+//              distance arithmetic without FMA; squared-distance thresholds for
+//              binning; per-block shared-memory histograms, one merge per frame
+#include <math.h>
+#include <string.h>
+
+#include <vector>
+
+#include "amepb_internal.cuh"
+#include "rdf_plan.h"
+
+namespace amepb {
+
+// ---------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------
+template <typename S>
+struct Vec4;
+template <>
+struct __align__(16) Vec4<float> {
+    float x, y, z, w;
+};
+template <>
+struct __align__(32) Vec4<double> {
+    double x, y, z, w;
+};
+
+__device__ __forceinline__ Vec4<float> load_vec4(const Vec4<float>* p) {
+    float4 v = __ldg(reinterpret_cast<const float4*>(p));
+    Vec4<float> r;
+    r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w;
+    return r;
+}
+__device__ __forceinline__ Vec4<double> load_vec4(const Vec4<double>* p) {
+    const double2* q = reinterpret_cast<const double2*>(p);
+    double2 a = __ldg(q), b = __ldg(q + 1);
+    Vec4<double> r;
+    r.x = a.x; r.y = a.y; r.z = b.x; r.w = b.y;
+    return r;
+}
+
+struct StatsOut {  // mirrors FrameStats, device side
+    double lo[3];
+    double hi[3];
+    double first[3];
+    int varies[3];
+    int pad;
+};
+
+// ---------------------------------------------------------------------------
+// stats kernel: per frame min / max / "column differs from particle 0"
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) stats_partial_kernel(const T* __restrict__ pts, long long n,
+                                                            StatsOut* __restrict__ partial) {
+    const int f = blockIdx.y;
+    const T* base = pts + (long long)f * n * 3;
+    const T f0 = base[0], f1 = base[1], f2 = base[2];
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    double lo0 = inf, lo1 = inf, lo2 = inf, hi0 = -inf, hi1 = -inf, hi2 = -inf;
+    int v0 = 0, v1 = 0, v2 = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const T x = base[3 * i], y = base[3 * i + 1], z = base[3 * i + 2];
+        v0 |= !(x == f0);
+        v1 |= !(y == f1);
+        v2 |= !(z == f2);
+        lo0 = fmin(lo0, (double)x); hi0 = fmax(hi0, (double)x);
+        lo1 = fmin(lo1, (double)y); hi1 = fmax(hi1, (double)y);
+        lo2 = fmin(lo2, (double)z); hi2 = fmax(hi2, (double)z);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        lo0 = fmin(lo0, __shfl_xor_sync(0xffffffffu, lo0, o));
+        lo1 = fmin(lo1, __shfl_xor_sync(0xffffffffu, lo1, o));
+        lo2 = fmin(lo2, __shfl_xor_sync(0xffffffffu, lo2, o));
+        hi0 = fmax(hi0, __shfl_xor_sync(0xffffffffu, hi0, o));
+        hi1 = fmax(hi1, __shfl_xor_sync(0xffffffffu, hi1, o));
+        hi2 = fmax(hi2, __shfl_xor_sync(0xffffffffu, hi2, o));
+        v0 |= __shfl_xor_sync(0xffffffffu, v0, o);
+        v1 |= __shfl_xor_sync(0xffffffffu, v1, o);
+        v2 |= __shfl_xor_sync(0xffffffffu, v2, o);
+    }
+    __shared__ double s_red[8][6];
+    __shared__ int s_var[8][3];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
+        s_red[warp][0] = lo0; s_red[warp][1] = lo1; s_red[warp][2] = lo2;
+        s_red[warp][3] = hi0; s_red[warp][4] = hi1; s_red[warp][5] = hi2;
+        s_var[warp][0] = v0; s_var[warp][1] = v1; s_var[warp][2] = v2;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        StatsOut o;
+        for (int d = 0; d < 3; ++d) { o.lo[d] = inf; o.hi[d] = -inf; o.varies[d] = 0; }
+        const int nw = blockDim.x >> 5;
+        for (int w = 0; w < nw; ++w)
+            for (int d = 0; d < 3; ++d) {
+                o.lo[d] = fmin(o.lo[d], s_red[w][d]);
+                o.hi[d] = fmax(o.hi[d], s_red[w][3 + d]);
+                o.varies[d] |= s_var[w][d];
+            }
+        o.first[0] = (double)f0; o.first[1] = (double)f1; o.first[2] = (double)f2;
+        o.pad = 0;
+        partial[(long long)f * gridDim.x + blockIdx.x] = o;
+    }
+}
+
+__global__ void stats_final_kernel(const StatsOut* __restrict__ partial, int nparts,
+                                   StatsOut* __restrict__ out) {
+    const int f = blockIdx.x;
+    if (threadIdx.x != 0) return;
+    StatsOut o = partial[(long long)f * nparts];
+    for (int p = 1; p < nparts; ++p) {
+        const StatsOut& q = partial[(long long)f * nparts + p];
+        for (int d = 0; d < 3; ++d) {
+            o.lo[d] = fmin(o.lo[d], q.lo[d]);
+            o.hi[d] = fmax(o.hi[d], q.hi[d]);
+            o.varies[d] |= q.varies[d];
+        }
+    }
+    out[f] = o;
+}
+
+// ---------------------------------------------------------------------------
+// cell placement: count pass and fill pass share one body
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int cell_index(double x, double g0, double inv_h, int n) {
+    int c = __double2int_rd((x - g0) * inv_h);  // NaN -> 0, saturating
+    return min(max(c, 0), n - 1);
+}
+
+// Targets with periodic images.  T: input element type, image storage is
+// float32 (amep/pbc.py:300-302).  FILL=false counts, FILL=true writes.
+template <typename T, bool FILL>
+__global__ void __launch_bounds__(256) place_images_kernel(const T* __restrict__ pts, long long n,
+                                                           const FramePlan* __restrict__ plans,
+                                                           unsigned* __restrict__ count,
+                                                           const unsigned* __restrict__ start,
+                                                           Vec4<float>* __restrict__ sorted) {
+    const int f = blockIdx.y;
+    const FramePlan& P = plans[f];
+    if (!P.valid) return;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const T* p = pts + ((long long)f * n + i) * 3;
+    float img[3][3];
+    int cell[3][3];
+    bool ok[3][3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const float b = (float)p[d];  // .astype(np.float32): round to nearest even
+        const float len = P.shift[d];
+#pragma unroll
+        for (int v = 0; v < 3; ++v) {
+            // v = 0: no shift, 1: -L, 2: +L.  base + v*box in float32 (amep/pbc.py:326)
+            const float vf = (v == 0) ? 0.0f : (v == 1 ? -1.0f : 1.0f);
+            const float x = __fadd_rn(b, __fmul_rn(vf, len));
+            const double xd = (double)x;
+            img[d][v] = x;
+            bool keep = (v == 0) || (P.nshift[d] == 3);
+            keep = keep && (xd < P.win_hi[d]) && (xd > P.win_lo[d]);    // strict window
+            keep = keep && (xd >= P.reg_lo[d]) && (xd <= P.reg_hi[d]);  // grid region
+            ok[d][v] = keep;
+            cell[d][v] = cell_index(xd, P.g0[d], P.inv_h[d], P.n[d]);
+        }
+    }
+#pragma unroll
+    for (int vz = 0; vz < 3; ++vz) {
+        if (!ok[2][vz]) continue;
+#pragma unroll
+        for (int vy = 0; vy < 3; ++vy) {
+            if (!ok[1][vy]) continue;
+#pragma unroll
+            for (int vx = 0; vx < 3; ++vx) {
+                if (!ok[0][vx]) continue;
+                const unsigned c = P.cell_base +
+                                   (unsigned)((cell[2][vz] * P.n[1] + cell[1][vy]) * P.n[0] + cell[0][vx]);
+                if (!FILL) {
+                    atomicAdd(&count[c], 1u);
+                } else {
+                    const unsigned slot = start[c] + atomicSub(&count[c], 1u) - 1u;
+                    Vec4<float> o;
+                    o.x = img[0][vx]; o.y = img[1][vy]; o.z = img[2][vz]; o.w = 0.0f;
+                    sorted[slot] = o;
+                }
+            }
+        }
+    }
+}
+
+// Plain points (queries, or targets without periodic images).  S: storage
+// type.  DROP_OUTSIDE: skip points outside the grid region (targets); queries
+// are clamped into the boundary cells instead.
+template <typename T, typename S, bool FILL, bool DROP_OUTSIDE>
+__global__ void __launch_bounds__(256) place_points_kernel(const T* __restrict__ pts, long long n,
+                                                           const FramePlan* __restrict__ plans,
+                                                           unsigned* __restrict__ count,
+                                                           const unsigned* __restrict__ start,
+                                                           Vec4<S>* __restrict__ sorted) {
+    const int f = blockIdx.y;
+    const FramePlan& P = plans[f];
+    if (!P.valid) return;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const T* p = pts + ((long long)f * n + i) * 3;
+    S v[3];
+    int c[3];
+    bool keep = true;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        v[d] = (S)p[d];
+        const double xd = (double)v[d];
+        if (DROP_OUTSIDE) keep = keep && (xd >= P.reg_lo[d]) && (xd <= P.reg_hi[d]);
+        c[d] = cell_index(xd, P.g0[d], P.inv_h[d], P.n[d]);
+    }
+    if (!keep) return;
+    const unsigned cc = P.cell_base + (unsigned)((c[2] * P.n[1] + c[1]) * P.n[0] + c[0]);
+    if (!FILL) {
+        atomicAdd(&count[cc], 1u);
+    } else {
+        const unsigned slot = start[cc] + atomicSub(&count[cc], 1u) - 1u;
+        Vec4<S> o;
+        o.x = v[0]; o.y = v[1]; o.z = v[2]; o.w = (S)0;
+        sorted[slot] = o;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// exclusive scan (three small kernels; arrays hold at most a few million cells)
+// ---------------------------------------------------------------------------
+constexpr int kScanBlock = 256;
+constexpr int kScanPerThread = 8;
+constexpr int kScanTile = kScanBlock * kScanPerThread;
+
+__device__ __forceinline__ unsigned block_exclusive_scan(unsigned v, unsigned* s_warp, unsigned* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned w = lane < (blockDim.x >> 5) ? s_warp[lane] : 0u;
+        unsigned winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
+        }
+        s_warp[lane] = winc - w;                 // exclusive warp offsets
+        if (lane == 31) s_warp[32] = winc;       // block total
+    }
+    __syncthreads();
+    *total = s_warp[32];
+    return s_warp[warp] + inc - v;
+}
+
+__global__ void __launch_bounds__(kScanBlock) scan_local_kernel(const unsigned* __restrict__ in,
+                                                                unsigned* __restrict__ out, long long len,
+                                                                unsigned* __restrict__ block_sums) {
+    __shared__ unsigned s_warp[33];
+    const long long base = (long long)blockIdx.x * kScanTile + (long long)threadIdx.x * kScanPerThread;
+    unsigned v[kScanPerThread];
+    unsigned sum = 0;
+#pragma unroll
+    for (int k = 0; k < kScanPerThread; ++k) {
+        v[k] = (base + k < len) ? in[base + k] : 0u;
+        sum += v[k];
+    }
+    unsigned total;
+    unsigned off = block_exclusive_scan(sum, s_warp, &total);
+#pragma unroll
+    for (int k = 0; k < kScanPerThread; ++k) {
+        if (base + k < len) out[base + k] = off;
+        off += v[k];
+    }
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024) scan_sums_kernel(unsigned* __restrict__ block_sums, int nblocks) {
+    __shared__ unsigned s_warp[33];
+    __shared__ unsigned s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nblocks; base += 1024) {
+        const int i = base + threadIdx.x;
+        const unsigned v = i < nblocks ? block_sums[i] : 0u;
+        unsigned total;
+        const unsigned off = block_exclusive_scan(v, s_warp, &total);
+        const unsigned carry = s_carry;
+        if (i < nblocks) block_sums[i] = carry + off;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry = carry + total;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(kScanBlock) scan_add_kernel(unsigned* __restrict__ out, long long len,
+                                                              const unsigned* __restrict__ block_sums) {
+    const unsigned add = block_sums[blockIdx.x];
+    const long long base = (long long)blockIdx.x * kScanTile + (long long)threadIdx.x * kScanPerThread;
+#pragma unroll
+    for (int k = 0; k < kScanPerThread; ++k)
+        if (base + k < len) out[base + k] += add;
+}
+
+// ---------------------------------------------------------------------------
+// pair kernel
+// ---------------------------------------------------------------------------
+template <typename AT>
+struct Arith;
+template <>
+struct Arith<float> {
+    static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+    static __device__ __forceinline__ int guess(float s, float e0, float inv_w) {
+        float d;
+        asm("sqrt.approx.f32 %0, %1;" : "=f"(d) : "f"(s));
+        return __float2int_rz((d - e0) * inv_w);
+    }
+};
+template <>
+struct Arith<double> {
+    static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+    static __device__ __forceinline__ int guess(double s, float e0, float inv_w) {
+        float d;
+        const float sf = __double2float_rn(s);
+        asm("sqrt.approx.f32 %0, %1;" : "=f"(d) : "f"(sf));
+        return __float2int_rz((d - e0) * inv_w);
+    }
+};
+
+struct PairArgs {
+    const FramePlan* plans;
+    const unsigned* tstart;
+    const unsigned* qstart;
+    const void* tsorted;
+    const void* qsorted;
+    const void* thr;                // [tables][nbins + 1] of the arithmetic type
+    unsigned long long* hist;       // [frames][nbins]
+    unsigned long long* counters;   // [0] task counter, [1] candidate pairs, [2] images
+    long long total_tasks;
+    long long total_cells;
+    int nbins;
+    int nframes;
+};
+
+constexpr unsigned long long kDirectPairs = 1ull << 17;  // larger warp tasks bypass the u32 histogram
+constexpr unsigned kUnitLimit = 1u << 21;                // flush after 2^31 counted pairs (units of 1024)
+constexpr int kPairThreads = 256;
+
+// One warp: all queries of one cell against one neighbour row (contiguous in
+// the sorted image array).  Lanes hold images, queries are broadcast.
+template <typename AT, typename NT, bool ZCONST, bool DIRECT>
+__device__ __forceinline__ void warp_pairs(const Vec4<AT>* __restrict__ qsorted, unsigned qa, unsigned qb,
+                                           const Vec4<NT>* __restrict__ tsorted, unsigned ta, unsigned tb,
+                                           const AT* __restrict__ thr, int nbins, AT thr_lo, AT thr_hi,
+                                           AT dz2c, float e0, float inv_w,
+                                           unsigned* __restrict__ s_hist,
+                                           unsigned long long* __restrict__ g_hist) {
+    const int lane = threadIdx.x & 31;
+    const AT nan = (AT)__int_as_float(0x7fc00000);
+    for (unsigned base = ta; base < tb; base += 32) {
+        const unsigned j = base + lane;
+        AT nx = nan, ny = nan, nz = nan;
+        if (j < tb) {
+            const Vec4<NT> nb = load_vec4(tsorted + j);
+            nx = (AT)nb.x; ny = (AT)nb.y; nz = (AT)nb.z;
+        }
+#pragma unroll 2
+        for (unsigned q = qa; q < qb; ++q) {
+            const Vec4<AT> qv = load_vec4(qsorted + q);
+            // diff = c - coords; (diff**2).sum(axis=1) : ((dx*dx + dy*dy) + dz*dz), no FMA
+            const AT dx = Arith<AT>::sub(qv.x, nx);
+            const AT dy = Arith<AT>::sub(qv.y, ny);
+            AT s = Arith<AT>::add(Arith<AT>::mul(dx, dx), Arith<AT>::mul(dy, dy));
+            if (ZCONST) {
+                s = Arith<AT>::add(s, dz2c);
+            } else {
+                const AT dz = Arith<AT>::sub(qv.z, nz);
+                s = Arith<AT>::add(s, Arith<AT>::mul(dz, dz));
+            }
+            if (s >= thr_lo && s < thr_hi) {
+                int g = Arith<AT>::guess(s, e0, inv_w);
+                g = max(0, min(g, nbins - 1));
+                while (s < thr[g]) --g;
+                while (s >= thr[g + 1]) ++g;
+                if (DIRECT) atomicAdd(&g_hist[g], 1ull);
+                else atomicAdd(&s_hist[g], 1u);
+            }
+        }
+    }
+}
+
+template <typename AT, typename NT, bool ZCONST, bool SMEM>
+__global__ void __launch_bounds__(kPairThreads) pair_kernel(PairArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int nbins = a.nbins;
+    AT* s_thr = reinterpret_cast<AT*>(smem_raw);
+    unsigned* s_hist = reinterpret_cast<unsigned*>(smem_raw + (((size_t)(nbins + 1) * sizeof(AT) + 15) & ~(size_t)15));
+    __shared__ FramePlan s_plan;
+    __shared__ long long s_task;
+    __shared__ unsigned s_units;
+    __shared__ int s_flush;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const Vec4<AT>* qsorted = reinterpret_cast<const Vec4<AT>*>(a.qsorted);
+    const Vec4<NT>* tsorted = reinterpret_cast<const Vec4<NT>*>(a.tsorted);
+    int cur = -1;
+    unsigned long long cand = 0;
+    if (tid == 0) s_units = 0;
+    __syncthreads();
+
+    for (;;) {
+        if (tid == 0) {
+            s_task = (long long)atomicAdd(&a.counters[0], 1ull);
+            const int fl = s_units >= kUnitLimit;
+            s_flush = fl;
+            if (fl) s_units = 0;
+        }
+        __syncthreads();
+        const long long t = s_task;
+        const bool done = t >= a.total_tasks;
+        int f = cur < 0 ? 0 : cur;
+        if (!done)
+            while (t >= a.plans[f].task_begin + a.plans[f].ntasks) ++f;
+        if (done || f != cur || s_flush) {
+            if (SMEM && cur >= 0) {
+                unsigned long long* row = a.hist + (long long)cur * nbins;
+                for (int b = tid; b < nbins; b += blockDim.x) {
+                    const unsigned v = s_hist[b];
+                    if (v) atomicAdd(&row[b], (unsigned long long)v);
+                }
+            }
+            if (done) break;
+            if (f != cur) {
+                const int* src = reinterpret_cast<const int*>(&a.plans[f]);
+                int* dst = reinterpret_cast<int*>(&s_plan);
+                for (int k = tid; k < (int)(sizeof(FramePlan) / sizeof(int)); k += blockDim.x) dst[k] = src[k];
+                if (SMEM) {
+                    const AT* tsrc = reinterpret_cast<const AT*>(a.thr) + (long long)a.plans[f].thr_index * (nbins + 1);
+                    for (int k = tid; k <= nbins; k += blockDim.x) s_thr[k] = tsrc[k];
+                }
+            }
+            if (SMEM)
+                for (int b = tid; b < nbins; b += blockDim.x) s_hist[b] = 0;
+            cur = f;
+            __syncthreads();
+        }
+        const FramePlan& P = s_plan;
+        const AT* thr = SMEM ? s_thr : reinterpret_cast<const AT*>(a.thr) + (long long)P.thr_index * (nbins + 1);
+        const AT thr_lo = thr[0], thr_hi = thr[nbins];
+        const AT dz2c = (AT)P.dz2c;
+        const float e0 = (float)P.bin_e0, inv_w = (float)P.bin_inv_w;
+        unsigned long long* g_hist = a.hist + (long long)f * nbins;
+
+        const long long lt = t - P.task_begin;
+        const int run_i = (int)(lt % P.runs_per_row);
+        const long long rowq = lt / P.runs_per_row;
+        const int cy = P.cq_lo[1] + (int)(rowq % P.cq_n[1]);
+        const int cz = P.cq_lo[2] + (int)(rowq / P.cq_n[1]);
+        const int cx0 = P.cq_lo[0] + run_i * P.run;
+        const int ncell = min(P.run, P.cq_lo[0] + P.cq_n[0] - cx0);
+        const int nwt = ncell * P.nrows;
+        const unsigned qrow = P.cell_base + (unsigned)((cz * P.n[1] + cy) * P.n[0]);
+
+        for (int wt = warp; wt < nwt; wt += nwarps) {
+            const int c = wt % ncell, r = wt / ncell;
+            const int cx = cx0 + c;
+            const int ny = cy + P.row_oy[r], nz = cz + P.row_oz[r];
+            if (ny < 0 || ny >= P.n[1] || nz < 0 || nz >= P.n[2]) continue;
+            const unsigned qa = __ldg(&a.qstart[qrow + cx]), qb = __ldg(&a.qstart[qrow + cx + 1]);
+            if (qa == qb) continue;
+            const int kx = P.row_kx[r];
+            const int x_lo = max(cx - kx, 0), x_hi = min(cx + kx, P.n[0] - 1);
+            const unsigned trow = P.cell_base + (unsigned)((nz * P.n[1] + ny) * P.n[0]);
+            const unsigned ta = __ldg(&a.tstart[trow + x_lo]), tb = __ldg(&a.tstart[trow + x_hi + 1]);
+            if (ta == tb) continue;
+            const unsigned long long npairs = (unsigned long long)(qb - qa) * (tb - ta);
+            const bool direct = !SMEM || npairs > kDirectPairs;
+            if (lane == 0) {
+                cand += npairs;
+                if (!direct) atomicAdd(&s_units, (unsigned)(npairs >> 10) + 1u);
+            }
+            if (direct)
+                warp_pairs<AT, NT, ZCONST, true>(qsorted, qa, qb, tsorted, ta, tb, thr, nbins, thr_lo, thr_hi,
+                                                 dz2c, e0, inv_w, s_hist, g_hist);
+            else
+                warp_pairs<AT, NT, ZCONST, false>(qsorted, qa, qb, tsorted, ta, tb, thr, nbins, thr_lo, thr_hi,
+                                                  dz2c, e0, inv_w, s_hist, g_hist);
+        }
+        __syncthreads();
+    }
+    if (lane == 0 && cand) atomicAdd(&a.counters[1], cand);
+    if (blockIdx.x == 0 && tid == 0) atomicAdd(&a.counters[2], (unsigned long long)a.tstart[a.total_cells]);
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+template <typename T>
+static int launch_stats(amepb_ctx* ctx, const T* pts, int64_t n, int nframes, StatsOut* d_partial,
+                        StatsOut* d_out, int nparts, cudaStream_t stream) {
+    dim3 grid(nparts, nframes);
+    stats_partial_kernel<T><<<grid, 256, 0, stream>>>(pts, (long long)n, d_partial);
+    AMEPB_LAUNCH_CHECK(ctx);
+    stats_final_kernel<<<nframes, 32, 0, stream>>>(d_partial, nparts, d_out);
+    AMEPB_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+static int stats_parts(const amepb_ctx* ctx, int64_t n, int nframes) {
+    int64_t per = (n + 256 * 8 - 1) / (256 * 8);
+    int64_t want = std::max<int64_t>(1, (int64_t)ctx->sm_count * 8 / std::max(1, nframes));
+    return (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(per, want), 1024));
+}
+
+// stats of [nframes][n][3] device array -> host FrameStats[]
+static int frame_stats(amepb_ctx* ctx, const void* pts, int dtype, int64_t n, int nframes,
+                       std::vector<FrameStats>& out, cudaStream_t stream, int slot) {
+    const int nparts = stats_parts(ctx, n, nframes);
+    int rc = ensure_device(ctx, BUF_STATS, sizeof(StatsOut) * ((size_t)nframes * nparts * 2 + (size_t)nframes * 2));
+    if (rc) return rc;
+    rc = ensure_pinned(ctx, sizeof(StatsOut) * (size_t)nframes * 2);
+    if (rc) return rc;
+    StatsOut* d_final = reinterpret_cast<StatsOut*>(ctx->bufs[BUF_STATS].p) + (size_t)slot * nframes;
+    StatsOut* d_partial = reinterpret_cast<StatsOut*>(ctx->bufs[BUF_STATS].p) + (size_t)2 * nframes +
+                          (size_t)slot * nframes * nparts;
+    if (dtype == AMEPB_F32) rc = launch_stats<float>(ctx, (const float*)pts, n, nframes, d_partial, d_final, nparts, stream);
+    else rc = launch_stats<double>(ctx, (const double*)pts, n, nframes, d_partial, d_final, nparts, stream);
+    if (rc) return rc;
+    StatsOut* h = reinterpret_cast<StatsOut*>(ctx->pinned) + (size_t)slot * nframes;
+    AMEPB_CUDA(ctx, cudaMemcpyAsync(h, d_final, sizeof(StatsOut) * nframes, cudaMemcpyDeviceToHost, stream));
+    AMEPB_CUDA(ctx, cudaStreamSynchronize(stream));
+    out.resize(nframes);
+    for (int f = 0; f < nframes; ++f) {
+        for (int d = 0; d < 3; ++d) {
+            out[f].lo[d] = h[f].lo[d];
+            out[f].hi[d] = h[f].hi[d];
+            out[f].first[d] = h[f].first[d];
+            out[f].varies[d] = h[f].varies[d];
+        }
+    }
+    return 0;
+}
+
+static int exclusive_scan(amepb_ctx* ctx, const unsigned* in, unsigned* out, long long len, cudaStream_t stream) {
+    const int nblocks = (int)((len + kScanTile - 1) / kScanTile);
+    int rc = ensure_device(ctx, BUF_SCAN, sizeof(unsigned) * (size_t)(nblocks + 1));
+    if (rc) return rc;
+    unsigned* sums = reinterpret_cast<unsigned*>(ctx->bufs[BUF_SCAN].p);
+    scan_local_kernel<<<nblocks, kScanBlock, 0, stream>>>(in, out, len, sums);
+    AMEPB_LAUNCH_CHECK(ctx);
+    if (nblocks > 1) {
+        scan_sums_kernel<<<1, 1024, 0, stream>>>(sums, nblocks);
+        AMEPB_LAUNCH_CHECK(ctx);
+        scan_add_kernel<<<nblocks, kScanBlock, 0, stream>>>(out, len, sums);
+        AMEPB_LAUNCH_CHECK(ctx);
+    }
+    return 0;
+}
+
+template <typename AT, typename NT>
+static int launch_pairs(amepb_ctx* ctx, const PairArgs& args, bool zconst, cudaStream_t stream) {
+    const int nbins = args.nbins;
+    const size_t thr_bytes = (((size_t)(nbins + 1) * sizeof(AT) + 15) & ~(size_t)15);
+    const size_t smem = thr_bytes + (size_t)nbins * sizeof(unsigned);
+    const bool use_smem = smem <= 40 * 1024;
+    void (*kern)(PairArgs) = nullptr;
+    if (use_smem) kern = zconst ? pair_kernel<AT, NT, true, true> : pair_kernel<AT, NT, false, true>;
+    else kern = zconst ? pair_kernel<AT, NT, true, false> : pair_kernel<AT, NT, false, false>;
+    const size_t dyn = use_smem ? smem : 16;
+    int per_sm = 0;
+    AMEPB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kPairThreads, dyn));
+    if (per_sm < 1) per_sm = 1;
+    long long blocks = (long long)ctx->sm_count * per_sm;
+    blocks = std::max<long long>(1, std::min<long long>(blocks, args.total_tasks));
+    kern<<<(unsigned)blocks, kPairThreads, dyn, stream>>>(args);
+    AMEPB_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+struct RdfCall {
+    const void* coords;
+    int coords_dtype;
+    int64_t n;
+    const void* other;  // may be NULL
+    int other_dtype;
+    int64_t m;
+    int space;
+    int64_t nframes;
+    const double* box;
+    int box_dtype;
+    const double* edges;
+    int64_t edges_stride;
+    int nbins;
+    int pbc;
+    uint64_t* hist_out;
+    int32_t* dim_out;
+    cudaStream_t stream;
+};
+
+static size_t elem_size(int dtype) { return dtype == AMEPB_F32 ? 4 : 8; }
+
+// One sub-batch: frames [f0, f0+nf) of the call; d_coords / d_other / d_hist
+// are device pointers to this sub-batch's data.
+static int rdf_sub_batch(amepb_ctx* ctx, const RdfCall& c, int64_t f0, int nf, const void* d_coords,
+                         const void* d_other, unsigned long long* d_hist, bool* bad_dim) {
+    cudaStream_t stream = c.stream;
+    const bool self = (c.other == nullptr);
+    const int qdtype = self ? c.coords_dtype : c.other_dtype;
+    const int64_t m = self ? c.n : c.m;
+    const void* d_query = self ? d_coords : d_other;
+    // arithmetic regime (amep/spatialcor.py:381): images are float32 with pbc,
+    // otherwise the targets keep their dtype; the query keeps its own dtype.
+    const bool targets_f64 = (!c.pbc && c.coords_dtype == AMEPB_F64);
+    const bool arith_f64 = targets_f64 || qdtype == AMEPB_F64;
+    const int nbins = c.nbins;
+
+    AMEPB_CUDA(ctx, cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * (size_t)nf * nbins, stream));
+
+    // ---- stats -> plans ------------------------------------------------------
+    std::vector<FrameStats> tstats, qstats;
+    int rc = frame_stats(ctx, d_coords, c.coords_dtype, c.n, nf, tstats, stream, 0);
+    if (rc) return rc;
+    if (!self) {
+        rc = frame_stats(ctx, d_other, c.other_dtype, c.m, nf, qstats, stream, 1);
+        if (rc) return rc;
+    }
+    std::vector<FramePlan> plans(nf);
+    long long total_cells = 0, total_tasks = 0, total_cap = 0;
+    bool all_zconst = true;
+    int k_used = 0;
+    for (int f = 0; f < nf; ++f) {
+        const FrameStats& ts = tstats[f];
+        const FrameStats& qs = self ? tstats[f] : qstats[f];
+        const int dim = dimension_from_stats(ts, c.n);
+        if (c.dim_out) c.dim_out[f0 + f] = dim;
+        FramePlan& P = plans[f];
+        const double* edges = c.edges + (c.edges_stride ? (f0 + f) * c.edges_stride : 0);
+        bool ok = true;
+        if (c.pbc && dim != 2 && dim != 3) {
+            *bad_dim = true;
+            ok = false;
+        }
+        PlanInputs in;
+        in.box_boundary = c.box + (f0 + f) * 6;
+        in.box_is_f32 = (c.box_dtype == AMEPB_F32);
+        in.pbc = c.pbc;
+        in.rc = edges[nbins];
+        in.n_targets = c.n;
+        in.n_queries = m;
+        in.cells_per_cutoff = ctx->rdf_k_override;
+        in.max_cells = std::max<int64_t>(4096, c.n * (c.pbc ? 2 : 1));
+        // edges must be usable: finite, non-decreasing
+        for (int i = 0; ok && i < nbins; ++i)
+            if (!(edges[i] <= edges[i + 1])) ok = false;
+        if (ok) ok = plan_frame(in, dim, ts, qs, P);
+        else memset(&P, 0, sizeof(P)), P.dim = dim;
+        P.thr_index = c.edges_stride ? f : 0;
+        P.cell_base = (unsigned)total_cells;
+        P.task_begin = total_tasks;
+        if (P.valid) {
+            const bool zc = !ts.varies[2] && !qs.varies[2];
+            all_zconst = all_zconst && zc;
+            if (zc) {
+                if (arith_f64) {
+                    const double qz = qs.first[2];
+                    const double nz = targets_f64 ? ts.first[2] : (double)(float)ts.first[2];
+                    const double dz = qz - nz;
+                    P.dz2c = dz * dz;
+                } else {
+                    const float qz = (float)qs.first[2];
+                    const float nz = (float)ts.first[2];
+                    const volatile float dz = qz - nz;
+                    const volatile float dz2 = dz * dz;
+                    P.dz2c = (double)dz2;
+                }
+            }
+            P.bin_e0 = edges[0];
+            const double width = edges[nbins] - edges[0];
+            P.bin_inv_w = width > 0 ? (double)nbins / width : 0.0;
+            total_cells += P.ncells;
+            total_tasks += P.ntasks;
+            long long cap = c.n;
+            if (c.pbc)
+                for (int d = 0; d < 3; ++d) cap *= (P.nshift[d] == 3 ? 2 : 1);
+            total_cap += cap;
+            for (int r = 0; r < P.nrows; ++r) k_used = std::max<int>(k_used, std::max<int>(P.row_kx[r], std::max(abs((int)P.row_oy[r]), abs((int)P.row_oz[r]))));
+        } else {
+            P.ntasks = 0;
+            P.ncells = 0;
+        }
+    }
+    ctx->rdf_info.frames += nf;
+    ctx->rdf_info.cells += total_cells;
+    ctx->rdf_info.block_tasks += total_tasks;
+    ctx->rdf_info.sub_batches += 1;
+    if (total_tasks == 0) return 0;
+    if (total_cells >= (1ll << 31) || total_cap >= (1ll << 32) || (long long)m * nf >= (1ll << 32))
+        return fail(ctx, AMEPB_E_NOMEM, "amepb_rdf_batch: sub-batch too large for 32-bit cell offsets");
+
+    // ---- thresholds ------------------------------------------------------------
+    const int ntables = c.edges_stride ? nf : 1;
+    const size_t at_size = arith_f64 ? 8 : 4;
+    const size_t thr_bytes = (size_t)ntables * (nbins + 1) * at_size;
+    const size_t plan_bytes = sizeof(FramePlan) * (size_t)nf;
+    rc = ensure_pinned(ctx, plan_bytes + thr_bytes + 64);
+    if (rc) return rc;
+    rc = ensure_device(ctx, BUF_PLANS, plan_bytes);
+    if (rc) return rc;
+    rc = ensure_device(ctx, BUF_THR, thr_bytes);
+    if (rc) return rc;
+    char* hp = reinterpret_cast<char*>(ctx->pinned);
+    memcpy(hp, plans.data(), plan_bytes);
+    char* hthr = hp + ((plan_bytes + 15) & ~(size_t)15);
+    for (int tb = 0; tb < ntables; ++tb) {
+        const double* edges = c.edges + (c.edges_stride ? (f0 + tb) * c.edges_stride : 0);
+        if (arith_f64) make_thresholds<double>(edges, nbins, reinterpret_cast<double*>(hthr) + (size_t)tb * (nbins + 1));
+        else make_thresholds<float>(edges, nbins, reinterpret_cast<float*>(hthr) + (size_t)tb * (nbins + 1));
+    }
+    AMEPB_CUDA(ctx, cudaMemcpyAsync(ctx->bufs[BUF_PLANS].p, hp, plan_bytes, cudaMemcpyHostToDevice, stream));
+    AMEPB_CUDA(ctx, cudaMemcpyAsync(ctx->bufs[BUF_THR].p, hthr, thr_bytes, cudaMemcpyHostToDevice, stream));
+    const FramePlan* d_plans = reinterpret_cast<const FramePlan*>(ctx->bufs[BUF_PLANS].p);
+
+    // ---- workspaces ------------------------------------------------------------
+    const size_t cell_bytes = sizeof(unsigned) * (size_t)(total_cells + 1);
+    const size_t tsz = targets_f64 ? sizeof(Vec4<double>) : sizeof(Vec4<float>);
+    const size_t qsz = arith_f64 ? sizeof(Vec4<double>) : sizeof(Vec4<float>);
+    if ((rc = ensure_device(ctx, BUF_TCOUNT, cell_bytes))) return rc;
+    if ((rc = ensure_device(ctx, BUF_TSTART, cell_bytes))) return rc;
+    if ((rc = ensure_device(ctx, BUF_QCOUNT, cell_bytes))) return rc;
+    if ((rc = ensure_device(ctx, BUF_QSTART, cell_bytes))) return rc;
+    if ((rc = ensure_device(ctx, BUF_TSORTED, tsz * (size_t)total_cap))) return rc;
+    if ((rc = ensure_device(ctx, BUF_QSORTED, qsz * (size_t)m * nf))) return rc;
+    if ((rc = ensure_device(ctx, BUF_MISC, 64))) return rc;
+    unsigned* tcount = reinterpret_cast<unsigned*>(ctx->bufs[BUF_TCOUNT].p);
+    unsigned* tstart = reinterpret_cast<unsigned*>(ctx->bufs[BUF_TSTART].p);
+    unsigned* qcount = reinterpret_cast<unsigned*>(ctx->bufs[BUF_QCOUNT].p);
+    unsigned* qstart = reinterpret_cast<unsigned*>(ctx->bufs[BUF_QSTART].p);
+    AMEPB_CUDA(ctx, cudaMemsetAsync(tcount, 0, cell_bytes, stream));
+    AMEPB_CUDA(ctx, cudaMemsetAsync(qcount, 0, cell_bytes, stream));
+    AMEPB_CUDA(ctx, cudaMemsetAsync(ctx->bufs[BUF_MISC].p, 0, sizeof(unsigned long long), stream));
+
+    // ---- cell build ------------------------------------------------------------
+    const dim3 tgrid((unsigned)((c.n + 255) / 256), nf), qgrid((unsigned)((m + 255) / 256), nf);
+    auto place_targets = [&](bool fill) -> int {
+        void* sorted = ctx->bufs[BUF_TSORTED].p;
+        if (c.pbc) {
+            if (c.coords_dtype == AMEPB_F32) {
+                if (fill) place_images_kernel<float, true><<<tgrid, 256, 0, stream>>>((const float*)d_coords, c.n, d_plans, tcount, tstart, (Vec4<float>*)sorted);
+                else place_images_kernel<float, false><<<tgrid, 256, 0, stream>>>((const float*)d_coords, c.n, d_plans, tcount, tstart, (Vec4<float>*)sorted);
+            } else {
+                if (fill) place_images_kernel<double, true><<<tgrid, 256, 0, stream>>>((const double*)d_coords, c.n, d_plans, tcount, tstart, (Vec4<float>*)sorted);
+                else place_images_kernel<double, false><<<tgrid, 256, 0, stream>>>((const double*)d_coords, c.n, d_plans, tcount, tstart, (Vec4<float>*)sorted);
+            }
+        } else if (c.coords_dtype == AMEPB_F32) {
+            if (fill) place_points_kernel<float, float, true, true><<<tgrid, 256, 0, stream>>>((const float*)d_coords, c.n, d_plans, tcount, tstart, (Vec4<float>*)sorted);
+            else place_points_kernel<float, float, false, true><<<tgrid, 256, 0, stream>>>((const float*)d_coords, c.n, d_plans, tcount, tstart, (Vec4<float>*)sorted);
+        } else {
+            if (fill) place_points_kernel<double, double, true, true><<<tgrid, 256, 0, stream>>>((const double*)d_coords, c.n, d_plans, tcount, tstart, (Vec4<double>*)sorted);
+            else place_points_kernel<double, double, false, true><<<tgrid, 256, 0, stream>>>((const double*)d_coords, c.n, d_plans, tcount, tstart, (Vec4<double>*)sorted);
+        }
+        AMEPB_LAUNCH_CHECK(ctx);
+        return 0;
+    };
+    auto place_queries = [&](bool fill) -> int {
+        void* sorted = ctx->bufs[BUF_QSORTED].p;
+        if (qdtype == AMEPB_F32 && !arith_f64) {
+            if (fill) place_points_kernel<float, float, true, false><<<qgrid, 256, 0, stream>>>((const float*)d_query, m, d_plans, qcount, qstart, (Vec4<float>*)sorted);
+            else place_points_kernel<float, float, false, false><<<qgrid, 256, 0, stream>>>((const float*)d_query, m, d_plans, qcount, qstart, (Vec4<float>*)sorted);
+        } else if (qdtype == AMEPB_F32) {
+            if (fill) place_points_kernel<float, double, true, false><<<qgrid, 256, 0, stream>>>((const float*)d_query, m, d_plans, qcount, qstart, (Vec4<double>*)sorted);
+            else place_points_kernel<float, double, false, false><<<qgrid, 256, 0, stream>>>((const float*)d_query, m, d_plans, qcount, qstart, (Vec4<double>*)sorted);
+        } else {
+            if (fill) place_points_kernel<double, double, true, false><<<qgrid, 256, 0, stream>>>((const double*)d_query, m, d_plans, qcount, qstart, (Vec4<double>*)sorted);
+            else place_points_kernel<double, double, false, false><<<qgrid, 256, 0, stream>>>((const double*)d_query, m, d_plans, qcount, qstart, (Vec4<double>*)sorted);
+        }
+        AMEPB_LAUNCH_CHECK(ctx);
+        return 0;
+    };
+    if ((rc = place_targets(false))) return rc;
+    if ((rc = place_queries(false))) return rc;
+    if ((rc = exclusive_scan(ctx, tcount, tstart, total_cells + 1, stream))) return rc;
+    if ((rc = exclusive_scan(ctx, qcount, qstart, total_cells + 1, stream))) return rc;
+    if ((rc = place_targets(true))) return rc;
+    if ((rc = place_queries(true))) return rc;
+
+    // ---- pairs -----------------------------------------------------------------
+    PairArgs args;
+    args.plans = d_plans;
+    args.tstart = tstart;
+    args.qstart = qstart;
+    args.tsorted = ctx->bufs[BUF_TSORTED].p;
+    args.qsorted = ctx->bufs[BUF_QSORTED].p;
+    args.thr = ctx->bufs[BUF_THR].p;
+    args.hist = d_hist;
+    args.counters = reinterpret_cast<unsigned long long*>(ctx->bufs[BUF_MISC].p);
+    args.total_tasks = total_tasks;
+    args.total_cells = total_cells;
+    args.nbins = nbins;
+    args.nframes = nf;
+    if (!arith_f64) rc = launch_pairs<float, float>(ctx, args, all_zconst, stream);
+    else if (!targets_f64) rc = launch_pairs<double, float>(ctx, args, all_zconst, stream);
+    else rc = launch_pairs<double, double>(ctx, args, all_zconst, stream);
+    if (rc) return rc;
+
+    ctx->rdf_info.cells_per_cutoff = k_used;
+    return 0;
+}
+
+}  // namespace amepb
+
+using namespace amepb;
+
+extern "C" {
+
+int amepb_rdf_set_cells_per_cutoff(amepb_ctx* ctx, int k) {
+    if (!ctx || k < 0 || k > kMaxCellsPerCutoff) return AMEPB_E_INVAL;
+    ctx->rdf_k_override = k;
+    return 0;
+}
+
+int amepb_rdf_last_info(amepb_ctx* ctx, amepb_rdf_info* info) {
+    if (!ctx || !info) return AMEPB_E_INVAL;
+    DeviceGuard guard(ctx->device);
+    if (ctx->bufs[BUF_MISC].p && ctx->rdf_info.block_tasks > 0) {
+        unsigned long long h[3] = {0, 0, 0};
+        AMEPB_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)ctx->last_stream));
+        AMEPB_CUDA(ctx, cudaMemcpy(h, ctx->bufs[BUF_MISC].p, sizeof(h), cudaMemcpyDeviceToHost));
+        ctx->rdf_info.candidate_pairs = (int64_t)h[1];
+        ctx->rdf_info.images = (int64_t)h[2];
+    }
+    *info = ctx->rdf_info;
+    return 0;
+}
+
+int amepb_frame_dimension(amepb_ctx* ctx, const void* coords, int dtype, int space, int64_t nframes,
+                          int64_t n, int32_t* dim_out, void* stream_) {
+    if (!ctx) return AMEPB_E_INVAL;
+    if (!coords || !dim_out || nframes < 0 || n <= 0 || (dtype != AMEPB_F32 && dtype != AMEPB_F64) ||
+        (space != AMEPB_DEVICE && space != AMEPB_HOST))
+        return fail(ctx, AMEPB_E_INVAL, "amepb_frame_dimension: invalid argument");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const size_t frame_bytes = (size_t)n * 3 * elem_size(dtype);
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(nframes, std::min<int64_t>(32768, (int64_t)((2ull << 30) / frame_bytes) + 1)));
+    std::vector<FrameStats> st;
+    for (int64_t f0 = 0; f0 < nframes; f0 += chunk) {
+        const int nf = (int)std::min<int64_t>(chunk, nframes - f0);
+        const void* d = (const char*)coords + (size_t)f0 * frame_bytes;
+        if (space == AMEPB_HOST) {
+            int rc = ensure_device(ctx, BUF_STAGE_A, frame_bytes * nf);
+            if (rc) return rc;
+            AMEPB_CUDA(ctx, cudaMemcpyAsync(ctx->bufs[BUF_STAGE_A].p, d, frame_bytes * nf, cudaMemcpyHostToDevice, stream));
+            d = ctx->bufs[BUF_STAGE_A].p;
+        }
+        int rc = frame_stats(ctx, d, dtype, n, nf, st, stream, 0);
+        if (rc) return rc;
+        for (int f = 0; f < nf; ++f) dim_out[f0 + f] = dimension_from_stats(st[f], n);
+    }
+    return 0;
+}
+
+int amepb_rdf_batch(amepb_ctx* ctx, const void* coords, int coords_dtype, int64_t n, const void* other,
+                    int other_dtype, int64_t m, int space, int64_t nframes, const double* box_boundary,
+                    int box_dtype, const double* edges, int64_t edges_stride, int32_t nbins, int pbc,
+                    uint64_t* hist_out, int32_t* dim_out, void* stream_) {
+    if (!ctx) return AMEPB_E_INVAL;
+    auto dtype_ok = [](int d) { return d == AMEPB_F32 || d == AMEPB_F64; };
+    if (!coords || !box_boundary || !edges || !hist_out)
+        return fail(ctx, AMEPB_E_INVAL, "amepb_rdf_batch: NULL pointer argument");
+    if (nframes < 0 || n <= 0 || nbins <= 0 || (other && m <= 0))
+        return fail(ctx, AMEPB_E_INVAL, "amepb_rdf_batch: nframes=%lld n=%lld m=%lld nbins=%d out of range",
+                    (long long)nframes, (long long)n, (long long)m, (int)nbins);
+    if (!dtype_ok(coords_dtype) || (other && !dtype_ok(other_dtype)) || !dtype_ok(box_dtype))
+        return fail(ctx, AMEPB_E_INVAL, "amepb_rdf_batch: unknown dtype code");
+    if (space != AMEPB_DEVICE && space != AMEPB_HOST)
+        return fail(ctx, AMEPB_E_INVAL, "amepb_rdf_batch: unknown memory space %d", space);
+    if (edges_stride != 0 && edges_stride < nbins + 1)
+        return fail(ctx, AMEPB_E_INVAL, "amepb_rdf_batch: edges_stride %lld < nbins+1", (long long)edges_stride);
+    DeviceGuard guard(ctx->device);
+    memset(&ctx->rdf_info, 0, sizeof(ctx->rdf_info));
+    const int64_t launches0 = ctx->launches;
+    if (nframes == 0) return 0;
+    ctx->last_stream = stream_;
+    {
+        int rc0 = ensure_device(ctx, BUF_MISC, 64);
+        if (rc0) return rc0;
+        AMEPB_CUDA(ctx, cudaMemsetAsync(ctx->bufs[BUF_MISC].p, 0, 64, (cudaStream_t)stream_));
+    }
+
+    RdfCall c;
+    c.coords = coords; c.coords_dtype = coords_dtype; c.n = n;
+    c.other = other; c.other_dtype = other_dtype; c.m = other ? m : n;
+    c.space = space; c.nframes = nframes; c.box = box_boundary; c.box_dtype = box_dtype;
+    c.edges = edges; c.edges_stride = edges_stride; c.nbins = nbins; c.pbc = pbc ? 1 : 0;
+    c.hist_out = hist_out; c.dim_out = dim_out; c.stream = (cudaStream_t)stream_;
+
+    // sub-batch size from a workspace budget
+    const size_t cbytes = (size_t)n * 3 * elem_size(coords_dtype);
+    const size_t obytes = other ? (size_t)m * 3 * elem_size(other_dtype) : 0;
+    const size_t per_frame = (size_t)n * (c.pbc ? 8 : 1) * 32 + (size_t)c.m * 32 +
+                             (size_t)std::max<int64_t>(4096, n * 2) * 16 +
+                             (space == AMEPB_HOST ? cbytes + obytes : 0);
+    size_t free_b = 0, total_b = 0;
+    AMEPB_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+    size_t budget = std::min<size_t>((size_t)24 << 30, (free_b + ctx->bufs[BUF_TSORTED].cap) / 3);
+    budget = std::max<size_t>(budget, per_frame);
+    int64_t fb = (int64_t)std::max<size_t>(1, budget / per_frame);
+    fb = std::min<int64_t>(fb, 16384);
+    fb = std::min<int64_t>(fb, std::max<int64_t>(1, (int64_t)((1ll << 31) / std::max<int64_t>(1, n * 8))));
+    fb = std::min<int64_t>(fb, nframes);
+
+    bool bad_dim = false;
+    for (int64_t f0 = 0; f0 < nframes; f0 += fb) {
+        const int nf = (int)std::min<int64_t>(fb, nframes - f0);
+        const void* d_coords = (const char*)coords + (size_t)f0 * cbytes;
+        const void* d_other = other ? (const char*)other + (size_t)f0 * obytes : nullptr;
+        unsigned long long* d_hist = reinterpret_cast<unsigned long long*>(hist_out) + (size_t)f0 * nbins;
+        if (space == AMEPB_HOST) {
+            int rc = ensure_device(ctx, BUF_STAGE_A, cbytes * nf);
+            if (rc) return rc;
+            AMEPB_CUDA(ctx, cudaMemcpyAsync(ctx->bufs[BUF_STAGE_A].p, d_coords, cbytes * nf, cudaMemcpyHostToDevice, c.stream));
+            d_coords = ctx->bufs[BUF_STAGE_A].p;
+            if (other) {
+                rc = ensure_device(ctx, BUF_STAGE_B, obytes * nf);
+                if (rc) return rc;
+                AMEPB_CUDA(ctx, cudaMemcpyAsync(ctx->bufs[BUF_STAGE_B].p, d_other, obytes * nf, cudaMemcpyHostToDevice, c.stream));
+                d_other = ctx->bufs[BUF_STAGE_B].p;
+            }
+            rc = ensure_device(ctx, BUF_STAGE_OUT, sizeof(unsigned long long) * (size_t)nf * nbins);
+            if (rc) return rc;
+            d_hist = reinterpret_cast<unsigned long long*>(ctx->bufs[BUF_STAGE_OUT].p);
+        }
+        int rc = rdf_sub_batch(ctx, c, f0, nf, d_coords, d_other, d_hist, &bad_dim);
+        if (rc) return rc;
+        if (space == AMEPB_HOST) {
+            AMEPB_CUDA(ctx, cudaMemcpyAsync(hist_out + (size_t)f0 * nbins, d_hist,
+                                            sizeof(unsigned long long) * (size_t)nf * nbins,
+                                            cudaMemcpyDeviceToHost, c.stream));
+            AMEPB_CUDA(ctx, cudaStreamSynchronize(c.stream));
+        }
+    }
+    ctx->rdf_info.kernel_launches = ctx->launches - launches0;
+    if (bad_dim)
+        return fail(ctx, AMEPB_E_DIMENSION,
+                    "amep.pbc.pbc_points: Only 2d or 3d systems are supported. Please check coords and enforce_nd.");
+    return 0;
+}
+
+}  // extern "C"

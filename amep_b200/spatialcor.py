@@ -1,0 +1,311 @@
+"""Drop-in for the RDF / S(q) functions of ``amep.spatialcor`` (AMEP 1.3.0).
+
+Same signatures, argument meaning and error behaviour as
+``amep.spatialcor.rdf`` (amep/spatialcor.py:421-649), ``sfiso`` (:1451-1687) and
+``sf2d`` (:1722-1940).  The per-particle work runs in libamepb's sm_100a
+kernels; what stays on the host is the parameter prologue (bin edges, q grid,
+unit vectors) and the normalisation epilogue, written as the same NumPy
+expressions as the reference because they define output dtype and rounding
+(SURVEY.md Appendix A).  ``coords`` may be a NumPy array or a (CUDA) torch
+tensor; results are NumPy arrays like the reference's.
+
+``njobs``, ``chunksize`` (except where it changes the result, see ``sf2d``) and
+``verbose`` are accepted and ignored: there is no process pool to size.
+The ``*_frames`` functions are the batched forms the evaluate classes use.
+"""
+from __future__ import annotations
+
+import logging
+
+import numpy as np
+
+from . import _core
+from .utils import (available_cpu_count, optimal_chunksize, runningmean,
+                    unit_vector_2D, unit_vector_3D)
+
+_log = logging.getLogger("amep_b200.spatialcor")
+
+__all__ = ["rdf", "sfiso", "sf2d", "rdf_frames", "sfiso_frames", "sf2d_frames"]
+
+
+def _box_numpy(box_boundary):
+    if _core._is_torch(box_boundary):
+        box_boundary = box_boundary.detach().cpu().numpy()
+    return np.asarray(box_boundary)
+
+
+# =============================================================================
+# RDF
+# =============================================================================
+def _rdf_edges(box_boundary, nbins, rmax):
+    """Bin edges as the reference builds them (amep/spatialcor.py:548-563): the
+    dtype follows ``rmax`` -- a float32 scalar when it defaults from a float32
+    box -- and NumPy later compares float64 distances against these values."""
+    if nbins is None:
+        nbins = 500
+    if rmax is None:
+        rmax = max(box_boundary[:, 1] - box_boundary[:, 0]) / 2
+    return np.linspace(0.0, rmax, nbins + 1), nbins
+
+
+def _rdf_normalise(hist, bins, box, n, n_other, dim):
+    """amep/spatialcor.py:639-649."""
+    if dim == 2:
+        area = np.pi * (bins[1:] ** 2 - bins[:-1] ** 2)
+        density = n / (box[0] * box[1])
+        res = hist / area / density / n_other
+    else:  # means dim=3
+        volume = 4 / 3 * np.pi * (bins[1:] ** 3 - bins[:-1] ** 3)
+        density = n / np.prod(box)
+        res = hist / volume / density / n_other
+    return res, runningmean(bins, 2)
+
+
+def rdf_frames(coords, box_boundary, other_coords=None, nbins=None, rmax=None, mode="diff",
+               pbc=True, return_counts=False, reduce=None):
+    """``rdf`` for a batch of frames ``[F, N, 3]`` in one library call.
+
+    ``box_boundary``: ``(3,2)`` or ``(F,3,2)``.  Returns ``(g [F, nbins], r [F, nbins])``
+    (plus the int64 counts with ``return_counts=True``).  ``reduce`` is an
+    optional callable applied to the device/host histogram before the epilogue
+    (the multi-GPU all-reduce hooks in here)."""
+    if mode not in ["diff", "kdtree"]:
+        raise ValueError(
+            f"amep.spatialcor.rdf: Invalid mode '{mode}'. Available modes "
+            "are 'diff' and 'kdtree'.")
+    pc = coords if isinstance(coords, _core.Particles) else _core.Particles(coords)
+    po = None
+    if other_coords is not None:
+        po = other_coords if isinstance(other_coords, _core.Particles) else _core.Particles(other_coords)
+    nf = pc.nframes
+    bb = _box_numpy(box_boundary)
+    per_frame_box = bb.ndim == 3
+    if per_frame_box and bb.shape[0] != nf:
+        raise ValueError("box_boundary must have shape (3,2) or (F,3,2)")
+    # host prologue: bin edges per frame (shared when the box is)
+    if per_frame_box:
+        edge_rows = [_rdf_edges(bb[f], nbins, rmax) for f in range(nf)]
+        nb = edge_rows[0][1]
+        edge_list = [e for e, _ in edge_rows]
+        edges = np.stack([np.asarray(e, dtype=np.float64) for e in edge_list])
+    else:
+        e, nb = _rdf_edges(bb, nbins, rmax)
+        edge_list = [e] * nf
+        edges = np.asarray(e, dtype=np.float64)
+    if np.any(np.diff(edges, axis=-1) < 0):
+        raise ValueError("`bins` must increase monotonically, when an array")
+    hist, dims = _core.rdf_histograms(pc, bb, edges, other=po, pbc=pbc)
+    if reduce is not None:
+        hist = reduce(hist)
+    if _core._is_torch(hist):
+        hist = hist.cpu().numpy()
+    n, n_other = pc.n, (pc.n if po is None else po.n)
+    g_rows, r_rows = [], []
+    for f in range(nf):
+        b = bb[f] if per_frame_box else bb
+        box = b[:, 1] - b[:, 0]
+        g, r = _rdf_normalise(hist[f], edge_list[f], box, n, n_other, int(dims[f]))
+        g_rows.append(g)
+        r_rows.append(r)
+    g_all, r_all = np.array(g_rows), np.array(r_rows)
+    if return_counts:
+        return g_all, r_all, hist
+    return g_all, r_all
+
+
+def rdf(coords, box_boundary, other_coords=None, nbins=None, rmax=None, mode="diff",
+        chunksize=None, njobs=1, pbc=True, verbose=False):
+    """Radial pair-distribution function of one frame; same contract as
+    ``amep.spatialcor.rdf`` (amep/spatialcor.py:421-649).
+
+    ``mode='kdtree'`` is served by the same exact-arithmetic kernel as
+    ``'diff'`` (the reference's two modes agree to rounding for
+    ``rmax <= min(L)/2``; its own test compares them after ``round(3)``,
+    test/test_spatialcor.py:73-102)."""
+    g, r = rdf_frames(coords, box_boundary, other_coords, nbins=nbins, rmax=rmax, mode=mode, pbc=pbc)
+    return g[0], r[0]
+
+
+# =============================================================================
+# isotropic S(q)
+# =============================================================================
+def _sfiso_directions(twod, num):
+    """Unit vectors of sfiso(mode='fast') (amep/spatialcor.py:1640-1647)."""
+    if twod:
+        theta = np.linspace(0, 360, num=num, endpoint=False)
+        return unit_vector_2D(theta)
+    theta = np.linspace(0, 180, num=int(num / 2), endpoint=False)
+    phi = np.linspace(0, 360, num=num, endpoint=False)
+    t, p = np.meshgrid(theta, phi)
+    return unit_vector_3D(t.flatten(), p.flatten())
+
+
+def _unique_directions(unit_vectors):
+    """Group directions that coincide up to sign (S_u = S_-u exactly in exact
+    arithmetic; rho(-q) = conj rho(q)).  Returns (representatives, weights)."""
+    reps, weights = [], []
+    for u in unit_vectors:
+        for i, r in enumerate(reps):
+            if np.max(np.abs(u - r)) <= 5e-16 or np.max(np.abs(u + r)) <= 5e-16:
+                weights[i] += 1
+                break
+        else:
+            reps.append(u)
+            weights.append(1)
+    return np.array(reps), np.array(weights, dtype=np.float64)
+
+
+def sfiso_frames(coords, box_boundary, N=None, qmax=20.0, twod=True, mode="std",
+                 other_coords=None, accuracy=0.5, num=64, reduce=None):
+    """``sfiso`` for a batch of frames -> ``(S [F, nq], q [F, nq])``."""
+    modes = ["std", "fast", "fft"]
+    pc = coords if isinstance(coords, _core.Particles) else _core.Particles(coords)
+    po = pc if other_coords is None else (
+        other_coords if isinstance(other_coords, _core.Particles) else _core.Particles(other_coords))
+    nf = pc.nframes
+    bb = _box_numpy(box_boundary)
+    per_frame_box = bb.ndim == 3
+    if mode not in modes:
+        _log.warning(f"Mode '{mode}' not available. Using mode 'fast'. Available modes are {modes}.")
+        mode = "fast"
+    if not twod and mode == "fft":
+        _log.warning("Mode 'fft' does only work for 2d systems. Since twod is False, mode 'std' is used.")
+        mode = "std"
+    if mode != "fast":
+        raise NotImplementedError(
+            f"amep_b200.spatialcor.sfiso: mode '{mode}' is not on the B200 hot path yet "
+            "(SURVEY.md section 8: Debye 'std' is N^2*nq and not a scale target; 'fft' is a next row). "
+            "Use mode='fast' (the default of amep.evaluate.SFiso).")
+    # q grid per frame (amep/spatialcor.py:1592-1598)
+    q_rows, dq_rows = [], []
+    for f in range(nf if per_frame_box else 1):
+        b = bb[f] if per_frame_box else bb
+        rmax = np.max(b[:, 1] - b[:, 0])
+        dq = 2 * np.pi / rmax
+        q_rows.append(np.arange(dq, qmax, dq))
+        dq_rows.append(float(dq))
+    nq = len(q_rows[0])
+    if any(len(q) != nq for q in q_rows):
+        raise ValueError("sfiso_frames: the box changes the number of q values between frames")
+    unit_vectors = _sfiso_directions(twod, num)
+    reps, weights = _unique_directions(unit_vectors)
+    if per_frame_box:
+        kvec = np.stack([dq * reps for dq in dq_rows])
+    else:
+        kvec = dq_rows[0] * reps
+    if nq == 0:
+        return np.zeros((nf, 0)), np.zeros((nf, 0))
+    ha = _core.sq_harmonics(pc, kvec, nq)
+    hb = ha if po is pc else _core.sq_harmonics(po, kvec, nq)
+    if reduce is not None:
+        ha = reduce(ha)
+        hb = ha if po is pc else reduce(hb)
+    if _core._is_torch(ha):
+        ha = ha.cpu().numpy()
+        hb = ha if po is pc else hb.cpu().numpy()
+    # (C_a C_b + S_a S_b) / sqrt(N_a N_b), mean over directions
+    # (amep/spatialcor.py:1440-1446, 1660-1664)
+    s_dir = (ha[..., 0] * hb[..., 0] + ha[..., 1] * hb[..., 1]) / np.sqrt(pc.n * po.n)
+    s = np.tensordot(weights, s_dir, axes=([0], [1])) / len(unit_vectors)
+    q = np.stack(q_rows) if per_frame_box else np.broadcast_to(q_rows[0], (nf, nq)).copy()
+    return s, q
+
+
+def sfiso(coords, box_boundary, N, qmax=20.0, twod=True, njobs=1, chunksize=None, mode="std",
+          other_coords=None, accuracy=0.5, num=64, verbose=False):
+    """Isotropic static structure factor of one frame; contract of
+    ``amep.spatialcor.sfiso`` (amep/spatialcor.py:1451-1687).  ``N`` is ignored
+    exactly as in the reference (:1579-1581)."""
+    s, q = sfiso_frames(coords, box_boundary, N, qmax=qmax, twod=twod, mode=mode,
+                        other_coords=other_coords, accuracy=accuracy, num=num)
+    return s[0], q[0]
+
+
+# =============================================================================
+# 2D S(q)
+# =============================================================================
+def _sf2d_chunksize(n, n_other, chunksize, njobs):
+    """amep/spatialcor.py:1860-1871.  Part of the result in mode 'std': every
+    chunk restarts a complex64 accumulator."""
+    if njobs > available_cpu_count():
+        njobs = available_cpu_count()
+    if chunksize is None:
+        chunksize = min(optimal_chunksize(n_other, n), optimal_chunksize(n, n_other))
+    if chunksize > n_other:
+        chunksize = int(n_other / njobs)
+    elif chunksize > n:
+        chunksize = int(n / njobs)
+    return chunksize
+
+
+def sf2d_frames(coords, box_boundary, other_coords=None, qmax=20.0, njobs=1, mode="std", Ntot=None,
+                accuracy=0.1, chunksize=None, accum="c64", reduce=None, return_modes=False):
+    """``sf2d`` for a batch of frames -> ``(S [F, ny, nx], Qx [F, ny, nx], Qy [F, ny, nx])``.
+
+    ``accum='c64'`` reproduces the reference's complex64 running sums (order and
+    chunking included); ``accum='f64'`` sums in float64 (closer to the exact
+    value than the reference itself)."""
+    pc = coords if isinstance(coords, _core.Particles) else _core.Particles(coords)
+    same = other_coords is None
+    po = pc if same else (other_coords if isinstance(other_coords, _core.Particles)
+                          else _core.Particles(other_coords))
+    nf = pc.nframes
+    bb = _box_numpy(box_boundary)
+    per_frame_box = bb.ndim == 3
+    if Ntot is None:
+        Ntot = pc.n
+    if accuracy < 0.0 or accuracy > 1.0:
+        raise ValueError(f"amep.spatialcor.sf2d: Accuracy must be between 0.0 and 1.0. Got {accuracy}.")
+    if mode not in ["std", "fft"]:
+        raise ValueError(f"Mode '{mode}' not available. Available modes are {['std', 'fft']}.")
+    if mode == "fft":
+        raise NotImplementedError(
+            "amep_b200.spatialcor.sf2d: mode 'fft' is not on the B200 hot path yet "
+            "(SURVEY.md section 8f, a next row); use mode='std'.")
+    # q axis per frame (amep/spatialcor.py:1849-1857)
+    q_rows = []
+    for f in range(nf if per_frame_box else 1):
+        b = bb[f] if per_frame_box else bb
+        box = b[:, 1] - b[:, 0]
+        rmax = np.abs(np.max(box))
+        dq = 2 * np.pi / rmax
+        q_rows.append(np.arange(dq, qmax, dq))
+    nq = len(q_rows[0])
+    if any(len(q) != nq for q in q_rows):
+        raise ValueError("sf2d_frames: the box changes the number of q values between frames")
+    cs = _sf2d_chunksize(pc.n, po.n, chunksize, njobs)
+    qpos = np.stack(q_rows) if per_frame_box else q_rows[0]
+    rho = _core.sf2d_modes(pc, qpos, nq, accum=accum, chunksize=cs)
+    rho_other = rho if same else _core.sf2d_modes(po, qpos, nq, accum=accum, chunksize=cs)
+    if reduce is not None:
+        rho = reduce(rho)
+        rho_other = rho if same else reduce(rho_other)
+    if _core._is_torch(rho):
+        rho = rho.cpu().numpy()
+        rho_other = rho if same else rho_other.cpu().numpy()
+    # S = Re(rho rho_other*) / Ntot in NumPy, like the reference (:1908) -- its
+    # complex64 multiply decides the last bit (SURVEY.md A.3 iii)
+    s = np.real(rho * rho_other.conj()) / Ntot
+    qx_rows, qy_rows = [], []
+    for q in q_rows:
+        axis = np.append(np.flip(-q), q)
+        gx, gy = np.meshgrid(axis, axis)
+        qx_rows.append(gx)
+        qy_rows.append(gy)
+    if per_frame_box:
+        qx_all, qy_all = np.stack(qx_rows), np.stack(qy_rows)
+    else:
+        qx_all = np.broadcast_to(qx_rows[0], (nf,) + qx_rows[0].shape).copy()
+        qy_all = np.broadcast_to(qy_rows[0], (nf,) + qy_rows[0].shape).copy()
+    if return_modes:
+        return s, qx_all, qy_all, rho, rho_other
+    return s, qx_all, qy_all
+
+
+def sf2d(coords, box_boundary, other_coords=None, qmax=20.0, njobs=1, mode="std", Ntot=None,
+         accuracy=0.1, chunksize=None, verbose=False, accum="c64"):
+    """2D static structure factor of one frame; contract of
+    ``amep.spatialcor.sf2d`` (amep/spatialcor.py:1722-1940)."""
+    s, qx, qy = sf2d_frames(coords, box_boundary, other_coords, qmax=qmax, njobs=njobs, mode=mode,
+                            Ntot=Ntot, accuracy=accuracy, chunksize=chunksize, accum=accum)
+    return s[0], qx[0], qy[0]

@@ -1,0 +1,180 @@
+/*
+ * amepb.h -- C ABI of libamepb.so: B200 (sm_100a) kernels for AMEP's
+ * spatial-correlation hot path (periodic RDF and static structure factor).
+ *
+ * The reference (AMEP 1.3.0, pure Python) has no FFI for this path; its only
+ * internal "operator" seam is the chunk-worker convention consumed by
+ * amep/utils.py:1928-2021 (compute_parallel).  Each entry point below replaces
+ * one of those workers (plus the image / grid set-up around it) and is what a
+ * ctypes binding inside the reference would call:
+ *
+ *   amepb_frame_dimension  <- amep/utils.py:1617-1667       dimension()
+ *   amepb_rdf_batch        <- amep/pbc.py:169-350           pbc_points(width=0.5)
+ *                             amep/spatialcor.py:348-388    __rdf_diff
+ *                             amep/spatialcor.py:566-600    chunk fan-out + sum
+ *   amepb_sq_harmonics     <- amep/spatialcor.py:1402-1448  __sf_iso_chunk_fast
+ *   amepb_sf2d_modes       <- amep/spatialcor.py:1690-1719  __sf2d_chunk_std
+ *                             amep/spatialcor.py:1876-1907  chunk fan-out + sum
+ *
+ * Conventions
+ *   - plain C types only; no exceptions cross the boundary;
+ *   - every call returns 0 on success, <0 for an invalid argument
+ *     (AMEPB_E_*), >0 for a cudaError_t; amepb_last_error() gives the text;
+ *   - `space` says where the *data* pointers (coords, other, out) live:
+ *     AMEPB_DEVICE = device pointers (e.g. torch tensor.data_ptr()), work is
+ *     enqueued on `stream`; AMEPB_HOST = host pointers, the library stages
+ *     them through the device itself (pinned memory gives overlap) and the
+ *     call returns when `out` is complete;
+ *   - small per-frame parameter arrays (box, edges, directions, dim_out) are
+ *     always HOST pointers;
+ *   - the caller owns every buffer; inputs are never modified;
+ *   - a context owns its device workspaces: use one per (device, host thread);
+ *   - there is no CPU fallback: without a CUDA device amepb_create fails.
+ */
+#ifndef AMEPB_H
+#define AMEPB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AMEPB_ABI_VERSION 1
+
+/* element types of coordinate / box arrays */
+#define AMEPB_F32 0
+#define AMEPB_F64 1
+
+/* memory space of data pointers */
+#define AMEPB_DEVICE 0
+#define AMEPB_HOST 1
+
+/* error codes (negative) */
+#define AMEPB_E_INVAL (-1)     /* bad argument                                          */
+#define AMEPB_E_DIMENSION (-2) /* a frame is neither 2D nor 3D (amep/pbc.py:290-294)   */
+#define AMEPB_E_NOMEM (-3)     /* workspace does not fit                                */
+#define AMEPB_E_NODEVICE (-4)  /* no usable CUDA device                                 */
+
+/* amepb_sf2d_modes accumulation */
+#define AMEPB_ACCUM_C64_REFERENCE 0 /* complex64 running sum in the reference's order */
+#define AMEPB_ACCUM_F64 1           /* float64 sums (more accurate than the reference) */
+
+typedef struct amepb_ctx amepb_ctx;
+
+/* counters of the last amepb_rdf_batch call on a context */
+typedef struct amepb_rdf_info {
+    int64_t frames;           /* frames processed                                  */
+    int64_t images;           /* periodic images kept in the cell grids            */
+    int64_t cells;            /* grid cells over all frames                        */
+    int64_t block_tasks;      /* scheduling units of the pair kernel               */
+    int64_t candidate_pairs;  /* query-image distances the pair kernel evaluated   */
+    int64_t kernel_launches;  /* CUDA kernels launched by the call                 */
+    int32_t cells_per_cutoff; /* grid refinement k (cell edge ~ rmax / k)          */
+    int32_t sub_batches;      /* how many sub-batches the frames were split into   */
+} amepb_rdf_info;
+
+int amepb_abi_version(void);
+
+/* Create / destroy a context bound to CUDA device `device`. */
+int amepb_create(int device, amepb_ctx** out);
+void amepb_destroy(amepb_ctx* ctx);
+
+/* Text of the last error on `ctx` (ctx may be NULL: last amepb_create error). */
+const char* amepb_last_error(const amepb_ctx* ctx);
+
+/*
+ * dimension() of every frame: number of non-constant columns of the (n,3)
+ * coordinate array, 3 for a single particle (amep/utils.py:1617-1667).
+ *   coords  [nframes][n][3] of `dtype`, in `space`
+ *   dim_out [nframes] host
+ */
+int amepb_frame_dimension(amepb_ctx* ctx, const void* coords, int dtype, int space,
+                          int64_t nframes, int64_t n, int32_t* dim_out, void* stream);
+
+/*
+ * Integer pair histograms of rdf(mode='diff') for a batch of frames.
+ *
+ *   coords        [nframes][n][3]   particles whose periodic images are the targets
+ *   other         [nframes][m][3]   query particles, or NULL (queries = coords, m ignored)
+ *   box_boundary  host [nframes][3][2] float64 (float32 boxes widened exactly);
+ *                 box_dtype says which type the caller's box had -- it decides the
+ *                 type `centre` is computed in (amep/pbc.py:273, 332-338)
+ *   edges         host float64 [nbins+1] (edges_stride == 0, shared by all frames)
+ *                 or [nframes][edges_stride]; the values NumPy compares against,
+ *                 i.e. float32 edges widened exactly (amep/spatialcor.py:563, 387)
+ *   pbc           non-zero: periodic images as pbc_points(width=0.5,
+ *                 fold_coords=False); zero: targets are `coords` themselves
+ *   hist_out      [nframes][nbins] uint64 in `space`, overwritten
+ *   dim_out       host [nframes], may be NULL: dimension(coords) per frame (the
+ *                 caller's epilogue needs it, amep/spatialcor.py:640-647)
+ *
+ * Arithmetic follows the reference exactly: images are
+ * float32; float32 queries give float32 distances, float64 queries float64
+ * ones; no fused multiply-add; d > 1e-3; explicit-edge binning with a
+ * right-inclusive last bin.  Counts are bit-exact.
+ *
+ * Returns AMEPB_E_DIMENSION if pbc and some frame has dimension not in {2,3}
+ * (dim_out is filled; hist_out rows of such frames are zero).
+ */
+int amepb_rdf_batch(amepb_ctx* ctx,
+                    const void* coords, int coords_dtype, int64_t n,
+                    const void* other, int other_dtype, int64_t m,
+                    int space, int64_t nframes,
+                    const double* box_boundary, int box_dtype,
+                    const double* edges, int64_t edges_stride, int32_t nbins,
+                    int pbc,
+                    uint64_t* hist_out, int32_t* dim_out, void* stream);
+
+/* Counters of the last amepb_rdf_batch call (valid after the call returned). */
+int amepb_rdf_last_info(amepb_ctx* ctx, amepb_rdf_info* info);
+
+/* Tuning knob (0 = automatic): grid refinement k used by amepb_rdf_batch. */
+int amepb_rdf_set_cells_per_cutoff(amepb_ctx* ctx, int k);
+
+/*
+ * Harmonic density modes along given wave vectors:
+ *   out[f][d][h] = ( sum_i cos((h+1) k_d . r_i),  sum_i sin((h+1) k_d . r_i) )
+ * for h = 0..nharm-1, in float64.  With k_d = dq * u_d these are the sums of
+ * sfiso(mode='fast') (amep/spatialcor.py:1440-1446) for q = dq, 2dq, ...
+ *
+ *   coords   [nframes][n][3] of `dtype` in `space`
+ *   kvec     host float64 [nframes][ndir][3]  (kvec_stride == ndir*3) or
+ *            [ndir][3] shared by all frames (kvec_stride == 0)
+ *   out      [nframes][ndir][nharm][2] float64 in `space`, overwritten
+ */
+int amepb_sq_harmonics(amepb_ctx* ctx, const void* coords, int dtype, int space,
+                       int64_t nframes, int64_t n,
+                       const double* kvec, int64_t kvec_stride, int32_t ndir, int32_t nharm,
+                       double* out, void* stream);
+
+/*
+ * Density modes on the sf2d grid: rho[f][iy][ix] = sum_i exp(-i (qx[ix] x_i + qy[iy] y_i))
+ * with qx = qy = (-q[nq-1], ..., -q[0], q[0], ..., q[nq-1])  (amep/spatialcor.py:1852-1857, 1874).
+ *
+ *   q         host float64, the positive half of the axis: [nq] (q_stride == 0,
+ *             shared by all frames) or [nframes][q_stride]
+ *   accum     AMEPB_ACCUM_C64_REFERENCE: per chunk of `chunksize` particles a
+ *             complex64 accumulator receives exp(...) (evaluated in float64)
+ *             particle by particle in index order, chunk sums are then added in
+ *             order in complex64 (amep/spatialcor.py:1715-1719, 1890-1891);
+ *             out is complex64 [nframes][2nq][2nq][2] float32.
+ *             AMEPB_ACCUM_F64: float64 sums (chunksize ignored); out is
+ *             [nframes][2nq][2nq][2] float64.
+ */
+int amepb_sf2d_modes(amepb_ctx* ctx, const void* coords, int dtype, int space,
+                     int64_t nframes, int64_t n,
+                     const double* q, int64_t q_stride, int32_t nq,
+                     int accum, int64_t chunksize,
+                     void* out, void* stream);
+
+/* CUDA kernels launched by this context since creation (for accounting). */
+int64_t amepb_kernel_launches(const amepb_ctx* ctx);
+
+/* Wait until all work the context enqueued on `stream` (and its own streams) is done. */
+int amepb_synchronize(amepb_ctx* ctx, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AMEPB_H */

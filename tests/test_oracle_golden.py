@@ -103,3 +103,39 @@ def test_frame_indices_rule():
     np.testing.assert_array_equal(orc.frame_indices(51, 0.9, 2), np.array([46, 50]))
     assert len(orc.frame_indices(10, 0.5, 50)) == 5
     assert len(orc.frame_indices(10, 0.0, None)) == 10
+
+
+# ---- the C restatement (oracle/rdf_oracle.c) against the same golden vectors -------------
+import c_oracle as corc  # noqa: E402
+
+
+@pytest.mark.parametrize("name", RDF_CASES)
+def test_c_oracle_rdf_counts_bit_exact(name):
+    z = _load(name)
+    other = z["other"] if "other" in z.files else None
+    hist, edges = corc.rdf_counts(z["coords"], z["box"], other, **rdf_kwargs(z))
+    np.testing.assert_array_equal(hist, z["counts"])
+    hist1, _ = corc.rdf_counts(z["coords"], z["box"], other, nthreads=1, **rdf_kwargs(z))
+    np.testing.assert_array_equal(hist1, z["counts"])
+
+
+@pytest.mark.parametrize("name", ["sfiso_2d_f64.npz", "sfiso_2d_f32.npz", "sfiso_3d_f64.npz",
+                                  "sfiso_3d_cross_f32.npz"])
+def test_c_oracle_sfiso(name):
+    z = _load(name)
+    other = z["other"] if "other" in z.files else None
+    s, q = corc.sfiso_fast(z["coords"], z["box"], qmax=float(z["qmax"]), twod=bool(z["twod"]),
+                           num=int(z["num"]), other_coords=other)
+    np.testing.assert_array_equal(q, z["q"])
+    # plain vs pairwise summation order: 1e-12 relative, not bit-exact
+    np.testing.assert_allclose(s, z["S"], rtol=1e-10, atol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["sf2d_f64_onechunk.npz", "sf2d_f32_chunks.npz", "sf2d_f64_cross.npz"])
+def test_c_oracle_sf2d_bit_exact(name):
+    z = _load(name)
+    other = z["other"] if "other" in z.files else None
+    cs = int(z["chunksize"])
+    s, qx, qy = corc.sf2d_std(z["coords"], z["box"], other, qmax=float(z["qmax"]),
+                              chunksize=None if cs < 0 else cs)
+    np.testing.assert_array_equal(s, z["S"])

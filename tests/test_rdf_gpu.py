@@ -1,0 +1,286 @@
+"""RDF parity on the GPU: libamepb (through the C ABI) against the reference's
+golden vectors and against the CPU oracle on seeded inputs.  Bit-exact."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import amep_oracle as orc
+import c_oracle as corc
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def sc():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import amep_b200
+    return amep_b200.spatialcor
+
+
+RDF_CASES = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "rdf_*.npz"))
+                   if "kdtree" not in p)
+
+
+def _kw(z):
+    kw = dict(pbc=bool(z["pbc"]))
+    if int(z["nbins"]) >= 0:
+        kw["nbins"] = int(z["nbins"])
+    if not bool(z["rmax_is_default"]):
+        kw["rmax"] = float(z["rmax"])
+    return kw
+
+
+@pytest.mark.parametrize("space", ["host", "device"])
+@pytest.mark.parametrize("name", RDF_CASES)
+def test_golden_bit_exact(sc, name, space):
+    z = np.load(os.path.join(GOLDEN, name))
+    coords = z["coords"]
+    other = z["other"] if "other" in z.files else None
+    if space == "device":
+        coords = torch.from_numpy(coords).cuda()
+        other = None if other is None else torch.from_numpy(other).cuda()
+    g, r, counts = sc.rdf_frames(coords, z["box"], other, return_counts=True, **_kw(z))
+    np.testing.assert_array_equal(counts[0], z["counts"])
+    g1, r1 = sc.rdf(coords, z["box"], other, **_kw(z))
+    assert g1.dtype == z["g"].dtype and r1.dtype == z["r"].dtype
+    np.testing.assert_array_equal(g1, z["g"])
+    np.testing.assert_array_equal(r1, z["r"])
+
+
+def test_reference_unittest_criterion(sc):
+    """test/test_spatialcor.py:73-102: mode='diff' and mode='kdtree' agree after round(3)."""
+    z = np.load(os.path.join(GOLDEN, "rdf_unittest_2d_f64.npz"))
+    gk = np.load(os.path.join(GOLDEN, "rdf_unittest_2d_kdtree.npz"))["g"]
+    gd, _ = sc.rdf(z["coords"], z["box"], nbins=50, pbc=True, rmax=5.0, mode="diff")
+    gt, _ = sc.rdf(z["coords"], z["box"], nbins=50, pbc=True, rmax=5.0, mode="kdtree")
+    assert (gd.round(3) == gk.round(3)).all()
+    assert (gt.round(3) == gk.round(3)).all()
+
+
+def _uniform(rng, n, box, dtype, spill=0.0):
+    lo, hi = box[:, 0], box[:, 1]
+    span = hi - lo
+    c = rng.uniform(lo - spill * span, hi + spill * span, (n, 3))
+    return c.astype(dtype)
+
+
+def _clustered(rng, n, box, dtype):
+    lo, hi = box[:, 0], box[:, 1]
+    span = hi - lo
+    centres = rng.uniform(lo, hi, (6, 3))
+    half = n // 2
+    blob = centres[rng.integers(0, 6, half)] + rng.normal(0, 0.04, (half, 3)) * span
+    blob = lo + np.mod(blob - lo, span)
+    rest = rng.uniform(lo, hi, (n - half, 3))
+    return np.concatenate([blob, rest]).astype(dtype)
+
+
+CASES = [
+    # name, dim, dtype, n, m(other) or None, box, kwargs, generator, spill
+    ("2d_f32_smallr", 2, np.float32, 6000, None, [[0, 80], [0, 80], [-0.5, 0.5]], dict(rmax=5.0, nbins=300), "uniform", 0.0),
+    ("2d_f64_smallr", 2, np.float64, 6000, None, [[0, 80], [0, 80], [-0.5, 0.5]], dict(rmax=5.0, nbins=300), "uniform", 0.0),
+    ("2d_f32_default", 2, np.float32, 3000, None, [[0, 50], [0, 50], [-0.5, 0.5]], dict(), "uniform", 0.0),
+    ("2d_f32_clustered", 2, np.float32, 6000, None, [[-40, 40], [-40, 40], [-0.5, 0.5]], dict(rmax=6.0, nbins=500), "clustered", 0.0),
+    ("2d_f32_spill", 2, np.float32, 3000, None, [[0, 40], [0, 30], [-0.5, 0.5]], dict(rmax=7.0, nbins=77), "uniform", 0.2),
+    ("2d_f64_cross", 2, np.float64, 4000, 1500, [[0, 60], [0, 60], [-0.5, 0.5]], dict(rmax=8.0, nbins=160), "uniform", 0.0),
+    ("3d_f32_smallr", 3, np.float32, 6000, None, [[0, 20], [0, 20], [0, 20]], dict(rmax=2.5, nbins=250), "uniform", 0.0),
+    ("3d_f64_smallr", 3, np.float64, 5000, None, [[0, 20], [0, 20], [0, 20]], dict(rmax=2.5, nbins=250), "uniform", 0.0),
+    ("3d_f32_default", 3, np.float32, 2500, None, [[-5, 5], [-5, 5], [-5, 5]], dict(), "uniform", 0.0),
+    ("3d_f32_clustered", 3, np.float32, 6000, None, [[0, 24], [0, 24], [0, 24]], dict(rmax=3.0, nbins=500), "clustered", 0.0),
+    ("3d_f32_cross_spill", 3, np.float32, 3000, 2000, [[0, 16], [0, 12], [0, 20]], dict(rmax=4.0, nbins=99), "uniform", 0.1),
+    ("3d_f64_thin", 3, np.float64, 3000, None, [[0, 30], [0, 30], [0, 3]], dict(rmax=6.0, nbins=120), "uniform", 0.0),
+    ("3d_f32_nopbc", 3, np.float32, 5000, None, [[0, 20], [0, 20], [0, 20]], dict(rmax=3.0, nbins=100, pbc=False), "uniform", 0.0),
+    ("3d_f64_nopbc", 3, np.float64, 5000, 1000, [[0, 20], [0, 20], [0, 20]], dict(rmax=3.0, nbins=100, pbc=False), "uniform", 0.0),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_oracle_seeded(sc, case):
+    name, dim, dtype, n, m, box, kw, gen, spill = case
+    rng = np.random.default_rng(abs(hash(name)) % (2 ** 31))
+    box = np.array(box, dtype=dtype)
+    make = _clustered if gen == "clustered" else (lambda r, k, b, d: _uniform(r, k, b, d, spill))
+    coords = make(rng, n, box.astype(np.float64), dtype)
+    other = None if m is None else make(rng, m, box.astype(np.float64), dtype)
+    if dim == 2:
+        coords[:, 2] = 0
+        if other is not None:
+            other[:, 2] = 0
+    want, _ = corc.rdf_counts(coords, box, other, **kw)
+    g, r, counts = sc.rdf_frames(coords, box, other, return_counts=True, **kw)
+    np.testing.assert_array_equal(counts[0], want)
+    assert want.sum() > 0
+    go, ro = orc.rdf_normalise(want, orc.rdf_edges(box, kw.get("nbins"), kw.get("rmax"))[0], coords, box,
+                               n if m is None else m)
+    np.testing.assert_array_equal(g[0], go)
+    np.testing.assert_array_equal(r[0], ro)
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 6])
+def test_grid_refinement_does_not_change_counts(sc, k):
+    from amep_b200 import _lib
+    rng = np.random.default_rng(7)
+    box = np.array([[0, 60], [0, 60], [-0.5, 0.5]], dtype=np.float32)
+    c = _uniform(rng, 8000, box.astype(np.float64), np.float32)
+    c[:, 2] = 0
+    want, _ = corc.rdf_counts(c, box, rmax=6.0, nbins=200)
+    ctx = _lib.context(0)
+    ctx.set_cells_per_cutoff(k)
+    try:
+        _, _, counts = sc.rdf_frames(c, box, rmax=6.0, nbins=200, return_counts=True)
+        info = ctx.rdf_info()
+    finally:
+        ctx.set_cells_per_cutoff(0)
+    np.testing.assert_array_equal(counts[0], want)
+    assert info["candidate_pairs"] >= want.sum()
+    box3 = np.array([[0, 18], [0, 18], [0, 18]], dtype=np.float32)
+    c3 = _uniform(rng, 5000, box3.astype(np.float64), np.float32)
+    want3, _ = corc.rdf_counts(c3, box3, rmax=3.0, nbins=100)
+    ctx.set_cells_per_cutoff(min(k, 4))
+    try:
+        _, _, counts3 = sc.rdf_frames(c3, box3, rmax=3.0, nbins=100, return_counts=True)
+    finally:
+        ctx.set_cells_per_cutoff(0)
+    np.testing.assert_array_equal(counts3[0], want3)
+
+
+def test_batch_of_frames_with_per_frame_boxes(sc):
+    rng = np.random.default_rng(11)
+    nf, n = 9, 1500
+    boxes = np.zeros((nf, 3, 2), dtype=np.float32)
+    coords = np.zeros((nf, n, 3), dtype=np.float32)
+    for f in range(nf):
+        L = 30 + 2 * f
+        boxes[f] = [[0, L], [-L / 2, L / 2], [-0.5, 0.5]]
+        coords[f, :, 0] = rng.uniform(0, L, n)
+        coords[f, :, 1] = rng.uniform(-L / 2, L / 2, n)
+    g, r, counts = sc.rdf_frames(torch.from_numpy(coords).cuda(), boxes, nbins=120, return_counts=True)
+    for f in range(nf):
+        want, edges = corc.rdf_counts(coords[f], boxes[f], nbins=120)
+        np.testing.assert_array_equal(counts[f], want)
+        go, ro = orc.rdf_normalise(want, edges, coords[f], boxes[f], n)
+        np.testing.assert_array_equal(g[f], go)
+        np.testing.assert_array_equal(r[f], ro)
+
+
+def test_many_small_frames_one_call(sc):
+    rng = np.random.default_rng(12)
+    nf, n = 64, 400
+    box = np.array([[0, 20], [0, 20], [-0.5, 0.5]], dtype=np.float32)
+    coords = np.zeros((nf, n, 3), dtype=np.float32)
+    coords[:, :, :2] = rng.uniform(0, 20, (nf, n, 2))
+    _, _, counts = sc.rdf_frames(coords, box, nbins=64, return_counts=True)
+    for f in range(0, nf, 7):
+        want, _ = orc.rdf_counts(coords[f], box, nbins=64)
+        np.testing.assert_array_equal(counts[f], want)
+
+
+def test_large_nbins_uses_global_path(sc):
+    rng = np.random.default_rng(13)
+    box = np.array([[0, 30], [0, 30], [-0.5, 0.5]], dtype=np.float64)
+    c = _uniform(rng, 2500, box, np.float64)
+    c[:, 2] = 0
+    for nbins in (1, 7, 20000):
+        want, _ = corc.rdf_counts(c, box, rmax=4.0, nbins=nbins)
+        _, _, counts = sc.rdf_frames(c, box, rmax=4.0, nbins=nbins, return_counts=True)
+        np.testing.assert_array_equal(counts[0], want)
+
+
+def test_edge_cases(sc):
+    box = np.array([[0, 10], [0, 10], [0, 10]], dtype=np.float64)
+    # a single particle is 3D (amep/utils.py:1650-1651); its own images sit at L > rmax
+    g, r = sc.rdf(np.array([[1.0, 2.0, 3.0]]), box, nbins=10)
+    assert g.shape == (10,) and np.all(g == 0)
+    # all particles identical: dimension 0 -> pbc_points raises ValueError (amep/pbc.py:290-294)
+    with pytest.raises(ValueError):
+        sc.rdf(np.ones((5, 3)), box, nbins=10)
+    with pytest.raises(ValueError):
+        sc.rdf(np.ones((5, 3)), box, nbins=10, mode="nope")
+    with pytest.raises(ValueError):
+        sc.rdf(np.ones((5, 2)), box, nbins=10)
+    # NaN / inf coordinates never enter a bin, as in np.histogram
+    rng = np.random.default_rng(14)
+    c = rng.uniform(0, 10, (800, 3))
+    c[5] = np.nan
+    c[9, 0] = np.inf
+    want, _ = orc.rdf_counts(c, box, rmax=3.0, nbins=30)
+    _, _, counts = sc.rdf_frames(c, box, rmax=3.0, nbins=30, return_counts=True)
+    np.testing.assert_array_equal(counts[0], want)
+    # coincident particles: d = 0 is dropped by the d > 1e-3 filter
+    c = rng.uniform(0, 10, (500, 3)).astype(np.float32)
+    c[100:110] = c[0]
+    want, _ = orc.rdf_counts(c, box.astype(np.float32), rmax=2.0, nbins=40)
+    _, _, counts = sc.rdf_frames(c, box.astype(np.float32), rmax=2.0, nbins=40, return_counts=True)
+    np.testing.assert_array_equal(counts[0], want)
+    # bins narrower than the 1e-3 filter
+    want, _ = orc.rdf_counts(c, box.astype(np.float32), rmax=0.05, nbins=500)
+    _, _, counts = sc.rdf_frames(c, box.astype(np.float32), rmax=0.05, nbins=500, return_counts=True)
+    np.testing.assert_array_equal(counts[0], want)
+
+
+def test_integer_and_noncontiguous_inputs(sc):
+    rng = np.random.default_rng(15)
+    box = np.array([[0, 40], [0, 40], [0, 40]])
+    ci = rng.integers(0, 40, (900, 3))
+    want, _ = orc.rdf_counts(ci, box, rmax=5.0, nbins=25)
+    _, _, counts = sc.rdf_frames(ci, box, rmax=5.0, nbins=25, return_counts=True)
+    np.testing.assert_array_equal(counts[0], want)
+    big = rng.uniform(0, 40, (900, 6))
+    view = big[:, ::2]
+    want, _ = orc.rdf_counts(view, box, rmax=5.0, nbins=25)
+    _, _, counts = sc.rdf_frames(view, box, rmax=5.0, nbins=25, return_counts=True)
+    np.testing.assert_array_equal(counts[0], want)
+
+
+def test_full_size_properties(sc):
+    """Size-independent checks at a size the brute-force oracle cannot reach:
+    grid refinements agree with each other bit for bit, the total matches the
+    ideal-gas expectation, and a random sample of queries matches the oracle."""
+    from amep_b200 import _lib
+    n, L, rmax = 400_000, 800.0, 10.0
+    g = torch.Generator(device="cuda").manual_seed(5)
+    c = torch.zeros((1, n, 3), device="cuda", dtype=torch.float32)
+    c[0, :, :2] = torch.rand((n, 2), generator=g, device="cuda") * L
+    box = np.array([[0, L], [0, L], [-0.5, 0.5]], dtype=np.float32)
+    ctx = _lib.context(0)
+    results = []
+    for k in (1, 2, 3):
+        ctx.set_cells_per_cutoff(k)
+        try:
+            _, _, counts = sc.rdf_frames(c, box, rmax=rmax, nbins=500, return_counts=True)
+        finally:
+            ctx.set_cells_per_cutoff(0)
+        results.append(counts[0])
+    np.testing.assert_array_equal(results[0], results[1])
+    np.testing.assert_array_equal(results[0], results[2])
+    total = results[0].sum()
+    expect = n * (n / L ** 2) * np.pi * rmax ** 2
+    assert abs(total - expect) < 6 * np.sqrt(expect)
+    # cross-RDF of a query sample against the oracle (exact)
+    host = c[0].cpu().numpy()
+    sample = host[:: n // 200][:200].copy()
+    want, _ = corc.rdf_counts(host, box, sample, rmax=rmax, nbins=500)
+    _, _, counts = sc.rdf_frames(c, box, torch.from_numpy(sample).cuda()[None], rmax=rmax, nbins=500,
+                                 return_counts=True)
+    np.testing.assert_array_equal(counts[0], want)
+
+
+def test_evaluate_rdf_matches_reference(sc):
+    import amep_b200
+    z = np.load(os.path.join(GOLDEN, "evaluate_rdf_f32.npz"))
+    for dev in ("cpu", "cuda"):
+        coords = z["coords"] if dev == "cpu" else torch.from_numpy(z["coords"]).cuda()
+        traj = amep_b200.TensorTrajectory(coords, z["box"])
+        ev = amep_b200.evaluate.RDF(traj, skip=float(z["skip"]), nav=int(z["nav"]), nbins=int(z["nbins"]))
+        np.testing.assert_array_equal(ev.indices, z["indices"])
+        np.testing.assert_array_equal(ev.frames, z["frames"])
+        np.testing.assert_array_equal(ev.avg, z["avg"][0])
+        np.testing.assert_array_equal(ev.r, z["avg"][1])
+        assert set(["avg", "frames", "indices", "r", "times"]).issubset(ev.keys())
+        assert ev["avg"] is ev.avg and ev.name == "rdf"
