@@ -47,6 +47,8 @@ struct amepb_ctx {
     amepb_rdf_info rdf_info;
     int rdf_k_override = 0;
     void* last_stream = nullptr;
+    bool sq_attr_harm = false;
+    bool sq_attr_sf2d = false;
 };
 
 namespace amepb {

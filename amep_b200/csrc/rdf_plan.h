@@ -307,6 +307,10 @@ inline bool plan_frame(const PlanInputs& in, int dim, const FrameStats& tgt, con
     double pairs_per_cell = std::max(1.0, ppc_q) * std::max(1.0, ppc_t) * nrows * (2 * kd[0] + 1);
     int run = (int)std::min<double>(64.0, std::max(1.0, floor(65536.0 / pairs_per_cell + 0.5)));
     run = std::min(run, P.cq_n[0]);
+    // at most 256 warp tasks per block task: with <= 2^22 pairs per warp task (larger ones
+    // bypass the shared histogram) a block task stays below 2^30 increments, so the
+    // 32-bit shared counters cannot overflow between two flush checks
+    run = std::min(run, std::max(1, 256 / std::max(1, nrows)));
     P.run = run;
     P.runs_per_row = (P.cq_n[0] + run - 1) / run;
     P.ntasks = (long long)P.runs_per_row * P.cq_n[1] * P.cq_n[2];

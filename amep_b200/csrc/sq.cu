@@ -1,18 +1,532 @@
-// sq.cu -- static structure factor kernels (placeholder until the S(q) kernels land).
+// sq.cu -- static structure factor kernels on sm_100a (FP64 pipe).
+//
+//   amepb_sq_harmonics  <- amep/spatialcor.py:1402-1448 (__sf_iso_chunk_fast): for every
+//       direction k_d the sums  sum_i cos(m k_d.r_i),  sum_i sin(m k_d.r_i),  m = 1..nharm.
+//       One sincos per (particle, direction); the harmonics follow from the Chebyshev
+//       recurrence c_{m+1} = 2 cos(phi) c_m - c_{m-1} (same for sin): 2 DFMA + 2 DADD per
+//       (particle, harmonic) for both sums.  Lane partials are reduced 16 harmonics at a
+//       time through a transposed shared-memory tile (no shuffles in the hot loop).
+//   amepb_sf2d_modes    <- amep/spatialcor.py:1690-1719 (__sf2d_chunk_std) + :1876-1907.
+//       exp(-i(qx x + qy y)) separates into per-axis tables built by a rotation recurrence.
+//       F64 mode: four real product sums (cc, ss, cs, sc) per (|qx|, |qy|) give all four
+//       quadrants: 4 DFMA per particle per quad point, 4x4 register tiles.
+//       C64 mode: the reference's arithmetic -- per chunk a complex64 accumulator, every
+//       term added in float64 and rounded to float32 (done on the FP64 pipe with the
+//       1.5*2^(e+29) constant: F2F runs at a quarter of the FP64 rate), chunk sums added in
+//       float32 in chunk order; particles strictly in index order.
+#include <math.h>
+
+#include <algorithm>
+
 #include "amepb_internal.cuh"
+
+namespace amepb {
+
+static size_t elem_bytes(int dtype) { return dtype == AMEPB_F32 ? 4 : 8; }
+
+// ---------------------------------------------------------------------------------------
+// harmonics (sfiso 'fast')
+// ---------------------------------------------------------------------------------------
+constexpr int kHarmThreads = 128;
+constexpr int kHarmP = 8;        // particles per thread
+constexpr int kHarmBlockM = 16;  // harmonics reduced per round
+constexpr int kHarmSeg = 512;    // harmonics per launch segment (shared accumulators)
+
+template <typename T>
+__global__ void __launch_bounds__(kHarmThreads) harmonics_kernel(
+    const T* __restrict__ coords, long long n, const double* __restrict__ kvec, long long kvec_stride,
+    int ndir, int h0, int hn, int nsplit, double* __restrict__ partial) {
+    extern __shared__ double smem_d[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int split = blockIdx.x, dir = blockIdx.y, frame = blockIdx.z;
+    double* my_part = smem_d + warp * (kHarmBlockM * 2 * 32);            // [16][2][32]
+    double* acc_base = smem_d + 4 * (kHarmBlockM * 2 * 32);               // [4][hn*2]
+    double* my_acc = acc_base + warp * (2 * hn);
+    for (int i = lane; i < 2 * hn; i += 32) my_acc[i] = 0.0;
+    __syncwarp();
+
+    const double* kv = kvec + (long long)frame * kvec_stride + dir * 3;
+    const double kx = kv[0], ky = kv[1], kz = kv[2];
+    const T* base = coords + (long long)frame * n * 3;
+    const long long tile_particles = (long long)kHarmThreads * kHarmP;
+    const long long ntiles = (n + tile_particles - 1) / tile_particles;
+
+    for (long long tile = split; tile < ntiles; tile += nsplit) {
+        double cp[kHarmP], cc[kHarmP], sp[kHarmP], sc[kHarmP], tx[kHarmP];
+#pragma unroll
+        for (int p = 0; p < kHarmP; ++p) {
+            const long long idx = tile * tile_particles + (long long)warp * 32 * kHarmP + p * 32 + lane;
+            if (idx < n) {
+                const double x = (double)base[3 * idx], y = (double)base[3 * idx + 1], z = (double)base[3 * idx + 2];
+                const double phi = (kx * x + ky * y) + kz * z;
+                double s1, c1;
+                sincos(phi, &s1, &c1);
+                tx[p] = 2.0 * c1;
+                if (h0 == 0) {
+                    cp[p] = 1.0; sp[p] = 0.0; cc[p] = c1; sc[p] = s1;
+                } else {
+                    sincos((double)h0 * phi, &sp[p], &cp[p]);
+                    sincos((double)(h0 + 1) * phi, &sc[p], &cc[p]);
+                }
+            } else {
+                cp[p] = cc[p] = sp[p] = sc[p] = tx[p] = 0.0;
+            }
+        }
+        for (int hb = 0; hb < hn; hb += kHarmBlockM) {
+#pragma unroll
+            for (int j = 0; j < kHarmBlockM; ++j) {
+                double sumc = cc[0], sums = sc[0];
+#pragma unroll
+                for (int p = 1; p < kHarmP; ++p) {
+                    sumc += cc[p];
+                    sums += sc[p];
+                }
+                my_part[(j * 2 + 0) * 32 + lane] = sumc;
+                my_part[(j * 2 + 1) * 32 + lane] = sums;
+#pragma unroll
+                for (int p = 0; p < kHarmP; ++p) {
+                    const double tc = fma(tx[p], cc[p], -cp[p]);
+                    const double ts = fma(tx[p], sc[p], -sp[p]);
+                    cp[p] = cc[p]; cc[p] = tc;
+                    sp[p] = sc[p]; sc[p] = ts;
+                }
+            }
+            __syncwarp();
+            // lane = row (harmonic j = lane/2, component lane&1); rotated reads are conflict free
+            double tot = 0.0;
+#pragma unroll 8
+            for (int i = 0; i < 32; ++i) tot += my_part[lane * 32 + ((i + lane) & 31)];
+            const int h = hb + (lane >> 1);
+            if (h < hn) my_acc[h * 2 + (lane & 1)] += tot;
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    double* out = partial + ((((long long)frame * ndir + dir) * nsplit + split) * (long long)hn) * 2;
+    for (int i = tid; i < 2 * hn; i += kHarmThreads)
+        out[i] = (acc_base[i] + acc_base[2 * hn + i]) + (acc_base[4 * hn + i] + acc_base[6 * hn + i]);
+}
+
+// out[f][d][h0+h][c] = sum over splits, in split order (deterministic)
+__global__ void harmonics_reduce_kernel(const double* __restrict__ partial, int nsplit, int hn, int h0,
+                                        int nharm, long long nfd, double* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = nfd * hn * 2;
+    if (i >= total) return;
+    const long long fd = i / (2 * hn);
+    const int r = (int)(i % (2 * hn));
+    double s = 0.0;
+    for (int k = 0; k < nsplit; ++k) s += partial[((fd * nsplit + k) * (long long)hn) * 2 + r];
+    out[(fd * nharm + h0) * 2 + r] = s;
+}
+
+// ---------------------------------------------------------------------------------------
+// sf2d tables: E[j][a] = (cos(q_a x_j), sin(q_a x_j)) for a run of 16 consecutive a
+// ---------------------------------------------------------------------------------------
+// Two exact seeds (sincos of fl(q*x), the reference's phase rounding) and a rotation
+// recurrence for the rest; w = E[a0+1] * conj(E[a0]).
+__device__ __forceinline__ void table_run16(double x, const double* __restrict__ q, int a0, int nq,
+                                            double2* __restrict__ dst, int dst_stride) {
+    const double2 zero = make_double2(0.0, 0.0);
+    if (a0 >= nq) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) dst[i * dst_stride] = zero;
+        return;
+    }
+    double c0, s0, c1, s1;
+    sincos(__dmul_rn(q[a0], x), &s0, &c0);
+    dst[0] = make_double2(c0, s0);
+    if (a0 + 1 >= nq) {
+#pragma unroll
+        for (int i = 1; i < 16; ++i) dst[i * dst_stride] = zero;
+        return;
+    }
+    sincos(__dmul_rn(q[a0 + 1], x), &s1, &c1);
+    dst[dst_stride] = make_double2(c1, s1);
+    const double wr = c1 * c0 + s1 * s0, wi = s1 * c0 - c1 * s0;
+    double cr = c1, ci = s1;
+#pragma unroll
+    for (int i = 2; i < 16; ++i) {
+        const double nr = cr * wr - ci * wi;
+        const double ni = cr * wi + ci * wr;
+        cr = nr; ci = ni;
+        dst[i * dst_stride] = (a0 + i < nq) ? make_double2(cr, ci) : zero;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// sf2d, float64 product sums
+// ---------------------------------------------------------------------------------------
+constexpr int kF64Threads = 256;   // 16 x 16 threads, 4 x 4 quad points each: 64 x 64 tile
+constexpr int kF64Stage = 32;      // particles per shared-memory stage
+
+template <typename T>
+__global__ void __launch_bounds__(kF64Threads, 1) sf2d_f64_kernel(
+    const T* __restrict__ coords, long long n, const double* __restrict__ qall, long long q_stride, int nq,
+    int ksplit, double* __restrict__ partial) {
+    // shared: X[stage][64], Y[stage][64] as double2 (64 KB, dynamic)
+    extern __shared__ __align__(16) unsigned char smem_f64[];
+    double2 (*sX)[64] = reinterpret_cast<double2 (*)[64]>(smem_f64);
+    double2 (*sY)[64] = reinterpret_cast<double2 (*)[64]>(smem_f64 + sizeof(double2) * kF64Stage * 64);
+    const int tid = threadIdx.x;
+    const int ta = tid & 15, tb = tid >> 4;
+    const int tiles = (nq + 63) / 64;
+    const int tile_a = blockIdx.x % tiles, tile_b = blockIdx.x / tiles;
+    const int split = blockIdx.y, frame = blockIdx.z;
+    const double* q = qall + (long long)frame * q_stride;
+    const T* base = coords + (long long)frame * n * 3;
+    const long long per = (n + ksplit - 1) / ksplit;
+    const long long j_begin = (long long)split * per;
+    const long long j_end = j_begin + per < n ? j_begin + per : n;
+
+    double acc[4][4][4];  // [ia][ib][cc, ss, cs, sc]
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[i][k][c] = 0.0;
+
+    for (long long j0 = j_begin; j0 < j_end; j0 += kF64Stage) {
+        // table build: thread -> (particle tid % 32, run tid / 32): runs 0-3 are X, 4-7 are Y
+        {
+            const int jj = tid & 31, run = tid >> 5;
+            const long long j = j0 + jj;
+            const bool isx = run < 4;
+            const int a0 = (isx ? tile_a : tile_b) * 64 + (run & 3) * 16;
+            double2* dst = (isx ? &sX[jj][0] : &sY[jj][0]) + (run & 3) * 16;
+            if (j < j_end) {
+                const double v = (double)base[3 * j + (isx ? 0 : 1)];
+                table_run16(v, q, a0, nq, dst, 1);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) dst[i] = make_double2(0.0, 0.0);
+            }
+        }
+        __syncthreads();
+#pragma unroll 2
+        for (int jj = 0; jj < kF64Stage; ++jj) {
+            double2 xa[4], yb[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                xa[i] = sX[jj][ta + 16 * i];
+                yb[i] = sY[jj][tb + 16 * i];
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    acc[i][k][0] = fma(xa[i].x, yb[k].x, acc[i][k][0]);
+                    acc[i][k][1] = fma(xa[i].y, yb[k].y, acc[i][k][1]);
+                    acc[i][k][2] = fma(xa[i].x, yb[k].y, acc[i][k][2]);
+                    acc[i][k][3] = fma(xa[i].y, yb[k].x, acc[i][k][3]);
+                }
+        }
+        __syncthreads();
+    }
+    // partial[f][split][4][nq][nq]
+    double* out = partial + (((long long)frame * ksplit + split) * 4) * (long long)nq * nq;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int a = tile_a * 64 + ta + 16 * i, b = tile_b * 64 + tb + 16 * k;
+            if (a < nq && b < nq)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) out[((long long)c * nq + b) * nq + a] = acc[i][k][c];
+        }
+}
+
+// combine the splits and expand the four quadrants: rho[f][iy][ix] complex128
+__global__ void sf2d_f64_finish_kernel(const double* __restrict__ partial, int ksplit, int nq, long long nframes,
+                                       double2* __restrict__ rho) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long per = (long long)nq * nq;
+    if (i >= nframes * per) return;
+    const long long f = i / per;
+    const int b = (int)((i % per) / nq), a = (int)(i % nq);
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int k = 0; k < ksplit; ++k)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) s[c] += partial[(((f * ksplit + k) * 4 + c) * (long long)nq + b) * nq + a];
+    const double cc = s[0], ss = s[1], cs = s[2], sc = s[3];
+    const double2 pp = make_double2(cc - ss, -(sc + cs));  // (+qa, +qb)
+    const double2 mp = make_double2(cc + ss, sc - cs);     // (-qa, +qb)
+    const int g = 2 * nq;
+    double2* r = rho + f * (long long)g * g;
+    const int ixp = nq + a, ixm = nq - 1 - a, iyp = nq + b, iym = nq - 1 - b;
+    r[(long long)iyp * g + ixp] = pp;
+    r[(long long)iyp * g + ixm] = mp;
+    r[(long long)iym * g + ixm] = make_double2(pp.x, -pp.y);
+    r[(long long)iym * g + ixp] = make_double2(mp.x, -mp.y);
+}
+
+// ---------------------------------------------------------------------------------------
+// sf2d, complex64 accumulation in the reference's order
+// ---------------------------------------------------------------------------------------
+constexpr int kC64Threads = 256;  // 16 x 16 quad points per block
+constexpr int kC64Stage = 128;    // particles per shared-memory stage
+
+// fl32(v) for a double v, on the FP64 pipe: adding 1.5*2^(e+29) rounds v to a multiple of
+// the float32 ulp of its binade (round to nearest even); the subtraction is exact.
+__device__ __forceinline__ double round_to_f32(double v) {
+    const int hi = (__double2hiint(v) & 0x7ff00000) + 0x01d80000;
+    const double m = __hiloint2double(hi, 0);
+    return __dsub_rn(__dadd_rn(v, m), m);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kC64Threads) sf2d_c64_kernel(
+    const T* __restrict__ coords, long long n, const double* __restrict__ qall, long long q_stride, int nq,
+    long long chunksize, float2* __restrict__ rho) {
+    extern __shared__ __align__(16) unsigned char smem_c64[];
+    double2 (*sX)[16] = reinterpret_cast<double2 (*)[16]>(smem_c64);
+    double2 (*sY)[16] = reinterpret_cast<double2 (*)[16]>(smem_c64 + sizeof(double2) * kC64Stage * 16);
+    const int tid = threadIdx.x;
+    const int ta = tid & 15, tb = tid >> 4;
+    const int tiles = (nq + 15) / 16;
+    const int tile_a = blockIdx.x % tiles, tile_b = blockIdx.x / tiles;
+    const int frame = blockIdx.y;
+    const double* q = qall + (long long)frame * q_stride;
+    const T* base = coords + (long long)frame * n * 3;
+
+    // chunk accumulators (float32 values held in doubles) and running totals (float32)
+    double ppr = 0.0, ppi = 0.0, mpr = 0.0, mpi = 0.0;
+    float tppr = 0.0f, tppi = 0.0f, tmpr = 0.0f, tmpi = 0.0f;
+    long long chunk_end = chunksize < n ? chunksize : n;
+
+    for (long long j0 = 0; j0 < n; j0 += kC64Stage) {
+        {
+            const int jj = tid & 127, isy = tid >> 7;
+            const long long j = j0 + jj;
+            double2* dst = isy ? &sY[jj][0] : &sX[jj][0];
+            if (j < n) {
+                const double v = (double)base[3 * j + isy];
+                table_run16(v, q, (isy ? tile_b : tile_a) * 16, nq, dst, 1);
+            }
+        }
+        __syncthreads();
+        const int lim = (int)((n - j0) < kC64Stage ? (n - j0) : kC64Stage);
+        for (int jj = 0; jj < lim; ++jj) {
+            const double2 xa = sX[jj][ta], yb = sY[jj][tb];
+            const double p1 = __dmul_rn(xa.x, yb.x), p2 = __dmul_rn(xa.y, yb.y);
+            const double p3 = __dmul_rn(xa.x, yb.y), p4 = __dmul_rn(xa.y, yb.x);
+            // exp(-i(qa x + qb y)) = (cc - ss) - i (sc + cs);  exp(-i(-qa x + qb y)) = (cc + ss) + i (sc - cs)
+            ppr = round_to_f32(__dadd_rn(ppr, __dsub_rn(p1, p2)));
+            ppi = round_to_f32(__dsub_rn(ppi, __dadd_rn(p4, p3)));
+            mpr = round_to_f32(__dadd_rn(mpr, __dadd_rn(p1, p2)));
+            mpi = round_to_f32(__dadd_rn(mpi, __dsub_rn(p4, p3)));
+            if (j0 + jj + 1 == chunk_end) {
+                // rhoq += res : complex64 + complex64 (amep/spatialcor.py:1890-1891)
+                tppr = __fadd_rn(tppr, (float)ppr); tppi = __fadd_rn(tppi, (float)ppi);
+                tmpr = __fadd_rn(tmpr, (float)mpr); tmpi = __fadd_rn(tmpi, (float)mpi);
+                ppr = ppi = mpr = mpi = 0.0;
+                chunk_end = chunk_end + chunksize < n ? chunk_end + chunksize : n;
+            }
+        }
+        __syncthreads();
+    }
+    const int a = tile_a * 16 + ta, b = tile_b * 16 + tb;
+    if (a < nq && b < nq) {
+        const int g = 2 * nq;
+        float2* r = rho + (long long)frame * g * g;
+        const int ixp = nq + a, ixm = nq - 1 - a, iyp = nq + b, iym = nq - 1 - b;
+        r[(long long)iyp * g + ixp] = make_float2(tppr, tppi);
+        r[(long long)iyp * g + ixm] = make_float2(tmpr, tmpi);
+        r[(long long)iym * g + ixm] = make_float2(tppr, -tppi);
+        r[(long long)iym * g + ixp] = make_float2(tmpr, -tmpi);
+    }
+}
+
+}  // namespace amepb
 
 using namespace amepb;
 
-extern "C" {
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+namespace {
 
-int amepb_sq_harmonics(amepb_ctx* ctx, const void*, int, int, int64_t, int64_t, const double*, int64_t,
-                       int32_t, int32_t, double*, void*) {
-    return fail(ctx, AMEPB_E_INVAL, "amepb_sq_harmonics: not built yet");
+// frames per staging chunk for host-space inputs
+int64_t stage_frames(int64_t nframes, size_t frame_bytes, size_t out_frame_bytes) {
+    const size_t budget = (size_t)2 << 30;
+    int64_t fb = (int64_t)std::max<size_t>(1, budget / std::max<size_t>(1, frame_bytes + out_frame_bytes));
+    return std::max<int64_t>(1, std::min<int64_t>(fb, std::min<int64_t>(nframes, 32768)));
 }
 
-int amepb_sf2d_modes(amepb_ctx* ctx, const void*, int, int, int64_t, int64_t, const double*, int64_t, int32_t,
-                     int, int64_t, void*, void*) {
-    return fail(ctx, AMEPB_E_INVAL, "amepb_sf2d_modes: not built yet");
+}  // namespace
+
+extern "C" {
+
+int amepb_sq_harmonics(amepb_ctx* ctx, const void* coords, int dtype, int space, int64_t nframes, int64_t n,
+                       const double* kvec, int64_t kvec_stride, int32_t ndir, int32_t nharm, double* out,
+                       void* stream_) {
+    if (!ctx) return AMEPB_E_INVAL;
+    if (!coords || !kvec || !out || nframes < 0 || n <= 0 || ndir <= 0 || nharm <= 0 ||
+        (dtype != AMEPB_F32 && dtype != AMEPB_F64) || (space != AMEPB_DEVICE && space != AMEPB_HOST) ||
+        (kvec_stride != 0 && kvec_stride < (int64_t)ndir * 3) || ndir > 65535)
+        return fail(ctx, AMEPB_E_INVAL, "amepb_sq_harmonics: invalid argument");
+    if (nframes == 0) return 0;
+    DeviceGuard guard(ctx->device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    ctx->last_stream = stream_;
+
+    const size_t frame_bytes = (size_t)n * 3 * elem_bytes(dtype);
+    const size_t out_frame = (size_t)ndir * nharm * 2 * sizeof(double);
+    const int64_t fb = space == AMEPB_HOST ? stage_frames(nframes, frame_bytes, out_frame)
+                                           : std::min<int64_t>(nframes, 32768);
+    // direction table on the device
+    const size_t kv_count = (size_t)(kvec_stride ? nframes * kvec_stride : (int64_t)ndir * 3);
+    int rc = ensure_pinned(ctx, kv_count * sizeof(double));
+    if (rc) return rc;
+    rc = ensure_device(ctx, BUF_SQ_A, kv_count * sizeof(double));
+    if (rc) return rc;
+    memcpy(ctx->pinned, kvec, kv_count * sizeof(double));
+    AMEPB_CUDA(ctx, cudaMemcpyAsync(ctx->bufs[BUF_SQ_A].p, ctx->pinned, kv_count * sizeof(double),
+                                    cudaMemcpyHostToDevice, stream));
+    const double* d_kvec = reinterpret_cast<const double*>(ctx->bufs[BUF_SQ_A].p);
+
+    const long long tile_particles = (long long)kHarmThreads * kHarmP;
+    const long long ntiles = (n + tile_particles - 1) / tile_particles;
+    const size_t smem_max = (size_t)(4 * kHarmBlockM * 2 * 32 + 4 * 2 * kHarmSeg) * sizeof(double);
+    if (!ctx->sq_attr_harm) {
+        AMEPB_CUDA(ctx, cudaFuncSetAttribute(harmonics_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+        AMEPB_CUDA(ctx, cudaFuncSetAttribute(harmonics_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+        ctx->sq_attr_harm = true;
+    }
+
+    for (int64_t f0 = 0; f0 < nframes; f0 += fb) {
+        const int nf = (int)std::min<int64_t>(fb, nframes - f0);
+        const void* d_coords = (const char*)coords + (size_t)f0 * frame_bytes;
+        double* d_out = out + (size_t)f0 * ndir * nharm * 2;
+        if (space == AMEPB_HOST) {
+            if ((rc = ensure_device(ctx, BUF_STAGE_A, frame_bytes * nf))) return rc;
+            if ((rc = ensure_device(ctx, BUF_STAGE_OUT, out_frame * nf))) return rc;
+            AMEPB_CUDA(ctx, cudaMemcpyAsync(ctx->bufs[BUF_STAGE_A].p, d_coords, frame_bytes * nf, cudaMemcpyHostToDevice, stream));
+            d_coords = ctx->bufs[BUF_STAGE_A].p;
+            d_out = reinterpret_cast<double*>(ctx->bufs[BUF_STAGE_OUT].p);
+        }
+        // splits of the particle range per (frame, direction)
+        const long long fd = (long long)nf * ndir;
+        long long nsplit = ((long long)ctx->sm_count * 6 + fd - 1) / fd;
+        nsplit = std::max<long long>(1, std::min<long long>(nsplit, ntiles));
+        for (int h0 = 0; h0 < nharm; h0 += kHarmSeg) {
+            const int hn = std::min<int>(kHarmSeg, nharm - h0);
+            const size_t part_bytes = (size_t)fd * nsplit * hn * 2 * sizeof(double);
+            if ((rc = ensure_device(ctx, BUF_SQ_B, part_bytes))) return rc;
+            double* d_part = reinterpret_cast<double*>(ctx->bufs[BUF_SQ_B].p);
+            const size_t smem = (size_t)(4 * kHarmBlockM * 2 * 32 + 4 * 2 * hn) * sizeof(double);
+            dim3 grid((unsigned)nsplit, (unsigned)ndir, (unsigned)nf);
+            const double* kv = d_kvec + (kvec_stride ? f0 * kvec_stride : 0);
+            if (dtype == AMEPB_F32)
+                harmonics_kernel<float><<<grid, kHarmThreads, smem, stream>>>((const float*)d_coords, n, kv, kvec_stride, ndir, h0, hn, (int)nsplit, d_part);
+            else
+                harmonics_kernel<double><<<grid, kHarmThreads, smem, stream>>>((const double*)d_coords, n, kv, kvec_stride, ndir, h0, hn, (int)nsplit, d_part);
+            AMEPB_LAUNCH_CHECK(ctx);
+            const long long total = fd * hn * 2;
+            harmonics_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(d_part, (int)nsplit, hn, h0, nharm, fd, d_out);
+            AMEPB_LAUNCH_CHECK(ctx);
+        }
+        if (space == AMEPB_HOST) {
+            AMEPB_CUDA(ctx, cudaMemcpyAsync(out + (size_t)f0 * ndir * nharm * 2, d_out, out_frame * nf, cudaMemcpyDeviceToHost, stream));
+            AMEPB_CUDA(ctx, cudaStreamSynchronize(stream));
+        }
+    }
+    return 0;
+}
+
+int amepb_sf2d_modes(amepb_ctx* ctx, const void* coords, int dtype, int space, int64_t nframes, int64_t n,
+                     const double* q, int64_t q_stride, int32_t nq, int accum, int64_t chunksize, void* out,
+                     void* stream_) {
+    if (!ctx) return AMEPB_E_INVAL;
+    if (!coords || !q || !out || nframes < 0 || n <= 0 || nq <= 0 || nq > 16384 ||
+        (dtype != AMEPB_F32 && dtype != AMEPB_F64) || (space != AMEPB_DEVICE && space != AMEPB_HOST) ||
+        (q_stride != 0 && q_stride < nq) || (accum != AMEPB_ACCUM_C64_REFERENCE && accum != AMEPB_ACCUM_F64))
+        return fail(ctx, AMEPB_E_INVAL, "amepb_sf2d_modes: invalid argument");
+    if (accum == AMEPB_ACCUM_C64_REFERENCE && chunksize <= 0)
+        return fail(ctx, AMEPB_E_INVAL, "amepb_sf2d_modes: chunksize must be positive in the complex64 mode");
+    if (nframes == 0) return 0;
+    DeviceGuard guard(ctx->device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    ctx->last_stream = stream_;
+
+    const size_t frame_bytes = (size_t)n * 3 * elem_bytes(dtype);
+    const size_t g = (size_t)2 * nq;
+    const size_t out_elem = accum == AMEPB_ACCUM_F64 ? sizeof(double2) : sizeof(float2);
+    const size_t out_frame = g * g * out_elem;
+    int64_t fb = space == AMEPB_HOST ? stage_frames(nframes, frame_bytes, out_frame)
+                                     : std::min<int64_t>(nframes, 32768);
+
+    const size_t q_count = (size_t)(q_stride ? nframes * q_stride : nq);
+    int rc = ensure_pinned(ctx, q_count * sizeof(double));
+    if (rc) return rc;
+    if ((rc = ensure_device(ctx, BUF_SQ_A, q_count * sizeof(double)))) return rc;
+    memcpy(ctx->pinned, q, q_count * sizeof(double));
+    AMEPB_CUDA(ctx, cudaMemcpyAsync(ctx->bufs[BUF_SQ_A].p, ctx->pinned, q_count * sizeof(double), cudaMemcpyHostToDevice, stream));
+    const double* d_q = reinterpret_cast<const double*>(ctx->bufs[BUF_SQ_A].p);
+
+    const size_t smem_f64 = sizeof(double2) * kF64Stage * 64 * 2;
+    const size_t smem_c64 = sizeof(double2) * kC64Stage * 16 * 2;
+    if (!ctx->sq_attr_sf2d) {
+        AMEPB_CUDA(ctx, cudaFuncSetAttribute(sf2d_f64_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f64));
+        AMEPB_CUDA(ctx, cudaFuncSetAttribute(sf2d_f64_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f64));
+        AMEPB_CUDA(ctx, cudaFuncSetAttribute(sf2d_c64_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c64));
+        AMEPB_CUDA(ctx, cudaFuncSetAttribute(sf2d_c64_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c64));
+        ctx->sq_attr_sf2d = true;
+    }
+    // float64 mode: bound the split-K scratch
+    int ksplit = 1;
+    if (accum == AMEPB_ACCUM_F64) {
+        const int tiles = (nq + 63) / 64;
+        const size_t per_split = (size_t)4 * nq * nq * sizeof(double);
+        fb = std::min<int64_t>(fb, std::max<int64_t>(1, (int64_t)(((size_t)1 << 30) / per_split)));
+        const long long blocks_fd = (long long)tiles * tiles * std::min<int64_t>(fb, nframes);
+        ksplit = (int)std::max<long long>(1, std::min<long long>(((long long)ctx->sm_count * 2 + blocks_fd - 1) / blocks_fd,
+                                                                  (n + 4 * kF64Stage - 1) / (4 * kF64Stage)));
+        while (ksplit > 1 && (size_t)ksplit * per_split * std::min<int64_t>(fb, nframes) > ((size_t)4 << 30)) --ksplit;
+    }
+
+    for (int64_t f0 = 0; f0 < nframes; f0 += fb) {
+        const int nf = (int)std::min<int64_t>(fb, nframes - f0);
+        const void* d_coords = (const char*)coords + (size_t)f0 * frame_bytes;
+        char* d_out = (char*)out + (size_t)f0 * out_frame;
+        if (space == AMEPB_HOST) {
+            if ((rc = ensure_device(ctx, BUF_STAGE_A, frame_bytes * nf))) return rc;
+            if ((rc = ensure_device(ctx, BUF_STAGE_OUT, out_frame * nf))) return rc;
+            AMEPB_CUDA(ctx, cudaMemcpyAsync(ctx->bufs[BUF_STAGE_A].p, d_coords, frame_bytes * nf, cudaMemcpyHostToDevice, stream));
+            d_coords = ctx->bufs[BUF_STAGE_A].p;
+            d_out = reinterpret_cast<char*>(ctx->bufs[BUF_STAGE_OUT].p);
+        }
+        const double* qf = d_q + (q_stride ? f0 * q_stride : 0);
+        if (accum == AMEPB_ACCUM_F64) {
+            const int tiles = (nq + 63) / 64;
+            const size_t part_bytes = (size_t)nf * ksplit * 4 * nq * nq * sizeof(double);
+            if ((rc = ensure_device(ctx, BUF_SQ_B, part_bytes))) return rc;
+            double* d_part = reinterpret_cast<double*>(ctx->bufs[BUF_SQ_B].p);
+            dim3 grid((unsigned)(tiles * tiles), (unsigned)ksplit, (unsigned)nf);
+            if (dtype == AMEPB_F32)
+                sf2d_f64_kernel<float><<<grid, kF64Threads, smem_f64, stream>>>((const float*)d_coords, n, qf, q_stride, nq, ksplit, d_part);
+            else
+                sf2d_f64_kernel<double><<<grid, kF64Threads, smem_f64, stream>>>((const double*)d_coords, n, qf, q_stride, nq, ksplit, d_part);
+            AMEPB_LAUNCH_CHECK(ctx);
+            const long long total = (long long)nf * nq * nq;
+            sf2d_f64_finish_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(d_part, ksplit, nq, nf, reinterpret_cast<double2*>(d_out));
+            AMEPB_LAUNCH_CHECK(ctx);
+        } else {
+            const int tiles = (nq + 15) / 16;
+            dim3 grid((unsigned)(tiles * tiles), (unsigned)nf);
+            if (dtype == AMEPB_F32)
+                sf2d_c64_kernel<float><<<grid, kC64Threads, smem_c64, stream>>>((const float*)d_coords, n, qf, q_stride, nq, chunksize, reinterpret_cast<float2*>(d_out));
+            else
+                sf2d_c64_kernel<double><<<grid, kC64Threads, smem_c64, stream>>>((const double*)d_coords, n, qf, q_stride, nq, chunksize, reinterpret_cast<float2*>(d_out));
+            AMEPB_LAUNCH_CHECK(ctx);
+        }
+        if (space == AMEPB_HOST) {
+            AMEPB_CUDA(ctx, cudaMemcpyAsync((char*)out + (size_t)f0 * out_frame, d_out, out_frame * nf, cudaMemcpyDeviceToHost, stream));
+            AMEPB_CUDA(ctx, cudaStreamSynchronize(stream));
+        }
+    }
+    return 0;
 }
 
 }  // extern "C"
