@@ -23,7 +23,7 @@ SYMBOLS = (
     "amepb_abi_version", "amepb_create", "amepb_destroy", "amepb_last_error",
     "amepb_frame_dimension", "amepb_rdf_batch", "amepb_rdf_last_info",
     "amepb_rdf_set_cells_per_cutoff", "amepb_sq_harmonics", "amepb_sf2d_modes",
-    "amepb_kernel_launches", "amepb_synchronize",
+    "amepb_kernel_launches", "amepb_synchronize", "amepb_set_timing", "amepb_last_kernel_ms",
 )
 
 
@@ -41,10 +41,13 @@ class RdfInfo(ctypes.Structure):
         ("kernel_launches", ctypes.c_int64),
         ("cells_per_cutoff", ctypes.c_int32),
         ("sub_batches", ctypes.c_int32),
+        ("pair_kernel_ms", ctypes.c_double),
+        ("build_ms", ctypes.c_double),
     ]
 
     def as_dict(self):
-        return {name: int(getattr(self, name)) for name, _ in self._fields_}
+        return {name: (float(getattr(self, name)) if typ is ctypes.c_double else int(getattr(self, name)))
+                for name, typ in self._fields_}
 
 
 _lib = None
@@ -105,6 +108,10 @@ def load():
         lib.amepb_kernel_launches.argtypes = [vp]
         lib.amepb_synchronize.restype = c.c_int
         lib.amepb_synchronize.argtypes = [vp, vp]
+        lib.amepb_set_timing.restype = c.c_int
+        lib.amepb_set_timing.argtypes = [vp, c.c_int]
+        lib.amepb_last_kernel_ms.restype = c.c_double
+        lib.amepb_last_kernel_ms.argtypes = [vp]
         if lib.amepb_abi_version() != ABI_VERSION:
             raise AmepbError(f"{LIB_PATH}: ABI version {lib.amepb_abi_version()} != {ABI_VERSION}")
         _lib = lib
@@ -138,6 +145,12 @@ class Context:
         info = RdfInfo()
         self.check(self.lib.amepb_rdf_last_info(self.handle, ctypes.byref(info)), "amepb_rdf_last_info")
         return info.as_dict()
+
+    def set_timing(self, enable: bool):
+        self.check(self.lib.amepb_set_timing(self.handle, 1 if enable else 0), "amepb_set_timing")
+
+    def last_kernel_ms(self) -> float:
+        return float(self.lib.amepb_last_kernel_ms(self.handle))
 
     def set_cells_per_cutoff(self, k: int):
         self.check(self.lib.amepb_rdf_set_cells_per_cutoff(self.handle, int(k)),

@@ -6,6 +6,7 @@
 #include <stdio.h>
 
 #include <string>
+#include <vector>
 
 #include "amepb.h"
 
@@ -48,6 +49,10 @@ struct amepb_ctx {
     int rdf_k_override = 0;
     void* last_stream = nullptr;
     bool sq_attr_harm = false;
+    bool timing = false;
+    std::vector<cudaEvent_t> ev_pool;     // reusable events
+    size_t ev_used = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pair, ev_build, ev_sq;
     bool sq_attr_sf2d = false;
 };
 
@@ -57,6 +62,10 @@ int fail(amepb_ctx* ctx, int code, const char* fmt, ...);
 int fail_cuda(amepb_ctx* ctx, cudaError_t e, const char* what, const char* file, int line);
 int ensure_device(amepb_ctx* ctx, int which, size_t bytes);
 int ensure_pinned(amepb_ctx* ctx, size_t bytes);
+
+cudaEvent_t timing_event(amepb_ctx* ctx, cudaStream_t stream);  // records and returns an event (or nullptr)
+double timing_total_ms(amepb_ctx* ctx, std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& spans);
+void timing_reset(amepb_ctx* ctx);
 
 struct DeviceGuard {
     int prev = -1;

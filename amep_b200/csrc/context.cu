@@ -65,6 +65,36 @@ int ensure_pinned(amepb_ctx* ctx, size_t bytes) {
     return 0;
 }
 
+cudaEvent_t timing_event(amepb_ctx* ctx, cudaStream_t stream) {
+    if (!ctx->timing) return nullptr;
+    if (ctx->ev_used == ctx->ev_pool.size()) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+        ctx->ev_pool.push_back(e);
+    }
+    cudaEvent_t e = ctx->ev_pool[ctx->ev_used++];
+    cudaEventRecord(e, stream);
+    return e;
+}
+
+double timing_total_ms(amepb_ctx* ctx, std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& spans) {
+    double total = 0.0;
+    for (auto& sp : spans) {
+        if (!sp.first || !sp.second) continue;
+        cudaEventSynchronize(sp.second);
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, sp.first, sp.second) == cudaSuccess) total += ms;
+    }
+    return total;
+}
+
+void timing_reset(amepb_ctx* ctx) {
+    ctx->ev_used = 0;
+    ctx->ev_pair.clear();
+    ctx->ev_build.clear();
+    ctx->ev_sq.clear();
+}
+
 }  // namespace amepb
 
 extern "C" {
@@ -108,6 +138,7 @@ void amepb_destroy(amepb_ctx* ctx) {
     for (int i = 0; i < BUF_COUNT; ++i)
         if (ctx->bufs[i].p) cudaFree(ctx->bufs[i].p);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     delete ctx;
 }
 
@@ -116,6 +147,18 @@ const char* amepb_last_error(const amepb_ctx* ctx) {
 }
 
 int64_t amepb_kernel_launches(const amepb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int amepb_set_timing(amepb_ctx* ctx, int enable) {
+    if (!ctx) return AMEPB_E_INVAL;
+    ctx->timing = enable != 0;
+    return 0;
+}
+
+double amepb_last_kernel_ms(amepb_ctx* ctx) {
+    if (!ctx) return 0.0;
+    amepb::DeviceGuard guard(ctx->device);
+    return amepb::timing_total_ms(ctx, ctx->ev_sq);
+}
 
 int amepb_synchronize(amepb_ctx* ctx, void* stream) {
     if (!ctx) return AMEPB_E_INVAL;

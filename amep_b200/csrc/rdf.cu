@@ -788,6 +788,7 @@ static int rdf_sub_batch(amepb_ctx* ctx, const RdfCall& c, int64_t f0, int nf, c
     AMEPB_CUDA(ctx, cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * (size_t)nf * nbins, stream));
 
     // ---- stats -> plans ------------------------------------------------------
+    cudaEvent_t ev_b0 = timing_event(ctx, stream);
     std::vector<FrameStats> tstats, qstats;
     int rc = frame_stats(ctx, d_coords, c.coords_dtype, c.n, nf, tstats, stream, 0);
     if (rc) return rc;
@@ -957,6 +958,8 @@ static int rdf_sub_batch(amepb_ctx* ctx, const RdfCall& c, int64_t f0, int nf, c
     if ((rc = exclusive_scan(ctx, qcount, qstart, total_cells + 1, stream))) return rc;
     if ((rc = place_targets(true))) return rc;
     if ((rc = place_queries(true))) return rc;
+    cudaEvent_t ev_b1 = timing_event(ctx, stream);
+    if (ev_b0 && ev_b1) ctx->ev_build.emplace_back(ev_b0, ev_b1);
 
     // ---- pairs -----------------------------------------------------------------
     PairArgs args;
@@ -977,6 +980,8 @@ static int rdf_sub_batch(amepb_ctx* ctx, const RdfCall& c, int64_t f0, int nf, c
     else if (!targets_f64) rc = launch_pairs<double, float>(ctx, args, all_zconst, stream);
     else rc = launch_pairs<double, double>(ctx, args, all_zconst, stream);
     if (rc) return rc;
+    cudaEvent_t ev_p1 = timing_event(ctx, stream);
+    if (ev_b1 && ev_p1) ctx->ev_pair.emplace_back(ev_b1, ev_p1);
 
     ctx->rdf_info.cells_per_cutoff = k_used;
     return 0;
@@ -1004,6 +1009,8 @@ int amepb_rdf_last_info(amepb_ctx* ctx, amepb_rdf_info* info) {
         ctx->rdf_info.candidate_pairs = (int64_t)h[1];
         ctx->rdf_info.images = (int64_t)h[2];
     }
+    ctx->rdf_info.pair_kernel_ms = timing_total_ms(ctx, ctx->ev_pair);
+    ctx->rdf_info.build_ms = timing_total_ms(ctx, ctx->ev_build);
     *info = ctx->rdf_info;
     return 0;
 }
@@ -1054,6 +1061,7 @@ int amepb_rdf_batch(amepb_ctx* ctx, const void* coords, int coords_dtype, int64_
         return fail(ctx, AMEPB_E_INVAL, "amepb_rdf_batch: edges_stride %lld < nbins+1", (long long)edges_stride);
     DeviceGuard guard(ctx->device);
     memset(&ctx->rdf_info, 0, sizeof(ctx->rdf_info));
+    timing_reset(ctx);
     const int64_t launches0 = ctx->launches;
     if (nframes == 0) return 0;
     ctx->last_stream = stream_;

@@ -370,6 +370,7 @@ int amepb_sq_harmonics(amepb_ctx* ctx, const void* coords, int dtype, int space,
     DeviceGuard guard(ctx->device);
     cudaStream_t stream = (cudaStream_t)stream_;
     ctx->last_stream = stream_;
+    timing_reset(ctx);
 
     const size_t frame_bytes = (size_t)n * 3 * elem_bytes(dtype);
     const size_t out_frame = (size_t)ndir * nharm * 2 * sizeof(double);
@@ -418,11 +419,14 @@ int amepb_sq_harmonics(amepb_ctx* ctx, const void* coords, int dtype, int space,
             const size_t smem = (size_t)(4 * kHarmBlockM * 2 * 32 + 4 * 2 * hn) * sizeof(double);
             dim3 grid((unsigned)nsplit, (unsigned)ndir, (unsigned)nf);
             const double* kv = d_kvec + (kvec_stride ? f0 * kvec_stride : 0);
+            cudaEvent_t ev0 = timing_event(ctx, stream);
             if (dtype == AMEPB_F32)
                 harmonics_kernel<float><<<grid, kHarmThreads, smem, stream>>>((const float*)d_coords, n, kv, kvec_stride, ndir, h0, hn, (int)nsplit, d_part);
             else
                 harmonics_kernel<double><<<grid, kHarmThreads, smem, stream>>>((const double*)d_coords, n, kv, kvec_stride, ndir, h0, hn, (int)nsplit, d_part);
             AMEPB_LAUNCH_CHECK(ctx);
+            cudaEvent_t ev1 = timing_event(ctx, stream);
+            if (ev0 && ev1) ctx->ev_sq.emplace_back(ev0, ev1);
             const long long total = fd * hn * 2;
             harmonics_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(d_part, (int)nsplit, hn, h0, nharm, fd, d_out);
             AMEPB_LAUNCH_CHECK(ctx);
@@ -449,6 +453,7 @@ int amepb_sf2d_modes(amepb_ctx* ctx, const void* coords, int dtype, int space, i
     DeviceGuard guard(ctx->device);
     cudaStream_t stream = (cudaStream_t)stream_;
     ctx->last_stream = stream_;
+    timing_reset(ctx);
 
     const size_t frame_bytes = (size_t)n * 3 * elem_bytes(dtype);
     const size_t g = (size_t)2 * nq;
@@ -498,6 +503,7 @@ int amepb_sf2d_modes(amepb_ctx* ctx, const void* coords, int dtype, int space, i
             d_out = reinterpret_cast<char*>(ctx->bufs[BUF_STAGE_OUT].p);
         }
         const double* qf = d_q + (q_stride ? f0 * q_stride : 0);
+        cudaEvent_t ev0 = timing_event(ctx, stream);
         if (accum == AMEPB_ACCUM_F64) {
             const int tiles = (nq + 63) / 64;
             const size_t part_bytes = (size_t)nf * ksplit * 4 * nq * nq * sizeof(double);
@@ -509,6 +515,10 @@ int amepb_sf2d_modes(amepb_ctx* ctx, const void* coords, int dtype, int space, i
             else
                 sf2d_f64_kernel<double><<<grid, kF64Threads, smem_f64, stream>>>((const double*)d_coords, n, qf, q_stride, nq, ksplit, d_part);
             AMEPB_LAUNCH_CHECK(ctx);
+            {
+                cudaEvent_t ev1 = timing_event(ctx, stream);
+                if (ev0 && ev1) ctx->ev_sq.emplace_back(ev0, ev1);
+            }
             const long long total = (long long)nf * nq * nq;
             sf2d_f64_finish_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(d_part, ksplit, nq, nf, reinterpret_cast<double2*>(d_out));
             AMEPB_LAUNCH_CHECK(ctx);
@@ -520,6 +530,8 @@ int amepb_sf2d_modes(amepb_ctx* ctx, const void* coords, int dtype, int space, i
             else
                 sf2d_c64_kernel<double><<<grid, kC64Threads, smem_c64, stream>>>((const double*)d_coords, n, qf, q_stride, nq, chunksize, reinterpret_cast<float2*>(d_out));
             AMEPB_LAUNCH_CHECK(ctx);
+            cudaEvent_t ev1 = timing_event(ctx, stream);
+            if (ev0 && ev1) ctx->ev_sq.emplace_back(ev0, ev1);
         }
         if (space == AMEPB_HOST) {
             AMEPB_CUDA(ctx, cudaMemcpyAsync((char*)out + (size_t)f0 * out_frame, d_out, out_frame * nf, cudaMemcpyDeviceToHost, stream));

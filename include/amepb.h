@@ -72,6 +72,9 @@ typedef struct amepb_rdf_info {
     int64_t kernel_launches;  /* CUDA kernels launched by the call                 */
     int32_t cells_per_cutoff; /* grid refinement k (cell edge ~ rmax / k)          */
     int32_t sub_batches;      /* how many sub-batches the frames were split into   */
+    double pair_kernel_ms;    /* CUDA-event time of the pair kernel launches (only  */
+                              /* with amepb_set_timing(ctx, 1)), else 0            */
+    double build_ms;          /* same for stats + cell build (count, scan, fill)   */
 } amepb_rdf_info;
 
 int amepb_abi_version(void);
@@ -167,6 +170,14 @@ int amepb_sf2d_modes(amepb_ctx* ctx, const void* coords, int dtype, int space,
                      const double* q, int64_t q_stride, int32_t nq,
                      int accum, int64_t chunksize,
                      void* out, void* stream);
+
+/* Record CUDA events around the kernels of amepb_rdf_batch / amepb_sq_* on the caller's
+ * stream so that amepb_rdf_last_info / amepb_last_kernel_ms can report device times. */
+int amepb_set_timing(amepb_ctx* ctx, int enable);
+
+/* Device time (ms, CUDA events on the launching stream) of the main kernel of the last
+ * amepb_sq_harmonics / amepb_sf2d_modes call; 0 unless timing is enabled. */
+double amepb_last_kernel_ms(amepb_ctx* ctx);
 
 /* CUDA kernels launched by this context since creation (for accounting). */
 int64_t amepb_kernel_launches(const amepb_ctx* ctx);
