@@ -22,7 +22,7 @@ ABI_VERSION = 1
 SYMBOLS = (
     "amepb_abi_version", "amepb_create", "amepb_destroy", "amepb_last_error",
     "amepb_frame_dimension", "amepb_rdf_batch", "amepb_rdf_last_info",
-    "amepb_rdf_set_cells_per_cutoff", "amepb_sq_harmonics", "amepb_sf2d_modes",
+    "amepb_rdf_set_cells_per_cutoff", "amepb_rdf_set_symmetric", "amepb_sq_harmonics", "amepb_sf2d_modes",
     "amepb_kernel_launches", "amepb_synchronize", "amepb_set_timing", "amepb_last_kernel_ms",
 )
 
@@ -98,6 +98,8 @@ def load():
         lib.amepb_rdf_last_info.argtypes = [vp, c.POINTER(RdfInfo)]
         lib.amepb_rdf_set_cells_per_cutoff.restype = c.c_int
         lib.amepb_rdf_set_cells_per_cutoff.argtypes = [vp, c.c_int]
+        lib.amepb_rdf_set_symmetric.restype = c.c_int
+        lib.amepb_rdf_set_symmetric.argtypes = [vp, c.c_int]
         lib.amepb_sq_harmonics.restype = c.c_int
         lib.amepb_sq_harmonics.argtypes = [vp, vp, c.c_int, c.c_int, i64, i64,
                                            c.POINTER(c.c_double), i64, i32, i32, vp, vp]
@@ -151,6 +153,9 @@ class Context:
 
     def last_kernel_ms(self) -> float:
         return float(self.lib.amepb_last_kernel_ms(self.handle))
+
+    def set_symmetric(self, enable: bool):
+        self.check(self.lib.amepb_rdf_set_symmetric(self.handle, 1 if enable else 0), "amepb_rdf_set_symmetric")
 
     def set_cells_per_cutoff(self, k: int):
         self.check(self.lib.amepb_rdf_set_cells_per_cutoff(self.handle, int(k)),

@@ -47,6 +47,7 @@ struct amepb_ctx {
     size_t pinned_cap = 0;
     amepb_rdf_info rdf_info;
     int rdf_k_override = 0;
+    bool rdf_symmetric = true;
     void* last_stream = nullptr;
     bool sq_attr_harm = false;
     bool timing = false;

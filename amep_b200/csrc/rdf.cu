@@ -205,6 +205,7 @@ __global__ void __launch_bounds__(256) place_images_kernel(const T* __restrict__
 #pragma unroll
             for (int vx = 0; vx < 3; ++vx) {
                 if (!ok[0][vx]) continue;
+                if (P.sym && (vx | vy | vz) == 0) continue;  // the unshifted image is the query itself
                 const unsigned c = P.cell_base +
                                    (unsigned)((cell[2][vz] * P.n[1] + cell[1][vy]) * P.n[0] + cell[0][vx]);
                 if (!FILL) {
@@ -428,7 +429,6 @@ struct PairArgs {
     int uniform;                    // every edge table is uniform (linspace-like)
 };
 
-constexpr unsigned long long kDirectPairs = 1ull << 22;  // larger warp tasks bypass the u32 histogram
 constexpr unsigned kUnitLimit = 1u << 21;                // flush after 2^31 counted pairs (units of 1024)
 constexpr int kPairThreads = 256;
 
@@ -471,7 +471,7 @@ template <typename AT, typename NT, bool ZCONST, bool DIRECT>
 __device__ __noinline__ void warp_pairs_general(const Vec4<AT>* __restrict__ qsorted, unsigned qa, unsigned qb,
                                                 const Vec4<NT>* __restrict__ tsorted, unsigned ta, unsigned tb,
                                                 const AT* __restrict__ thr, int nbins, AT dz2c, float inv_w,
-                                                float c_magic, unsigned* __restrict__ s_hist,
+                                                float c_magic, unsigned weight, unsigned* __restrict__ s_hist,
                                                 unsigned long long* __restrict__ g_hist) {
     const int lane = threadIdx.x & 31;
     const AT nan = (AT)__int_as_float(0x7fc00000);
@@ -490,8 +490,8 @@ __device__ __noinline__ void warp_pairs_general(const Vec4<AT>* __restrict__ qso
                 int g = max((int)bin_guess(Arith<AT>::approx(s), inv_w, c_magic, (unsigned)nbins) - 1, 0);
                 while (s < thr[g]) --g;
                 while (s >= thr[g + 1]) ++g;
-                if (DIRECT) atomicAdd(&g_hist[g], 1ull);
-                else atomicAdd(&s_hist[g], 1u);
+                if (DIRECT) atomicAdd(&g_hist[g], (unsigned long long)weight);
+                else atomicAdd(&s_hist[g], weight);
             }
         }
     }
@@ -509,9 +509,9 @@ __device__ __forceinline__ void pair_update(const Vec4<AT>& qv, AT nx, AT ny, AT
     const AT s = pair_s<AT, ZCONST>(qv, nx, ny, nz, dz2c);
     const unsigned k = bin_guess(Arith<AT>::approx(s), inv_w, c_magic, kmax);
     const AT t = Arith<AT>::load_thr(thr_addr + (k << Arith<AT>::kThrShift));
-    unsigned addr = hist_addr_m1 + (k << 2);  // &hist[k - 1]
+    unsigned addr = hist_addr_m1 + (k << 2);  // &hist[k - 1] (of the weight-W half, see pair_kernel)
     if (s >= t) addr += 4;
-    Arith<AT>::template inc_if_in_range<W>(addr, s, thr_lo, thr_hi);
+    Arith<AT>::template inc_if_in_range<1>(addr, s, thr_lo, thr_hi);
 }
 
 template <typename AT, typename NT, bool ZCONST, int W>
@@ -546,14 +546,23 @@ __device__ __forceinline__ void warp_pairs_fast(const Vec4<AT>* __restrict__ qso
     }
 }
 
-template <typename AT, typename NT, bool ZCONST, bool SMEM>
-__global__ void __launch_bounds__(kPairThreads) pair_kernel(PairArgs a) {
+// SYM: queries and unshifted targets are the same particles with identical stored values
+// (self RDF in the float32 regime, or without periodic images).  Then s(i,j) == s(j,i) bit for
+// bit, so real-real pairs are evaluated once over the upper half shell and counted twice; the
+// shifted images ("ghosts", a separate cell-sorted array) are not symmetric in floating point
+// and are evaluated for every ordered (query, ghost) pair.
+template <typename AT, typename NT, bool ZCONST, bool SMEM, bool SYM>
+__global__ void __launch_bounds__(kPairThreads, 5) pair_kernel(PairArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nbins = a.nbins;
     AT* s_thr = reinterpret_cast<AT*>(smem_raw);  // T[0..nbins], see warp_pairs_fast
     unsigned* s_hist = reinterpret_cast<unsigned*>(smem_raw + (((size_t)(nbins + 1) * sizeof(AT) + 15) & ~(size_t)15));
+    // SYM: a second histogram half collects the pairs that count twice, so that every
+    // increment is +1 (ATOMS.POPC.INC); the halves are combined as h1 + 2*h2 at flush time
+    const int hist_len = SYM ? 2 * nbins : nbins;
     const unsigned thr_addr = (unsigned)__cvta_generic_to_shared(s_thr);
     const unsigned hist_addr_m1 = (unsigned)__cvta_generic_to_shared(s_hist) - 4u;
+    const unsigned hist2_addr_m1 = hist_addr_m1 + 4u * (unsigned)nbins;
     __shared__ AT s_range[2];  // thr_lo, thr_hi of the current frame
     __shared__ FramePlan s_plan;
     __shared__ long long s_task;
@@ -585,8 +594,9 @@ __global__ void __launch_bounds__(kPairThreads) pair_kernel(PairArgs a) {
             if (SMEM && cur >= 0) {
                 unsigned long long* row = a.hist + (long long)cur * nbins;
                 for (int b = tid; b < nbins; b += blockDim.x) {
-                    const unsigned v = s_hist[b];
-                    if (v) atomicAdd(&row[b], (unsigned long long)v);
+                    unsigned long long v = s_hist[b];
+                    if (SYM) v += 2ull * s_hist[nbins + b];
+                    if (v) atomicAdd(&row[b], v);
                 }
             }
             if (done) break;
@@ -604,7 +614,7 @@ __global__ void __launch_bounds__(kPairThreads) pair_kernel(PairArgs a) {
                 }
             }
             if (SMEM)
-                for (int b = tid; b < nbins; b += blockDim.x) s_hist[b] = 0;
+                for (int b = tid; b < hist_len; b += blockDim.x) s_hist[b] = 0;
             cur = f;
             __syncthreads();
         }
@@ -628,33 +638,89 @@ __global__ void __launch_bounds__(kPairThreads) pair_kernel(PairArgs a) {
         const int cz = P.cq_lo[2] + (int)(rowq / P.cq_n[1]);
         const int cx0 = P.cq_lo[0] + run_i * P.run;
         const int ncell = min(P.run, P.cq_lo[0] + P.cq_n[0] - cx0);
-        const int nwt = ncell * P.nrows;
-        const unsigned qrow = P.cell_base + (unsigned)((cz * P.n[1] + cy) * P.n[0]);
+        const int nrows = P.nrows;
+        const int row0 = P.row0;
+        const unsigned long long direct_pairs = P.direct_pairs;
+        const int n0 = P.n[0], n1 = P.n[1], n2 = P.n[2];
+        const unsigned qrow = P.cell_base + (unsigned)((cz * n1 + cy) * n0);
 
-        for (int wt = warp; wt < nwt; wt += nwarps) {
-            const int c = wt % ncell, r = wt / ncell;
-            const int cx = cx0 + c;
-            const int ny = cy + P.row_oy[r], nz = cz + P.row_oz[r];
-            if (ny < 0 || ny >= P.n[1] || nz < 0 || nz >= P.n[2]) continue;
+        // One warp per query cell of the run (rsplit == 1), or rsplit warps sharing a cell,
+        // each walking every rsplit-th neighbour row.
+        const int rsplit = P.rsplit;
+        for (int wtk = warp; wtk < ncell * rsplit; wtk += nwarps) {
+            const int part = wtk / ncell;
+            const int cx = cx0 + (wtk - part * ncell);
             const unsigned qa = __ldg(&a.qstart[qrow + cx]), qb = __ldg(&a.qstart[qrow + cx + 1]);
             if (qa == qb) continue;
-            const int kx = P.row_kx[r];
-            const int x_lo = max(cx - kx, 0), x_hi = min(cx + kx, P.n[0] - 1);
-            const unsigned trow = P.cell_base + (unsigned)((nz * P.n[1] + ny) * P.n[0]);
-            const unsigned ta = __ldg(&a.tstart[trow + x_lo]), tb = __ldg(&a.tstart[trow + x_hi + 1]);
-            if (ta == tb) continue;
-            const unsigned long long npairs = (unsigned long long)(qb - qa) * (tb - ta);
-            const bool direct = !SMEM || npairs > kDirectPairs;
-            if (lane == 0) {
-                cand += npairs;
-                if (!direct) atomicAdd(&s_units, (unsigned)(npairs >> 10) + 1u);
+            // pass 0: real targets (SYM: upper half shell, own row to the right, own cell);
+            // pass 1 (SYM only): shifted images, all rows, skipped where none can live
+            const int npass = SYM ? 2 : 1;
+            for (int pass = 0; pass < npass; ++pass) {
+                const bool real = SYM && pass == 0;
+                int r_begin = 0, r_end = nrows;
+                if (real) r_begin = row0;
+                if (SYM && pass == 1) {
+                    const int kx0 = P.kd[0], ky = P.kd[1], kz = P.kd[2];
+                    if (cx - kx0 >= P.gfree_lo[0] && cx + kx0 <= P.gfree_hi[0] && cy - ky >= P.gfree_lo[1] &&
+                        cy + ky <= P.gfree_hi[1] && cz - kz >= P.gfree_lo[2] && cz + kz <= P.gfree_hi[2])
+                        break;
+                }
+                const unsigned* starts = real ? a.qstart : a.tstart;
+                for (int r = r_begin + part; r < r_end; r += rsplit) {
+                    const int ny = cy + P.row_oy[r], nz = cz + P.row_oz[r];
+                    if (ny < 0 || ny >= n1 || nz < 0 || nz >= n2) continue;
+                    const int kx = P.row_kx[r];
+                    int x_lo = max(cx - kx, 0);
+                    const int x_hi = min(cx + kx, n0 - 1);
+                    // in the query's own row only the own cell (both orders, weight 1) and the
+                    // cells to its right (weight 2) are visited in the symmetric pass
+                    int nseg = 1;
+                    if (real && r == row0) {
+                        x_lo = cx;
+                        nseg = 2;
+                    }
+                    const unsigned trow = P.cell_base + (unsigned)((nz * n1 + ny) * n0);
+                    for (int seg = 0; seg < nseg; ++seg) {
+                        int s_lo = x_lo, s_hi = x_hi;
+                        unsigned weight = real ? 2u : 1u;
+                        if (nseg == 2) {
+                            if (seg == 0) {
+                                s_hi = cx;
+                                weight = 1u;
+                            } else {
+                                s_lo = cx + 1;
+                                if (s_lo > s_hi) break;
+                            }
+                        }
+                        const unsigned ta = __ldg(&starts[trow + s_lo]), tb = __ldg(&starts[trow + s_hi + 1]);
+                        if (ta == tb) continue;
+                        const unsigned long long npairs = (unsigned long long)(qb - qa) * (tb - ta);
+                        const bool direct = !SMEM || npairs > direct_pairs;
+                        if (lane == 0) {
+                            cand += npairs;
+                            if (!direct) atomicAdd(&s_units, (unsigned)(npairs >> 10) + 1u);
+                        }
+                        if (real) {
+                            // real targets are the cell-sorted queries themselves (NT == AT in this mode)
+                            if (direct)
+                                warp_pairs_general<AT, AT, ZCONST, true>(qsorted, qa, qb, qsorted, ta, tb, thr, nbins,
+                                                                         dz2c, inv_w, c_magic, weight, s_hist, g_hist);
+                            else if (weight == 2)
+                                warp_pairs_fast<AT, AT, ZCONST, 2>(qsorted, qa, qb, qsorted, ta, tb, thr_lo, thr_hi, dz2c,
+                                                                   inv_w, c_magic, (unsigned)nbins, thr_addr, hist2_addr_m1);
+                            else
+                                warp_pairs_fast<AT, AT, ZCONST, 1>(qsorted, qa, qb, qsorted, ta, tb, thr_lo, thr_hi, dz2c,
+                                                                   inv_w, c_magic, (unsigned)nbins, thr_addr, hist_addr_m1);
+                        } else if (direct) {
+                            warp_pairs_general<AT, NT, ZCONST, true>(qsorted, qa, qb, tsorted, ta, tb, thr, nbins, dz2c,
+                                                                     inv_w, c_magic, 1u, s_hist, g_hist);
+                        } else {
+                            warp_pairs_fast<AT, NT, ZCONST, 1>(qsorted, qa, qb, tsorted, ta, tb, thr_lo, thr_hi, dz2c,
+                                                               inv_w, c_magic, (unsigned)nbins, thr_addr, hist_addr_m1);
+                        }
+                    }
+                }
             }
-            if (direct)
-                warp_pairs_general<AT, NT, ZCONST, true>(qsorted, qa, qb, tsorted, ta, tb, thr, nbins, dz2c, inv_w,
-                                                         c_magic, s_hist, g_hist);
-            else
-                warp_pairs_fast<AT, NT, ZCONST, 1>(qsorted, qa, qb, tsorted, ta, tb, thr_lo, thr_hi, dz2c, inv_w,
-                                                   c_magic, (unsigned)nbins, thr_addr, hist_addr_m1);
         }
         __syncthreads();
     }
@@ -727,16 +793,17 @@ static int exclusive_scan(amepb_ctx* ctx, const unsigned* in, unsigned* out, lon
     return 0;
 }
 
-template <typename AT, typename NT>
+template <typename AT, typename NT, bool SYM>
 static int launch_pairs(amepb_ctx* ctx, const PairArgs& args, bool zconst, cudaStream_t stream) {
     const int nbins = args.nbins;
-    const size_t smem = (((size_t)(nbins + 1) * sizeof(AT) + 15) & ~(size_t)15) + (size_t)nbins * sizeof(unsigned);
+    const size_t smem = (((size_t)(nbins + 1) * sizeof(AT) + 15) & ~(size_t)15) +
+                        (size_t)nbins * sizeof(unsigned) * (SYM ? 2 : 1);
     // the one-comparison bin correction needs uniform edges (args.uniform) and nbins <= 2^17;
     // the tables must fit in shared memory
     const bool use_smem = smem <= 40 * 1024 && args.uniform && nbins <= (1 << 17);
     void (*kern)(PairArgs) = nullptr;
-    if (use_smem) kern = zconst ? pair_kernel<AT, NT, true, true> : pair_kernel<AT, NT, false, true>;
-    else kern = zconst ? pair_kernel<AT, NT, true, false> : pair_kernel<AT, NT, false, false>;
+    if (use_smem) kern = zconst ? pair_kernel<AT, NT, true, true, SYM> : pair_kernel<AT, NT, false, true, SYM>;
+    else kern = zconst ? pair_kernel<AT, NT, true, false, SYM> : pair_kernel<AT, NT, false, false, SYM>;
     const size_t dyn = use_smem ? smem : 16;
     int per_sm = 0;
     AMEPB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kPairThreads, dyn));
@@ -861,6 +928,18 @@ static int rdf_sub_batch(amepb_ctx* ctx, const RdfCall& c, int64_t f0, int nf, c
             P.ncells = 0;
         }
     }
+    // symmetric mode: self RDF whose stored queries equal the unshifted targets bit for bit
+    // (float32 regime, or no images at all) and whose particles all pass the image window
+    bool sym = ctx->rdf_symmetric && self && (c.coords_dtype == AMEPB_F32 || !c.pbc);
+    for (int f = 0; sym && f < nf; ++f) {
+        const FramePlan& P = plans[f];
+        if (!P.valid || !c.pbc) continue;
+        for (int d = 0; d < 3; ++d) {
+            const double lo = (double)(float)tstats[f].lo[d], hi = (double)(float)tstats[f].hi[d];
+            if (!(lo > P.win_lo[d]) || !(hi < P.win_hi[d])) sym = false;
+        }
+    }
+    for (int f = 0; f < nf; ++f) plans[f].sym = sym ? 1 : 0;
     ctx->rdf_info.frames += nf;
     ctx->rdf_info.cells += total_cells;
     ctx->rdf_info.block_tasks += total_tasks;
@@ -952,11 +1031,12 @@ static int rdf_sub_batch(amepb_ctx* ctx, const RdfCall& c, int64_t f0, int nf, c
         AMEPB_LAUNCH_CHECK(ctx);
         return 0;
     };
-    if ((rc = place_targets(false))) return rc;
+    const bool have_targets = !(sym && !c.pbc);  // symmetric mode without images: the queries are the targets
+    if (have_targets && (rc = place_targets(false))) return rc;
     if ((rc = place_queries(false))) return rc;
     if ((rc = exclusive_scan(ctx, tcount, tstart, total_cells + 1, stream))) return rc;
     if ((rc = exclusive_scan(ctx, qcount, qstart, total_cells + 1, stream))) return rc;
-    if ((rc = place_targets(true))) return rc;
+    if (have_targets && (rc = place_targets(true))) return rc;
     if ((rc = place_queries(true))) return rc;
     cudaEvent_t ev_b1 = timing_event(ctx, stream);
     if (ev_b0 && ev_b1) ctx->ev_build.emplace_back(ev_b0, ev_b1);
@@ -976,9 +1056,12 @@ static int rdf_sub_batch(amepb_ctx* ctx, const RdfCall& c, int64_t f0, int nf, c
     args.nbins = nbins;
     args.nframes = nf;
     args.uniform = uniform ? 1 : 0;
-    if (!arith_f64) rc = launch_pairs<float, float>(ctx, args, all_zconst, stream);
-    else if (!targets_f64) rc = launch_pairs<double, float>(ctx, args, all_zconst, stream);
-    else rc = launch_pairs<double, double>(ctx, args, all_zconst, stream);
+    if (sym) {
+        if (!arith_f64) rc = launch_pairs<float, float, true>(ctx, args, all_zconst, stream);
+        else rc = launch_pairs<double, double, true>(ctx, args, all_zconst, stream);
+    } else if (!arith_f64) rc = launch_pairs<float, float, false>(ctx, args, all_zconst, stream);
+    else if (!targets_f64) rc = launch_pairs<double, float, false>(ctx, args, all_zconst, stream);
+    else rc = launch_pairs<double, double, false>(ctx, args, all_zconst, stream);
     if (rc) return rc;
     cudaEvent_t ev_p1 = timing_event(ctx, stream);
     if (ev_b1 && ev_p1) ctx->ev_pair.emplace_back(ev_b1, ev_p1);
@@ -992,6 +1075,12 @@ static int rdf_sub_batch(amepb_ctx* ctx, const RdfCall& c, int64_t f0, int nf, c
 using namespace amepb;
 
 extern "C" {
+
+int amepb_rdf_set_symmetric(amepb_ctx* ctx, int enable) {
+    if (!ctx) return AMEPB_E_INVAL;
+    ctx->rdf_symmetric = enable != 0;
+    return 0;
+}
 
 int amepb_rdf_set_cells_per_cutoff(amepb_ctx* ctx, int k) {
     if (!ctx || k < 0 || k > kMaxCellsPerCutoff) return AMEPB_E_INVAL;

@@ -124,14 +124,21 @@ struct FramePlan {
     unsigned ncells;
     int nrows;             // neighbour rows
     int run;               // query cells per block task (along x)
+    int rsplit;            // warps sharing one query cell (strided over its neighbour rows)
     int runs_per_row;
     int thr_index;         // threshold table of this frame
     int valid;             // 0: nothing to do for this frame
     int dim;               // dimension(coords)
+    unsigned direct_pairs; // warp tasks with more pairs than this bypass the 32-bit shared histogram
+    int row0;              // index of the (oy, oz) = (0, 0) row; rows after it are the "upper" half shell
+    int sym;               // symmetric mode: real-real pairs once (weight 2), ghosts separately
+    int kd[3];             // neighbourhood half-widths in cells
+    int gfree_lo[3];       // cells [gfree_lo, gfree_hi] (all dims) cannot hold ghost images
+    int gfree_hi[3];
     signed char row_oy[kMaxRows];
     signed char row_oz[kMaxRows];
     signed char row_kx[kMaxRows];
-    char pad_[5];
+    char pad_[1];
 };
 
 struct PlanInputs {
@@ -272,6 +279,7 @@ inline bool plan_frame(const PlanInputs& in, int dim, const FrameStats& tgt, con
     }
     if (kd[1] > kMaxCellsPerCutoff || kd[2] > kMaxCellsPerCutoff) return false;  // cannot happen: h >= rcs/k
     P.ncells = (unsigned)(n[0] * (long long)n[1] * n[2]);
+    for (int d = 0; d < 3; ++d) P.kd[d] = kd[d];
 
     // neighbour rows: all (oy, oz) cell offsets that can hold an image within
     // the cutoff of a query in the centre cell, with the x half-width needed
@@ -283,6 +291,7 @@ inline bool plan_frame(const PlanInputs& in, int dim, const FrameStats& tgt, con
             double rem = rcs * rcs - gy * gy - gz * gz;
             if (rem < 0) continue;
             int kx = (n[0] == 1) ? 0 : (int)std::min<double>(kd[0], floor(sqrt(rem) / h[0]) + 1);
+            if (oy == 0 && oz == 0) P.row0 = nrows;
             P.row_oy[nrows] = (signed char)oy;
             P.row_oz[nrows] = (signed char)oz;
             P.row_kx[nrows] = (signed char)kx;
@@ -301,17 +310,45 @@ inline bool plan_frame(const PlanInputs& in, int dim, const FrameStats& tgt, con
         cells_q *= P.cq_n[d];
     }
 
+    // cells that cannot hold a shifted image (symmetric mode skips the ghost pass there):
+    // a shifted image of a particle in [tgt.lo, tgt.hi] lies outside (tgt.hi - L, tgt.lo + L)
+    // in at least one shifted dimension
+    for (int d = 0; d < 3; ++d) {
+        P.gfree_lo[d] = 0;
+        P.gfree_hi[d] = n[d] - 1;
+        if (in.pbc && P.nshift[d] == 3) {
+            const double len = fabs((double)P.shift[d]);
+            // slack: float32 rounding of the cast and of base + shift
+            const double slack = 1e-5 * (fabs(tgt.lo[d]) + fabs(tgt.hi[d]) + len + 1.0);
+            P.gfree_lo[d] = cell_of(tgt.hi[d] - len + slack, P.g0[d], P.inv_h[d], n[d]) + 1;
+            P.gfree_hi[d] = cell_of(tgt.lo[d] + len - slack, P.g0[d], P.inv_h[d], n[d]) - 1;
+        }
+    }
+
     // block tasks: runs of query cells along x
     double ppc_t = n_est / std::max(1.0, (double)P.ncells);
     double ppc_q = (double)in.n_queries / std::max(1.0, cells_q);
     double pairs_per_cell = std::max(1.0, ppc_q) * std::max(1.0, ppc_t) * nrows * (2 * kd[0] + 1);
-    int run = (int)std::min<double>(64.0, std::max(1.0, floor(65536.0 / pairs_per_cell + 0.5)));
-    run = std::min(run, P.cq_n[0]);
-    // at most 256 warp tasks per block task: with <= 2^22 pairs per warp task (larger ones
-    // bypass the shared histogram) a block task stays below 2^30 increments, so the
-    // 32-bit shared counters cannot overflow between two flush checks
-    run = std::min(run, std::max(1, 256 / std::max(1, nrows)));
+    // A block task is `run` consecutive query cells; its 8 warps each take one cell (run a
+    // multiple of 8) or, for heavy cells, a strided 1/rsplit share of the cell's neighbour rows.
+    // Aim at ~2.6e5 candidate pairs per block task.
+    int run = (int)std::min<double>(64.0, std::max(1.0, floor(262144.0 / pairs_per_cell + 0.5)));
+    int rsplit = 1;
+    if (run >= 8) run = (run / 8) * 8;
+    else if (run >= 4) { run = 4; rsplit = 2; }
+    else if (run >= 2) { run = 2; rsplit = 4; }
+    else { run = 1; rsplit = 8; }
+    if (run > P.cq_n[0]) {
+        run = P.cq_n[0];
+        rsplit = run >= 8 ? 1 : (run >= 4 ? 2 : (run >= 2 ? 4 : 8));
+    }
     P.run = run;
+    P.rsplit = rsplit;
+    // 32-bit shared-memory counters: a block task has at most run * (2*nrows + 1) warp tasks
+    // (rows, the split own row, the ghost pass); warp tasks with more pairs than direct_pairs
+    // bypass the shared histogram, so a block task adds fewer than 2^31 increments and the
+    // flush check between block tasks (at 2^31) keeps every counter below 2^32
+    P.direct_pairs = (unsigned)std::min<double>(4194304.0, 2147483648.0 / ((double)run * (2 * nrows + 1)));
     P.runs_per_row = (P.cq_n[0] + run - 1) / run;
     P.ntasks = (long long)P.runs_per_row * P.cq_n[1] * P.cq_n[2];
     P.valid = 1;

@@ -135,6 +135,12 @@ int amepb_rdf_last_info(amepb_ctx* ctx, amepb_rdf_info* info);
 /* Tuning knob (0 = automatic): grid refinement k used by amepb_rdf_batch. */
 int amepb_rdf_set_cells_per_cutoff(amepb_ctx* ctx, int k);
 
+/* Tuning knob (default 1): allow the symmetric evaluation of self RDFs (each unordered
+ * pair of unshifted particles once, counted twice -- valid where s(i,j) == s(j,i) bit for
+ * bit: float32 regime or no periodic images).  0 forces every ordered pair to be evaluated.
+ * The counts are identical either way. */
+int amepb_rdf_set_symmetric(amepb_ctx* ctx, int enable);
+
 /*
  * Harmonic density modes along given wave vectors:
  *   out[f][d][h] = ( sum_i cos((h+1) k_d . r_i),  sum_i sin((h+1) k_d . r_i) )

@@ -138,7 +138,7 @@ def test_grid_refinement_does_not_change_counts(sc, k):
     finally:
         ctx.set_cells_per_cutoff(0)
     np.testing.assert_array_equal(counts[0], want)
-    assert info["candidate_pairs"] >= want.sum()
+    assert 2 * info["candidate_pairs"] >= want.sum()   # symmetric mode evaluates unordered pairs once
     box3 = np.array([[0, 18], [0, 18], [0, 18]], dtype=np.float32)
     c3 = _uniform(rng, 5000, box3.astype(np.float64), np.float32)
     want3, _ = corc.rdf_counts(c3, box3, rmax=3.0, nbins=100)
@@ -148,6 +148,32 @@ def test_grid_refinement_does_not_change_counts(sc, k):
     finally:
         ctx.set_cells_per_cutoff(0)
     np.testing.assert_array_equal(counts3[0], want3)
+
+
+@pytest.mark.parametrize("case", [c for c in CASES if c[4] is None and (c[2] is np.float32 or not c[6].get("pbc", True))],
+                         ids=lambda c: c[0])
+def test_symmetric_and_ordered_evaluation_agree(sc, case):
+    """Self RDFs in the float32 regime are evaluated over unordered pairs (x2); forcing
+    every ordered pair must give the same integers, and fewer distance evaluations."""
+    from amep_b200 import _lib
+    name, dim, dtype, n, m, box, kw, gen, spill = case
+    rng = np.random.default_rng(abs(hash(name)) % (2 ** 31))
+    box = np.array(box, dtype=dtype)
+    make = _clustered if gen == "clustered" else (lambda r, k, b, d: _uniform(r, k, b, d, spill))
+    coords = make(rng, n, box.astype(np.float64), dtype)
+    if dim == 2:
+        coords[:, 2] = 0
+    ctx = _lib.context(0)
+    out = {}
+    for mode in (True, False):
+        ctx.set_symmetric(mode)
+        try:
+            _, _, counts = sc.rdf_frames(coords, box, return_counts=True, **kw)
+            out[mode] = (counts[0], ctx.rdf_info()["candidate_pairs"])
+        finally:
+            ctx.set_symmetric(True)
+    np.testing.assert_array_equal(out[True][0], out[False][0])
+    assert out[True][1] < 0.9 * out[False][1]
 
 
 def test_batch_of_frames_with_per_frame_boxes(sc):

@@ -88,15 +88,22 @@ __global__ void cvt_kernel(double* out, int iters, double a) {
 }
 
 // shared-memory histogram atomics: `active` lanes of 32 hit pseudo-random bins
-__global__ void atoms_kernel(unsigned* out, int iters, int nbins, int active) {
+// (nbins must be a power of two).  inc == 1 compiles to ATOMS.POPC.INC, any other
+// run-time value to ATOMS.ADD.
+template <bool POPC>
+__global__ void atoms_kernel(unsigned* out, int iters, int nbins, int active, unsigned inc) {
     extern __shared__ unsigned hist[];
     for (int i = threadIdx.x; i < nbins; i += blockDim.x) hist[i] = 0;
     __syncthreads();
     unsigned x = threadIdx.x * 2654435761u + blockIdx.x * 40503u + 12345u;
     const bool on = (threadIdx.x & 31) < active;
+    const unsigned mask = nbins - 1;
     for (int it = 0; it < iters; ++it) {
         x = x * 1664525u + 1013904223u;
-        if (on) atomicAdd(&hist[(x >> 8) % nbins], 1u);
+        if (on) {
+            if (POPC) atomicAdd(&hist[(x >> 8) & mask], 1u);
+            else atomicAdd(&hist[(x >> 8) & mask], inc);
+        }
     }
     __syncthreads();
     unsigned s = 0;
@@ -145,9 +152,12 @@ int main() {
     ms = time_ms([&] { cvt_kernel<ILP><<<blocks, threads>>>((double*)buf, iters / 4, 0.25); });
     printf(", \"cvt_f64_f32_roundtrip_gops\": %.1f", nthreads * (iters / 4) * ILP / ms / 1e6);
     for (int active : {32, 16, 8}) {
-        for (int nbins : {500, 64}) {
-            ms = time_ms([&] { atoms_kernel<<<blocks, threads, nbins * 4>>>((unsigned*)buf, iters, nbins, active); });
-            printf(", \"atoms_nbins%d_active%d_gops\": %.1f", nbins, active,
+        for (int nbins : {512, 64}) {
+            ms = time_ms([&] { atoms_kernel<true><<<blocks, threads, nbins * 4>>>((unsigned*)buf, iters, nbins, active, 1u); });
+            printf(", \"atoms_popc_inc_nbins%d_active%d_gops\": %.1f", nbins, active,
+                   nthreads * iters * active / 32.0 / ms / 1e6);
+            ms = time_ms([&] { atoms_kernel<false><<<blocks, threads, nbins * 4>>>((unsigned*)buf, iters, nbins, active, 2u); });
+            printf(", \"atoms_add_nbins%d_active%d_gops\": %.1f", nbins, active,
                    nthreads * iters * active / 32.0 / ms / 1e6);
         }
     }
