@@ -598,6 +598,7 @@ __global__ void __launch_bounds__(kPairThreads, 5) pair_kernel(PairArgs a) {
                     if (SYM) v += 2ull * s_hist[nbins + b];
                     if (v) atomicAdd(&row[b], v);
                 }
+                __syncthreads();  // the zeroing below maps bins to other threads than the loop above
             }
             if (done) break;
             if (f != cur) {

@@ -207,6 +207,27 @@ def test_many_small_frames_one_call(sc):
         np.testing.assert_array_equal(counts[f], want)
 
 
+def test_many_frames_batch_equals_single_frame_calls(sc):
+    """Persistent blocks switch frames many times inside one launch; the batch must equal
+    frame-by-frame calls (and the host-memory path the device-memory path) bit for bit."""
+    g = torch.Generator(device="cuda").manual_seed(21)
+    nf, n, L = 96, 20000, 180.0
+    c = torch.zeros((nf, n, 3), device="cuda", dtype=torch.float32)
+    c[:, :, :2] = torch.rand((nf, n, 2), generator=g, device="cuda") * L
+    box = np.array([[0, L], [0, L], [-0.5, 0.5]], dtype=np.float32)
+    _, _, batch = sc.rdf_frames(c, box, rmax=10.0, nbins=500, return_counts=True)
+    _, _, batch2 = sc.rdf_frames(c, box, rmax=10.0, nbins=500, return_counts=True)
+    np.testing.assert_array_equal(batch, batch2)
+    host = c.cpu().numpy()
+    _, _, via_host = sc.rdf_frames(host, box, rmax=10.0, nbins=500, return_counts=True)
+    np.testing.assert_array_equal(batch, via_host)
+    for f in (0, 17, 95):
+        _, _, one = sc.rdf_frames(c[f:f + 1], box, rmax=10.0, nbins=500, return_counts=True)
+        np.testing.assert_array_equal(batch[f], one[0])
+    want, _ = corc.rdf_counts(host[40], box, rmax=10.0, nbins=500)
+    np.testing.assert_array_equal(batch[40], want)
+
+
 def test_large_nbins_uses_global_path(sc):
     rng = np.random.default_rng(13)
     box = np.array([[0, 30], [0, 30], [-0.5, 0.5]], dtype=np.float64)
