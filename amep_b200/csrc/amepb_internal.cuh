@@ -50,10 +50,14 @@ struct amepb_ctx {
     bool rdf_symmetric = true;
     void* last_stream = nullptr;
     bool sq_attr_harm = false;
+    cudaStream_t copy_stream = nullptr;   // host-space staging
+    cudaStream_t compute_stream = nullptr; // host-space calls made on the NULL stream
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr};
+    cudaEvent_t ev_computed[2] = {nullptr, nullptr};
     bool timing = false;
     std::vector<cudaEvent_t> ev_pool;     // reusable events
     size_t ev_used = 0;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pair, ev_build, ev_sq;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pair, ev_build, ev_sq, ev_copy;
     bool sq_attr_sf2d = false;
 };
 

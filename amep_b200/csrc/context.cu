@@ -93,6 +93,7 @@ void timing_reset(amepb_ctx* ctx) {
     ctx->ev_pair.clear();
     ctx->ev_build.clear();
     ctx->ev_sq.clear();
+    ctx->ev_copy.clear();
 }
 
 }  // namespace amepb
@@ -139,6 +140,12 @@ void amepb_destroy(amepb_ctx* ctx) {
         if (ctx->bufs[i].p) cudaFree(ctx->bufs[i].p);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+    for (int b = 0; b < 2; ++b) {
+        if (ctx->ev_copied[b]) cudaEventDestroy(ctx->ev_copied[b]);
+        if (ctx->ev_computed[b]) cudaEventDestroy(ctx->ev_computed[b]);
+    }
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->compute_stream) cudaStreamDestroy(ctx->compute_stream);
     delete ctx;
 }
 

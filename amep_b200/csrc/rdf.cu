@@ -16,6 +16,8 @@
 //              distance arithmetic without FMA; squared-distance thresholds for
 //              binning; per-block shared-memory histograms, one merge per frame
 #include <math.h>
+#include <stdlib.h>
+#include <time.h>
 #include <string.h>
 
 #include <vector>
@@ -729,6 +731,14 @@ __global__ void __launch_bounds__(kPairThreads, 5) pair_kernel(PairArgs a) {
     if (blockIdx.x == 0 && tid == 0) atomicAdd(&a.counters[2], (unsigned long long)a.tstart[a.total_cells]);
 }
 
+// Small parameter blocks (plans, thresholds) are pulled from mapped pinned host memory by
+// the SMs instead of a copy-engine transfer (see frame_stats).
+__global__ void upload_kernel(int* __restrict__ dst, const int* __restrict__ src, long long nwords) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nwords;
+         i += (long long)gridDim.x * blockDim.x)
+        dst[i] = src[i];
+}
+
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
@@ -757,14 +767,15 @@ static int frame_stats(amepb_ctx* ctx, const void* pts, int dtype, int64_t n, in
     if (rc) return rc;
     rc = ensure_pinned(ctx, sizeof(StatsOut) * (size_t)nframes * 2);
     if (rc) return rc;
-    StatsOut* d_final = reinterpret_cast<StatsOut*>(ctx->bufs[BUF_STATS].p) + (size_t)slot * nframes;
+    // The per-frame result goes straight to pinned host memory (mapped into the device address
+    // space under UVA): no copy-engine transfer, which would queue behind a large staging
+    // copy of the host-buffer path and stall the whole pipeline.
+    StatsOut* h = reinterpret_cast<StatsOut*>(ctx->pinned) + (size_t)slot * nframes;
     StatsOut* d_partial = reinterpret_cast<StatsOut*>(ctx->bufs[BUF_STATS].p) + (size_t)2 * nframes +
                           (size_t)slot * nframes * nparts;
-    if (dtype == AMEPB_F32) rc = launch_stats<float>(ctx, (const float*)pts, n, nframes, d_partial, d_final, nparts, stream);
-    else rc = launch_stats<double>(ctx, (const double*)pts, n, nframes, d_partial, d_final, nparts, stream);
+    if (dtype == AMEPB_F32) rc = launch_stats<float>(ctx, (const float*)pts, n, nframes, d_partial, h, nparts, stream);
+    else rc = launch_stats<double>(ctx, (const double*)pts, n, nframes, d_partial, h, nparts, stream);
     if (rc) return rc;
-    StatsOut* h = reinterpret_cast<StatsOut*>(ctx->pinned) + (size_t)slot * nframes;
-    AMEPB_CUDA(ctx, cudaMemcpyAsync(h, d_final, sizeof(StatsOut) * nframes, cudaMemcpyDeviceToHost, stream));
     AMEPB_CUDA(ctx, cudaStreamSynchronize(stream));
     out.resize(nframes);
     for (int f = 0; f < nframes; ++f) {
@@ -972,8 +983,15 @@ static int rdf_sub_batch(amepb_ctx* ctx, const RdfCall& c, int64_t f0, int nf, c
         if (arith_f64) make_thresholds<double>(edges, nbins, reinterpret_cast<double*>(hthr) + (size_t)tb * (nbins + 1));
         else make_thresholds<float>(edges, nbins, reinterpret_cast<float*>(hthr) + (size_t)tb * (nbins + 1));
     }
-    AMEPB_CUDA(ctx, cudaMemcpyAsync(ctx->bufs[BUF_PLANS].p, hp, plan_bytes, cudaMemcpyHostToDevice, stream));
-    AMEPB_CUDA(ctx, cudaMemcpyAsync(ctx->bufs[BUF_THR].p, hthr, thr_bytes, cudaMemcpyHostToDevice, stream));
+    {
+        const long long pw = (long long)(plan_bytes / sizeof(int)), tw = (long long)((thr_bytes + 3) / sizeof(int));
+        upload_kernel<<<(unsigned)std::min<long long>(64, (pw + 255) / 256), 256, 0, stream>>>(
+            reinterpret_cast<int*>(ctx->bufs[BUF_PLANS].p), reinterpret_cast<const int*>(hp), pw);
+        AMEPB_LAUNCH_CHECK(ctx);
+        upload_kernel<<<(unsigned)std::min<long long>(64, (tw + 255) / 256), 256, 0, stream>>>(
+            reinterpret_cast<int*>(ctx->bufs[BUF_THR].p), reinterpret_cast<const int*>(hthr), tw);
+        AMEPB_LAUNCH_CHECK(ctx);
+    }
     const FramePlan* d_plans = reinterpret_cast<const FramePlan*>(ctx->bufs[BUF_PLANS].p);
 
     // ---- workspaces ------------------------------------------------------------
@@ -1167,6 +1185,12 @@ int amepb_rdf_batch(amepb_ctx* ctx, const void* coords, int coords_dtype, int64_
     c.space = space; c.nframes = nframes; c.box = box_boundary; c.box_dtype = box_dtype;
     c.edges = edges; c.edges_stride = edges_stride; c.nbins = nbins; c.pbc = pbc ? 1 : 0;
     c.hist_out = hist_out; c.dim_out = dim_out; c.stream = (cudaStream_t)stream_;
+    if (space == AMEPB_HOST && stream_ == nullptr) {
+        // host-space calls on the NULL stream get a private compute stream: the legacy default
+        // stream would serialise against the staging copies of other blocking streams
+        if (!ctx->compute_stream) AMEPB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->compute_stream, cudaStreamNonBlocking));
+        if (!getenv("AMEPB_HOST_NULL_STREAM")) c.stream = ctx->compute_stream;
+    }
 
     // sub-batch size from a workspace budget
     const size_t cbytes = (size_t)n * 3 * elem_size(coords_dtype);
@@ -1184,33 +1208,95 @@ int amepb_rdf_batch(amepb_ctx* ctx, const void* coords, int coords_dtype, int64_
     fb = std::min<int64_t>(fb, nframes);
 
     bool bad_dim = false;
-    for (int64_t f0 = 0; f0 < nframes; f0 += fb) {
-        const int nf = (int)std::min<int64_t>(fb, nframes - f0);
-        const void* d_coords = (const char*)coords + (size_t)f0 * cbytes;
-        const void* d_other = other ? (const char*)other + (size_t)f0 * obytes : nullptr;
-        unsigned long long* d_hist = reinterpret_cast<unsigned long long*>(hist_out) + (size_t)f0 * nbins;
-        if (space == AMEPB_HOST) {
-            int rc = ensure_device(ctx, BUF_STAGE_A, cbytes * nf);
+    if (space == AMEPB_DEVICE) {
+        for (int64_t f0 = 0; f0 < nframes; f0 += fb) {
+            const int nf = (int)std::min<int64_t>(fb, nframes - f0);
+            const void* d_coords = (const char*)coords + (size_t)f0 * cbytes;
+            const void* d_other = other ? (const char*)other + (size_t)f0 * obytes : nullptr;
+            unsigned long long* d_hist = reinterpret_cast<unsigned long long*>(hist_out) + (size_t)f0 * nbins;
+            int rc = rdf_sub_batch(ctx, c, f0, nf, d_coords, d_other, d_hist, &bad_dim);
             if (rc) return rc;
-            AMEPB_CUDA(ctx, cudaMemcpyAsync(ctx->bufs[BUF_STAGE_A].p, d_coords, cbytes * nf, cudaMemcpyHostToDevice, c.stream));
-            d_coords = ctx->bufs[BUF_STAGE_A].p;
-            if (other) {
-                rc = ensure_device(ctx, BUF_STAGE_B, obytes * nf);
-                if (rc) return rc;
-                AMEPB_CUDA(ctx, cudaMemcpyAsync(ctx->bufs[BUF_STAGE_B].p, d_other, obytes * nf, cudaMemcpyHostToDevice, c.stream));
-                d_other = ctx->bufs[BUF_STAGE_B].p;
-            }
-            rc = ensure_device(ctx, BUF_STAGE_OUT, sizeof(unsigned long long) * (size_t)nf * nbins);
-            if (rc) return rc;
-            d_hist = reinterpret_cast<unsigned long long*>(ctx->bufs[BUF_STAGE_OUT].p);
         }
-        int rc = rdf_sub_batch(ctx, c, f0, nf, d_coords, d_other, d_hist, &bad_dim);
+    } else {
+        // Host buffers: double-buffered staging.  The copy of sub-batch i+1 runs on the
+        // context's copy stream while sub-batch i is computed on the caller's stream.
+        size_t stage_target = (size_t)192 << 20;
+        if (const char* env = getenv("AMEPB_STAGE_MB")) stage_target = (size_t)std::max(1, atoi(env)) << 20;
+        fb = std::min<int64_t>(fb, std::max<int64_t>(1, (int64_t)(stage_target / std::max<size_t>(1, cbytes + obytes))));
+        const int64_t nsub = (nframes + fb - 1) / fb;
+        int rc = ensure_device(ctx, BUF_STAGE_A, 2 * cbytes * fb);
         if (rc) return rc;
-        if (space == AMEPB_HOST) {
-            AMEPB_CUDA(ctx, cudaMemcpyAsync(hist_out + (size_t)f0 * nbins, d_hist,
-                                            sizeof(unsigned long long) * (size_t)nf * nbins,
-                                            cudaMemcpyDeviceToHost, c.stream));
-            AMEPB_CUDA(ctx, cudaStreamSynchronize(c.stream));
+        if (other && (rc = ensure_device(ctx, BUF_STAGE_B, 2 * obytes * fb))) return rc;
+        if ((rc = ensure_device(ctx, BUF_STAGE_OUT, sizeof(unsigned long long) * (size_t)nframes * nbins))) return rc;
+        if (!ctx->copy_stream) {
+            AMEPB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+            for (int b = 0; b < 2; ++b) {
+                AMEPB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_copied[b], cudaEventDisableTiming));
+                AMEPB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_computed[b], cudaEventDisableTiming));
+            }
+        }
+        char* stage_a = reinterpret_cast<char*>(ctx->bufs[BUF_STAGE_A].p);
+        char* stage_b = other ? reinterpret_cast<char*>(ctx->bufs[BUF_STAGE_B].p) : nullptr;
+        unsigned long long* d_hist = reinterpret_cast<unsigned long long*>(ctx->bufs[BUF_STAGE_OUT].p);
+        auto enqueue_copy = [&](int64_t i) -> int {
+            const int b = (int)(i & 1);
+            const int64_t f0 = i * fb;
+            const int nf = (int)std::min<int64_t>(fb, nframes - f0);
+            if (i >= 2) AMEPB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_computed[b], 0));
+            cudaEvent_t ec0 = timing_event(ctx, ctx->copy_stream);
+            AMEPB_CUDA(ctx, cudaMemcpyAsync(stage_a + (size_t)b * cbytes * fb, (const char*)coords + (size_t)f0 * cbytes,
+                                            cbytes * nf, cudaMemcpyHostToDevice, ctx->copy_stream));
+            if (other)
+                AMEPB_CUDA(ctx, cudaMemcpyAsync(stage_b + (size_t)b * obytes * fb, (const char*)other + (size_t)f0 * obytes,
+                                                obytes * nf, cudaMemcpyHostToDevice, ctx->copy_stream));
+            AMEPB_CUDA(ctx, cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream));
+            cudaEvent_t ec1 = timing_event(ctx, ctx->copy_stream);
+            if (ec0 && ec1) ctx->ev_copy.emplace_back(ec0, ec1);
+            return 0;
+        };
+        // the copy stream must not start before work already queued on the caller's stream
+        // could still be reading the staging buffers of an earlier call
+        AMEPB_CUDA(ctx, cudaStreamSynchronize(c.stream));
+        if ((rc = enqueue_copy(0))) return rc;
+        const bool trace = getenv("AMEPB_TRACE") != nullptr;
+        auto now_ms = []() {
+            timespec ts;
+            clock_gettime(CLOCK_MONOTONIC, &ts);
+            return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+        };
+        for (int64_t i = 0; i < nsub; ++i) {
+            const int b = (int)(i & 1);
+            const int64_t f0 = i * fb;
+            const int nf = (int)std::min<int64_t>(fb, nframes - f0);
+            const double t0 = now_ms();
+            if (i + 1 < nsub && (rc = enqueue_copy(i + 1))) return rc;
+            if (trace) fprintf(stderr, "[amepb] sub %lld: enqueue_copy took %.3f ms (host)\n", (long long)i, now_ms() - t0);
+            AMEPB_CUDA(ctx, cudaStreamWaitEvent(c.stream, ctx->ev_copied[b], 0));
+            rc = rdf_sub_batch(ctx, c, f0, nf, stage_a + (size_t)b * cbytes * fb,
+                               other ? stage_b + (size_t)b * obytes * fb : nullptr, d_hist + (size_t)f0 * nbins, &bad_dim);
+            if (rc) return rc;
+            AMEPB_CUDA(ctx, cudaEventRecord(ctx->ev_computed[b], c.stream));
+        }
+        // one device->host transfer of all histograms at the end (a per-sub-batch copy would
+        // queue behind the next staging copy and stall the stream)
+        AMEPB_CUDA(ctx, cudaMemcpyAsync(hist_out, d_hist, sizeof(unsigned long long) * (size_t)nframes * nbins,
+                                        cudaMemcpyDeviceToHost, c.stream));
+        AMEPB_CUDA(ctx, cudaStreamSynchronize(c.stream));
+        if (trace && ctx->timing && !ctx->ev_build.empty()) {
+            cudaEvent_t t0 = ctx->ev_copy.empty() ? ctx->ev_build[0].first : ctx->ev_copy[0].first;
+            auto rel = [&](cudaEvent_t e) {
+                float ms = 0;
+                cudaEventElapsedTime(&ms, t0, e);
+                return ms;
+            };
+            for (size_t i = 0; i < ctx->ev_build.size(); ++i) {
+                fprintf(stderr, "[amepb] sub %zu: copy %.2f-%.2f  build %.2f-%.2f  pair %.2f-%.2f ms\n", i,
+                        i < ctx->ev_copy.size() ? rel(ctx->ev_copy[i].first) : -1.f,
+                        i < ctx->ev_copy.size() ? rel(ctx->ev_copy[i].second) : -1.f,
+                        rel(ctx->ev_build[i].first), rel(ctx->ev_build[i].second),
+                        i < ctx->ev_pair.size() ? rel(ctx->ev_pair[i].first) : -1.f,
+                        i < ctx->ev_pair.size() ? rel(ctx->ev_pair[i].second) : -1.f);
+            }
         }
     }
     ctx->rdf_info.kernel_launches = ctx->launches - launches0;

@@ -285,6 +285,16 @@ def run_gpu(args):
     hist_np = hist_host.numpy()
     for _ in range(2):
         _core.rdf_histograms(host_np, box, edges, out=hist_np, device=local)
+    # raw pinned host->device copy rate of the same buffer (the floor of any host-buffer path)
+    scratch = torch.empty_like(coords[:ef])
+    torch.cuda.synchronize()
+    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    h0.record()
+    scratch.copy_(host, non_blocking=True)
+    h1.record()
+    torch.cuda.synchronize()
+    h2d_gbs = host.numel() * 4 / (h0.elapsed_time(h1) * 1e-3) / 1e9
+    del scratch
     barrier()
     t0 = time.perf_counter()
     e2e_steps = max(2, args.steps)
@@ -353,7 +363,9 @@ def run_gpu(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, world),
         "e2e": {"value": e2e_value, "unit": "pair-evals/s", "h2d_bytes_per_step": ef * n * 12 * world,
-                "d2h_bytes_per_step": ef * NBINS * 8 * world, "frames_per_gpu": ef},
+                "d2h_bytes_per_step": ef * NBINS * 8 * world, "frames_per_gpu": ef,
+                "pinned_h2d_copy_gbs": h2d_gbs,
+                "h2d_floor_ms_per_frame": n * 12 / (h2d_gbs * 1e9) * 1e3},
         "gpu_launches": int(agg[0].item()),
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
         "ms_per_frame": elapsed_ms / args.steps / nf, "pair_kernel_ms_per_frame": pair_ms / args.steps / nf,
