@@ -15,6 +15,7 @@
 //       1.5*2^(e+29) constant: F2F runs at a quarter of the FP64 rate), chunk sums added in
 //       float32 in chunk order; particles strictly in index order.
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -28,7 +29,7 @@ static size_t elem_bytes(int dtype) { return dtype == AMEPB_F32 ? 4 : 8; }
 // harmonics (sfiso 'fast')
 // ---------------------------------------------------------------------------------------
 constexpr int kHarmThreads = 128;
-constexpr int kHarmP = 8;        // particles per thread
+constexpr int kHarmP = 8;        // particles per thread (the tree sum below is written for 8)
 constexpr int kHarmBlockM = 16;  // harmonics reduced per round
 constexpr int kHarmSeg = 512;    // harmonics per launch segment (shared accumulators)
 
@@ -75,12 +76,9 @@ __global__ void __launch_bounds__(kHarmThreads) harmonics_kernel(
         for (int hb = 0; hb < hn; hb += kHarmBlockM) {
 #pragma unroll
             for (int j = 0; j < kHarmBlockM; ++j) {
-                double sumc = cc[0], sums = sc[0];
-#pragma unroll
-                for (int p = 1; p < kHarmP; ++p) {
-                    sumc += cc[p];
-                    sums += sc[p];
-                }
+                // pairwise tree (depth 3) instead of a serial chain of 7 dependent DADDs
+                const double sumc = ((cc[0] + cc[1]) + (cc[2] + cc[3])) + ((cc[4] + cc[5]) + (cc[6] + cc[7]));
+                const double sums = ((sc[0] + sc[1]) + (sc[2] + sc[3])) + ((sc[4] + sc[5]) + (sc[6] + sc[7]));
                 my_part[(j * 2 + 0) * 32 + lane] = sumc;
                 my_part[(j * 2 + 1) * 32 + lane] = sums;
 #pragma unroll
@@ -93,9 +91,15 @@ __global__ void __launch_bounds__(kHarmThreads) harmonics_kernel(
             }
             __syncwarp();
             // lane = row (harmonic j = lane/2, component lane&1); rotated reads are conflict free
-            double tot = 0.0;
-#pragma unroll 8
-            for (int i = 0; i < 32; ++i) tot += my_part[lane * 32 + ((i + lane) & 31)];
+            double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+                t0 += my_part[lane * 32 + ((i + lane) & 31)];
+                t1 += my_part[lane * 32 + ((i + 1 + lane) & 31)];
+                t2 += my_part[lane * 32 + ((i + 2 + lane) & 31)];
+                t3 += my_part[lane * 32 + ((i + 3 + lane) & 31)];
+            }
+            const double tot = (t0 + t1) + (t2 + t3);
             const int h = hb + (lane >> 1);
             if (h < hn) my_acc[h * 2 + (lane & 1)] += tot;
             __syncwarp();
@@ -160,7 +164,7 @@ __device__ __forceinline__ void table_run16(double x, const double* __restrict__
 constexpr int kF64Threads = 256;   // 16 x 16 threads, 4 x 4 quad points each: 64 x 64 tile
 constexpr int kF64Stage = 32;      // particles per shared-memory stage
 
-template <typename T>
+template <typename T, int UNROLL>
 __global__ void __launch_bounds__(kF64Threads, 1) sf2d_f64_kernel(
     const T* __restrict__ coords, long long n, const double* __restrict__ qall, long long q_stride, int nq,
     int ksplit, double* __restrict__ partial) {
@@ -204,7 +208,7 @@ __global__ void __launch_bounds__(kF64Threads, 1) sf2d_f64_kernel(
             }
         }
         __syncthreads();
-#pragma unroll 2
+#pragma unroll UNROLL
         for (int jj = 0; jj < kF64Stage; ++jj) {
             double2 xa[4], yb[4];
 #pragma unroll
@@ -409,8 +413,32 @@ int amepb_sq_harmonics(amepb_ctx* ctx, const void* coords, int dtype, int space,
         }
         // splits of the particle range per (frame, direction)
         const long long fd = (long long)nf * ndir;
-        long long nsplit = ((long long)ctx->sm_count * 6 + fd - 1) / fd;
-        nsplit = std::max<long long>(1, std::min<long long>(nsplit, ntiles));
+        // split the particle range so that the blocks fill whole waves of resident blocks
+        int occ = 1;
+        {
+            const size_t smem_seg = (size_t)(4 * kHarmBlockM * 2 * 32 + 4 * 2 * std::min<int>(kHarmSeg, nharm)) * sizeof(double);
+            if (dtype == AMEPB_F32)
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, harmonics_kernel<float>, kHarmThreads, smem_seg);
+            else
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, harmonics_kernel<double>, kHarmThreads, smem_seg);
+            if (occ < 1) occ = 1;
+        }
+        const long long wave = (long long)ctx->sm_count * occ;
+        long long nsplit = 1;
+        {
+            const long long max_split = std::max<long long>(1, std::min<long long>(ntiles, 4 * wave / std::max<long long>(1, fd) + 1));
+            double best_eff = -1.0;
+            for (long long k = 1; k <= max_split; ++k) {
+                const long long blocks = fd * k;
+                const long long waves = (blocks + wave - 1) / wave;
+                const double eff = (double)blocks / (double)(waves * wave);
+                if (eff > best_eff + 1e-9) {
+                    best_eff = eff;
+                    nsplit = k;
+                }
+                if (waves >= 2 && eff > 0.97) break;
+            }
+        }
         for (int h0 = 0; h0 < nharm; h0 += kHarmSeg) {
             const int hn = std::min<int>(kHarmSeg, nharm - h0);
             const size_t part_bytes = (size_t)fd * nsplit * hn * 2 * sizeof(double);
@@ -473,8 +501,10 @@ int amepb_sf2d_modes(amepb_ctx* ctx, const void* coords, int dtype, int space, i
     const size_t smem_f64 = sizeof(double2) * kF64Stage * 64 * 2;
     const size_t smem_c64 = sizeof(double2) * kC64Stage * 16 * 2;
     if (!ctx->sq_attr_sf2d) {
-        AMEPB_CUDA(ctx, cudaFuncSetAttribute(sf2d_f64_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f64));
-        AMEPB_CUDA(ctx, cudaFuncSetAttribute(sf2d_f64_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f64));
+        AMEPB_CUDA(ctx, cudaFuncSetAttribute(sf2d_f64_kernel<float, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f64));
+        AMEPB_CUDA(ctx, cudaFuncSetAttribute(sf2d_f64_kernel<float, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f64));
+        AMEPB_CUDA(ctx, cudaFuncSetAttribute(sf2d_f64_kernel<float, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f64));
+        AMEPB_CUDA(ctx, cudaFuncSetAttribute(sf2d_f64_kernel<double, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f64));
         AMEPB_CUDA(ctx, cudaFuncSetAttribute(sf2d_c64_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c64));
         AMEPB_CUDA(ctx, cudaFuncSetAttribute(sf2d_c64_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c64));
         ctx->sq_attr_sf2d = true;
@@ -486,8 +516,21 @@ int amepb_sf2d_modes(amepb_ctx* ctx, const void* coords, int dtype, int space, i
         const size_t per_split = (size_t)4 * nq * nq * sizeof(double);
         fb = std::min<int64_t>(fb, std::max<int64_t>(1, (int64_t)(((size_t)1 << 30) / per_split)));
         const long long blocks_fd = (long long)tiles * tiles * std::min<int64_t>(fb, nframes);
-        ksplit = (int)std::max<long long>(1, std::min<long long>(((long long)ctx->sm_count * 2 + blocks_fd - 1) / blocks_fd,
-                                                                  (n + 4 * kF64Stage - 1) / (4 * kF64Stage)));
+        // one block per SM (register bound): pick the particle split whose block count fills
+        // whole waves of SMs best, preferring 2-6 waves
+        const long long max_split = std::max<long long>(1, std::min<long long>(64, (n + 8 * kF64Stage - 1) / (8 * kF64Stage)));
+        double best_eff = -1.0;
+        for (long long k = 1; k <= max_split; ++k) {
+            const long long blocks = blocks_fd * k;
+            const long long waves = (blocks + ctx->sm_count - 1) / ctx->sm_count;
+            double eff = (double)blocks / (double)(waves * ctx->sm_count);
+            if (waves > 8) eff *= 0.98;  // more splits = more partial sums to combine
+            if (eff > best_eff + 1e-9) {
+                best_eff = eff;
+                ksplit = (int)k;
+            }
+            if (waves >= 6 && eff > 0.95) break;
+        }
         while (ksplit > 1 && (size_t)ksplit * per_split * std::min<int64_t>(fb, nframes) > ((size_t)4 << 30)) --ksplit;
     }
 
@@ -510,10 +553,16 @@ int amepb_sf2d_modes(amepb_ctx* ctx, const void* coords, int dtype, int space, i
             if ((rc = ensure_device(ctx, BUF_SQ_B, part_bytes))) return rc;
             double* d_part = reinterpret_cast<double*>(ctx->bufs[BUF_SQ_B].p);
             dim3 grid((unsigned)(tiles * tiles), (unsigned)ksplit, (unsigned)nf);
-            if (dtype == AMEPB_F32)
-                sf2d_f64_kernel<float><<<grid, kF64Threads, smem_f64, stream>>>((const float*)d_coords, n, qf, q_stride, nq, ksplit, d_part);
+            const char* un = getenv("AMEPB_SF2D_UNROLL");
+            const int unroll = un ? atoi(un) : 2;
+            if (dtype == AMEPB_F32 && unroll == 1)
+                sf2d_f64_kernel<float, 1><<<grid, kF64Threads, smem_f64, stream>>>((const float*)d_coords, n, qf, q_stride, nq, ksplit, d_part);
+            else if (dtype == AMEPB_F32 && unroll == 4)
+                sf2d_f64_kernel<float, 4><<<grid, kF64Threads, smem_f64, stream>>>((const float*)d_coords, n, qf, q_stride, nq, ksplit, d_part);
+            else if (dtype == AMEPB_F32)
+                sf2d_f64_kernel<float, 2><<<grid, kF64Threads, smem_f64, stream>>>((const float*)d_coords, n, qf, q_stride, nq, ksplit, d_part);
             else
-                sf2d_f64_kernel<double><<<grid, kF64Threads, smem_f64, stream>>>((const double*)d_coords, n, qf, q_stride, nq, ksplit, d_part);
+                sf2d_f64_kernel<double, 2><<<grid, kF64Threads, smem_f64, stream>>>((const double*)d_coords, n, qf, q_stride, nq, ksplit, d_part);
             AMEPB_LAUNCH_CHECK(ctx);
             {
                 cudaEvent_t ev1 = timing_event(ctx, stream);

@@ -169,7 +169,9 @@ def run_reference(args):
         return
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import c_oracle as corc
-    threads = min(len(os.sched_getaffinity(0)), corc.max_threads()) if hasattr(os, "sched_getaffinity") else corc.max_threads()
+    # all host cores of this process (torchrun exports OMP_NUM_THREADS=1; the oracle sets its
+    # own thread count explicitly)
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     n = args.particles
     nq = args.cpu_queries or max(threads * 4, int(1.5 * auto_cpu_queries(n, threads)) // max(1, args.steps + args.warmup))
     for _ in range(args.warmup):
@@ -350,7 +352,7 @@ def run_gpu(args):
     if not args.no_cpu and world == 1:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import c_oracle as corc
-        threads = min(len(os.sched_getaffinity(0)), corc.max_threads())
+        threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
         nq = args.cpu_queries or auto_cpu_queries(n, threads)
         rate, dt, pairs, nimg = cpu_reference_rate(n, nq, threads)
         cpu = {"value": rate, "unit": "pair-evals/s", "cores": threads, "kind": "port",
@@ -403,9 +405,9 @@ def sq_section(torch, dist, _core, ctx, dev, world, rank):
         return float(t.item())
 
     # sfiso(mode='fast'), 3D LJ-like density (configs[2] shape at reduced N): rho=0.8, qmax=20, num=8
-    n3 = 1_000_000
+    n3, nf3 = 1_000_000, 4
     L3 = float((n3 / 0.8) ** (1 / 3))
-    c3 = torch.rand((1, n3, 3), generator=gen, device=dev, dtype=torch.float32) * L3
+    c3 = torch.rand((nf3, n3, 3), generator=gen, device=dev, dtype=torch.float32) * L3
     box3 = np.array([[0, L3], [0, L3], [0, L3]], dtype=np.float32)
     res = {}
 
@@ -413,14 +415,14 @@ def sq_section(torch, dist, _core, ctx, dev, world, rank):
         res["s"], res["q"] = sc.sfiso_frames(c3, box3, None, qmax=20.0, twod=False, mode="fast", num=8)
     ms = timed(run_sfiso)
     nq = res["q"].shape[1]
-    out["sfiso_fast"] = {"workload": f"3D uniform rho=0.8, N={n3}, qmax=20, num=8 (nq={nq}, 32 directions, 13 unique), 1 frame per GPU",
-                         "terms_per_s": n3 * nq * 32 * world / (ms * 1e-3), "ms": ms, "kernel_ms": ctx.last_kernel_ms(),
-                         "unique_terms_per_s": n3 * nq * 13 * world / (ms * 1e-3), "dtype": "f64"}
+    out["sfiso_fast"] = {"workload": f"3D uniform rho=0.8, N={n3}, qmax=20, num=8 (nq={nq}, 32 directions, 13 unique), {nf3} frames per GPU",
+                         "terms_per_s": nf3 * n3 * nq * 32 * world / (ms * 1e-3), "ms": ms, "kernel_ms": ctx.last_kernel_ms(),
+                         "unique_terms_per_s": nf3 * n3 * nq * 13 * world / (ms * 1e-3), "dtype": "f64"}
     del c3
     # sf2d(mode='std'), configs[3]: 256k particles, 512 x 512 q grid
-    n2, L2 = 262_144, 512.0
-    c2 = torch.zeros((1, n2, 3), device=dev, dtype=torch.float32)
-    c2[0, :, :2] = torch.rand((n2, 2), generator=gen, device=dev, dtype=torch.float32) * L2
+    n2, L2, nf2 = 262_144, 512.0, 8
+    c2 = torch.zeros((nf2, n2, 3), device=dev, dtype=torch.float32)
+    c2[:, :, :2] = torch.rand((nf2, n2, 2), generator=gen, device=dev, dtype=torch.float32) * L2
     box2 = np.array([[0, L2], [0, L2], [-0.5, 0.5]], dtype=np.float32)
     qmax2 = 256.5 * 2 * np.pi / 512.0
     for accum in ("c64", "f64"):
@@ -429,9 +431,9 @@ def sq_section(torch, dist, _core, ctx, dev, world, rank):
         ms = timed(run_sf2d, reps=2)
         g = res["s2"].shape[1]
         out["sf2d_std_" + accum] = {
-            "workload": f"configs[3]: 2D uniform N={n2}, {g}x{g} q grid, 1 frame per GPU, "
+            "workload": f"configs[3]: 2D uniform N={n2}, {g}x{g} q grid, {nf2} frames per GPU, "
                         + ("complex64 accumulation in the reference's order" if accum == "c64" else "float64 accumulation"),
-            "terms_per_s": n2 * g * g * world / (ms * 1e-3), "ms": ms, "kernel_ms": ctx.last_kernel_ms(),
+            "terms_per_s": nf2 * n2 * g * g * world / (ms * 1e-3), "ms": ms, "kernel_ms": ctx.last_kernel_ms(),
             "dtype": "f64 (rounded to f32 per add)" if accum == "c64" else "f64"}
     return out
 
