@@ -215,6 +215,46 @@ def sq_harmonics(coords, kvec, nharm, device=None):
     return out
 
 
+def sq_debye(coords, other, q, twod, device=None):
+    """Debye sums ``out[f, k] = sum_ij K(q_k d_ij)`` over all ordered pairs (amepb_sq_debye).
+
+    ``q``: float64 ``[nq]`` (shared) or ``[F, nq]``; ``other`` may be None (= coords)."""
+    pc = coords if isinstance(coords, Particles) else Particles(coords)
+    po = None
+    if other is not None:
+        po = other if isinstance(other, Particles) else Particles(other)
+        if pc.on_device != po.on_device:
+            dev = (pc if pc.on_device else po).tensor.device
+            pc, po = pc.to_device(dev), po.to_device(dev)
+    nf = pc.nframes
+    qa = np.ascontiguousarray(np.asarray(q, dtype=np.float64))
+    if qa.ndim == 1:
+        nq, stride = qa.shape[0], 0
+    elif qa.ndim == 2 and qa.shape[0] == nf:
+        nq, stride = qa.shape[1], qa.shape[1]
+    else:
+        raise ValueError("q must have shape (nq,) or (F, nq)")
+    dev_index = _device_of(pc, device)
+    ctx = _lib.context(dev_index)
+    if pc.on_device:
+        import torch
+        out = torch.empty((nf, nq), dtype=torch.float64, device=pc.tensor.device)
+        optr, space = out.data_ptr(), _lib.DEVICE
+    else:
+        out = np.empty((nf, nq), dtype=np.float64)
+        optr, space = out.ctypes.data, _lib.HOST
+    if nq == 0:
+        return out
+    rc = ctx.lib.amepb_sq_debye(
+        ctx.handle, ctypes.c_void_p(pc.ptr()), pc.dtype, pc.n,
+        ctypes.c_void_p(po.ptr()) if po is not None else None, po.dtype if po is not None else 0,
+        po.n if po is not None else 0, space, nf,
+        qa.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), stride, nq, 1 if twod else 0,
+        ctypes.c_void_p(optr), _stream_for(dev_index, pc.on_device))
+    ctx.check(rc, "amepb_sq_debye")
+    return out
+
+
 def sf2d_modes(coords, qpos, nq, accum="c64", chunksize=0, device=None):
     """rho(q) on the sf2d grid (amepb_sf2d_modes) -> complex array ``[F, 2nq, 2nq]``.
 

@@ -313,13 +313,13 @@ __global__ void __launch_bounds__(kC64Threads) sf2d_c64_kernel(
         const int lim = (int)((n - j0) < kC64Stage ? (n - j0) : kC64Stage);
         for (int jj = 0; jj < lim; ++jj) {
             const double2 xa = sX[jj][ta], yb = sY[jj][tb];
-            const double p1 = __dmul_rn(xa.x, yb.x), p2 = __dmul_rn(xa.y, yb.y);
-            const double p3 = __dmul_rn(xa.x, yb.y), p4 = __dmul_rn(xa.y, yb.x);
             // exp(-i(qa x + qb y)) = (cc - ss) - i (sc + cs);  exp(-i(-qa x + qb y)) = (cc + ss) + i (sc - cs)
-            ppr = round_to_f32(__dadd_rn(ppr, __dsub_rn(p1, p2)));
-            ppi = round_to_f32(__dsub_rn(ppi, __dadd_rn(p4, p3)));
-            mpr = round_to_f32(__dadd_rn(mpr, __dadd_rn(p1, p2)));
-            mpi = round_to_f32(__dadd_rn(mpi, __dsub_rn(p4, p3)));
+            // acc + term in float64 as two fused multiply-adds (the term itself is never formed:
+            // 8 DFMA instead of 4 DMUL + 8 DADD), then the float32 rounding of the reference
+            ppr = round_to_f32(fma(-xa.y, yb.y, fma(xa.x, yb.x, ppr)));
+            ppi = round_to_f32(fma(-xa.x, yb.y, fma(-xa.y, yb.x, ppi)));
+            mpr = round_to_f32(fma(xa.y, yb.y, fma(xa.x, yb.x, mpr)));
+            mpi = round_to_f32(fma(-xa.x, yb.y, fma(xa.y, yb.x, mpi)));
             if (j0 + jj + 1 == chunk_end) {
                 // rhoq += res : complex64 + complex64 (amep/spatialcor.py:1890-1891)
                 tppr = __fadd_rn(tppr, (float)ppr); tppi = __fadd_rn(tppi, (float)ppi);
@@ -340,6 +340,98 @@ __global__ void __launch_bounds__(kC64Threads) sf2d_c64_kernel(
         r[(long long)iym * g + ixm] = make_float2(tppr, -tppi);
         r[(long long)iym * g + ixp] = make_float2(tmpr, -tmpi);
     }
+}
+
+// ---------------------------------------------------------------------------------------
+// Debye scattering sum (sfiso 'std'): out[k] = sum over all ordered pairs (a_i, b_j) of
+// J0(q_k d_ij) (2D) or sin(q_k d_ij)/(q_k d_ij) (3D), no periodic images; zero distances
+// contribute 1 (amep/spatialcor.py:1363-1399).  Distances are rounded like the reference
+// (float32 coordinates, float32 distance and argument); the kernel and the sum are float64.
+// ---------------------------------------------------------------------------------------
+constexpr int kDebyeThreads = 256;
+constexpr int kDebyeTileB = 16;   // b particles held in registers per thread
+
+template <typename TA, typename TB, bool TWOD>
+__global__ void __launch_bounds__(kDebyeThreads) debye_kernel(
+    const TA* __restrict__ a, long long na, const TB* __restrict__ b, long long nb,
+    const double* __restrict__ qall, long long q_stride, int nq, double* __restrict__ partial) {
+    extern __shared__ double s_acc[];  // [8 warps][nq]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int frame = blockIdx.y;
+    const TA* fa = a + (long long)frame * na * 3;
+    const TB* fb = b + (long long)frame * nb * 3;
+    const double* q = qall + (long long)frame * q_stride;
+    double* my_acc = s_acc + (size_t)warp * nq;
+    for (int k = lane; k < nq; k += 32) my_acc[k] = 0.0;
+    __syncwarp();
+    const long long tiles_a = (na + kDebyeThreads - 1) / kDebyeThreads;
+    const long long tiles_b = (nb + kDebyeTileB - 1) / kDebyeTileB;
+    for (long long tile = blockIdx.x; tile < tiles_a * tiles_b; tile += gridDim.x) {
+        const long long ta = tile % tiles_a, tb = tile / tiles_a;
+        const long long i = ta * kDebyeThreads + tid;
+        float d32[kDebyeTileB];
+        bool have[kDebyeTileB];
+        float ax = 0.f, ay = 0.f, az = 0.f;
+        const bool have_a = i < na;
+        if (have_a) {
+            ax = (float)fa[3 * i]; ay = (float)fa[3 * i + 1]; az = (float)fa[3 * i + 2];
+        }
+#pragma unroll
+        for (int j = 0; j < kDebyeTileB; ++j) {
+            const long long jj = tb * kDebyeTileB + j;
+            have[j] = have_a && jj < nb;
+            d32[j] = 0.f;
+            if (have[j]) {
+                // scipy cdist on float32 input: differences and the root in float64, then .astype(float32)
+                const double dx = (double)ax - (double)(float)fb[3 * jj];
+                const double dy = (double)ay - (double)(float)fb[3 * jj + 1];
+                const double dz = (double)az - (double)(float)fb[3 * jj + 2];
+                d32[j] = (float)sqrt(dx * dx + dy * dy + dz * dz);
+            }
+        }
+        for (int k = 0; k < nq; ++k) {
+            const float q32 = (float)q[k];
+            double sum = 0.0;
+#pragma unroll
+            for (int j = 0; j < kDebyeTileB; ++j) {
+                if (!have[j]) continue;
+                double term = 1.0;
+                if (d32[j] != 0.f) {
+                    if (TWOD) {
+                        term = j0((double)__fmul_rn(d32[j], q32));
+                    } else {
+                        // x = d * (q/pi) in float32, y = pi*x in float32, sin(y)/y (np.sinc)
+                        const float x = __fmul_rn(d32[j], __fdiv_rn(q32, 3.14159274f));
+                        const double y = (double)__fmul_rn(3.14159274f, x);
+                        term = y != 0.0 ? sin(y) / y : 1.0;
+                    }
+                }
+                sum += term;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            if (lane == 0) my_acc[k] += sum;
+        }
+    }
+    __syncthreads();
+    double* out = partial + ((long long)frame * gridDim.x + blockIdx.x) * nq;
+    for (int k = tid; k < nq; k += kDebyeThreads) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < kDebyeThreads / 32; ++w) v += s_acc[(size_t)w * nq + k];
+        out[k] = v;
+    }
+}
+
+__global__ void debye_reduce_kernel(const double* __restrict__ partial, int nblocks, int nq, long long nframes,
+                                    double* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nframes * nq) return;
+    const long long f = i / nq;
+    const int k = (int)(i % nq);
+    double s = 0.0;
+    for (int b = 0; b < nblocks; ++b) s += partial[(f * nblocks + b) * nq + k];
+    out[i] = s;
 }
 
 }  // namespace amepb
@@ -586,6 +678,84 @@ int amepb_sf2d_modes(amepb_ctx* ctx, const void* coords, int dtype, int space, i
             AMEPB_CUDA(ctx, cudaMemcpyAsync((char*)out + (size_t)f0 * out_frame, d_out, out_frame * nf, cudaMemcpyDeviceToHost, stream));
             AMEPB_CUDA(ctx, cudaStreamSynchronize(stream));
         }
+    }
+    return 0;
+}
+
+int amepb_sq_debye(amepb_ctx* ctx, const void* coords, int dtype, int64_t n, const void* other, int other_dtype,
+                   int64_t m, int space, int64_t nframes, const double* q, int64_t q_stride, int32_t nq, int twod,
+                   double* out, void* stream_) {
+    if (!ctx) return AMEPB_E_INVAL;
+    auto ok_dtype = [](int d) { return d == AMEPB_F32 || d == AMEPB_F64; };
+    if (!coords || !q || !out || nframes < 0 || n <= 0 || nq <= 0 || nq > 4096 || !ok_dtype(dtype) ||
+        (other && (!ok_dtype(other_dtype) || m <= 0)) || (space != AMEPB_DEVICE && space != AMEPB_HOST) ||
+        (q_stride != 0 && q_stride < nq) || nframes > 65535)
+        return fail(ctx, AMEPB_E_INVAL, "amepb_sq_debye: invalid argument");
+    if (nframes == 0) return 0;
+    DeviceGuard guard(ctx->device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    ctx->last_stream = stream_;
+    timing_reset(ctx);
+    if (!other) {
+        other = coords;
+        other_dtype = dtype;
+        m = n;
+    }
+    const size_t abytes = (size_t)n * 3 * elem_bytes(dtype) * nframes;
+    const size_t bbytes = (size_t)m * 3 * elem_bytes(other_dtype) * nframes;
+    const void* d_a = coords;
+    const void* d_b = other;
+    double* d_out = out;
+    int rc;
+    if (space == AMEPB_HOST) {
+        if ((rc = ensure_device(ctx, BUF_STAGE_A, abytes))) return rc;
+        AMEPB_CUDA(ctx, cudaMemcpyAsync(ctx->bufs[BUF_STAGE_A].p, coords, abytes, cudaMemcpyHostToDevice, stream));
+        d_a = ctx->bufs[BUF_STAGE_A].p;
+        if (other == coords) {
+            d_b = d_a;
+        } else {
+            if ((rc = ensure_device(ctx, BUF_STAGE_B, bbytes))) return rc;
+            AMEPB_CUDA(ctx, cudaMemcpyAsync(ctx->bufs[BUF_STAGE_B].p, other, bbytes, cudaMemcpyHostToDevice, stream));
+            d_b = ctx->bufs[BUF_STAGE_B].p;
+        }
+        if ((rc = ensure_device(ctx, BUF_STAGE_OUT, sizeof(double) * (size_t)nframes * nq))) return rc;
+        d_out = reinterpret_cast<double*>(ctx->bufs[BUF_STAGE_OUT].p);
+    }
+    const size_t q_count = (size_t)(q_stride ? nframes * q_stride : nq);
+    if ((rc = ensure_pinned(ctx, q_count * sizeof(double)))) return rc;
+    if ((rc = ensure_device(ctx, BUF_SQ_A, q_count * sizeof(double)))) return rc;
+    memcpy(ctx->pinned, q, q_count * sizeof(double));
+    AMEPB_CUDA(ctx, cudaMemcpyAsync(ctx->bufs[BUF_SQ_A].p, ctx->pinned, q_count * sizeof(double), cudaMemcpyHostToDevice, stream));
+    const double* d_q = reinterpret_cast<const double*>(ctx->bufs[BUF_SQ_A].p);
+
+    const long long tiles = ((n + kDebyeThreads - 1) / kDebyeThreads) * ((m + kDebyeTileB - 1) / kDebyeTileB);
+    const int nblocks = (int)std::max<long long>(1, std::min<long long>(tiles, std::max<long long>(1, (long long)ctx->sm_count * 8 / nframes)));
+    if ((rc = ensure_device(ctx, BUF_SQ_B, sizeof(double) * (size_t)nframes * nblocks * nq))) return rc;
+    double* d_part = reinterpret_cast<double*>(ctx->bufs[BUF_SQ_B].p);
+    const size_t smem = sizeof(double) * (size_t)(kDebyeThreads / 32) * nq;
+    dim3 grid((unsigned)nblocks, (unsigned)nframes);
+    cudaEvent_t ev0 = timing_event(ctx, stream);
+#define AMEPB_DEBYE(TA, TB)                                                                                       \
+    do {                                                                                                          \
+        if (twod)                                                                                                 \
+            debye_kernel<TA, TB, true><<<grid, kDebyeThreads, smem, stream>>>((const TA*)d_a, n, (const TB*)d_b, m, d_q, q_stride, nq, d_part); \
+        else                                                                                                      \
+            debye_kernel<TA, TB, false><<<grid, kDebyeThreads, smem, stream>>>((const TA*)d_a, n, (const TB*)d_b, m, d_q, q_stride, nq, d_part); \
+    } while (0)
+    if (dtype == AMEPB_F32 && other_dtype == AMEPB_F32) AMEPB_DEBYE(float, float);
+    else if (dtype == AMEPB_F32) AMEPB_DEBYE(float, double);
+    else if (other_dtype == AMEPB_F32) AMEPB_DEBYE(double, float);
+    else AMEPB_DEBYE(double, double);
+#undef AMEPB_DEBYE
+    AMEPB_LAUNCH_CHECK(ctx);
+    cudaEvent_t ev1 = timing_event(ctx, stream);
+    if (ev0 && ev1) ctx->ev_sq.emplace_back(ev0, ev1);
+    const long long total = (long long)nframes * nq;
+    debye_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(d_part, nblocks, nq, nframes, d_out);
+    AMEPB_LAUNCH_CHECK(ctx);
+    if (space == AMEPB_HOST) {
+        AMEPB_CUDA(ctx, cudaMemcpyAsync(out, d_out, sizeof(double) * (size_t)nframes * nq, cudaMemcpyDeviceToHost, stream));
+        AMEPB_CUDA(ctx, cudaStreamSynchronize(stream));
     }
     return 0;
 }

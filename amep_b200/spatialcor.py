@@ -171,11 +171,10 @@ def sfiso_frames(coords, box_boundary, N=None, qmax=20.0, twod=True, mode="std",
     if not twod and mode == "fft":
         _log.warning("Mode 'fft' does only work for 2d systems. Since twod is False, mode 'std' is used.")
         mode = "std"
-    if mode != "fast":
+    if mode == "fft":
         raise NotImplementedError(
-            f"amep_b200.spatialcor.sfiso: mode '{mode}' is not on the B200 hot path yet "
-            "(SURVEY.md section 8: Debye 'std' is N^2*nq and not a scale target; 'fft' is a next row). "
-            "Use mode='fast' (the default of amep.evaluate.SFiso).")
+            "amep_b200.spatialcor.sfiso: mode 'fft' is not on the B200 hot path yet "
+            "(SURVEY.md section 8f, a next row). Use mode='fast' or mode='std'.")
     # q grid per frame (amep/spatialcor.py:1592-1598)
     q_rows, dq_rows = [], []
     for f in range(nf if per_frame_box else 1):
@@ -187,6 +186,20 @@ def sfiso_frames(coords, box_boundary, N=None, qmax=20.0, twod=True, mode="std",
     nq = len(q_rows[0])
     if any(len(q) != nq for q in q_rows):
         raise ValueError("sfiso_frames: the box changes the number of q values between frames")
+    if mode == "std":
+        # Debye scattering formula over all ordered pairs, no periodic images
+        # (amep/spatialcor.py:1363-1399, 1617-1634)
+        if nq == 0:
+            return np.zeros((nf, 0)), np.zeros((nf, 0))
+        qarr = np.stack(q_rows) if per_frame_box else q_rows[0]
+        sums = _core.sq_debye(pc, None if po is pc else po, qarr, twod)
+        if reduce is not None:
+            sums = reduce(sums)
+        if _core._is_torch(sums):
+            sums = sums.cpu().numpy()
+        s = sums / np.sqrt(pc.n * po.n)
+        q = np.stack(q_rows) if per_frame_box else np.broadcast_to(q_rows[0], (nf, nq)).copy()
+        return s, q
     unit_vectors = _sfiso_directions(twod, num)
     reps, weights = _unique_directions(unit_vectors)
     if per_frame_box:

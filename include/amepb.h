@@ -13,6 +13,7 @@
  *                             amep/spatialcor.py:348-388    __rdf_diff
  *                             amep/spatialcor.py:566-600    chunk fan-out + sum
  *   amepb_sq_harmonics     <- amep/spatialcor.py:1402-1448  __sf_iso_chunk_fast
+ *   amepb_sq_debye         <- amep/spatialcor.py:1324-1399  __sf_iso_chunk_std
  *   amepb_sf2d_modes       <- amep/spatialcor.py:1690-1719  __sf2d_chunk_std
  *                             amep/spatialcor.py:1876-1907  chunk fan-out + sum
  *
@@ -156,6 +157,21 @@ int amepb_sq_harmonics(amepb_ctx* ctx, const void* coords, int dtype, int space,
                        int64_t nframes, int64_t n,
                        const double* kvec, int64_t kvec_stride, int32_t ndir, int32_t nharm,
                        double* out, void* stream);
+
+/*
+ * Debye scattering sum of sfiso(mode='std') (amep/spatialcor.py:1324-1399, distances from
+ * amep/pbc.py:1178-1206: all ordered pairs, no periodic images):
+ *   out[f][k] = sum_{i in coords, j in other} K(q_k d_ij),  K = J0 (twod) or sin(x)/x,
+ * zero distances contributing 1.  Distances and arguments are rounded to float32 like the
+ * reference; K and the sum are evaluated in float64 (the reference sums in float32).
+ *   other  may be NULL (other = coords);  q  host float64 [nq] (q_stride 0) or [nframes][q_stride]
+ *   out    [nframes][nq] float64 in `space`
+ */
+int amepb_sq_debye(amepb_ctx* ctx, const void* coords, int dtype, int64_t n,
+                   const void* other, int other_dtype, int64_t m,
+                   int space, int64_t nframes,
+                   const double* q, int64_t q_stride, int32_t nq, int twod,
+                   double* out, void* stream);
 
 /*
  * Density modes on the sf2d grid: rho[f][iy][ix] = sum_i exp(-i (qx[ix] x_i + qy[iy] y_i))

@@ -161,6 +161,22 @@ def main():
                         S=s, q=q, qmax=15.0, twod=False, num=8)
     print(f"sfiso_3d: nq={len(q)}")
 
+    # ---- sfiso(mode='std'), Debye formula ------------------------------------------
+    rng = np.random.default_rng(211)
+    c2s = np.zeros((300, 3))
+    c2s[:, :2] = rng.uniform(0, 18, (300, 2))
+    c2s[7] = c2s[3]                                   # a coincident pair (zero distance)
+    s, q = amep.spatialcor.sfiso(c2s, box2, len(c2s), qmax=10.0, twod=True, mode="std")
+    np.savez_compressed(os.path.join(GOLDEN, "sfiso_std_2d_f64.npz"), coords=c2s, box=box2, S=s, q=q,
+                        qmax=10.0, twod=True)
+    a3 = rng.uniform(0, 9, (260, 3)).astype(np.float32)
+    b3 = rng.uniform(0, 9, (150, 3)).astype(np.float32)
+    s, q = amep.spatialcor.sfiso(a3, box3.astype(np.float32), len(a3), qmax=12.0, twod=False, mode="std",
+                                 other_coords=b3, chunksize=64)
+    np.savez_compressed(os.path.join(GOLDEN, "sfiso_std_3d_cross_f32.npz"), coords=a3, other=b3,
+                        box=box3.astype(np.float32), S=s, q=q, qmax=12.0, twod=False, chunksize=64)
+    print(f"sfiso_std: nq={len(q)} dtype={s.dtype}")
+
     # ---- sf2d(mode='std') -----------------------------------------------------
     rng = np.random.default_rng(301)
     box2 = np.array([[0, 20], [0, 20], [-0.5, 0.5]], dtype=np.float64)

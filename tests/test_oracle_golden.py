@@ -70,6 +70,21 @@ def test_sfiso_fast_bit_exact(name):
     np.testing.assert_array_equal(s, z["S"])
 
 
+@pytest.mark.parametrize("name", ["sfiso_std_2d_f64.npz", "sfiso_std_3d_cross_f32.npz"])
+def test_sfiso_std_debye_bit_exact(name):
+    z = _load(name)
+    other = z["other"] if "other" in z.files else None
+    cs = int(z["chunksize"]) if "chunksize" in z.files else None
+    s, q = orc.sfiso_std(z["coords"], z["box"], qmax=float(z["qmax"]), twod=bool(z["twod"]),
+                         other_coords=other, chunksize=cs)
+    np.testing.assert_array_equal(q, z["q"])
+    np.testing.assert_array_equal(s, z["S"])
+    # the reference's float32 evaluation sits ~1e-5 from the float64 evaluation of the same sum
+    s64, _ = orc.sfiso_std_f64(z["coords"], z["box"], qmax=float(z["qmax"]), twod=bool(z["twod"]),
+                               other_coords=other)
+    assert np.max(np.abs(s64 - s) / np.maximum(np.abs(s64), 1e-2)) < 2e-4
+
+
 @pytest.mark.parametrize("name", ["sf2d_f64_onechunk.npz", "sf2d_f32_chunks.npz", "sf2d_f64_cross.npz"])
 def test_sf2d_std_bit_exact(name):
     z = _load(name)

@@ -82,7 +82,33 @@ def test_sfiso_modes_and_errors(sc):
     s2, _ = sc.sfiso(c, box, 200, qmax=5.0, twod=True, mode="fast", num=8)
     np.testing.assert_array_equal(s1, s2)
     with pytest.raises(NotImplementedError):
-        sc.sfiso(c, box, 200, qmax=5.0, twod=True, mode="std")
+        sc.sfiso(c, box, 200, qmax=5.0, twod=True, mode="fft")
+
+
+@pytest.mark.parametrize("space", ["host", "device"])
+@pytest.mark.parametrize("name", ["sfiso_std_2d_f64.npz", "sfiso_std_3d_cross_f32.npz"])
+def test_sfiso_std_debye(sc, name, space):
+    """mode='std' (the default of amep.spatialcor.sfiso): Debye sum.  The reference sums
+    float32 terms in float32 (its own noise is ~1e-5 relative, tests/test_oracle_golden.py);
+    the kernel rounds distances/arguments like the reference but sums in float64, so it
+    matches the float64 restatement to 1e-6 and the reference to the reference's noise."""
+    z = np.load(os.path.join(GOLDEN, name))
+    coords = z["coords"]
+    other = z["other"] if "other" in z.files else None
+    if space == "device":
+        coords = torch.from_numpy(coords).cuda()
+        other = None if other is None else torch.from_numpy(other).cuda()
+    s, q = sc.sfiso(coords, z["box"], len(z["coords"]), qmax=float(z["qmax"]), twod=bool(z["twod"]),
+                    mode="std", other_coords=other)
+    np.testing.assert_array_equal(q, z["q"])
+    want64, _ = orc.sfiso_std_f64(z["coords"], z["box"], qmax=float(z["qmax"]), twod=bool(z["twod"]),
+                                  other_coords=z["other"] if "other" in z.files else None)
+    _close(s, want64, rtol=1e-6, atol_scale=1e-6)
+    assert np.max(np.abs(s - z["S"]) / np.maximum(np.abs(z["S"]), 1e-2)) < 2e-4
+    # default mode of the function is 'std' as in the reference
+    s_default, _ = sc.sfiso(coords, z["box"], len(z["coords"]), qmax=float(z["qmax"]), twod=bool(z["twod"]),
+                            other_coords=other)
+    np.testing.assert_array_equal(s_default, s)
 
 
 @pytest.mark.parametrize("space", ["host", "device"])
