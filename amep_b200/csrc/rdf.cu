@@ -359,18 +359,6 @@ struct Arith<float> {
         asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
         return v;
     }
-    // histogram increment, predicated on thr_lo <= s < thr_hi without a branch
-    // histogram += W iff thr_lo <= s < thr_hi (ptxas wraps the predicated atomic in a
-    // short branch region; W = 1 becomes ATOMS.POPC.INC)
-    template <int W>
-    static __device__ __forceinline__ void inc_if_in_range(unsigned addr, float s, float lo, float hi) {
-        asm volatile(
-            "{\n\t.reg .pred p, q;\n\t"
-            "setp.ge.f32 p, %1, %2;\n\t"
-            "setp.lt.and.f32 q, %1, %3, p;\n\t"
-            "@q red.shared.add.u32 [%0], %4;\n\t}"
-            ::"r"(addr), "f"(s), "f"(lo), "f"(hi), "n"(W) : "memory");
-    }
     static constexpr int kThrShift = 2;
 };
 template <>
@@ -379,25 +367,18 @@ struct Arith<double> {
     static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
     static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
     // Truncating double->float on the integer pipe (F2F runs at 1/4 of the FP64 rate).
-    // Valid for s in the float32 normal range; anything else is outside [thr_lo, thr_hi)
-    // or is clamped by the caller.
+    // Exact enough for the bin guess when s is in the float32 normal range.
     static __device__ __forceinline__ float approx(double s) {
         const unsigned hi = (unsigned)__double2hiint(s), lo = (unsigned)__double2loint(s);
-        return __uint_as_float(__funnelshift_l(lo, hi - 0x38000000u, 3));
+        // saturate: s >= 2^128, inf and NaN (and, through the unsigned wrap, s < 2^-126) map to
+        // a huge finite float, whose guess clamps to the last slot; tiny s is below thr_lo anyway
+        const unsigned e = min(hi - 0x38000000u, 0x0fefffffu);
+        return __uint_as_float(__funnelshift_l(lo, e, 3));
     }
     static __device__ __forceinline__ double load_thr(unsigned addr) {
         double v;
         asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
         return v;
-    }
-    template <int W>
-    static __device__ __forceinline__ void inc_if_in_range(unsigned addr, double s, double lo, double hi) {
-        asm volatile(
-            "{\n\t.reg .pred p, q;\n\t"
-            "setp.ge.f64 p, %1, %2;\n\t"
-            "setp.lt.and.f64 q, %1, %3, p;\n\t"
-            "@q red.shared.add.u32 [%0], %4;\n\t}"
-            ::"r"(addr), "d"(s), "d"(lo), "d"(hi), "n"(W) : "memory");
     }
     static constexpr int kThrShift = 3;
 };
@@ -501,26 +482,35 @@ __device__ __noinline__ void warp_pairs_general(const Vec4<AT>* __restrict__ qso
 
 // Hot version.  Shared memory holds T[k], k = 0..nbins: T[0] = 0, T[k] = thr[k] -- the
 // squared distance at which bin k starts (T[nbins] = end of the last bin).  bin = k - 1 +
-// (s >= T[k]) for the guess k; the increment is predicated on thr_lo <= s < thr_hi.
+// (s >= T[k]) for the guess k; pairs outside [thr_lo, thr_hi) end up in a dump slot.
 // No branches in the loop body; kQueryUnroll queries are in flight per lane.
 constexpr int kQueryUnroll = 4;
-template <typename AT, bool ZCONST, int W>
-__device__ __forceinline__ void pair_update(const Vec4<AT>& qv, AT nx, AT ny, AT nz, AT thr_lo, AT thr_hi, AT dz2c,
+// Unconditional +1 (ATOMS.POPC.INC: lanes hitting the same address are merged by the
+// hardware, measured in tools/microbench.cu).  Pairs outside the histogram range are sent to a
+// dump slot instead of being predicated off: ptxas wraps a predicated shared atomic in a
+// branch region, which costs more issue slots than the extra lanes cost wavefronts.
+__device__ __forceinline__ void smem_inc(unsigned addr) {
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
+}
+
+template <typename AT, bool ZCONST>
+__device__ __forceinline__ void pair_update(const Vec4<AT>& qv, AT nx, AT ny, AT nz, AT thr_lo, AT dz2c,
                                             float inv_w, float c_magic, unsigned kmax, unsigned thr_addr,
-                                            unsigned hist_addr_m1) {
+                                            unsigned hist_addr_m1, unsigned dump_addr) {
     const AT s = pair_s<AT, ZCONST>(qv, nx, ny, nz, dz2c);
     const unsigned k = bin_guess(Arith<AT>::approx(s), inv_w, c_magic, kmax);
     const AT t = Arith<AT>::load_thr(thr_addr + (k << Arith<AT>::kThrShift));
-    unsigned addr = hist_addr_m1 + (k << 2);  // &hist[k - 1] (of the weight-W half, see pair_kernel)
-    if (s >= t) addr += 4;
-    Arith<AT>::template inc_if_in_range<1>(addr, s, thr_lo, thr_hi);
+    unsigned addr = hist_addr_m1 + (k << 2);  // &hist[k - 1]
+    if (s >= t) addr += 4;                    // s >= T[nbins] (beyond the last edge) lands in hist[nbins], the dump slot
+    if (!(s >= thr_lo)) addr = dump_addr;     // d <= 1e-3, below the first edge, or NaN
+    smem_inc(addr);
 }
 
-template <typename AT, typename NT, bool ZCONST, int W>
+template <typename AT, typename NT, bool ZCONST>
 __device__ __forceinline__ void warp_pairs_fast(const Vec4<AT>* __restrict__ qsorted, unsigned qa, unsigned qb,
                                                 const Vec4<NT>* __restrict__ tsorted, unsigned ta, unsigned tb,
-                                                AT thr_lo, AT thr_hi, AT dz2c, float inv_w, float c_magic,
-                                                unsigned kmax, unsigned thr_addr, unsigned hist_addr_m1) {
+                                                AT thr_lo, AT dz2c, float inv_w, float c_magic, unsigned kmax,
+                                                unsigned thr_addr, unsigned hist_addr_m1, unsigned dump_addr) {
     const int lane = threadIdx.x & 31;
     const AT nan = (AT)__int_as_float(0x7fc00000);
     for (unsigned base = ta; base < tb; base += 32) {
@@ -537,13 +527,13 @@ __device__ __forceinline__ void warp_pairs_fast(const Vec4<AT>* __restrict__ qso
             for (int u = 0; u < kQueryUnroll; ++u) qv[u] = load_query<AT, ZCONST>(qsorted + q + u);
 #pragma unroll
             for (int u = 0; u < kQueryUnroll; ++u)
-                pair_update<AT, ZCONST, W>(qv[u], nx, ny, nz, thr_lo, thr_hi, dz2c, inv_w, c_magic, kmax, thr_addr,
-                                           hist_addr_m1);
+                pair_update<AT, ZCONST>(qv[u], nx, ny, nz, thr_lo, dz2c, inv_w, c_magic, kmax, thr_addr, hist_addr_m1,
+                                        dump_addr);
         }
         for (; q < qb; ++q) {
             const Vec4<AT> qv = load_query<AT, ZCONST>(qsorted + q);
-            pair_update<AT, ZCONST, W>(qv, nx, ny, nz, thr_lo, thr_hi, dz2c, inv_w, c_magic, kmax, thr_addr,
-                                       hist_addr_m1);
+            pair_update<AT, ZCONST>(qv, nx, ny, nz, thr_lo, dz2c, inv_w, c_magic, kmax, thr_addr, hist_addr_m1,
+                                    dump_addr);
         }
     }
 }
@@ -561,10 +551,12 @@ __global__ void __launch_bounds__(kPairThreads, 5) pair_kernel(PairArgs a) {
     unsigned* s_hist = reinterpret_cast<unsigned*>(smem_raw + (((size_t)(nbins + 1) * sizeof(AT) + 15) & ~(size_t)15));
     // SYM: a second histogram half collects the pairs that count twice, so that every
     // increment is +1 (ATOMS.POPC.INC); the halves are combined as h1 + 2*h2 at flush time
-    const int hist_len = SYM ? 2 * nbins : nbins;
+    // each half has nbins + 1 entries: entry nbins is the dump slot for out-of-range pairs
+    const int hist_len = (SYM ? 2 : 1) * (nbins + 1);
     const unsigned thr_addr = (unsigned)__cvta_generic_to_shared(s_thr);
     const unsigned hist_addr_m1 = (unsigned)__cvta_generic_to_shared(s_hist) - 4u;
-    const unsigned hist2_addr_m1 = hist_addr_m1 + 4u * (unsigned)nbins;
+    const unsigned hist2_addr_m1 = hist_addr_m1 + 4u * (unsigned)(nbins + 1);
+    const unsigned dump_addr = hist_addr_m1 + 4u * (unsigned)(nbins + 1);
     __shared__ AT s_range[2];  // thr_lo, thr_hi of the current frame
     __shared__ FramePlan s_plan;
     __shared__ long long s_task;
@@ -597,7 +589,7 @@ __global__ void __launch_bounds__(kPairThreads, 5) pair_kernel(PairArgs a) {
                 unsigned long long* row = a.hist + (long long)cur * nbins;
                 for (int b = tid; b < nbins; b += blockDim.x) {
                     unsigned long long v = s_hist[b];
-                    if (SYM) v += 2ull * s_hist[nbins + b];
+                    if (SYM) v += 2ull * s_hist[nbins + 1 + b];
                     if (v) atomicAdd(&row[b], v);
                 }
                 __syncthreads();  // the zeroing below maps bins to other threads than the loop above
@@ -708,18 +700,16 @@ __global__ void __launch_bounds__(kPairThreads, 5) pair_kernel(PairArgs a) {
                             if (direct)
                                 warp_pairs_general<AT, AT, ZCONST, true>(qsorted, qa, qb, qsorted, ta, tb, thr, nbins,
                                                                          dz2c, inv_w, c_magic, weight, s_hist, g_hist);
-                            else if (weight == 2)
-                                warp_pairs_fast<AT, AT, ZCONST, 2>(qsorted, qa, qb, qsorted, ta, tb, thr_lo, thr_hi, dz2c,
-                                                                   inv_w, c_magic, (unsigned)nbins, thr_addr, hist2_addr_m1);
                             else
-                                warp_pairs_fast<AT, AT, ZCONST, 1>(qsorted, qa, qb, qsorted, ta, tb, thr_lo, thr_hi, dz2c,
-                                                                   inv_w, c_magic, (unsigned)nbins, thr_addr, hist_addr_m1);
+                                warp_pairs_fast<AT, AT, ZCONST>(qsorted, qa, qb, qsorted, ta, tb, thr_lo, dz2c, inv_w, c_magic,
+                                                                (unsigned)nbins, thr_addr,
+                                                                weight == 2 ? hist2_addr_m1 : hist_addr_m1, dump_addr);
                         } else if (direct) {
                             warp_pairs_general<AT, NT, ZCONST, true>(qsorted, qa, qb, tsorted, ta, tb, thr, nbins, dz2c,
                                                                      inv_w, c_magic, 1u, s_hist, g_hist);
                         } else {
-                            warp_pairs_fast<AT, NT, ZCONST, 1>(qsorted, qa, qb, tsorted, ta, tb, thr_lo, thr_hi, dz2c,
-                                                               inv_w, c_magic, (unsigned)nbins, thr_addr, hist_addr_m1);
+                            warp_pairs_fast<AT, NT, ZCONST>(qsorted, qa, qb, tsorted, ta, tb, thr_lo, dz2c, inv_w, c_magic,
+                                                            (unsigned)nbins, thr_addr, hist_addr_m1, dump_addr);
                         }
                     }
                 }
@@ -809,7 +799,7 @@ template <typename AT, typename NT, bool SYM>
 static int launch_pairs(amepb_ctx* ctx, const PairArgs& args, bool zconst, cudaStream_t stream) {
     const int nbins = args.nbins;
     const size_t smem = (((size_t)(nbins + 1) * sizeof(AT) + 15) & ~(size_t)15) +
-                        (size_t)nbins * sizeof(unsigned) * (SYM ? 2 : 1);
+                        (size_t)(nbins + 1) * sizeof(unsigned) * (SYM ? 2 : 1);
     // the one-comparison bin correction needs uniform edges (args.uniform) and nbins <= 2^17;
     // the tables must fit in shared memory
     const bool use_smem = smem <= 40 * 1024 && args.uniform && nbins <= (1 << 17);

@@ -249,7 +249,7 @@ inline bool plan_frame(const PlanInputs& in, int dim, const FrameStats& tgt, con
     int n[3];
     if (k <= 0) {
         const int kmax = (dim == 3) ? 4 : kMaxCellsPerCutoff;
-        const double want_ppc = (dim == 3) ? 10.0 : 12.0;
+        const double want_ppc = (dim == 3) ? 20.0 : 12.0;
         k = 1;
         for (int kk = 2; kk <= kmax; ++kk) {
             double cells = cells_for(kk, n);

@@ -81,6 +81,7 @@ static void check_thresholds(std::mt19937_64& rng, bool edges_f32, double rmax, 
 
 struct Img {
     float x[3];
+    int ghost;  // shifted image
 };
 
 // Walk the plan exactly like the kernels do and histogram the pairs.
@@ -138,6 +139,7 @@ static void check_plan(std::mt19937_64& rng, int dim, bool box_f32, const double
                 int v[3] = {vx, vy, vz};
                 for (int i = 0; i < n; ++i) {
                     Img im; bool keep = true;
+                    im.ghost = (vx != 0 || vy != 0 || vz != 0);
                     for (int d = 0; d < 3; ++d) {
                         float b = (float)tgt[3 * (size_t)i + d];
                         im.x[d] = b + (float)v[d] * P.shift[d];
@@ -214,6 +216,74 @@ static void check_plan(std::mt19937_64& rng, int dim, bool box_f32, const double
     for (int b = 0; b < nb; ++b) {
         sw += want[b]; sg += got[b];
         CHECK(want[b] == got[b], "%s: bin %d want %lld got %lld", tag, b, want[b], got[b]);
+    }
+    // symmetric mode (self RDF, float32): upper half shell x2, own row split, ghosts separately,
+    // ghost-free neighbourhoods skipped -- the walk of pair_kernel<..., SYM=true>
+    if (self && sizeof(QT) == 4) {
+        bool inside = true;
+        for (int d = 0; d < 3; ++d)
+            if (!((double)(float)ts.lo[d] > P.win_lo[d]) || !((double)(float)ts.hi[d] < P.win_hi[d])) inside = false;
+        if (inside) {
+            std::vector<long long> sym(nb, 0);
+            std::vector<std::vector<int>> gcell(P.ncells);
+            for (size_t j = 0; j < kept.size(); ++j) {
+                if (!kept[j].ghost) continue;
+                int c[3];
+                for (int d = 0; d < 3; ++d) c[d] = cell_of((double)kept[j].x[d], P.g0[d], P.inv_h[d], P.n[d]);
+                gcell[(c[2] * P.n[1] + c[1]) * P.n[0] + c[0]].push_back((int)j);
+            }
+            auto qdist = [&](int q, int q2) {
+                Img im;
+                for (int d = 0; d < 3; ++d) im.x[d] = (float)qry[3 * (size_t)q2 + d];
+                return dist(&qry[3 * (size_t)q], im);
+            };
+            for (long long t = 0; t < P.ntasks; ++t) {
+                int run_i = (int)(t % P.runs_per_row);
+                long long rowq = t / P.runs_per_row;
+                int cy = P.cq_lo[1] + (int)(rowq % P.cq_n[1]);
+                int cz = P.cq_lo[2] + (int)(rowq / P.cq_n[1]);
+                int cx0 = P.cq_lo[0] + run_i * P.run;
+                int ncell = std::min(P.run, P.cq_lo[0] + P.cq_n[0] - cx0);
+                for (int wtk = 0; wtk < ncell * P.rsplit; ++wtk) {
+                    int part = wtk / ncell, cx = cx0 + (wtk - part * ncell);
+                    const std::vector<int>& qs = qcell[(cz * P.n[1] + cy) * P.n[0] + cx];
+                    for (int pass = 0; pass < 2; ++pass) {
+                        bool real = pass == 0;
+                        int r_begin = real ? P.row0 : 0;
+                        if (!real && cx - P.kd[0] >= P.gfree_lo[0] && cx + P.kd[0] <= P.gfree_hi[0] &&
+                            cy - P.kd[1] >= P.gfree_lo[1] && cy + P.kd[1] <= P.gfree_hi[1] &&
+                            cz - P.kd[2] >= P.gfree_lo[2] && cz + P.kd[2] <= P.gfree_hi[2])
+                            break;
+                        for (int r = r_begin + part; r < P.nrows; r += P.rsplit) {
+                            int ny = cy + P.row_oy[r], nz = cz + P.row_oz[r];
+                            if (ny < 0 || ny >= P.n[1] || nz < 0 || nz >= P.n[2]) continue;
+                            int kx = P.row_kx[r];
+                            int x_lo = std::max(cx - kx, 0), x_hi = std::min(cx + kx, P.n[0] - 1);
+                            if (real && r == P.row0) x_lo = cx;
+                            for (int x = x_lo; x <= x_hi; ++x) {
+                                int cellid = (nz * P.n[1] + ny) * P.n[0] + x;
+                                long long w = real ? ((r == P.row0 && x == cx) ? 1 : 2) : 1;
+                                if (real) {
+                                    for (int q : qs)
+                                        for (int q2 : qcell[cellid]) {
+                                            int b = numpy_bin(qdist(q, q2), e);
+                                            if (b >= 0) sym[b] += w;
+                                        }
+                                } else {
+                                    for (int q : qs)
+                                        for (int j : gcell[cellid]) {
+                                            int b = numpy_bin(dist(&qry[3 * (size_t)q], kept[j]), e);
+                                            if (b >= 0) sym[b] += w;
+                                        }
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            for (int b = 0; b < nb; ++b)
+                CHECK(want[b] == sym[b], "%s: symmetric walk bin %d want %lld got %lld", tag, b, want[b], sym[b]);
+        }
     }
     printf("  %-28s cells=%dx%dx%d rows=%d run=%d tasks=%lld images=%zu/%zu pairs=%lld\n", tag, P.n[0], P.n[1],
            P.n[2], P.nrows, P.run, P.ntasks, kept.size(), all.size(), sw);

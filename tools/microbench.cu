@@ -111,6 +111,28 @@ __global__ void atoms_kernel(unsigned* out, int iters, int nbins, int active, un
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// half of the lanes increment one common "dump" bin, the other half random bins: the
+// access pattern of an unconditional histogram update where out-of-range pairs go to a
+// dump slot.  POPC=true -> ATOMS.POPC.INC.
+template <bool POPC>
+__global__ void atoms_dump_kernel(unsigned* out, int iters, int nbins, unsigned inc) {
+    extern __shared__ unsigned hist[];
+    for (int i = threadIdx.x; i <= nbins; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    unsigned x = threadIdx.x * 2654435761u + blockIdx.x * 40503u + 12345u;
+    const unsigned mask = nbins - 1;
+    for (int it = 0; it < iters; ++it) {
+        x = x * 1664525u + 1013904223u;
+        const unsigned bin = (x & 0x10000u) ? ((x >> 8) & mask) : (unsigned)nbins;
+        if (POPC) atomicAdd(&hist[bin], 1u);
+        else atomicAdd(&hist[bin], inc);
+    }
+    __syncthreads();
+    unsigned s = 0;
+    for (int i = threadIdx.x; i <= nbins; i += blockDim.x) s += hist[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 template <typename F>
 static double time_ms(F launch, int reps = 5) {
     cudaEvent_t a, b;
@@ -161,6 +183,10 @@ int main() {
                    nthreads * iters * active / 32.0 / ms / 1e6);
         }
     }
+    ms = time_ms([&] { atoms_dump_kernel<true><<<blocks, threads, 513 * 4>>>((unsigned*)buf, iters, 512, 1u); });
+    printf(", \"atoms_popc_inc_half_dump_gops\": %.1f", nthreads * iters / ms / 1e6);
+    ms = time_ms([&] { atoms_dump_kernel<false><<<blocks, threads, 513 * 4>>>((unsigned*)buf, iters, 512, 2u); });
+    printf(", \"atoms_add_half_dump_gops\": %.1f", nthreads * iters / ms / 1e6);
     printf("}\n");
     return 0;
 }
