@@ -510,7 +510,10 @@ template <typename AT, typename NT, bool ZCONST>
 __device__ __forceinline__ void warp_pairs_fast(const Vec4<AT>* __restrict__ qsorted, unsigned qa, unsigned qb,
                                                 const Vec4<NT>* __restrict__ tsorted, unsigned ta, unsigned tb,
                                                 AT thr_lo, AT dz2c, float inv_w, float c_magic, unsigned kmax,
-                                                unsigned thr_addr, unsigned hist_addr_m1, unsigned dump_addr) {
+                                                unsigned thr_addr, unsigned hist_lo_m1, unsigned hist_hi_m1,
+                                                unsigned split, unsigned dump_addr) {
+    // targets with index < split count into the histogram at hist_lo_m1, the others into
+    // hist_hi_m1 (the symmetric pass mixes weight-1 own-cell pairs and weight-2 pairs in one range)
     const int lane = threadIdx.x & 31;
     const AT nan = (AT)__int_as_float(0x7fc00000);
     for (unsigned base = ta; base < tb; base += 32) {
@@ -520,6 +523,7 @@ __device__ __forceinline__ void warp_pairs_fast(const Vec4<AT>* __restrict__ qso
             const Vec4<NT> nb = load_vec4(tsorted + j);
             nx = (AT)nb.x; ny = (AT)nb.y; nz = (AT)nb.z;
         }
+        const unsigned hist_addr_m1 = j < split ? hist_lo_m1 : hist_hi_m1;
         unsigned q = qa;
         for (; q + kQueryUnroll <= qb; q += kQueryUnroll) {
             Vec4<AT> qv[kQueryUnroll];
@@ -668,26 +672,12 @@ __global__ void __launch_bounds__(kPairThreads, 5) pair_kernel(PairArgs a) {
                     int x_lo = max(cx - kx, 0);
                     const int x_hi = min(cx + kx, n0 - 1);
                     // in the query's own row only the own cell (both orders, weight 1) and the
-                    // cells to its right (weight 2) are visited in the symmetric pass
-                    int nseg = 1;
-                    if (real && r == row0) {
-                        x_lo = cx;
-                        nseg = 2;
-                    }
+                    // cells to its right (weight 2) are visited in the symmetric pass, as one range
+                    const bool own_row = real && r == row0;
+                    if (own_row) x_lo = cx;
                     const unsigned trow = P.cell_base + (unsigned)((nz * n1 + ny) * n0);
-                    for (int seg = 0; seg < nseg; ++seg) {
-                        int s_lo = x_lo, s_hi = x_hi;
-                        unsigned weight = real ? 2u : 1u;
-                        if (nseg == 2) {
-                            if (seg == 0) {
-                                s_hi = cx;
-                                weight = 1u;
-                            } else {
-                                s_lo = cx + 1;
-                                if (s_lo > s_hi) break;
-                            }
-                        }
-                        const unsigned ta = __ldg(&starts[trow + s_lo]), tb = __ldg(&starts[trow + s_hi + 1]);
+                    {
+                        const unsigned ta = __ldg(&starts[trow + x_lo]), tb = __ldg(&starts[trow + x_hi + 1]);
                         if (ta == tb) continue;
                         const unsigned long long npairs = (unsigned long long)(qb - qa) * (tb - ta);
                         const bool direct = !SMEM || npairs > direct_pairs;
@@ -696,20 +686,31 @@ __global__ void __launch_bounds__(kPairThreads, 5) pair_kernel(PairArgs a) {
                             if (!direct) atomicAdd(&s_units, (unsigned)(npairs >> 10) + 1u);
                         }
                         if (real) {
-                            // real targets are the cell-sorted queries themselves (NT == AT in this mode)
-                            if (direct)
-                                warp_pairs_general<AT, AT, ZCONST, true>(qsorted, qa, qb, qsorted, ta, tb, thr, nbins,
-                                                                         dz2c, inv_w, c_magic, weight, s_hist, g_hist);
-                            else
+                            // real targets are the cell-sorted queries themselves (NT == AT in this mode);
+                            // the own cell is [qa, qb) of the same array
+                            if (direct) {
+                                if (own_row) {
+                                    warp_pairs_general<AT, AT, ZCONST, true>(qsorted, qa, qb, qsorted, ta, qb, thr, nbins,
+                                                                             dz2c, inv_w, c_magic, 1u, s_hist, g_hist);
+                                    if (qb < tb)
+                                        warp_pairs_general<AT, AT, ZCONST, true>(qsorted, qa, qb, qsorted, qb, tb, thr, nbins,
+                                                                                 dz2c, inv_w, c_magic, 2u, s_hist, g_hist);
+                                } else {
+                                    warp_pairs_general<AT, AT, ZCONST, true>(qsorted, qa, qb, qsorted, ta, tb, thr, nbins,
+                                                                             dz2c, inv_w, c_magic, 2u, s_hist, g_hist);
+                                }
+                            } else {
                                 warp_pairs_fast<AT, AT, ZCONST>(qsorted, qa, qb, qsorted, ta, tb, thr_lo, dz2c, inv_w, c_magic,
-                                                                (unsigned)nbins, thr_addr,
-                                                                weight == 2 ? hist2_addr_m1 : hist_addr_m1, dump_addr);
+                                                                (unsigned)nbins, thr_addr, hist_addr_m1, hist2_addr_m1,
+                                                                own_row ? qb : 0u, dump_addr);
+                            }
                         } else if (direct) {
                             warp_pairs_general<AT, NT, ZCONST, true>(qsorted, qa, qb, tsorted, ta, tb, thr, nbins, dz2c,
                                                                      inv_w, c_magic, 1u, s_hist, g_hist);
                         } else {
                             warp_pairs_fast<AT, NT, ZCONST>(qsorted, qa, qb, tsorted, ta, tb, thr_lo, dz2c, inv_w, c_magic,
-                                                            (unsigned)nbins, thr_addr, hist_addr_m1, dump_addr);
+                                                            (unsigned)nbins, thr_addr, hist_addr_m1, hist_addr_m1, 0u,
+                                                            dump_addr);
                         }
                     }
                 }
