@@ -311,16 +311,23 @@ __global__ void __launch_bounds__(kC64Threads) sf2d_c64_kernel(
         }
         __syncthreads();
         const int lim = (int)((n - j0) < kC64Stage ? (n - j0) : kC64Stage);
-        for (int jj = 0; jj < lim; ++jj) {
-            const double2 xa = sX[jj][ta], yb = sY[jj][tb];
-            // exp(-i(qa x + qb y)) = (cc - ss) - i (sc + cs);  exp(-i(-qa x + qb y)) = (cc + ss) + i (sc - cs)
-            // acc + term in float64 as two fused multiply-adds (the term itself is never formed:
-            // 8 DFMA instead of 4 DMUL + 8 DADD), then the float32 rounding of the reference
-            ppr = round_to_f32(fma(-xa.y, yb.y, fma(xa.x, yb.x, ppr)));
-            ppi = round_to_f32(fma(-xa.x, yb.y, fma(-xa.y, yb.x, ppi)));
-            mpr = round_to_f32(fma(xa.y, yb.y, fma(xa.x, yb.x, mpr)));
-            mpi = round_to_f32(fma(-xa.x, yb.y, fma(xa.y, yb.x, mpi)));
-            if (j0 + jj + 1 == chunk_end) {
+        int jj = 0;
+        while (jj < lim) {
+            // run to the next chunk boundary (or the end of the stage) without per-particle checks
+            const long long to_chunk = chunk_end - (j0 + jj);
+            const int seg_end = jj + (int)(to_chunk < (long long)(lim - jj) ? to_chunk : (long long)(lim - jj));
+#pragma unroll 4
+            for (; jj < seg_end; ++jj) {
+                const double2 xa = sX[jj][ta], yb = sY[jj][tb];
+                // exp(-i(qa x + qb y)) = (cc - ss) - i (sc + cs);  exp(-i(-qa x + qb y)) = (cc + ss) + i (sc - cs)
+                // acc + term in float64 as two fused multiply-adds (the term itself is never formed:
+                // 8 DFMA instead of 4 DMUL + 8 DADD), then the float32 rounding of the reference
+                ppr = round_to_f32(fma(-xa.y, yb.y, fma(xa.x, yb.x, ppr)));
+                ppi = round_to_f32(fma(-xa.x, yb.y, fma(-xa.y, yb.x, ppi)));
+                mpr = round_to_f32(fma(xa.y, yb.y, fma(xa.x, yb.x, mpr)));
+                mpi = round_to_f32(fma(-xa.x, yb.y, fma(xa.y, yb.x, mpi)));
+            }
+            if (j0 + jj == chunk_end) {
                 // rhoq += res : complex64 + complex64 (amep/spatialcor.py:1890-1891)
                 tppr = __fadd_rn(tppr, (float)ppr); tppi = __fadd_rn(tppi, (float)ppi);
                 tmpr = __fadd_rn(tmpr, (float)mpr); tmpi = __fadd_rn(tmpi, (float)mpi);

@@ -343,7 +343,9 @@ def run_gpu(args):
         "flops_per_unit": FLOPS_PER_PAIR_2D, "units_per_launch": pairs_local / max(1, info["sub_batches"]),
         "avg_launch_ms": pair_ms_avg, "share_of_step": pair_ms / elapsed_ms,
         "candidate_pairs_per_s": info["candidate_pairs"] * args.steps / (pair_ms * 1e-3) if pair_ms > 0 else 0.0,
-        "traffic": peaks.get("pair_kernel_dram_bytes_per_launch"),
+        "traffic": (peaks["pair_kernel_dram_bytes_per_frame"] * nf / max(1, info["sub_batches"])
+                    if "pair_kernel_dram_bytes_per_frame" in peaks else None),
+        "traffic_source": peaks.get("pair_kernel_dram_source"),
         "hbm_gbs_peak": json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs")
         if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0,
     }
