@@ -161,7 +161,7 @@ __device__ __forceinline__ void table_run16(double x, const double* __restrict__
 // ---------------------------------------------------------------------------------------
 // sf2d, float64 product sums
 // ---------------------------------------------------------------------------------------
-constexpr int kF64Threads = 256;   // 16 x 16 threads, 4 x 4 quad points each: 64 x 64 tile
+constexpr int kF64Threads = 256;   // 8 warps x 32 lanes, 2 x 8 quad points per thread: 64 x 64 tile
 constexpr int kF64Stage = 32;      // particles per shared-memory stage
 
 template <typename T, int UNROLL>
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(kF64Threads, 1) sf2d_f64_kernel(
     double2 (*sX)[64] = reinterpret_cast<double2 (*)[64]>(smem_f64);
     double2 (*sY)[64] = reinterpret_cast<double2 (*)[64]>(smem_f64 + sizeof(double2) * kF64Stage * 64);
     const int tid = threadIdx.x;
-    const int ta = tid & 15, tb = tid >> 4;
+    const int lane = tid & 31, warp = tid >> 5;   // lanes: qx = lane, lane + 32; warp: 8 consecutive qy
     const int tiles = (nq + 63) / 64;
     const int tile_a = blockIdx.x % tiles, tile_b = blockIdx.x / tiles;
     const int split = blockIdx.y, frame = blockIdx.z;
@@ -183,11 +183,14 @@ __global__ void __launch_bounds__(kF64Threads, 1) sf2d_f64_kernel(
     const long long j_begin = (long long)split * per;
     const long long j_end = j_begin + per < n ? j_begin + per : n;
 
-    double acc[4][4][4];  // [ia][ib][cc, ss, cs, sc]
+    // 2 x 8 register tile: the two X entries are conflict-free per-lane loads, the eight Y
+    // entries are warp-uniform broadcasts (16 shared-memory wavefronts per particle and warp
+    // instead of 24 with a 4 x 4 tile over 16 x 16 threads)
+    double acc[2][8][4];  // [ia][ib][cc, ss, cs, sc]
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 2; ++i)
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
+        for (int k = 0; k < 8; ++k)
 #pragma unroll
             for (int c = 0; c < 4; ++c) acc[i][k][c] = 0.0;
 
@@ -210,16 +213,15 @@ __global__ void __launch_bounds__(kF64Threads, 1) sf2d_f64_kernel(
         __syncthreads();
 #pragma unroll UNROLL
         for (int jj = 0; jj < kF64Stage; ++jj) {
-            double2 xa[4], yb[4];
+            double2 xa[2], yb[8];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                xa[i] = sX[jj][ta + 16 * i];
-                yb[i] = sY[jj][tb + 16 * i];
-            }
+            for (int i = 0; i < 2; ++i) xa[i] = sX[jj][lane + 32 * i];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int k = 0; k < 8; ++k) yb[k] = sY[jj][warp * 8 + k];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
                     acc[i][k][0] = fma(xa[i].x, yb[k].x, acc[i][k][0]);
                     acc[i][k][1] = fma(xa[i].y, yb[k].y, acc[i][k][1]);
                     acc[i][k][2] = fma(xa[i].x, yb[k].y, acc[i][k][2]);
@@ -231,10 +233,10 @@ __global__ void __launch_bounds__(kF64Threads, 1) sf2d_f64_kernel(
     // partial[f][split][4][nq][nq]
     double* out = partial + (((long long)frame * ksplit + split) * 4) * (long long)nq * nq;
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 2; ++i)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int a = tile_a * 64 + ta + 16 * i, b = tile_b * 64 + tb + 16 * k;
+        for (int k = 0; k < 8; ++k) {
+            const int a = tile_a * 64 + lane + 32 * i, b = tile_b * 64 + warp * 8 + k;
             if (a < nq && b < nq)
 #pragma unroll
                 for (int c = 0; c < 4; ++c) out[((long long)c * nq + b) * nq + a] = acc[i][k][c];
@@ -268,8 +270,10 @@ __global__ void sf2d_f64_finish_kernel(const double* __restrict__ partial, int k
 // ---------------------------------------------------------------------------------------
 // sf2d, complex64 accumulation in the reference's order
 // ---------------------------------------------------------------------------------------
-constexpr int kC64Threads = 256;  // 16 x 16 quad points per block
-constexpr int kC64Stage = 128;    // particles per shared-memory stage
+constexpr int kC64Threads = 256;  // 8 warps: lanes = 32 qx values, each warp 2 qy values
+constexpr int kC64TileA = 32;
+constexpr int kC64TileB = 16;
+constexpr int kC64Stage = 64;     // particles per shared-memory stage
 
 // fl32(v) for a double v, on the FP64 pipe: adding 1.5*2^(e+29) rounds v to a multiple of
 // the float32 ulp of its binade (round to nearest even); the subtraction is exact.
@@ -279,34 +283,38 @@ __device__ __forceinline__ double round_to_f32(double v) {
     return __dsub_rn(__dadd_rn(v, m), m);
 }
 
+// One thread owns the quad points (qa, qb0) and (qa, qb1): the X entry is loaded once per
+// particle and lane (conflict free, 4 wavefronts per warp), the two Y entries are
+// warp-uniform broadcasts -- 3 shared-memory wavefronts per quad-point step instead of 8
+// with a 16 x 16 thread tile, which had the shared pipe at 62 % (ncu) next to the FP64 pipe.
 template <typename T>
 __global__ void __launch_bounds__(kC64Threads) sf2d_c64_kernel(
     const T* __restrict__ coords, long long n, const double* __restrict__ qall, long long q_stride, int nq,
     long long chunksize, float2* __restrict__ rho) {
     extern __shared__ __align__(16) unsigned char smem_c64[];
-    double2 (*sX)[16] = reinterpret_cast<double2 (*)[16]>(smem_c64);
-    double2 (*sY)[16] = reinterpret_cast<double2 (*)[16]>(smem_c64 + sizeof(double2) * kC64Stage * 16);
-    const int tid = threadIdx.x;
-    const int ta = tid & 15, tb = tid >> 4;
-    const int tiles = (nq + 15) / 16;
-    const int tile_a = blockIdx.x % tiles, tile_b = blockIdx.x / tiles;
+    double2 (*sX)[kC64TileA] = reinterpret_cast<double2 (*)[kC64TileA]>(smem_c64);
+    double2 (*sY)[kC64TileB] = reinterpret_cast<double2 (*)[kC64TileB]>(smem_c64 + sizeof(double2) * kC64Stage * kC64TileA);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tiles_a = (nq + kC64TileA - 1) / kC64TileA;
+    const int tile_a = blockIdx.x % tiles_a, tile_b = blockIdx.x / tiles_a;
     const int frame = blockIdx.y;
     const double* q = qall + (long long)frame * q_stride;
     const T* base = coords + (long long)frame * n * 3;
 
-    // chunk accumulators (float32 values held in doubles) and running totals (float32)
-    double ppr = 0.0, ppi = 0.0, mpr = 0.0, mpi = 0.0;
-    float tppr = 0.0f, tppi = 0.0f, tmpr = 0.0f, tmpi = 0.0f;
+    // chunk accumulators (float32 values held in doubles) and running totals (float32):
+    // [quad point 0 / 1][pp real, pp imag, mp real, mp imag]
+    double acc[2][4] = {{0.0, 0.0, 0.0, 0.0}, {0.0, 0.0, 0.0, 0.0}};
+    float tot[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
     long long chunk_end = chunksize < n ? chunksize : n;
 
     for (long long j0 = 0; j0 < n; j0 += kC64Stage) {
-        {
-            const int jj = tid & 127, isy = tid >> 7;
+        // tables: 2 X runs and 1 Y run of 16 entries per particle -> 192 of the 256 threads
+        if (tid < 3 * kC64Stage) {
+            const int jj = tid % kC64Stage, run = tid / kC64Stage;   // run 0,1: X; run 2: Y
             const long long j = j0 + jj;
-            double2* dst = isy ? &sY[jj][0] : &sX[jj][0];
             if (j < n) {
-                const double v = (double)base[3 * j + isy];
-                table_run16(v, q, (isy ? tile_b : tile_a) * 16, nq, dst, 1);
+                if (run < 2) table_run16((double)base[3 * j], q, tile_a * kC64TileA + run * 16, nq, &sX[jj][run * 16], 1);
+                else table_run16((double)base[3 * j + 1], q, tile_b * kC64TileB, nq, &sY[jj][0], 1);
             }
         }
         __syncthreads();
@@ -316,36 +324,51 @@ __global__ void __launch_bounds__(kC64Threads) sf2d_c64_kernel(
             // run to the next chunk boundary (or the end of the stage) without per-particle checks
             const long long to_chunk = chunk_end - (j0 + jj);
             const int seg_end = jj + (int)(to_chunk < (long long)(lim - jj) ? to_chunk : (long long)(lim - jj));
-#pragma unroll 4
+            // operands of the next particle are fetched while the current one is accumulated
+            double2 xa = sX[jj][lane], y0 = sY[jj][2 * warp], y1 = sY[jj][2 * warp + 1];
+#pragma unroll 2
             for (; jj < seg_end; ++jj) {
-                const double2 xa = sX[jj][ta], yb = sY[jj][tb];
-                // exp(-i(qa x + qb y)) = (cc - ss) - i (sc + cs);  exp(-i(-qa x + qb y)) = (cc + ss) + i (sc - cs)
-                // acc + term in float64 as two fused multiply-adds (the term itself is never formed:
-                // 8 DFMA instead of 4 DMUL + 8 DADD), then the float32 rounding of the reference
-                ppr = round_to_f32(fma(-xa.y, yb.y, fma(xa.x, yb.x, ppr)));
-                ppi = round_to_f32(fma(-xa.x, yb.y, fma(-xa.y, yb.x, ppi)));
-                mpr = round_to_f32(fma(xa.y, yb.y, fma(xa.x, yb.x, mpr)));
-                mpi = round_to_f32(fma(-xa.x, yb.y, fma(xa.y, yb.x, mpi)));
+                const int nx = jj + 1 < kC64Stage ? jj + 1 : jj;
+                const double2 xa_n = sX[nx][lane], y0_n = sY[nx][2 * warp], y1_n = sY[nx][2 * warp + 1];
+#pragma unroll
+                for (int p = 0; p < 2; ++p) {
+                    const double2 yb = p == 0 ? y0 : y1;
+                    // exp(-i(qa x + qb y)) = (cc - ss) - i (sc + cs);  exp(-i(-qa x + qb y)) = (cc + ss) + i (sc - cs)
+                    // acc + term in float64 as two fused multiply-adds, then the float32 rounding of the reference
+                    acc[p][0] = round_to_f32(fma(-xa.y, yb.y, fma(xa.x, yb.x, acc[p][0])));
+                    acc[p][1] = round_to_f32(fma(-xa.x, yb.y, fma(-xa.y, yb.x, acc[p][1])));
+                    acc[p][2] = round_to_f32(fma(xa.y, yb.y, fma(xa.x, yb.x, acc[p][2])));
+                    acc[p][3] = round_to_f32(fma(-xa.x, yb.y, fma(xa.y, yb.x, acc[p][3])));
+                }
+                xa = xa_n; y0 = y0_n; y1 = y1_n;
             }
             if (j0 + jj == chunk_end) {
                 // rhoq += res : complex64 + complex64 (amep/spatialcor.py:1890-1891)
-                tppr = __fadd_rn(tppr, (float)ppr); tppi = __fadd_rn(tppi, (float)ppi);
-                tmpr = __fadd_rn(tmpr, (float)mpr); tmpi = __fadd_rn(tmpi, (float)mpi);
-                ppr = ppi = mpr = mpi = 0.0;
+#pragma unroll
+                for (int p = 0; p < 2; ++p)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        tot[p][c] = __fadd_rn(tot[p][c], (float)acc[p][c]);
+                        acc[p][c] = 0.0;
+                    }
                 chunk_end = chunk_end + chunksize < n ? chunk_end + chunksize : n;
             }
         }
         __syncthreads();
     }
-    const int a = tile_a * 16 + ta, b = tile_b * 16 + tb;
-    if (a < nq && b < nq) {
-        const int g = 2 * nq;
-        float2* r = rho + (long long)frame * g * g;
-        const int ixp = nq + a, ixm = nq - 1 - a, iyp = nq + b, iym = nq - 1 - b;
-        r[(long long)iyp * g + ixp] = make_float2(tppr, tppi);
-        r[(long long)iyp * g + ixm] = make_float2(tmpr, tmpi);
-        r[(long long)iym * g + ixm] = make_float2(tppr, -tppi);
-        r[(long long)iym * g + ixp] = make_float2(tmpr, -tmpi);
+    const int a = tile_a * kC64TileA + lane;
+    const int g = 2 * nq;
+    float2* r = rho + (long long)frame * g * g;
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        const int b = tile_b * kC64TileB + 2 * warp + p;
+        if (a < nq && b < nq) {
+            const int ixp = nq + a, ixm = nq - 1 - a, iyp = nq + b, iym = nq - 1 - b;
+            r[(long long)iyp * g + ixp] = make_float2(tot[p][0], tot[p][1]);
+            r[(long long)iyp * g + ixm] = make_float2(tot[p][2], tot[p][3]);
+            r[(long long)iym * g + ixm] = make_float2(tot[p][0], -tot[p][1]);
+            r[(long long)iym * g + ixp] = make_float2(tot[p][2], -tot[p][3]);
+        }
     }
 }
 
@@ -598,7 +621,7 @@ int amepb_sf2d_modes(amepb_ctx* ctx, const void* coords, int dtype, int space, i
     const double* d_q = reinterpret_cast<const double*>(ctx->bufs[BUF_SQ_A].p);
 
     const size_t smem_f64 = sizeof(double2) * kF64Stage * 64 * 2;
-    const size_t smem_c64 = sizeof(double2) * kC64Stage * 16 * 2;
+    const size_t smem_c64 = sizeof(double2) * kC64Stage * (kC64TileA + kC64TileB);
     if (!ctx->sq_attr_sf2d) {
         AMEPB_CUDA(ctx, cudaFuncSetAttribute(sf2d_f64_kernel<float, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f64));
         AMEPB_CUDA(ctx, cudaFuncSetAttribute(sf2d_f64_kernel<float, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f64));
@@ -671,8 +694,8 @@ int amepb_sf2d_modes(amepb_ctx* ctx, const void* coords, int dtype, int space, i
             sf2d_f64_finish_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(d_part, ksplit, nq, nf, reinterpret_cast<double2*>(d_out));
             AMEPB_LAUNCH_CHECK(ctx);
         } else {
-            const int tiles = (nq + 15) / 16;
-            dim3 grid((unsigned)(tiles * tiles), (unsigned)nf);
+            const int tiles_a = (nq + kC64TileA - 1) / kC64TileA, tiles_b = (nq + kC64TileB - 1) / kC64TileB;
+            dim3 grid((unsigned)(tiles_a * tiles_b), (unsigned)nf);
             if (dtype == AMEPB_F32)
                 sf2d_c64_kernel<float><<<grid, kC64Threads, smem_c64, stream>>>((const float*)d_coords, n, qf, q_stride, nq, chunksize, reinterpret_cast<float2*>(d_out));
             else

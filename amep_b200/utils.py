@@ -63,6 +63,18 @@ def unit_vector_3D(theta, phi):
         return np.array([np.sin(theta) * np.cos(phi), np.sin(theta) * np.sin(phi), np.cos(theta)])
 
 
+def sq_from_sf2d(S, Qx, Qy):
+    """Radial average of a 2D structure factor -> ``(S(q), q)`` (amep/utils.py:1255-1311):
+    rings of width dq = grid spacing, mean of ``S`` over the grid points of each ring.
+    A few hundred thousand grid points at most: host NumPy, like the other epilogues."""
+    radius = np.sqrt(Qx ** 2 + Qy ** 2)
+    dq = np.max([np.abs(Qx[0, 1] - Qx[0, 0]), np.abs(Qy[1, 0] - Qy[0, 0])])
+    rings = np.arange(0, np.min([np.max(Qx), np.max(Qy)]), dq)
+    weighted, edges = np.histogram(radius, weights=S, bins=rings, density=False)
+    counts = np.histogram(radius, bins=rings)[0]
+    return weighted / counts, runningmean(edges, 2)
+
+
 def dimension(coords, verbose: bool = False) -> int:
     """``amep.utils.dimension`` (amep/utils.py:1617-1667) evaluated by the
     stats kernel (amepb_frame_dimension); shape errors are raised on the host."""

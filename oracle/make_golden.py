@@ -195,6 +195,9 @@ def main():
     np.savez_compressed(os.path.join(GOLDEN, "sf2d_f64_cross.npz"), coords=c2, other=o2, box=box2,
                         S=s, Qx=qx, Qy=qy, qmax=3.0, chunksize=64)
     print(f"sf2d: grid={s.shape} dtype={s.dtype}")
+    z = np.load(os.path.join(GOLDEN, "sf2d_f64_onechunk.npz"))
+    sq, qr = amep.utils.sq_from_sf2d(z["S"], z["Qx"], z["Qy"])
+    np.savez_compressed(os.path.join(GOLDEN, "sq_from_sf2d.npz"), S=z["S"], Qx=z["Qx"], Qy=z["Qy"], sq=sq, q=qr)
 
     # ---- evaluate.RDF semantics via the reference's average_func -----------------
     class Frame:

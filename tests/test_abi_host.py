@@ -90,3 +90,33 @@ def test_plan_and_thresholds_host_logic():
                     src, "-o", exe], check=True)
     out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
     assert "ALL OK" in out, out
+
+
+def test_sq_from_sf2d_matches_reference():
+    from amep_b200.utils import sq_from_sf2d
+    from conftest import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "sq_from_sf2d.npz"))
+    sq, q = sq_from_sf2d(z["S"], z["Qx"], z["Qy"])
+    np.testing.assert_array_equal(q, z["q"])
+    np.testing.assert_array_equal(sq, z["sq"])
+
+
+def test_tensor_trajectory_protocol():
+    """The stand-in trajectory offers what the evaluate classes use of amep's (amep/base.py:429-1080, 1263-1312)."""
+    import amep_b200
+    rng = np.random.default_rng(3)
+    coords = rng.uniform(0, 5, (6, 40, 3)).astype(np.float32)
+    types = np.array([1] * 25 + [2] * 15)
+    box = np.array([[0, 5], [0, 5], [0, 5]], dtype=np.float32)
+    traj = amep_b200.TensorTrajectory(coords, box, times=np.arange(6) * 0.1, types=types)
+    assert len(traj) == 6 and traj[2].n() == 40 and traj[2].n(ptype=2) == 15
+    np.testing.assert_array_equal(traj[-1].coords(ptype=1), coords[5, :25])
+    np.testing.assert_array_equal(traj[1].center, np.mean(box, axis=1))
+    frames = traj[np.array([0, 3])]
+    assert [f.time for f in frames] == [0.0, 0.30000000000000004]
+    stack, b = traj.stack([1, 2, 3], ptype=2)
+    np.testing.assert_array_equal(stack, coords[1:4, 25:])
+    stack, b = traj.stack([4, 0])
+    np.testing.assert_array_equal(stack, coords[[4, 0]])
+    with pytest.raises(IndexError):
+        traj[6]

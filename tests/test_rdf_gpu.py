@@ -331,3 +331,21 @@ def test_evaluate_rdf_matches_reference(sc):
         np.testing.assert_array_equal(ev.r, z["avg"][1])
         assert set(["avg", "frames", "indices", "r", "times"]).issubset(ev.keys())
         assert ev["avg"] is ev.avg and ev.name == "rdf"
+
+
+def test_evaluate_rdf_particle_types_and_cross(sc):
+    """evaluate.RDF(ptype=, other=) against the oracle (amep/evaluate.py:513-542)."""
+    import amep_b200
+    rng = np.random.default_rng(41)
+    nf, n, L = 5, 1200, 22.0
+    coords = rng.uniform(0, L, (nf, n, 3)).astype(np.float32)
+    types = np.array([1] * 700 + [2] * 500)
+    box = np.array([[0, L], [0, L], [0, L]], dtype=np.float32)
+    for dev in ("cpu", "cuda"):
+        data = coords if dev == "cpu" else torch.from_numpy(coords).cuda()
+        traj = amep_b200.TensorTrajectory(data, box, types=types)
+        ev = amep_b200.evaluate.RDF(traj, skip=0.0, nav=3, ptype=1, other=2, rmax=4.0, nbins=80, max_workers=4, njobs=2)
+        idx = orc.frame_indices(nf, 0.0, 3)
+        rows = [orc.rdf(coords[i][types == 1], box, coords[i][types == 2], rmax=4.0, nbins=80) for i in idx]
+        np.testing.assert_array_equal(ev.frames, np.array(rows))
+        np.testing.assert_array_equal(ev.avg, np.mean(np.array(rows), axis=0)[0])

@@ -16,8 +16,9 @@ if case == "sfiso":
     print("sfiso nq", q.shape[1], "kernel ms", ctx.last_kernel_ms())
 else:
     n, L = 262_144, 512.0
-    c = torch.zeros((1, n, 3), device="cuda", dtype=torch.float32)
-    c[0, :, :2] = torch.rand((n, 2), generator=g, device="cuda", dtype=torch.float32) * L
+    nf = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+    c = torch.zeros((nf, n, 3), device="cuda", dtype=torch.float32)
+    c[:, :, :2] = torch.rand((nf, n, 2), generator=g, device="cuda", dtype=torch.float32) * L
     box = np.array([[0, L], [0, L], [-0.5, 0.5]], dtype=np.float32)
     accum = "f64" if case == "sf2d_f64" else "c64"
     for _ in range(2):
