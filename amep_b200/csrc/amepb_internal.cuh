@@ -25,6 +25,7 @@ enum {
     BUF_QSTART,        // query cell offsets
     BUF_TSORTED,       // images in cell order
     BUF_QSORTED,       // queries in cell order
+    BUF_QRANK,         // rank of each query inside its cell (fused self placement)
     BUF_SCAN,          // scan block sums
     BUF_MISC,          // task counter, candidate counter
     BUF_STAGE_A,       // host-space staging: coords

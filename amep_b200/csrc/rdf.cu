@@ -166,17 +166,10 @@ __device__ __forceinline__ int cell_index(double x, double g0, double inv_h, int
 // Targets with periodic images.  T: input element type, image storage is
 // float32 (amep/pbc.py:300-302).  FILL=false counts, FILL=true writes.
 template <typename T, bool FILL>
-__global__ void __launch_bounds__(256) place_images_kernel(const T* __restrict__ pts, long long n,
-                                                           const FramePlan* __restrict__ plans,
-                                                           unsigned* __restrict__ count,
-                                                           const unsigned* __restrict__ start,
-                                                           Vec4<float>* __restrict__ sorted) {
-    const int f = blockIdx.y;
-    const FramePlan& P = plans[f];
-    if (!P.valid) return;
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const T* p = pts + ((long long)f * n + i) * 3;
+__device__ __forceinline__ void place_images_body(const T* __restrict__ p, const FramePlan& P,
+                                                  unsigned* __restrict__ count,
+                                                  const unsigned* __restrict__ start,
+                                                  Vec4<float>* __restrict__ sorted) {
     float img[3][3];
     int cell[3][3];
     bool ok[3][3];
@@ -221,6 +214,57 @@ __global__ void __launch_bounds__(256) place_images_kernel(const T* __restrict__
             }
         }
     }
+}
+
+template <typename T, bool FILL>
+__global__ void __launch_bounds__(256) place_images_kernel(const T* __restrict__ pts, long long n,
+                                                           const FramePlan* __restrict__ plans,
+                                                           unsigned* __restrict__ count,
+                                                           const unsigned* __restrict__ start,
+                                                           Vec4<float>* __restrict__ sorted) {
+    const int f = blockIdx.y;
+    const FramePlan& P = plans[f];
+    if (!P.valid) return;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    place_images_body<T, FILL>(pts + ((long long)f * n + i) * 3, P, count, start, sorted);
+}
+
+// Self RDF with periodic images: queries and images of one particle in a single pass over the
+// coordinates.  The count pass keeps each query's rank inside its cell, so the fill pass
+// needs no second atomic for the queries.
+template <typename T, typename AT, bool FILL>
+__global__ void __launch_bounds__(256) place_self_kernel(const T* __restrict__ pts, long long n,
+                                                         const FramePlan* __restrict__ plans,
+                                                         unsigned* __restrict__ tcount,
+                                                         const unsigned* __restrict__ tstart,
+                                                         Vec4<float>* __restrict__ tsorted,
+                                                         unsigned* __restrict__ qcount,
+                                                         const unsigned* __restrict__ qstart,
+                                                         Vec4<AT>* __restrict__ qsorted,
+                                                         unsigned* __restrict__ qrank) {
+    const int f = blockIdx.y;
+    const FramePlan& P = plans[f];
+    if (!P.valid) return;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const T* p = pts + ((long long)f * n + i) * 3;
+    AT v[3];
+    int c[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        v[d] = (AT)p[d];
+        c[d] = cell_index((double)v[d], P.g0[d], P.inv_h[d], P.n[d]);
+    }
+    const unsigned cc = P.cell_base + (unsigned)((c[2] * P.n[1] + c[1]) * P.n[0] + c[0]);
+    if (!FILL) {
+        qrank[(long long)f * n + i] = atomicAdd(&qcount[cc], 1u);
+    } else {
+        Vec4<AT> o;
+        o.x = v[0]; o.y = v[1]; o.z = v[2]; o.w = (AT)0;
+        qsorted[qstart[cc] + qrank[(long long)f * n + i]] = o;
+    }
+    place_images_body<T, FILL>(p, P, tcount, tstart, tsorted);
 }
 
 // Plain points (queries, or targets without periodic images).  S: storage
@@ -1042,12 +1086,39 @@ static int rdf_sub_batch(amepb_ctx* ctx, const RdfCall& c, int64_t f0, int nf, c
         return 0;
     };
     const bool have_targets = !(sym && !c.pbc);  // symmetric mode without images: the queries are the targets
-    if (have_targets && (rc = place_targets(false))) return rc;
-    if ((rc = place_queries(false))) return rc;
+    const bool fused = self && c.pbc;              // one pass over the coordinates for queries and images
+    unsigned* qrank = nullptr;
+    if (fused) {
+        if ((rc = ensure_device(ctx, BUF_QRANK, sizeof(unsigned) * (size_t)m * nf))) return rc;
+        qrank = reinterpret_cast<unsigned*>(ctx->bufs[BUF_QRANK].p);
+    }
+    auto place_self = [&](bool fill) -> int {
+        Vec4<float>* ts = reinterpret_cast<Vec4<float>*>(ctx->bufs[BUF_TSORTED].p);
+        void* qs = ctx->bufs[BUF_QSORTED].p;
+        if (c.coords_dtype == AMEPB_F32) {
+            if (fill) place_self_kernel<float, float, true><<<tgrid, 256, 0, stream>>>((const float*)d_coords, c.n, d_plans, tcount, tstart, ts, qcount, qstart, (Vec4<float>*)qs, qrank);
+            else place_self_kernel<float, float, false><<<tgrid, 256, 0, stream>>>((const float*)d_coords, c.n, d_plans, tcount, tstart, ts, qcount, qstart, (Vec4<float>*)qs, qrank);
+        } else {
+            if (fill) place_self_kernel<double, double, true><<<tgrid, 256, 0, stream>>>((const double*)d_coords, c.n, d_plans, tcount, tstart, ts, qcount, qstart, (Vec4<double>*)qs, qrank);
+            else place_self_kernel<double, double, false><<<tgrid, 256, 0, stream>>>((const double*)d_coords, c.n, d_plans, tcount, tstart, ts, qcount, qstart, (Vec4<double>*)qs, qrank);
+        }
+        AMEPB_LAUNCH_CHECK(ctx);
+        return 0;
+    };
+    if (fused) {
+        if ((rc = place_self(false))) return rc;
+    } else {
+        if (have_targets && (rc = place_targets(false))) return rc;
+        if ((rc = place_queries(false))) return rc;
+    }
     if ((rc = exclusive_scan(ctx, tcount, tstart, total_cells + 1, stream))) return rc;
     if ((rc = exclusive_scan(ctx, qcount, qstart, total_cells + 1, stream))) return rc;
-    if (have_targets && (rc = place_targets(true))) return rc;
-    if ((rc = place_queries(true))) return rc;
+    if (fused) {
+        if ((rc = place_self(true))) return rc;
+    } else {
+        if (have_targets && (rc = place_targets(true))) return rc;
+        if ((rc = place_queries(true))) return rc;
+    }
     cudaEvent_t ev_b1 = timing_event(ctx, stream);
     if (ev_b0 && ev_b1) ctx->ev_build.emplace_back(ev_b0, ev_b1);
 
