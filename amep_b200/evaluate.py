@@ -213,12 +213,13 @@ def _assemble_pair(a, b, lo, hi, nsel, group):
 class SF2d(_FrameAverage):
     """Two-dimensional static structure factor, time-averaged (amep/evaluate.py:1183-1522).
 
-    ``rotate`` defaults to True in the reference (a psi_6 alignment prologue,
-    amep/evaluate.py:1349-1377); that prologue is a next row,
-    so ``rotate=True`` raises here and the default is False."""
+    ``rotate`` defaults to True as in the reference (a psi_6 alignment prologue,
+    amep/evaluate.py:1349-1377).  That prologue is a next row of the scope table
+     and not built yet, so the default *raises* instead of silently
+    computing the unrotated structure factor: pass ``rotate=False`` explicitly."""
 
     def __init__(self, traj, skip: float = 0.0, nav: int = 10, ptype=None, other=None,
-                 rotate: bool = False, ftype=None, max_workers=1, distributed=None, group=None,
+                 rotate: bool = True, ftype=None, max_workers=1, distributed=None, group=None,
                  **kwargs) -> None:
         super().__init__()
         self.name = "sf2d"

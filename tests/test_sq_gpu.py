@@ -213,4 +213,4 @@ def test_evaluate_sfiso_and_sf2d(sc):
     np.testing.assert_array_equal(ev2.qx, want[1])
     assert ev2.frames.shape[0] == 3 and ev2.frames.shape[1] == 3
     with pytest.raises(NotImplementedError):
-        amep_b200.evaluate.SF2d(traj, rotate=True)
+        amep_b200.evaluate.SF2d(traj)  # the reference's default is rotate=True: loud, not silent
