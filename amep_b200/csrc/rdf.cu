@@ -163,6 +163,16 @@ __device__ __forceinline__ int cell_index(double x, double g0, double inv_h, int
     return min(max(c, 0), n - 1);
 }
 
+// Float32 queries in cell order, laid out for the packed pair arithmetic of the pair kernel:
+// xy[i] = (x[2i], x[2i+1], y[2i], y[2i+1]) for i < n/2, followed by z[0..n).
+__device__ __forceinline__ void store_query_pairs(float* __restrict__ base, long long n, unsigned slot, float x,
+                                                  float y, float z) {
+    float* xy = base + (size_t)(slot >> 1) * 4 + (slot & 1u);
+    xy[0] = x;
+    xy[2] = y;
+    base[2 * n + slot] = z;
+}
+
 // Targets with periodic images.  T: input element type, image storage is
 // float32 (amep/pbc.py:300-302).  FILL=false counts, FILL=true writes.
 template <typename T, bool FILL>
@@ -242,7 +252,8 @@ __global__ void __launch_bounds__(256) place_self_kernel(const T* __restrict__ p
                                                          unsigned* __restrict__ qcount,
                                                          const unsigned* __restrict__ qstart,
                                                          Vec4<AT>* __restrict__ qsorted,
-                                                         unsigned* __restrict__ qrank) {
+                                                         unsigned* __restrict__ qrank,
+                                                         float* __restrict__ qsoa, long long qsoa_n) {
     const int f = blockIdx.y;
     const FramePlan& P = plans[f];
     if (!P.valid) return;
@@ -262,7 +273,12 @@ __global__ void __launch_bounds__(256) place_self_kernel(const T* __restrict__ p
     } else {
         Vec4<AT> o;
         o.x = v[0]; o.y = v[1]; o.z = v[2]; o.w = (AT)0;
-        qsorted[qstart[cc] + qrank[(long long)f * n + i]] = o;
+        const unsigned slot = qstart[cc] + qrank[(long long)f * n + i];
+        qsorted[slot] = o;
+        if constexpr (sizeof(AT) == 4)
+            if (qsoa) {
+                store_query_pairs(qsoa, qsoa_n, slot, (float)v[0], (float)v[1], (float)v[2]);
+            }
     }
     place_images_body<T, FILL>(p, P, tcount, tstart, tsorted);
 }
@@ -275,7 +291,8 @@ __global__ void __launch_bounds__(256) place_points_kernel(const T* __restrict__
                                                            const FramePlan* __restrict__ plans,
                                                            unsigned* __restrict__ count,
                                                            const unsigned* __restrict__ start,
-                                                           Vec4<S>* __restrict__ sorted) {
+                                                           Vec4<S>* __restrict__ sorted,
+                                                           float* __restrict__ soa = nullptr, long long soa_n = 0) {
     const int f = blockIdx.y;
     const FramePlan& P = plans[f];
     if (!P.valid) return;
@@ -301,6 +318,10 @@ __global__ void __launch_bounds__(256) place_points_kernel(const T* __restrict__
         Vec4<S> o;
         o.x = v[0]; o.y = v[1]; o.z = v[2]; o.w = (S)0;
         sorted[slot] = o;
+        if constexpr (sizeof(S) == 4)
+            if (soa) {
+                store_query_pairs(soa, soa_n, slot, (float)v[0], (float)v[1], (float)v[2]);
+            }
     }
 }
 
@@ -429,16 +450,49 @@ struct Arith<double> {
 
 // Bin guess without an F2I: one MUFU.SQRT and one FFMA whose constant term carries the
 // round-to-integer magic number 1.5*2^23.  With x = (sqrt(s) - e0) / width it returns
-// k = round(x + 0.5 - kGuessBias) clamped to [0, kmax].  The approximation error of x is
-// below x*2^-22 <= kGuessBias for nbins <= 2^17 and the edges are uniform (checked on
-// the host), so the true bin is k-1 or k: one comparison with thr[k] settles it.
-constexpr float kGuessBias = 0.0625f;
-__device__ __forceinline__ unsigned bin_guess(float s_approx, float inv_w, float c_magic, unsigned kmax) {
+// k = round(x) clamped to [0, kclamp] (a negative k wraps and clamps too).  The error of x
+// stays far below 1/2 for nbins <= 2^17 and uniform edges (checked on the host), so
+// the pair lies in bin k-1 or k: one comparison with the start of bin k settles it.
+__device__ __forceinline__ unsigned bin_guess(float s_approx, float inv_w, float c_magic, unsigned kclamp) {
     float d;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(d) : "f"(s_approx));
     const float t = fmaf(d, inv_w, c_magic);
-    return min((unsigned)(__float_as_int(t) - 0x4b400000), kmax);
+    return min((unsigned)(__float_as_int(t) - 0x4b400000), kclamp);
 }
+
+// Packed float32 pairs: sm_100 executes add/mul/fma on two floats of a 64-bit register pair
+// in one issue slot (FADD2 / FMUL2 / FFMA2, each lane IEEE round-to-nearest like the scalar
+// instruction; tools/f32x2_probe.cu).  The pair kernel is issue-bound, so the float32
+// regime evaluates two queries per lane and step with them.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+// a + b with a single rounding, written as a*one + b where `one` is 1.0f passed at run time:
+// ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (also with --fmad=false), which would
+// skip the rounding of the product that the reference's (diff**2).sum() performs.  An fma
+// cannot absorb the multiply that feeds it, and a*1 is exact.
+__device__ __forceinline__ f32x2 add2_unfused(f32x2 a, f32x2 b, f32x2 one2) { return fma2(a, one2, b); }
 
 struct PairArgs {
     const FramePlan* plans;
@@ -453,24 +507,33 @@ struct PairArgs {
     long long total_cells;
     int nbins;
     int nframes;
-    int uniform;                    // every edge table is uniform (linspace-like)
+    int uniform;                    // every edge table is uniform (linspace-like) and fit for the one-comparison binning
+    const float* qsoa;              // float32 regime: queries in cell order, see store_query_pairs
+    long long qsoa_n;               // number of query slots (even)
+    float one;                      // 1.0f, opaque to the compiler (see add2_unfused)
 };
 
+// float32 regime: every warp gathers the neighbourhood of its query cell into a shared buffer
+// of kStageCap targets (x[] | y[] (| z[])) and walks it in full 32-lane passes
+constexpr unsigned kStageCap = 256;
 constexpr unsigned kUnitLimit = 1u << 21;                // flush after 2^31 counted pairs (units of 1024)
 constexpr int kPairThreads = 256;
 
-template <typename AT, bool ZCONST>
+// ZMODE 0: three coordinates; 1: every z equal, dz*dz is the per-frame constant dz2c;
+// 2: like 1 with dz2c == 0 (s + 0 == s, the addition is dropped)
+template <typename AT, int ZMODE>
 __device__ __forceinline__ AT pair_s(const Vec4<AT>& qv, AT nx, AT ny, AT nz, AT dz2c) {
     // diff = c - coords; (diff**2).sum(axis=1) : ((dx*dx + dy*dy) + dz*dz), no FMA
     const AT dx = Arith<AT>::sub(qv.x, nx);
     const AT dy = Arith<AT>::sub(qv.y, ny);
     AT s = Arith<AT>::add(Arith<AT>::mul(dx, dx), Arith<AT>::mul(dy, dy));
-    if (ZCONST) return Arith<AT>::add(s, dz2c);
+    if (ZMODE == 2) return s;
+    if (ZMODE == 1) return Arith<AT>::add(s, dz2c);
     const AT dz = Arith<AT>::sub(qv.z, nz);
     return Arith<AT>::add(s, Arith<AT>::mul(dz, dz));
 }
 
-template <typename AT, bool ZCONST>
+template <typename AT, bool XY_ONLY>
 __device__ __forceinline__ Vec4<AT> load_query(const Vec4<AT>* p);
 template <>
 __device__ __forceinline__ Vec4<float> load_query<float, true>(const Vec4<float>* p) {
@@ -494,7 +557,7 @@ __device__ __forceinline__ Vec4<double> load_query<double, false>(const Vec4<dou
 // One warp: all queries of one cell against one neighbour row (contiguous in the
 // sorted image array).  Lanes hold images in registers, queries are broadcast loads.
 // General version: threshold table anywhere, search loops, shared or global histogram.
-template <typename AT, typename NT, bool ZCONST, bool DIRECT>
+template <typename AT, typename NT, int ZMODE, bool DIRECT>
 __device__ __noinline__ void warp_pairs_general(const Vec4<AT>* __restrict__ qsorted, unsigned qa, unsigned qb,
                                                 const Vec4<NT>* __restrict__ tsorted, unsigned ta, unsigned tb,
                                                 const AT* __restrict__ thr, int nbins, AT dz2c, float inv_w,
@@ -512,7 +575,7 @@ __device__ __noinline__ void warp_pairs_general(const Vec4<AT>* __restrict__ qso
         }
         for (unsigned q = qa; q < qb; ++q) {
             const Vec4<AT> qv = load_vec4(qsorted + q);
-            const AT s = pair_s<AT, ZCONST>(qv, nx, ny, nz, dz2c);
+            const AT s = pair_s<AT, ZMODE>(qv, nx, ny, nz, dz2c);
             if (s >= thr_lo && s < thr_hi) {
                 int g = max((int)bin_guess(Arith<AT>::approx(s), inv_w, c_magic, (unsigned)nbins) - 1, 0);
                 while (s < thr[g]) --g;
@@ -524,40 +587,125 @@ __device__ __noinline__ void warp_pairs_general(const Vec4<AT>* __restrict__ qso
     }
 }
 
-// Hot version.  Shared memory holds T[k], k = 0..nbins: T[0] = 0, T[k] = thr[k] -- the
-// squared distance at which bin k starts (T[nbins] = end of the last bin).  bin = k - 1 +
-// (s >= T[k]) for the guess k; pairs outside [thr_lo, thr_hi) end up in a dump slot.
+// Hot version.  Shared memory holds T[k], k = 0..nbins+1: T[0] = thr[0] (the smallest counted
+// s), T[k] = thr[k] -- the squared distance at which bin k starts, T[nbins] = end of the last
+// bin, T[nbins+1] = NaN.  A histogram half has nbins + 2 slots: slot 0 and slot nbins + 1 are
+// dump slots, bin b lives in slot b + 1.  With the guess k the pair goes to slot
+// k + (s >= T[k]): pairs below thr[0] have k == 0 (host check: fast_binning_ok) and fall into
+// slot 0, pairs beyond the last edge, NaN and inf into slot nbins + 1.
 // No branches in the loop body; kQueryUnroll queries are in flight per lane.
 constexpr int kQueryUnroll = 4;
 // Unconditional +1 (ATOMS.POPC.INC: lanes hitting the same address are merged by the
-// hardware, measured in tools/microbench.cu).  Pairs outside the histogram range are sent to a
-// dump slot instead of being predicated off: ptxas wraps a predicated shared atomic in a
-// branch region, which costs more issue slots than the extra lanes cost wavefronts.
+// hardware, measured in tools/microbench.cu).  Out-of-range pairs are sent to a dump slot
+// instead of being predicated off: ptxas wraps a predicated shared atomic in a branch
+// region, which costs more issue slots than the extra lanes cost wavefronts.
 __device__ __forceinline__ void smem_inc(unsigned addr) {
     asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
 }
 
-template <typename AT, bool ZCONST>
-__device__ __forceinline__ void pair_update(const Vec4<AT>& qv, AT nx, AT ny, AT nz, AT thr_lo, AT dz2c,
-                                            float inv_w, float c_magic, unsigned kmax, unsigned thr_addr,
-                                            unsigned hist_addr_m1, unsigned dump_addr) {
-    const AT s = pair_s<AT, ZCONST>(qv, nx, ny, nz, dz2c);
-    const unsigned k = bin_guess(Arith<AT>::approx(s), inv_w, c_magic, kmax);
+template <typename AT>
+__device__ __forceinline__ void slot_update(AT s, unsigned k, unsigned thr_addr, unsigned hist_addr) {
     const AT t = Arith<AT>::load_thr(thr_addr + (k << Arith<AT>::kThrShift));
-    unsigned addr = hist_addr_m1 + (k << 2);  // &hist[k - 1]
-    if (s >= t) addr += 4;                    // s >= T[nbins] (beyond the last edge) lands in hist[nbins], the dump slot
-    if (!(s >= thr_lo)) addr = dump_addr;     // d <= 1e-3, below the first edge, or NaN
+    unsigned addr = hist_addr + (k << 2);
+    if (s >= t) addr += 4;
     smem_inc(addr);
 }
 
-template <typename AT, typename NT, bool ZCONST>
+template <typename AT, int ZMODE>
+__device__ __forceinline__ void pair_update(const Vec4<AT>& qv, AT nx, AT ny, AT nz, AT dz2c, float inv_w,
+                                            float c_magic, unsigned kclamp, unsigned thr_addr,
+                                            unsigned hist_addr) {
+    const AT s = pair_s<AT, ZMODE>(qv, nx, ny, nz, dz2c);
+    slot_update<AT>(s, bin_guess(Arith<AT>::approx(s), inv_w, c_magic, kclamp), thr_addr, hist_addr);
+}
+
+// Two queries (packed) against the lane's target.
+template <int ZMODE>
+__device__ __forceinline__ void pair_update2(f32x2 qx, f32x2 qy, f32x2 qz, float nx, float ny, float nz,
+                                             float one, float dz2c, float inv_w, float c_magic, unsigned kclamp,
+                                             unsigned thr_addr, unsigned hist_addr) {
+    const f32x2 one2 = pack2(one, one);
+    const f32x2 dx = sub2(qx, pack2(nx, nx)), dy = sub2(qy, pack2(ny, ny));
+    f32x2 s2 = add2_unfused(mul2(dx, dx), mul2(dy, dy), one2);
+    if (ZMODE == 1) s2 = add2_unfused(s2, pack2(dz2c, dz2c), one2);
+    if (ZMODE == 0) {
+        const f32x2 dz = sub2(qz, pack2(nz, nz));
+        s2 = add2_unfused(mul2(dz, dz), s2, one2);
+    }
+    float s0, s1, d0, d1, t0, t1;
+    unpack2(s2, s0, s1);
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(d0) : "f"(s0));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(d1) : "f"(s1));
+    unpack2(fma2(pack2(d0, d1), pack2(inv_w, inv_w), pack2(c_magic, c_magic)), t0, t1);
+    slot_update<float>(s0, min((unsigned)(__float_as_int(t0) - 0x4b400000), kclamp), thr_addr, hist_addr);
+    slot_update<float>(s1, min((unsigned)(__float_as_int(t1) - 0x4b400000), kclamp), thr_addr, hist_addr);
+}
+
+__host__ __device__ inline size_t pair_thr_bytes(int nbins, size_t at_size) {
+    return ((size_t)(nbins + 2) * at_size + 15) & ~(size_t)15;
+}
+
+struct FastArgs {
+    float inv_w, c_magic, one;
+    unsigned kclamp, thr_addr;
+    const float* qsoa;      // float32 regime only
+    long long qsoa_n;
+};
+
+// All queries [qa, qb) of a cell against the lane's target, float32 regime: packed pairs of
+// queries from the pair-interleaved copy (see store_query_pairs); the 16-byte loads need an
+// even query index, so an odd first and an odd last query are done alone.
+template <int ZMODE>
+__device__ __forceinline__ void query_loop_f32(const FastArgs& fa, unsigned qa, unsigned qb, float nx, float ny,
+                                               float nz, float dz2c, unsigned hist_addr) {
+    const float* __restrict__ sxy = fa.qsoa;
+    const float* __restrict__ sz = fa.qsoa + 2 * fa.qsoa_n;
+    auto single = [&](unsigned qi) {
+        const float* e = sxy + (size_t)(qi >> 1) * 4 + (qi & 1u);
+        Vec4<float> qv;
+        qv.x = __ldg(e); qv.y = __ldg(e + 2); qv.z = ZMODE == 0 ? __ldg(sz + qi) : 0.0f; qv.w = 0.0f;
+        pair_update<float, ZMODE>(qv, nx, ny, nz, dz2c, fa.inv_w, fa.c_magic, fa.kclamp, fa.thr_addr, hist_addr);
+    };
+    auto packed = [&](const float4& xy, f32x2 z) {
+        pair_update2<ZMODE>(pack2(xy.x, xy.y), pack2(xy.z, xy.w), z, nx, ny, nz, fa.one, dz2c, fa.inv_w, fa.c_magic,
+                            fa.kclamp, fa.thr_addr, hist_addr);
+    };
+    unsigned q = qa;
+#ifdef AMEPB_DEBUG_NOPACK
+    for (; q < qb; ++q) single(q);
+    return;
+#endif
+    if (q & 1u) {
+        single(q);
+        ++q;
+    }
+    for (; q + 4 <= qb; q += 4) {
+        const float4* pxy = reinterpret_cast<const float4*>(sxy) + (q >> 1);
+        const float4 xy0 = __ldg(pxy), xy1 = __ldg(pxy + 1);
+        f32x2 z0 = 0ull, z1 = 0ull;
+        if (ZMODE == 0) {
+            z0 = __ldg(reinterpret_cast<const f32x2*>(sz + q));
+            z1 = __ldg(reinterpret_cast<const f32x2*>(sz + q + 2));
+        }
+        packed(xy0, z0);
+        packed(xy1, z1);
+    }
+    if (q + 2 <= qb) {
+        const float4 xy0 = __ldg(reinterpret_cast<const float4*>(sxy) + (q >> 1));
+        const f32x2 z0 = ZMODE == 0 ? __ldg(reinterpret_cast<const f32x2*>(sz + q)) : 0ull;
+        packed(xy0, z0);
+        q += 2;
+    }
+    if (q < qb) single(q);
+}
+
+template <typename AT, typename NT, int ZMODE>
 __device__ __forceinline__ void warp_pairs_fast(const Vec4<AT>* __restrict__ qsorted, unsigned qa, unsigned qb,
                                                 const Vec4<NT>* __restrict__ tsorted, unsigned ta, unsigned tb,
-                                                AT thr_lo, AT dz2c, float inv_w, float c_magic, unsigned kmax,
-                                                unsigned thr_addr, unsigned hist_lo_m1, unsigned hist_hi_m1,
-                                                unsigned split, unsigned dump_addr) {
-    // targets with index < split count into the histogram at hist_lo_m1, the others into
-    // hist_hi_m1 (the symmetric pass mixes weight-1 own-cell pairs and weight-2 pairs in one range)
+                                                AT dz2c, const FastArgs& fa, unsigned hist_lo, unsigned hist_hi,
+                                                unsigned split) {
+    // targets with index < split count into the histogram half at hist_lo, the others into
+    // hist_hi (the symmetric pass mixes weight-1 own-cell pairs and weight-2 pairs in one range)
     const int lane = threadIdx.x & 31;
     const AT nan = (AT)__int_as_float(0x7fc00000);
     for (unsigned base = ta; base < tb; base += 32) {
@@ -567,21 +715,24 @@ __device__ __forceinline__ void warp_pairs_fast(const Vec4<AT>* __restrict__ qso
             const Vec4<NT> nb = load_vec4(tsorted + j);
             nx = (AT)nb.x; ny = (AT)nb.y; nz = (AT)nb.z;
         }
-        const unsigned hist_addr_m1 = j < split ? hist_lo_m1 : hist_hi_m1;
+        const unsigned hist_addr = j < split ? hist_lo : hist_hi;
         unsigned q = qa;
-        for (; q + kQueryUnroll <= qb; q += kQueryUnroll) {
-            Vec4<AT> qv[kQueryUnroll];
+        if constexpr (sizeof(AT) == 4) {
+            query_loop_f32<ZMODE>(fa, qa, qb, nx, ny, nz, dz2c, hist_addr);
+        } else {
+            for (; q + kQueryUnroll <= qb; q += kQueryUnroll) {
+                Vec4<AT> qv[kQueryUnroll];
 #pragma unroll
-            for (int u = 0; u < kQueryUnroll; ++u) qv[u] = load_query<AT, ZCONST>(qsorted + q + u);
+                for (int u = 0; u < kQueryUnroll; ++u) qv[u] = load_query<AT, ZMODE != 0>(qsorted + q + u);
 #pragma unroll
-            for (int u = 0; u < kQueryUnroll; ++u)
-                pair_update<AT, ZCONST>(qv[u], nx, ny, nz, thr_lo, dz2c, inv_w, c_magic, kmax, thr_addr, hist_addr_m1,
-                                        dump_addr);
-        }
-        for (; q < qb; ++q) {
-            const Vec4<AT> qv = load_query<AT, ZCONST>(qsorted + q);
-            pair_update<AT, ZCONST>(qv, nx, ny, nz, thr_lo, dz2c, inv_w, c_magic, kmax, thr_addr, hist_addr_m1,
-                                    dump_addr);
+                for (int u = 0; u < kQueryUnroll; ++u)
+                    pair_update<AT, ZMODE>(qv[u], nx, ny, nz, dz2c, fa.inv_w, fa.c_magic, fa.kclamp, fa.thr_addr,
+                                           hist_addr);
+            }
+            for (; q < qb; ++q) {
+                const Vec4<AT> qv = load_query<AT, ZMODE != 0>(qsorted + q);
+                pair_update<AT, ZMODE>(qv, nx, ny, nz, dz2c, fa.inv_w, fa.c_magic, fa.kclamp, fa.thr_addr, hist_addr);
+            }
         }
     }
 }
@@ -591,27 +742,29 @@ __device__ __forceinline__ void warp_pairs_fast(const Vec4<AT>* __restrict__ qso
 // bit, so real-real pairs are evaluated once over the upper half shell and counted twice; the
 // shifted images ("ghosts", a separate cell-sorted array) are not symmetric in floating point
 // and are evaluated for every ordered (query, ghost) pair.
-template <typename AT, typename NT, bool ZCONST, bool SMEM, bool SYM>
+template <typename AT, typename NT, int ZMODE, bool SMEM, bool SYM>
 __global__ void __launch_bounds__(kPairThreads, 5) pair_kernel(PairArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nbins = a.nbins;
-    AT* s_thr = reinterpret_cast<AT*>(smem_raw);  // T[0..nbins], see warp_pairs_fast
-    unsigned* s_hist = reinterpret_cast<unsigned*>(smem_raw + (((size_t)(nbins + 1) * sizeof(AT) + 15) & ~(size_t)15));
+    AT* s_thr = reinterpret_cast<AT*>(smem_raw);  // T[0..nbins+1], see warp_pairs_fast
+    unsigned* s_hist = reinterpret_cast<unsigned*>(smem_raw + pair_thr_bytes(nbins, sizeof(AT)));
     // SYM: a second histogram half collects the pairs that count twice, so that every
-    // increment is +1 (ATOMS.POPC.INC); the halves are combined as h1 + 2*h2 at flush time
-    // each half has nbins + 1 entries: entry nbins is the dump slot for out-of-range pairs
-    const int hist_len = (SYM ? 2 : 1) * (nbins + 1);
-    const unsigned thr_addr = (unsigned)__cvta_generic_to_shared(s_thr);
-    const unsigned hist_addr_m1 = (unsigned)__cvta_generic_to_shared(s_hist) - 4u;
-    const unsigned hist2_addr_m1 = hist_addr_m1 + 4u * (unsigned)(nbins + 1);
-    const unsigned dump_addr = hist_addr_m1 + 4u * (unsigned)(nbins + 1);
-    __shared__ AT s_range[2];  // thr_lo, thr_hi of the current frame
+    // increment is +1 (ATOMS.POPC.INC); the halves are combined as h1 + 2*h2 at flush time.
+    // A half has nbins + 2 slots: bin b in slot b + 1, slots 0 and nbins + 1 are dump slots.
+    const int half_len = nbins + 2;
+    const int hist_len = (SYM ? 2 : 1) * half_len;
+    const unsigned hist_addr = (unsigned)__cvta_generic_to_shared(s_hist);
+    const unsigned hist2_addr = hist_addr + 4u * (unsigned)half_len;
+    constexpr int kStageComp = ZMODE == 0 ? 3 : 2;
+    float* s_stage = reinterpret_cast<float*>(smem_raw + pair_thr_bytes(nbins, sizeof(AT)) +
+                                              (((size_t)hist_len * sizeof(unsigned) + 15) & ~(size_t)15));
+    __shared__ int s_next;
     __shared__ FramePlan s_plan;
     __shared__ long long s_task;
     __shared__ unsigned s_units;
     __shared__ int s_flush;
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const Vec4<AT>* qsorted = reinterpret_cast<const Vec4<AT>*>(a.qsorted);
     const Vec4<NT>* tsorted = reinterpret_cast<const Vec4<NT>*>(a.tsorted);
     int cur = -1;
@@ -622,6 +775,7 @@ __global__ void __launch_bounds__(kPairThreads, 5) pair_kernel(PairArgs a) {
     for (;;) {
         if (tid == 0) {
             s_task = (long long)atomicAdd(&a.counters[0], 1ull);
+            s_next = blockDim.x >> 5;
             const int fl = s_units >= kUnitLimit;
             s_flush = fl;
             if (fl) s_units = 0;
@@ -636,8 +790,8 @@ __global__ void __launch_bounds__(kPairThreads, 5) pair_kernel(PairArgs a) {
             if (SMEM && cur >= 0) {
                 unsigned long long* row = a.hist + (long long)cur * nbins;
                 for (int b = tid; b < nbins; b += blockDim.x) {
-                    unsigned long long v = s_hist[b];
-                    if (SYM) v += 2ull * s_hist[nbins + 1 + b];
+                    unsigned long long v = s_hist[b + 1];
+                    if (SYM) v += 2ull * s_hist[half_len + b + 1];
                     if (v) atomicAdd(&row[b], v);
                 }
                 __syncthreads();  // the zeroing below maps bins to other threads than the loop above
@@ -649,11 +803,8 @@ __global__ void __launch_bounds__(kPairThreads, 5) pair_kernel(PairArgs a) {
                 for (int k = tid; k < (int)(sizeof(FramePlan) / sizeof(int)); k += blockDim.x) dst[k] = src[k];
                 if (SMEM) {
                     const AT* tsrc = reinterpret_cast<const AT*>(a.thr) + (long long)a.plans[f].thr_index * (nbins + 1);
-                    for (int k = tid; k <= nbins; k += blockDim.x) s_thr[k] = k == 0 ? (AT)0 : tsrc[k];
-                    if (tid == 0) {
-                        s_range[0] = tsrc[0];
-                        s_range[1] = tsrc[nbins];
-                    }
+                    for (int k = tid; k <= nbins + 1; k += blockDim.x)
+                        s_thr[k] = k <= nbins ? tsrc[k] : (AT)__int_as_float(0x7fc00000);
                 }
             }
             if (SMEM)
@@ -663,15 +814,18 @@ __global__ void __launch_bounds__(kPairThreads, 5) pair_kernel(PairArgs a) {
         }
         const FramePlan& P = s_plan;
         const AT* thr = reinterpret_cast<const AT*>(a.thr) + (long long)P.thr_index * (nbins + 1);
-        AT thr_lo = (AT)0, thr_hi = (AT)0;
-        if (SMEM) {
-            thr_lo = s_range[0];
-            thr_hi = s_range[1];
-        }
         const AT dz2c = (AT)P.dz2c;
-        // k = round(sqrt(s)*inv_w - e0*inv_w + 0.5 - bias); the magic constant does the rounding
+        // k = round(sqrt(s)*inv_w - e0*inv_w); the magic constant does the rounding
         const float inv_w = (float)P.bin_inv_w;
-        const float c_magic = 12582912.0f + 0.5f - kGuessBias - (float)(P.bin_e0 * P.bin_inv_w);
+        const float c_magic = 12582912.0f - (float)(P.bin_e0 * P.bin_inv_w);
+        FastArgs fa;
+        fa.inv_w = inv_w;
+        fa.c_magic = c_magic;
+        fa.one = a.one;
+        fa.kclamp = (unsigned)(nbins + 1);
+        fa.thr_addr = (unsigned)__cvta_generic_to_shared(s_thr);
+        fa.qsoa = a.qsoa;
+        fa.qsoa_n = a.qsoa_n;
         unsigned long long* g_hist = a.hist + (long long)f * nbins;
 
         const long long lt = t - P.task_begin;
@@ -690,11 +844,145 @@ __global__ void __launch_bounds__(kPairThreads, 5) pair_kernel(PairArgs a) {
         // One warp per query cell of the run (rsplit == 1), or rsplit warps sharing a cell,
         // each walking every rsplit-th neighbour row.
         const int rsplit = P.rsplit;
-        for (int wtk = warp; wtk < ncell * rsplit; wtk += nwarps) {
+        // the items of a block task are handed out dynamically, so that a warp with light cells
+        // takes more of them instead of waiting at the barrier
+        for (int wtk = warp; wtk < ncell * rsplit;
+#ifdef AMEPB_DEBUG_STATIC
+             wtk += (int)(blockDim.x >> 5)) {
+#else
+             wtk = __shfl_sync(0xffffffffu, lane == 0 ? atomicAdd(&s_next, 1) : 0, 0)) {
+#endif
             const int part = wtk / ncell;
             const int cx = cx0 + (wtk - part * ncell);
             const unsigned qa = __ldg(&a.qstart[qrow + cx]), qb = __ldg(&a.qstart[qrow + cx + 1]);
             if (qa == qb) continue;
+#ifdef AMEPB_DEBUG_NOSTAGE
+            if constexpr (false) {
+#else
+            if constexpr (SMEM && sizeof(AT) == 4) {
+#endif
+                // ---- float32 regime: stage the neighbourhood, then full passes ----------------
+                const unsigned nq = qb - qa;
+                float* bx = s_stage + (size_t)warp * (kStageCap * kStageComp);
+                float* by = bx + kStageCap;
+                float* bz = by + kStageCap;  // ZMODE == 0 only
+                // entries: [0] own cell (SYM), [1, G] ghost rows (SYM, if any can be near),
+                // then the real rows (SYM: upper half shell) -- weight-1 entries first
+                int G = 0;
+                if (SYM) {
+                    const int kx0 = P.kd[0], ky = P.kd[1], kz = P.kd[2];
+                    const bool gfree = cx - kx0 >= P.gfree_lo[0] && cx + kx0 <= P.gfree_hi[0] && cy - ky >= P.gfree_lo[1] &&
+                                       cy + ky <= P.gfree_hi[1] && cz - kz >= P.gfree_lo[2] && cz + kz <= P.gfree_hi[2];
+                    G = gfree ? 0 : nrows;
+                }
+                const int E = SYM ? 1 + G + (nrows - row0) : nrows;
+                unsigned fill = 0, lo_end = 0;
+                unsigned long long staged = 0, oversize = 0;
+                auto flush_stage = [&]() {
+                    __syncwarp();
+                    for (unsigned g0 = 0; g0 < fill; g0 += 32) {
+                        const unsigned g = g0 + lane;
+                        float nx = __int_as_float(0x7fc00000), ny = nx, nz = nx;
+                        if (g < fill) {
+                            nx = bx[g];
+                            ny = by[g];
+                            if (ZMODE == 0) nz = bz[g];
+                        }
+                        // (idle lanes hold NaN targets and end up in a dump slot: without a second half
+                        // that must be the first half's)
+                        query_loop_f32<ZMODE>(fa, qa, qb, nx, ny, nz, dz2c,
+                                              (!SYM || g < lo_end) ? hist_addr : hist2_addr);
+                    }
+                    __syncwarp();
+                    fill = 0;
+                    lo_end = 0;
+                };
+                for (int eb = 0; eb < E; eb += 32) {
+                    const int e = eb + lane;
+                    unsigned start = 0, len = 0, flags = 0;  // flags bit 0: counts twice, bit 1: lives in the query array
+                    if (e < E) {
+                        int r = -1;
+                        if (SYM) {
+                            if (e == 0) {
+                                flags = 2;
+                                if (part == 0) {
+                                    start = qa;
+                                    len = nq;
+                                }
+                            } else if (e <= G) {
+                                r = e - 1;
+                                if (r % rsplit != part) r = -1;
+                            } else {
+                                r = row0 + (e - 1 - G);
+                                flags = 3;
+                                if ((r - row0) % rsplit != part) r = -1;
+                            }
+                        } else {
+                            r = e;
+                            if (r % rsplit != part) r = -1;
+                        }
+                        if (r >= 0) {
+                            const int ny = cy + P.row_oy[r], nz = cz + P.row_oz[r];
+                            if (ny >= 0 && ny < n1 && nz >= 0 && nz < n2) {
+                                const int kx = P.row_kx[r];
+                                int x_lo = max(cx - kx, 0);
+                                const int x_hi = min(cx + kx, n0 - 1);
+                                if (flags == 3 && r == row0) x_lo = cx + 1;  // own row: only the cells to the right
+                                if (x_lo <= x_hi) {
+                                    const unsigned* starts = (flags & 2) ? a.qstart : a.tstart;
+                                    const unsigned trow = P.cell_base + (unsigned)((nz * n1 + ny) * n0);
+                                    start = __ldg(&starts[trow + x_lo]);
+                                    len = __ldg(&starts[trow + x_hi + 1]) - start;
+                                }
+                            }
+                        }
+                    }
+                    unsigned todo = __ballot_sync(0xffffffffu, len != 0);
+                    while (todo) {
+                        const int src = __ffs(todo) - 1;
+                        todo &= todo - 1;
+                        const unsigned st = __shfl_sync(0xffffffffu, start, src), ln = __shfl_sync(0xffffffffu, len, src);
+                        const unsigned fl = __shfl_sync(0xffffffffu, flags, src);
+                        const Vec4<float>* arr = (fl & 2) ? reinterpret_cast<const Vec4<float>*>(qsorted)
+                                                          : reinterpret_cast<const Vec4<float>*>(tsorted);
+                        const unsigned long long npairs = (unsigned long long)nq * ln;
+                        if (npairs > direct_pairs) {  // giant cells: straight to the global histogram
+                            oversize += npairs;
+                            warp_pairs_general<float, float, ZMODE == 0 ? 0 : 1, true>(
+                                reinterpret_cast<const Vec4<float>*>(qsorted), qa, qb, arr, st, st + ln,
+                                reinterpret_cast<const float*>(thr), nbins, (float)dz2c, inv_w, c_magic, (fl & 1) ? 2u : 1u,
+                                s_hist, g_hist);
+                            continue;
+                        }
+                        staged += npairs;
+                        unsigned off = 0;
+                        while (off < ln) {
+                            const unsigned n = min(ln - off, kStageCap - fill);
+                            for (unsigned i = lane; i < n; i += 32) {
+                                if (ZMODE == 0) {
+                                    const Vec4<float> v = load_vec4(arr + st + off + i);
+                                    bx[fill + i] = v.x;
+                                    by[fill + i] = v.y;
+                                    bz[fill + i] = v.z;
+                                } else {
+                                    const float2 v = __ldg(reinterpret_cast<const float2*>(arr + st + off + i));
+                                    bx[fill + i] = v.x;
+                                    by[fill + i] = v.y;
+                                }
+                            }
+                            fill += n;
+                            off += n;
+                            if (!(fl & 1)) lo_end = fill;
+                            if (fill == kStageCap) flush_stage();
+                        }
+                    }
+                }
+                if (fill) flush_stage();
+                if (lane == 0) {
+                    cand += staged + oversize;
+                    if (staged) atomicAdd(&s_units, (unsigned)(staged >> 10) + 1u);
+                }
+            } else {
             // pass 0: real targets (SYM: upper half shell, own row to the right, own cell);
             // pass 1 (SYM only): shifted images, all rows, skipped where none can live
             const int npass = SYM ? 2 : 1;
@@ -734,31 +1022,29 @@ __global__ void __launch_bounds__(kPairThreads, 5) pair_kernel(PairArgs a) {
                             // the own cell is [qa, qb) of the same array
                             if (direct) {
                                 if (own_row) {
-                                    warp_pairs_general<AT, AT, ZCONST, true>(qsorted, qa, qb, qsorted, ta, qb, thr, nbins,
+                                    warp_pairs_general<AT, AT, ZMODE == 0 ? 0 : 1, true>(qsorted, qa, qb, qsorted, ta, qb, thr, nbins,
                                                                              dz2c, inv_w, c_magic, 1u, s_hist, g_hist);
                                     if (qb < tb)
-                                        warp_pairs_general<AT, AT, ZCONST, true>(qsorted, qa, qb, qsorted, qb, tb, thr, nbins,
+                                        warp_pairs_general<AT, AT, ZMODE == 0 ? 0 : 1, true>(qsorted, qa, qb, qsorted, qb, tb, thr, nbins,
                                                                                  dz2c, inv_w, c_magic, 2u, s_hist, g_hist);
                                 } else {
-                                    warp_pairs_general<AT, AT, ZCONST, true>(qsorted, qa, qb, qsorted, ta, tb, thr, nbins,
+                                    warp_pairs_general<AT, AT, ZMODE == 0 ? 0 : 1, true>(qsorted, qa, qb, qsorted, ta, tb, thr, nbins,
                                                                              dz2c, inv_w, c_magic, 2u, s_hist, g_hist);
                                 }
                             } else {
-                                warp_pairs_fast<AT, AT, ZCONST>(qsorted, qa, qb, qsorted, ta, tb, thr_lo, dz2c, inv_w, c_magic,
-                                                                (unsigned)nbins, thr_addr, hist_addr_m1, hist2_addr_m1,
-                                                                own_row ? qb : 0u, dump_addr);
+                                warp_pairs_fast<AT, AT, ZMODE>(qsorted, qa, qb, qsorted, ta, tb, dz2c, fa, hist_addr,
+                                                               hist2_addr, own_row ? qb : 0u);
                             }
                         } else if (direct) {
-                            warp_pairs_general<AT, NT, ZCONST, true>(qsorted, qa, qb, tsorted, ta, tb, thr, nbins, dz2c,
+                            warp_pairs_general<AT, NT, ZMODE == 0 ? 0 : 1, true>(qsorted, qa, qb, tsorted, ta, tb, thr, nbins, dz2c,
                                                                      inv_w, c_magic, 1u, s_hist, g_hist);
                         } else {
-                            warp_pairs_fast<AT, NT, ZCONST>(qsorted, qa, qb, tsorted, ta, tb, thr_lo, dz2c, inv_w, c_magic,
-                                                            (unsigned)nbins, thr_addr, hist_addr_m1, hist_addr_m1, 0u,
-                                                            dump_addr);
+                            warp_pairs_fast<AT, NT, ZMODE>(qsorted, qa, qb, tsorted, ta, tb, dz2c, fa, hist_addr, hist_addr, 0u);
                         }
                     }
                 }
             }
+            }  // per-row walk (float64 regimes, tables outside shared memory)
         }
         __syncthreads();
     }
@@ -841,17 +1127,23 @@ static int exclusive_scan(amepb_ctx* ctx, const unsigned* in, unsigned* out, lon
 }
 
 template <typename AT, typename NT, bool SYM>
-static int launch_pairs(amepb_ctx* ctx, const PairArgs& args, bool zconst, cudaStream_t stream) {
+static int launch_pairs(amepb_ctx* ctx, const PairArgs& args, int zmode, cudaStream_t stream) {
     const int nbins = args.nbins;
-    const size_t smem = (((size_t)(nbins + 1) * sizeof(AT) + 15) & ~(size_t)15) +
-                        (size_t)(nbins + 1) * sizeof(unsigned) * (SYM ? 2 : 1);
+    const size_t smem = pair_thr_bytes(nbins, sizeof(AT)) + (size_t)(nbins + 2) * sizeof(unsigned) * (SYM ? 2 : 1);
     // the one-comparison bin correction needs uniform edges (args.uniform) and nbins <= 2^17;
     // the tables must fit in shared memory
     const bool use_smem = smem <= 40 * 1024 && args.uniform && nbins <= (1 << 17);
     void (*kern)(PairArgs) = nullptr;
-    if (use_smem) kern = zconst ? pair_kernel<AT, NT, true, true, SYM> : pair_kernel<AT, NT, false, true, SYM>;
-    else kern = zconst ? pair_kernel<AT, NT, true, false, SYM> : pair_kernel<AT, NT, false, false, SYM>;
-    const size_t dyn = use_smem ? smem : 16;
+    if (use_smem)
+        kern = zmode == 2 ? pair_kernel<AT, NT, 2, true, SYM>
+                          : (zmode == 1 ? pair_kernel<AT, NT, 1, true, SYM> : pair_kernel<AT, NT, 0, true, SYM>);
+    else kern = zmode != 0 ? pair_kernel<AT, NT, 1, false, SYM> : pair_kernel<AT, NT, 0, false, SYM>;
+    size_t dyn = use_smem ? smem : 16;
+    if (use_smem && sizeof(AT) == 4) {
+        // per-warp staging buffers of the float32 regime (see kStageCap)
+        dyn = ((dyn + 15) & ~(size_t)15) + (size_t)(kPairThreads / 32) * kStageCap * (zmode == 0 ? 3 : 2) * sizeof(float);
+        AMEPB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    }
     int per_sm = 0;
     AMEPB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kPairThreads, dyn));
     if (per_sm < 1) per_sm = 1;
@@ -1015,6 +1307,8 @@ static int rdf_sub_batch(amepb_ctx* ctx, const RdfCall& c, int64_t f0, int nf, c
         const double w = (edges[nbins] - edges[0]) / nbins;
         for (int i = 0; i <= nbins && uniform; ++i)
             if (!(fabs(edges[i] - (edges[0] + i * w)) <= 0.01 * w)) uniform = false;
+        // pairs below the first counted distance (d <= 1e-3 or d < edges[0]) must round to guess 0
+        if (!(w > 0) || !((std::max(1e-3, edges[0]) - edges[0]) / w < 0.45)) uniform = false;
         if (arith_f64) make_thresholds<double>(edges, nbins, reinterpret_cast<double*>(hthr) + (size_t)tb * (nbins + 1));
         else make_thresholds<float>(edges, nbins, reinterpret_cast<float*>(hthr) + (size_t)tb * (nbins + 1));
     }
@@ -1049,6 +1343,13 @@ static int rdf_sub_batch(amepb_ctx* ctx, const RdfCall& c, int64_t f0, int nf, c
     AMEPB_CUDA(ctx, cudaMemsetAsync(ctx->bufs[BUF_MISC].p, 0, sizeof(unsigned long long), stream));
 
     // ---- cell build ------------------------------------------------------------
+    // float32 regime: a second, pair-interleaved copy of the cell-sorted queries (store_query_pairs)
+    float* qsoa = nullptr;
+    const long long qsoa_n = ((long long)m * nf + 1) & ~1ll;
+    if (!arith_f64) {
+        if ((rc = ensure_device(ctx, BUF_QSOA, sizeof(float) * 3 * (size_t)qsoa_n))) return rc;
+        qsoa = reinterpret_cast<float*>(ctx->bufs[BUF_QSOA].p);
+    }
     const dim3 tgrid((unsigned)((c.n + 255) / 256), nf), qgrid((unsigned)((m + 255) / 256), nf);
     auto place_targets = [&](bool fill) -> int {
         void* sorted = ctx->bufs[BUF_TSORTED].p;
@@ -1073,7 +1374,7 @@ static int rdf_sub_batch(amepb_ctx* ctx, const RdfCall& c, int64_t f0, int nf, c
     auto place_queries = [&](bool fill) -> int {
         void* sorted = ctx->bufs[BUF_QSORTED].p;
         if (qdtype == AMEPB_F32 && !arith_f64) {
-            if (fill) place_points_kernel<float, float, true, false><<<qgrid, 256, 0, stream>>>((const float*)d_query, m, d_plans, qcount, qstart, (Vec4<float>*)sorted);
+            if (fill) place_points_kernel<float, float, true, false><<<qgrid, 256, 0, stream>>>((const float*)d_query, m, d_plans, qcount, qstart, (Vec4<float>*)sorted, qsoa, qsoa_n);
             else place_points_kernel<float, float, false, false><<<qgrid, 256, 0, stream>>>((const float*)d_query, m, d_plans, qcount, qstart, (Vec4<float>*)sorted);
         } else if (qdtype == AMEPB_F32) {
             if (fill) place_points_kernel<float, double, true, false><<<qgrid, 256, 0, stream>>>((const float*)d_query, m, d_plans, qcount, qstart, (Vec4<double>*)sorted);
@@ -1096,11 +1397,11 @@ static int rdf_sub_batch(amepb_ctx* ctx, const RdfCall& c, int64_t f0, int nf, c
         Vec4<float>* ts = reinterpret_cast<Vec4<float>*>(ctx->bufs[BUF_TSORTED].p);
         void* qs = ctx->bufs[BUF_QSORTED].p;
         if (c.coords_dtype == AMEPB_F32) {
-            if (fill) place_self_kernel<float, float, true><<<tgrid, 256, 0, stream>>>((const float*)d_coords, c.n, d_plans, tcount, tstart, ts, qcount, qstart, (Vec4<float>*)qs, qrank);
-            else place_self_kernel<float, float, false><<<tgrid, 256, 0, stream>>>((const float*)d_coords, c.n, d_plans, tcount, tstart, ts, qcount, qstart, (Vec4<float>*)qs, qrank);
+            if (fill) place_self_kernel<float, float, true><<<tgrid, 256, 0, stream>>>((const float*)d_coords, c.n, d_plans, tcount, tstart, ts, qcount, qstart, (Vec4<float>*)qs, qrank, qsoa, qsoa_n);
+            else place_self_kernel<float, float, false><<<tgrid, 256, 0, stream>>>((const float*)d_coords, c.n, d_plans, tcount, tstart, ts, qcount, qstart, (Vec4<float>*)qs, qrank, nullptr, 0);
         } else {
-            if (fill) place_self_kernel<double, double, true><<<tgrid, 256, 0, stream>>>((const double*)d_coords, c.n, d_plans, tcount, tstart, ts, qcount, qstart, (Vec4<double>*)qs, qrank);
-            else place_self_kernel<double, double, false><<<tgrid, 256, 0, stream>>>((const double*)d_coords, c.n, d_plans, tcount, tstart, ts, qcount, qstart, (Vec4<double>*)qs, qrank);
+            if (fill) place_self_kernel<double, double, true><<<tgrid, 256, 0, stream>>>((const double*)d_coords, c.n, d_plans, tcount, tstart, ts, qcount, qstart, (Vec4<double>*)qs, qrank, nullptr, 0);
+            else place_self_kernel<double, double, false><<<tgrid, 256, 0, stream>>>((const double*)d_coords, c.n, d_plans, tcount, tstart, ts, qcount, qstart, (Vec4<double>*)qs, qrank, nullptr, 0);
         }
         AMEPB_LAUNCH_CHECK(ctx);
         return 0;
@@ -1137,12 +1438,18 @@ static int rdf_sub_batch(amepb_ctx* ctx, const RdfCall& c, int64_t f0, int nf, c
     args.nbins = nbins;
     args.nframes = nf;
     args.uniform = uniform ? 1 : 0;
+    args.qsoa = qsoa;
+    args.qsoa_n = qsoa_n;
+    args.one = 1.0f;
+    int zmode = all_zconst ? 2 : 0;
+    for (int f = 0; f < nf && zmode == 2; ++f)
+        if (plans[f].valid && plans[f].dz2c != 0.0) zmode = 1;
     if (sym) {
-        if (!arith_f64) rc = launch_pairs<float, float, true>(ctx, args, all_zconst, stream);
-        else rc = launch_pairs<double, double, true>(ctx, args, all_zconst, stream);
-    } else if (!arith_f64) rc = launch_pairs<float, float, false>(ctx, args, all_zconst, stream);
-    else if (!targets_f64) rc = launch_pairs<double, float, false>(ctx, args, all_zconst, stream);
-    else rc = launch_pairs<double, double, false>(ctx, args, all_zconst, stream);
+        if (!arith_f64) rc = launch_pairs<float, float, true>(ctx, args, zmode, stream);
+        else rc = launch_pairs<double, double, true>(ctx, args, zmode, stream);
+    } else if (!arith_f64) rc = launch_pairs<float, float, false>(ctx, args, zmode, stream);
+    else if (!targets_f64) rc = launch_pairs<double, float, false>(ctx, args, zmode, stream);
+    else rc = launch_pairs<double, double, false>(ctx, args, zmode, stream);
     if (rc) return rc;
     cudaEvent_t ev_p1 = timing_event(ctx, stream);
     if (ev_b1 && ev_p1) ctx->ev_pair.emplace_back(ev_b1, ev_p1);

@@ -83,9 +83,19 @@ class ClockSampler:
             os.close(fd)
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+                 "-lms", "200"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
+
+    def wait_first_sample(self, timeout=5.0):
+        t0 = time.perf_counter()
+        while self.proc is not None and time.perf_counter() - t0 < timeout:
+            try:
+                if os.path.getsize(self.path) > 0:
+                    return
+            except OSError:
+                return
+            time.sleep(0.05)
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
@@ -247,13 +257,16 @@ def run_gpu(args):
         if world > 1:
             dist.all_reduce(table, op=dist.ReduceOp.SUM)
 
+    # nvidia-smi is started (and has written its first sample) before the warm-up, so that its
+    # start-up cost never lands inside the timed region; it then samples warm-up + timed steps.
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        sampler.wait_first_sample()
     for _ in range(args.warmup):
         step()
     barrier()
     launches0 = ctx.kernel_launches()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     pair_ms = build_ms = 0.0
     barrier()
@@ -300,8 +313,11 @@ def run_gpu(args):
     barrier()
     t0 = time.perf_counter()
     e2e_steps = max(2, args.steps)
+    e2e_step_ms = []
     for _ in range(e2e_steps):
+        ts = time.perf_counter()
         _core.rdf_histograms(host_np, box, edges, out=hist_np, device=local)   # returns when hist_np is complete
+        e2e_step_ms.append(round((time.perf_counter() - ts) * 1e3, 3))
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
@@ -369,7 +385,7 @@ def run_gpu(args):
         "e2e": {"value": e2e_value, "unit": "pair-evals/s", "h2d_bytes_per_step": ef * n * 12 * world,
                 "d2h_bytes_per_step": ef * NBINS * 8 * world, "frames_per_gpu": ef,
                 "pinned_h2d_copy_gbs": h2d_gbs,
-                "h2d_floor_ms_per_frame": n * 12 / (h2d_gbs * 1e9) * 1e3},
+                "h2d_floor_ms_per_frame": n * 12 / (h2d_gbs * 1e9) * 1e3, "step_ms": e2e_step_ms},
         "gpu_launches": int(agg[0].item()),
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
         "ms_per_frame": elapsed_ms / args.steps / nf, "pair_kernel_ms_per_frame": pair_ms / args.steps / nf,
