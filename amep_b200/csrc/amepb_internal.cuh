@@ -26,7 +26,6 @@ enum {
     BUF_TSORTED,       // images in cell order
     BUF_QSORTED,       // queries in cell order
     BUF_QRANK,         // rank of each query inside its cell (fused self placement)
-    BUF_QSOA,          // float32 queries in cell order, pair-interleaved (rdf.cu: store_query_pairs)
     BUF_SCAN,          // scan block sums
     BUF_MISC,          // task counter, candidate counter
     BUF_STAGE_A,       // host-space staging: coords

@@ -163,16 +163,6 @@ __device__ __forceinline__ int cell_index(double x, double g0, double inv_h, int
     return min(max(c, 0), n - 1);
 }
 
-// Float32 queries in cell order, laid out for the packed pair arithmetic of the pair kernel:
-// xy[i] = (x[2i], x[2i+1], y[2i], y[2i+1]) for i < n/2, followed by z[0..n).
-__device__ __forceinline__ void store_query_pairs(float* __restrict__ base, long long n, unsigned slot, float x,
-                                                  float y, float z) {
-    float* xy = base + (size_t)(slot >> 1) * 4 + (slot & 1u);
-    xy[0] = x;
-    xy[2] = y;
-    base[2 * n + slot] = z;
-}
-
 // Targets with periodic images.  T: input element type, image storage is
 // float32 (amep/pbc.py:300-302).  FILL=false counts, FILL=true writes.
 template <typename T, bool FILL>
@@ -252,8 +242,7 @@ __global__ void __launch_bounds__(256) place_self_kernel(const T* __restrict__ p
                                                          unsigned* __restrict__ qcount,
                                                          const unsigned* __restrict__ qstart,
                                                          Vec4<AT>* __restrict__ qsorted,
-                                                         unsigned* __restrict__ qrank,
-                                                         float* __restrict__ qsoa, long long qsoa_n) {
+                                                         unsigned* __restrict__ qrank) {
     const int f = blockIdx.y;
     const FramePlan& P = plans[f];
     if (!P.valid) return;
@@ -273,12 +262,7 @@ __global__ void __launch_bounds__(256) place_self_kernel(const T* __restrict__ p
     } else {
         Vec4<AT> o;
         o.x = v[0]; o.y = v[1]; o.z = v[2]; o.w = (AT)0;
-        const unsigned slot = qstart[cc] + qrank[(long long)f * n + i];
-        qsorted[slot] = o;
-        if constexpr (sizeof(AT) == 4)
-            if (qsoa) {
-                store_query_pairs(qsoa, qsoa_n, slot, (float)v[0], (float)v[1], (float)v[2]);
-            }
+        qsorted[qstart[cc] + qrank[(long long)f * n + i]] = o;
     }
     place_images_body<T, FILL>(p, P, tcount, tstart, tsorted);
 }
@@ -291,8 +275,7 @@ __global__ void __launch_bounds__(256) place_points_kernel(const T* __restrict__
                                                            const FramePlan* __restrict__ plans,
                                                            unsigned* __restrict__ count,
                                                            const unsigned* __restrict__ start,
-                                                           Vec4<S>* __restrict__ sorted,
-                                                           float* __restrict__ soa = nullptr, long long soa_n = 0) {
+                                                           Vec4<S>* __restrict__ sorted) {
     const int f = blockIdx.y;
     const FramePlan& P = plans[f];
     if (!P.valid) return;
@@ -318,10 +301,6 @@ __global__ void __launch_bounds__(256) place_points_kernel(const T* __restrict__
         Vec4<S> o;
         o.x = v[0]; o.y = v[1]; o.z = v[2]; o.w = (S)0;
         sorted[slot] = o;
-        if constexpr (sizeof(S) == 4)
-            if (soa) {
-                store_query_pairs(soa, soa_n, slot, (float)v[0], (float)v[1], (float)v[2]);
-            }
     }
 }
 
@@ -508,14 +487,13 @@ struct PairArgs {
     int nbins;
     int nframes;
     int uniform;                    // every edge table is uniform (linspace-like) and fit for the one-comparison binning
-    const float* qsoa;              // float32 regime: queries in cell order, see store_query_pairs
-    long long qsoa_n;               // number of query slots (even)
     float one;                      // 1.0f, opaque to the compiler (see add2_unfused)
 };
 
 // float32 regime: every warp gathers the neighbourhood of its query cell into a shared buffer
 // of kStageCap targets (x[] | y[] (| z[])) and walks it in full 32-lane passes
-constexpr unsigned kStageCap = 256;
+constexpr unsigned kStageCap = 256;   // targets per warp and chunk
+constexpr unsigned kQueryCap = 64;    // queries per warp and chunk
 constexpr unsigned kUnitLimit = 1u << 21;                // flush after 2^31 counted pairs (units of 1024)
 constexpr int kPairThreads = 256;
 
@@ -648,55 +626,32 @@ __host__ __device__ inline size_t pair_thr_bytes(int nbins, size_t at_size) {
 struct FastArgs {
     float inv_w, c_magic, one;
     unsigned kclamp, thr_addr;
-    const float* qsoa;      // float32 regime only
-    long long qsoa_n;
 };
 
-// All queries [qa, qb) of a cell against the lane's target, float32 regime: packed pairs of
-// queries from the pair-interleaved copy (see store_query_pairs); the 16-byte loads need an
-// even query index, so an odd first and an odd last query are done alone.
+// All staged queries of a warp against the lane's target, float32 regime.  The queries sit in
+// shared memory as (x[2i], x[2i+1], y[2i], y[2i+1]) quads (+ z pairs), padded with NaN to an
+// even count nq2: one broadcast LDS.128 feeds two packed pair evaluations.
 template <int ZMODE>
-__device__ __forceinline__ void query_loop_f32(const FastArgs& fa, unsigned qa, unsigned qb, float nx, float ny,
+__device__ __forceinline__ void query_loop_f32(const FastArgs& fa, const float4* __restrict__ sq_xy,
+                                               const f32x2* __restrict__ sq_z, unsigned nq2, float nx, float ny,
                                                float nz, float dz2c, unsigned hist_addr) {
-    const float* __restrict__ sxy = fa.qsoa;
-    const float* __restrict__ sz = fa.qsoa + 2 * fa.qsoa_n;
-    auto single = [&](unsigned qi) {
-        const float* e = sxy + (size_t)(qi >> 1) * 4 + (qi & 1u);
-        Vec4<float> qv;
-        qv.x = __ldg(e); qv.y = __ldg(e + 2); qv.z = ZMODE == 0 ? __ldg(sz + qi) : 0.0f; qv.w = 0.0f;
-        pair_update<float, ZMODE>(qv, nx, ny, nz, dz2c, fa.inv_w, fa.c_magic, fa.kclamp, fa.thr_addr, hist_addr);
-    };
     auto packed = [&](const float4& xy, f32x2 z) {
         pair_update2<ZMODE>(pack2(xy.x, xy.y), pack2(xy.z, xy.w), z, nx, ny, nz, fa.one, dz2c, fa.inv_w, fa.c_magic,
                             fa.kclamp, fa.thr_addr, hist_addr);
     };
-    unsigned q = qa;
-#ifdef AMEPB_DEBUG_NOPACK
-    for (; q < qb; ++q) single(q);
-    return;
-#endif
-    if (q & 1u) {
-        single(q);
-        ++q;
-    }
-    for (; q + 4 <= qb; q += 4) {
-        const float4* pxy = reinterpret_cast<const float4*>(sxy) + (q >> 1);
-        const float4 xy0 = __ldg(pxy), xy1 = __ldg(pxy + 1);
+    unsigned u = 0;  // in pairs of queries
+    const unsigned np = nq2 >> 1;
+    for (; u + 2 <= np; u += 2) {
+        const float4 xy0 = sq_xy[u], xy1 = sq_xy[u + 1];
         f32x2 z0 = 0ull, z1 = 0ull;
         if (ZMODE == 0) {
-            z0 = __ldg(reinterpret_cast<const f32x2*>(sz + q));
-            z1 = __ldg(reinterpret_cast<const f32x2*>(sz + q + 2));
+            z0 = sq_z[u];
+            z1 = sq_z[u + 1];
         }
         packed(xy0, z0);
         packed(xy1, z1);
     }
-    if (q + 2 <= qb) {
-        const float4 xy0 = __ldg(reinterpret_cast<const float4*>(sxy) + (q >> 1));
-        const f32x2 z0 = ZMODE == 0 ? __ldg(reinterpret_cast<const f32x2*>(sz + q)) : 0ull;
-        packed(xy0, z0);
-        q += 2;
-    }
-    if (q < qb) single(q);
+    if (u < np) packed(sq_xy[u], ZMODE == 0 ? sq_z[u] : 0ull);
 }
 
 template <typename AT, typename NT, int ZMODE>
@@ -717,9 +672,7 @@ __device__ __forceinline__ void warp_pairs_fast(const Vec4<AT>* __restrict__ qso
         }
         const unsigned hist_addr = j < split ? hist_lo : hist_hi;
         unsigned q = qa;
-        if constexpr (sizeof(AT) == 4) {
-            query_loop_f32<ZMODE>(fa, qa, qb, nx, ny, nz, dz2c, hist_addr);
-        } else {
+        {
             for (; q + kQueryUnroll <= qb; q += kQueryUnroll) {
                 Vec4<AT> qv[kQueryUnroll];
 #pragma unroll
@@ -755,7 +708,8 @@ __global__ void __launch_bounds__(kPairThreads, 5) pair_kernel(PairArgs a) {
     const int hist_len = (SYM ? 2 : 1) * half_len;
     const unsigned hist_addr = (unsigned)__cvta_generic_to_shared(s_hist);
     const unsigned hist2_addr = hist_addr + 4u * (unsigned)half_len;
-    constexpr int kStageComp = ZMODE == 0 ? 3 : 2;
+    constexpr unsigned kStageComp = ZMODE == 0 ? 3 : 2;
+    constexpr unsigned kStageFloats = (kStageCap + kQueryCap) * kStageComp;  // per warp
     float* s_stage = reinterpret_cast<float*>(smem_raw + pair_thr_bytes(nbins, sizeof(AT)) +
                                               (((size_t)hist_len * sizeof(unsigned) + 15) & ~(size_t)15));
     __shared__ int s_next;
@@ -824,8 +778,6 @@ __global__ void __launch_bounds__(kPairThreads, 5) pair_kernel(PairArgs a) {
         fa.one = a.one;
         fa.kclamp = (unsigned)(nbins + 1);
         fa.thr_addr = (unsigned)__cvta_generic_to_shared(s_thr);
-        fa.qsoa = a.qsoa;
-        fa.qsoa_n = a.qsoa_n;
         unsigned long long* g_hist = a.hist + (long long)f * nbins;
 
         const long long lt = t - P.task_begin;
@@ -838,6 +790,7 @@ __global__ void __launch_bounds__(kPairThreads, 5) pair_kernel(PairArgs a) {
         const int nrows = P.nrows;
         const int row0 = P.row0;
         const unsigned long long direct_pairs = P.direct_pairs;
+        const bool small_ok = direct_pairs >= (unsigned long long)kQueryCap * kStageCap;
         const int n0 = P.n[0], n1 = P.n[1], n2 = P.n[2];
         const unsigned qrow = P.cell_base + (unsigned)((cz * n1 + cy) * n0);
 
@@ -847,25 +800,21 @@ __global__ void __launch_bounds__(kPairThreads, 5) pair_kernel(PairArgs a) {
         // the items of a block task are handed out dynamically, so that a warp with light cells
         // takes more of them instead of waiting at the barrier
         for (int wtk = warp; wtk < ncell * rsplit;
-#ifdef AMEPB_DEBUG_STATIC
-             wtk += (int)(blockDim.x >> 5)) {
-#else
              wtk = __shfl_sync(0xffffffffu, lane == 0 ? atomicAdd(&s_next, 1) : 0, 0)) {
-#endif
             const int part = wtk / ncell;
             const int cx = cx0 + (wtk - part * ncell);
             const unsigned qa = __ldg(&a.qstart[qrow + cx]), qb = __ldg(&a.qstart[qrow + cx + 1]);
             if (qa == qb) continue;
-#ifdef AMEPB_DEBUG_NOSTAGE
-            if constexpr (false) {
-#else
             if constexpr (SMEM && sizeof(AT) == 4) {
-#endif
-                // ---- float32 regime: stage the neighbourhood, then full passes ----------------
-                const unsigned nq = qb - qa;
-                float* bx = s_stage + (size_t)warp * (kStageCap * kStageComp);
+                // ---- float32 regime: stage queries and neighbourhood, then full passes ---------
+                float* wbase = s_stage + (size_t)warp * kStageFloats;
+                float* bx = wbase;               // targets x[] | y[] (| z[])
                 float* by = bx + kStageCap;
-                float* bz = by + kStageCap;  // ZMODE == 0 only
+                float* bz = by + kStageCap;      // ZMODE == 0 only
+                float* sq_xy = wbase + kStageCap * kStageComp;   // queries, see query_loop_f32
+                float* sq_z = sq_xy + 2 * kQueryCap;             // ZMODE == 0 only
+                const Vec4<float>* qarr = reinterpret_cast<const Vec4<float>*>(qsorted);
+                const Vec4<float>* tarr = reinterpret_cast<const Vec4<float>*>(tsorted);
                 // entries: [0] own cell (SYM), [1, G] ghost rows (SYM, if any can be near),
                 // then the real rows (SYM: upper half shell) -- weight-1 entries first
                 int G = 0;
@@ -876,108 +825,138 @@ __global__ void __launch_bounds__(kPairThreads, 5) pair_kernel(PairArgs a) {
                     G = gfree ? 0 : nrows;
                 }
                 const int E = SYM ? 1 + G + (nrows - row0) : nrows;
-                unsigned fill = 0, lo_end = 0;
                 unsigned long long staged = 0, oversize = 0;
-                auto flush_stage = [&]() {
+                for (unsigned qc = qa; qc < qb; qc += kQueryCap) {
+                    const unsigned nqc = min(kQueryCap, qb - qc);
+                    const unsigned nq2 = (nqc + 1u) & ~1u;
                     __syncwarp();
-                    for (unsigned g0 = 0; g0 < fill; g0 += 32) {
-                        const unsigned g = g0 + lane;
-                        float nx = __int_as_float(0x7fc00000), ny = nx, nz = nx;
-                        if (g < fill) {
-                            nx = bx[g];
-                            ny = by[g];
-                            if (ZMODE == 0) nz = bz[g];
-                        }
-                        // (idle lanes hold NaN targets and end up in a dump slot: without a second half
-                        // that must be the first half's)
-                        query_loop_f32<ZMODE>(fa, qa, qb, nx, ny, nz, dz2c,
-                                              (!SYM || g < lo_end) ? hist_addr : hist2_addr);
-                    }
-                    __syncwarp();
-                    fill = 0;
-                    lo_end = 0;
-                };
-                for (int eb = 0; eb < E; eb += 32) {
-                    const int e = eb + lane;
-                    unsigned start = 0, len = 0, flags = 0;  // flags bit 0: counts twice, bit 1: lives in the query array
-                    if (e < E) {
-                        int r = -1;
-                        if (SYM) {
-                            if (e == 0) {
-                                flags = 2;
-                                if (part == 0) {
-                                    start = qa;
-                                    len = nq;
-                                }
-                            } else if (e <= G) {
-                                r = e - 1;
-                                if (r % rsplit != part) r = -1;
+                    for (unsigned i = lane; i < nq2; i += 32) {
+                        float x = __int_as_float(0x7fc00000), y = x, z = x;
+                        if (i < nqc) {
+                            if (ZMODE == 0) {
+                                const Vec4<float> v = load_vec4(qarr + qc + i);
+                                x = v.x; y = v.y; z = v.z;
                             } else {
-                                r = row0 + (e - 1 - G);
-                                flags = 3;
-                                if ((r - row0) % rsplit != part) r = -1;
-                            }
-                        } else {
-                            r = e;
-                            if (r % rsplit != part) r = -1;
-                        }
-                        if (r >= 0) {
-                            const int ny = cy + P.row_oy[r], nz = cz + P.row_oz[r];
-                            if (ny >= 0 && ny < n1 && nz >= 0 && nz < n2) {
-                                const int kx = P.row_kx[r];
-                                int x_lo = max(cx - kx, 0);
-                                const int x_hi = min(cx + kx, n0 - 1);
-                                if (flags == 3 && r == row0) x_lo = cx + 1;  // own row: only the cells to the right
-                                if (x_lo <= x_hi) {
-                                    const unsigned* starts = (flags & 2) ? a.qstart : a.tstart;
-                                    const unsigned trow = P.cell_base + (unsigned)((nz * n1 + ny) * n0);
-                                    start = __ldg(&starts[trow + x_lo]);
-                                    len = __ldg(&starts[trow + x_hi + 1]) - start;
-                                }
+                                const float2 v = __ldg(reinterpret_cast<const float2*>(qarr + qc + i));
+                                x = v.x; y = v.y;
                             }
                         }
+                        float* e = sq_xy + (i >> 1) * 4 + (i & 1u);
+                        e[0] = x;
+                        e[2] = y;
+                        if (ZMODE == 0) sq_z[i] = z;
                     }
-                    unsigned todo = __ballot_sync(0xffffffffu, len != 0);
-                    while (todo) {
-                        const int src = __ffs(todo) - 1;
-                        todo &= todo - 1;
-                        const unsigned st = __shfl_sync(0xffffffffu, start, src), ln = __shfl_sync(0xffffffffu, len, src);
-                        const unsigned fl = __shfl_sync(0xffffffffu, flags, src);
-                        const Vec4<float>* arr = (fl & 2) ? reinterpret_cast<const Vec4<float>*>(qsorted)
-                                                          : reinterpret_cast<const Vec4<float>*>(tsorted);
-                        const unsigned long long npairs = (unsigned long long)nq * ln;
-                        if (npairs > direct_pairs) {  // giant cells: straight to the global histogram
-                            oversize += npairs;
-                            warp_pairs_general<float, float, ZMODE == 0 ? 0 : 1, true>(
-                                reinterpret_cast<const Vec4<float>*>(qsorted), qa, qb, arr, st, st + ln,
-                                reinterpret_cast<const float*>(thr), nbins, (float)dz2c, inv_w, c_magic, (fl & 1) ? 2u : 1u,
-                                s_hist, g_hist);
-                            continue;
+                    unsigned fill = 0, lo_end = 0;
+                    auto flush_stage = [&]() {
+                        __syncwarp();
+                        for (unsigned g0 = 0; g0 < fill; g0 += 32) {
+                            const unsigned g = g0 + lane;
+                            float nx = __int_as_float(0x7fc00000), ny = nx, nz = nx;
+                            if (g < fill) {
+                                nx = bx[g];
+                                ny = by[g];
+                                if (ZMODE == 0) nz = bz[g];
+                            }
+                            // (idle lanes hold NaN targets and end up in a dump slot: without a second
+                            // half that must be the first half's)
+                            query_loop_f32<ZMODE>(fa, reinterpret_cast<const float4*>(sq_xy),
+                                                  reinterpret_cast<const f32x2*>(sq_z), nq2, nx, ny, nz, dz2c,
+                                                  (!SYM || g < lo_end) ? hist_addr : hist2_addr);
                         }
-                        staged += npairs;
-                        unsigned off = 0;
-                        while (off < ln) {
-                            const unsigned n = min(ln - off, kStageCap - fill);
-                            for (unsigned i = lane; i < n; i += 32) {
-                                if (ZMODE == 0) {
-                                    const Vec4<float> v = load_vec4(arr + st + off + i);
-                                    bx[fill + i] = v.x;
-                                    by[fill + i] = v.y;
-                                    bz[fill + i] = v.z;
+                        __syncwarp();
+                        fill = 0;
+                        lo_end = 0;
+                    };
+                    auto copy_targets = [&](const Vec4<float>* src, unsigned n, unsigned at) {
+                        for (unsigned i = lane; i < n; i += 32) {
+                            if (ZMODE == 0) {
+                                const Vec4<float> v = load_vec4(src + i);
+                                bx[at + i] = v.x;
+                                by[at + i] = v.y;
+                                bz[at + i] = v.z;
+                            } else {
+                                const float2 v = __ldg(reinterpret_cast<const float2*>(src + i));
+                                bx[at + i] = v.x;
+                                by[at + i] = v.y;
+                            }
+                        }
+                    };
+                    for (int eb = 0; eb < E; eb += 32) {
+                        const int e = eb + lane;
+                        unsigned start = 0, len = 0, flags = 0;  // flags bit 0: counts twice, bit 1: lives in the query array
+                        if (e < E) {
+                            int r = -1;
+                            if (SYM) {
+                                if (e == 0) {
+                                    flags = 2;
+                                    if (part == 0) {
+                                        start = qa;
+                                        len = qb - qa;
+                                    }
+                                } else if (e <= G) {
+                                    r = e - 1;
+                                    if (r % rsplit != part) r = -1;
                                 } else {
-                                    const float2 v = __ldg(reinterpret_cast<const float2*>(arr + st + off + i));
-                                    bx[fill + i] = v.x;
-                                    by[fill + i] = v.y;
+                                    r = row0 + (e - 1 - G);
+                                    flags = 3;
+                                    if ((r - row0) % rsplit != part) r = -1;
+                                }
+                            } else {
+                                r = e;
+                                if (r % rsplit != part) r = -1;
+                            }
+                            if (r >= 0) {
+                                const int ny = cy + P.row_oy[r], nz = cz + P.row_oz[r];
+                                if (ny >= 0 && ny < n1 && nz >= 0 && nz < n2) {
+                                    const int kx = P.row_kx[r];
+                                    int x_lo = max(cx - kx, 0);
+                                    const int x_hi = min(cx + kx, n0 - 1);
+                                    if (flags == 3 && r == row0) x_lo = cx + 1;  // own row: only the cells to the right
+                                    if (x_lo <= x_hi) {
+                                        const unsigned* starts = (flags & 2) ? a.qstart : a.tstart;
+                                        const unsigned trow = P.cell_base + (unsigned)((nz * n1 + ny) * n0);
+                                        start = __ldg(&starts[trow + x_lo]);
+                                        len = __ldg(&starts[trow + x_hi + 1]) - start;
+                                    }
                                 }
                             }
-                            fill += n;
-                            off += n;
-                            if (!(fl & 1)) lo_end = fill;
-                            if (fill == kStageCap) flush_stage();
+                        }
+                        unsigned todo = __ballot_sync(0xffffffffu, len != 0);
+                        while (todo) {
+                            const int src = __ffs(todo) - 1;
+                            todo &= todo - 1;
+                            const unsigned st = __shfl_sync(0xffffffffu, start, src), ln = __shfl_sync(0xffffffffu, len, src);
+                            const unsigned fl = __shfl_sync(0xffffffffu, flags, src);
+                            const Vec4<float>* arr = ((fl & 2) ? qarr : tarr) + st;
+                            if (fill + ln <= kStageCap && small_ok) {  // the usual case: the row fits
+                                copy_targets(arr, ln, fill);
+                                fill += ln;
+                                if (!(fl & 1)) lo_end = fill;
+                                staged += nqc * ln;   // at most kQueryCap * kStageCap
+                                continue;
+                            }
+                            const unsigned long long npairs = (unsigned long long)nqc * ln;
+                            if (npairs > direct_pairs) {  // giant cells: straight to the global histogram
+                                oversize += npairs;
+                                warp_pairs_general<float, float, ZMODE == 0 ? 0 : 1, true>(
+                                    qarr, qc, qc + nqc, arr, 0u, ln, reinterpret_cast<const float*>(thr), nbins,
+                                    (float)dz2c, inv_w, c_magic, (fl & 1) ? 2u : 1u, s_hist, g_hist);
+                                continue;
+                            }
+                            staged += npairs;
+                            unsigned off = 0;
+                            while (off < ln) {
+                                const unsigned n = min(ln - off, kStageCap - fill);
+                                copy_targets(arr + off, n, fill);
+                                fill += n;
+                                off += n;
+                                if (!(fl & 1)) lo_end = fill;
+                                if (fill == kStageCap) flush_stage();
+                            }
                         }
                     }
+                    if (fill) flush_stage();
                 }
-                if (fill) flush_stage();
                 if (lane == 0) {
                     cand += staged + oversize;
                     if (staged) atomicAdd(&s_units, (unsigned)(staged >> 10) + 1u);
@@ -1141,7 +1120,8 @@ static int launch_pairs(amepb_ctx* ctx, const PairArgs& args, int zmode, cudaStr
     size_t dyn = use_smem ? smem : 16;
     if (use_smem && sizeof(AT) == 4) {
         // per-warp staging buffers of the float32 regime (see kStageCap)
-        dyn = ((dyn + 15) & ~(size_t)15) + (size_t)(kPairThreads / 32) * kStageCap * (zmode == 0 ? 3 : 2) * sizeof(float);
+        dyn = ((dyn + 15) & ~(size_t)15) +
+              (size_t)(kPairThreads / 32) * (kStageCap + kQueryCap) * (zmode == 0 ? 3 : 2) * sizeof(float);
         AMEPB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     }
     int per_sm = 0;
@@ -1343,13 +1323,6 @@ static int rdf_sub_batch(amepb_ctx* ctx, const RdfCall& c, int64_t f0, int nf, c
     AMEPB_CUDA(ctx, cudaMemsetAsync(ctx->bufs[BUF_MISC].p, 0, sizeof(unsigned long long), stream));
 
     // ---- cell build ------------------------------------------------------------
-    // float32 regime: a second, pair-interleaved copy of the cell-sorted queries (store_query_pairs)
-    float* qsoa = nullptr;
-    const long long qsoa_n = ((long long)m * nf + 1) & ~1ll;
-    if (!arith_f64) {
-        if ((rc = ensure_device(ctx, BUF_QSOA, sizeof(float) * 3 * (size_t)qsoa_n))) return rc;
-        qsoa = reinterpret_cast<float*>(ctx->bufs[BUF_QSOA].p);
-    }
     const dim3 tgrid((unsigned)((c.n + 255) / 256), nf), qgrid((unsigned)((m + 255) / 256), nf);
     auto place_targets = [&](bool fill) -> int {
         void* sorted = ctx->bufs[BUF_TSORTED].p;
@@ -1374,7 +1347,7 @@ static int rdf_sub_batch(amepb_ctx* ctx, const RdfCall& c, int64_t f0, int nf, c
     auto place_queries = [&](bool fill) -> int {
         void* sorted = ctx->bufs[BUF_QSORTED].p;
         if (qdtype == AMEPB_F32 && !arith_f64) {
-            if (fill) place_points_kernel<float, float, true, false><<<qgrid, 256, 0, stream>>>((const float*)d_query, m, d_plans, qcount, qstart, (Vec4<float>*)sorted, qsoa, qsoa_n);
+            if (fill) place_points_kernel<float, float, true, false><<<qgrid, 256, 0, stream>>>((const float*)d_query, m, d_plans, qcount, qstart, (Vec4<float>*)sorted);
             else place_points_kernel<float, float, false, false><<<qgrid, 256, 0, stream>>>((const float*)d_query, m, d_plans, qcount, qstart, (Vec4<float>*)sorted);
         } else if (qdtype == AMEPB_F32) {
             if (fill) place_points_kernel<float, double, true, false><<<qgrid, 256, 0, stream>>>((const float*)d_query, m, d_plans, qcount, qstart, (Vec4<double>*)sorted);
@@ -1397,11 +1370,11 @@ static int rdf_sub_batch(amepb_ctx* ctx, const RdfCall& c, int64_t f0, int nf, c
         Vec4<float>* ts = reinterpret_cast<Vec4<float>*>(ctx->bufs[BUF_TSORTED].p);
         void* qs = ctx->bufs[BUF_QSORTED].p;
         if (c.coords_dtype == AMEPB_F32) {
-            if (fill) place_self_kernel<float, float, true><<<tgrid, 256, 0, stream>>>((const float*)d_coords, c.n, d_plans, tcount, tstart, ts, qcount, qstart, (Vec4<float>*)qs, qrank, qsoa, qsoa_n);
-            else place_self_kernel<float, float, false><<<tgrid, 256, 0, stream>>>((const float*)d_coords, c.n, d_plans, tcount, tstart, ts, qcount, qstart, (Vec4<float>*)qs, qrank, nullptr, 0);
+            if (fill) place_self_kernel<float, float, true><<<tgrid, 256, 0, stream>>>((const float*)d_coords, c.n, d_plans, tcount, tstart, ts, qcount, qstart, (Vec4<float>*)qs, qrank);
+            else place_self_kernel<float, float, false><<<tgrid, 256, 0, stream>>>((const float*)d_coords, c.n, d_plans, tcount, tstart, ts, qcount, qstart, (Vec4<float>*)qs, qrank);
         } else {
-            if (fill) place_self_kernel<double, double, true><<<tgrid, 256, 0, stream>>>((const double*)d_coords, c.n, d_plans, tcount, tstart, ts, qcount, qstart, (Vec4<double>*)qs, qrank, nullptr, 0);
-            else place_self_kernel<double, double, false><<<tgrid, 256, 0, stream>>>((const double*)d_coords, c.n, d_plans, tcount, tstart, ts, qcount, qstart, (Vec4<double>*)qs, qrank, nullptr, 0);
+            if (fill) place_self_kernel<double, double, true><<<tgrid, 256, 0, stream>>>((const double*)d_coords, c.n, d_plans, tcount, tstart, ts, qcount, qstart, (Vec4<double>*)qs, qrank);
+            else place_self_kernel<double, double, false><<<tgrid, 256, 0, stream>>>((const double*)d_coords, c.n, d_plans, tcount, tstart, ts, qcount, qstart, (Vec4<double>*)qs, qrank);
         }
         AMEPB_LAUNCH_CHECK(ctx);
         return 0;
@@ -1438,8 +1411,6 @@ static int rdf_sub_batch(amepb_ctx* ctx, const RdfCall& c, int64_t f0, int nf, c
     args.nbins = nbins;
     args.nframes = nf;
     args.uniform = uniform ? 1 : 0;
-    args.qsoa = qsoa;
-    args.qsoa_n = qsoa_n;
     args.one = 1.0f;
     int zmode = all_zconst ? 2 : 0;
     for (int f = 0; f < nf && zmode == 2; ++f)
