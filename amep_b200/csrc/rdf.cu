@@ -496,6 +496,10 @@ constexpr unsigned kStageCap = 256;   // targets per warp and chunk
 constexpr unsigned kQueryCap = 64;    // queries per warp and chunk
 constexpr unsigned kUnitLimit = 1u << 21;                // flush after 2^31 counted pairs (units of 1024)
 constexpr int kPairThreads = 256;
+#ifndef AMEPB_PAIR_BLOCKS
+#define AMEPB_PAIR_BLOCKS 5
+#endif
+constexpr int kPairBlocksPerSM = AMEPB_PAIR_BLOCKS;
 
 // ZMODE 0: three coordinates; 1: every z equal, dz*dz is the per-frame constant dz2c;
 // 2: like 1 with dz2c == 0 (s + 0 == s, the addition is dropped)
@@ -628,30 +632,51 @@ struct FastArgs {
     unsigned kclamp, thr_addr;
 };
 
+// Explicit shared-space accesses (32-bit addresses): the staging buffers are addressed from one
+// per-warp base register instead of generic pointers the compiler keeps re-deriving.
+__device__ __forceinline__ float lds_f32(unsigned addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float4 lds_v4(unsigned addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ f32x2 lds_b64(unsigned addr) {
+    f32x2 v;
+    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_f32(unsigned addr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
 // All staged queries of a warp against the lane's target, float32 regime.  The queries sit in
 // shared memory as (x[2i], x[2i+1], y[2i], y[2i+1]) quads (+ z pairs), padded with NaN to an
 // even count nq2: one broadcast LDS.128 feeds two packed pair evaluations.
 template <int ZMODE>
-__device__ __forceinline__ void query_loop_f32(const FastArgs& fa, const float4* __restrict__ sq_xy,
-                                               const f32x2* __restrict__ sq_z, unsigned nq2, float nx, float ny,
-                                               float nz, float dz2c, unsigned hist_addr) {
+__device__ __forceinline__ void query_loop_f32(const FastArgs& fa, unsigned sq_xy, unsigned sq_z, unsigned nq2,
+                                               float nx, float ny, float nz, float dz2c, unsigned hist_addr) {
     auto packed = [&](const float4& xy, f32x2 z) {
         pair_update2<ZMODE>(pack2(xy.x, xy.y), pack2(xy.z, xy.w), z, nx, ny, nz, fa.one, dz2c, fa.inv_w, fa.c_magic,
                             fa.kclamp, fa.thr_addr, hist_addr);
     };
-    unsigned u = 0;  // in pairs of queries
+    unsigned u = 0;  // in pairs of queries: 16 bytes of sq_xy, 8 bytes of sq_z each
     const unsigned np = nq2 >> 1;
+#pragma unroll 2
     for (; u + 2 <= np; u += 2) {
-        const float4 xy0 = sq_xy[u], xy1 = sq_xy[u + 1];
+        const float4 xy0 = lds_v4(sq_xy + u * 16), xy1 = lds_v4(sq_xy + u * 16 + 16);
         f32x2 z0 = 0ull, z1 = 0ull;
         if (ZMODE == 0) {
-            z0 = sq_z[u];
-            z1 = sq_z[u + 1];
+            z0 = lds_b64(sq_z + u * 8);
+            z1 = lds_b64(sq_z + u * 8 + 8);
         }
         packed(xy0, z0);
         packed(xy1, z1);
     }
-    if (u < np) packed(sq_xy[u], ZMODE == 0 ? sq_z[u] : 0ull);
+    if (u < np) packed(lds_v4(sq_xy + u * 16), ZMODE == 0 ? lds_b64(sq_z + u * 8) : 0ull);
 }
 
 template <typename AT, typename NT, int ZMODE>
@@ -696,7 +721,7 @@ __device__ __forceinline__ void warp_pairs_fast(const Vec4<AT>* __restrict__ qso
 // shifted images ("ghosts", a separate cell-sorted array) are not symmetric in floating point
 // and are evaluated for every ordered (query, ghost) pair.
 template <typename AT, typename NT, int ZMODE, bool SMEM, bool SYM>
-__global__ void __launch_bounds__(kPairThreads, 5) pair_kernel(PairArgs a) {
+__global__ void __launch_bounds__(kPairThreads, kPairBlocksPerSM) pair_kernel(PairArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nbins = a.nbins;
     AT* s_thr = reinterpret_cast<AT*>(smem_raw);  // T[0..nbins+1], see warp_pairs_fast
@@ -710,8 +735,10 @@ __global__ void __launch_bounds__(kPairThreads, 5) pair_kernel(PairArgs a) {
     const unsigned hist2_addr = hist_addr + 4u * (unsigned)half_len;
     constexpr unsigned kStageComp = ZMODE == 0 ? 3 : 2;
     constexpr unsigned kStageFloats = (kStageCap + kQueryCap) * kStageComp;  // per warp
-    float* s_stage = reinterpret_cast<float*>(smem_raw + pair_thr_bytes(nbins, sizeof(AT)) +
-                                              (((size_t)hist_len * sizeof(unsigned) + 15) & ~(size_t)15));
+    // per-warp staging area of the float32 regime, as a shared-space address
+    const unsigned stage_addr = (unsigned)__cvta_generic_to_shared(smem_raw) +
+                                (unsigned)(pair_thr_bytes(nbins, sizeof(AT)) + (((size_t)hist_len * sizeof(unsigned) + 15) & ~(size_t)15)) +
+                                (threadIdx.x >> 5) * (unsigned)(kStageFloats * sizeof(float));
     __shared__ int s_next;
     __shared__ FramePlan s_plan;
     __shared__ long long s_task;
@@ -801,18 +828,17 @@ __global__ void __launch_bounds__(kPairThreads, 5) pair_kernel(PairArgs a) {
         // takes more of them instead of waiting at the barrier
         for (int wtk = warp; wtk < ncell * rsplit;
              wtk = __shfl_sync(0xffffffffu, lane == 0 ? atomicAdd(&s_next, 1) : 0, 0)) {
-            const int part = wtk / ncell;
+            const int part = rsplit == 1 ? 0 : wtk / ncell;
             const int cx = cx0 + (wtk - part * ncell);
             const unsigned qa = __ldg(&a.qstart[qrow + cx]), qb = __ldg(&a.qstart[qrow + cx + 1]);
             if (qa == qb) continue;
             if constexpr (SMEM && sizeof(AT) == 4) {
                 // ---- float32 regime: stage queries and neighbourhood, then full passes ---------
-                float* wbase = s_stage + (size_t)warp * kStageFloats;
-                float* bx = wbase;               // targets x[] | y[] (| z[])
-                float* by = bx + kStageCap;
-                float* bz = by + kStageCap;      // ZMODE == 0 only
-                float* sq_xy = wbase + kStageCap * kStageComp;   // queries, see query_loop_f32
-                float* sq_z = sq_xy + 2 * kQueryCap;             // ZMODE == 0 only
+                const unsigned bx = stage_addr;                     // targets x[] | y[] (| z[])
+                const unsigned by = bx + 4 * kStageCap;
+                const unsigned bz = by + 4 * kStageCap;             // ZMODE == 0 only
+                const unsigned sq_xy = bx + 4 * kStageCap * kStageComp;  // queries, see query_loop_f32
+                const unsigned sq_z = sq_xy + 8 * kQueryCap;        // ZMODE == 0 only
                 const Vec4<float>* qarr = reinterpret_cast<const Vec4<float>*>(qsorted);
                 const Vec4<float>* tarr = reinterpret_cast<const Vec4<float>*>(tsorted);
                 // entries: [0] own cell (SYM), [1, G] ghost rows (SYM, if any can be near),
@@ -830,6 +856,7 @@ __global__ void __launch_bounds__(kPairThreads, 5) pair_kernel(PairArgs a) {
                     const unsigned nqc = min(kQueryCap, qb - qc);
                     const unsigned nq2 = (nqc + 1u) & ~1u;
                     __syncwarp();
+#pragma unroll 1
                     for (unsigned i = lane; i < nq2; i += 32) {
                         float x = __int_as_float(0x7fc00000), y = x, z = x;
                         if (i < nqc) {
@@ -841,10 +868,10 @@ __global__ void __launch_bounds__(kPairThreads, 5) pair_kernel(PairArgs a) {
                                 x = v.x; y = v.y;
                             }
                         }
-                        float* e = sq_xy + (i >> 1) * 4 + (i & 1u);
-                        e[0] = x;
-                        e[2] = y;
-                        if (ZMODE == 0) sq_z[i] = z;
+                        const unsigned e = sq_xy + (i >> 1) * 16 + (i & 1u) * 4;
+                        sts_f32(e, x);
+                        sts_f32(e + 8, y);
+                        if (ZMODE == 0) sts_f32(sq_z + 4 * i, z);
                     }
                     unsigned fill = 0, lo_end = 0;
                     auto flush_stage = [&]() {
@@ -853,14 +880,13 @@ __global__ void __launch_bounds__(kPairThreads, 5) pair_kernel(PairArgs a) {
                             const unsigned g = g0 + lane;
                             float nx = __int_as_float(0x7fc00000), ny = nx, nz = nx;
                             if (g < fill) {
-                                nx = bx[g];
-                                ny = by[g];
-                                if (ZMODE == 0) nz = bz[g];
+                                nx = lds_f32(bx + 4 * g);
+                                ny = lds_f32(by + 4 * g);
+                                if (ZMODE == 0) nz = lds_f32(bz + 4 * g);
                             }
                             // (idle lanes hold NaN targets and end up in a dump slot: without a second
                             // half that must be the first half's)
-                            query_loop_f32<ZMODE>(fa, reinterpret_cast<const float4*>(sq_xy),
-                                                  reinterpret_cast<const f32x2*>(sq_z), nq2, nx, ny, nz, dz2c,
+                            query_loop_f32<ZMODE>(fa, sq_xy, sq_z, nq2, nx, ny, nz, dz2c,
                                                   (!SYM || g < lo_end) ? hist_addr : hist2_addr);
                         }
                         __syncwarp();
@@ -868,16 +894,18 @@ __global__ void __launch_bounds__(kPairThreads, 5) pair_kernel(PairArgs a) {
                         lo_end = 0;
                     };
                     auto copy_targets = [&](const Vec4<float>* src, unsigned n, unsigned at) {
+#pragma unroll 1
                         for (unsigned i = lane; i < n; i += 32) {
+                            const unsigned o = 4 * (at + i);
                             if (ZMODE == 0) {
                                 const Vec4<float> v = load_vec4(src + i);
-                                bx[at + i] = v.x;
-                                by[at + i] = v.y;
-                                bz[at + i] = v.z;
+                                sts_f32(bx + o, v.x);
+                                sts_f32(by + o, v.y);
+                                sts_f32(bz + o, v.z);
                             } else {
                                 const float2 v = __ldg(reinterpret_cast<const float2*>(src + i));
-                                bx[at + i] = v.x;
-                                by[at + i] = v.y;
+                                sts_f32(bx + o, v.x);
+                                sts_f32(by + o, v.y);
                             }
                         }
                     };
@@ -895,15 +923,15 @@ __global__ void __launch_bounds__(kPairThreads, 5) pair_kernel(PairArgs a) {
                                     }
                                 } else if (e <= G) {
                                     r = e - 1;
-                                    if (r % rsplit != part) r = -1;
+                                    if (rsplit > 1 && r % rsplit != part) r = -1;
                                 } else {
                                     r = row0 + (e - 1 - G);
                                     flags = 3;
-                                    if ((r - row0) % rsplit != part) r = -1;
+                                    if (rsplit > 1 && (r - row0) % rsplit != part) r = -1;
                                 }
                             } else {
                                 r = e;
-                                if (r % rsplit != part) r = -1;
+                                if (rsplit > 1 && r % rsplit != part) r = -1;
                             }
                             if (r >= 0) {
                                 const int ny = cy + P.row_oy[r], nz = cz + P.row_oz[r];
