@@ -163,33 +163,63 @@ __device__ __forceinline__ int cell_index(double x, double g0, double inv_h, int
     return min(max(c, 0), n - 1);
 }
 
+// The placement kernels read the head of their frame's plan (everything before the neighbour
+// row tables) from shared memory.
+constexpr int kPlanHeadWords = (int)(offsetof(FramePlan, row_oy) / sizeof(int));
+__device__ __forceinline__ const FramePlan& stage_plan_head(const FramePlan* __restrict__ plans, int f, int* s_words) {
+    const int* src = reinterpret_cast<const int*>(plans + f);
+    for (int k = threadIdx.x; k < kPlanHeadWords; k += blockDim.x) s_words[k] = src[k];
+    __syncthreads();
+    return *reinterpret_cast<const FramePlan*>(s_words);
+}
+
 // Targets with periodic images.  T: input element type, image storage is
 // float32 (amep/pbc.py:300-302).  FILL=false counts, FILL=true writes.
+// An image is kept iff it passes the strict window of pbc_points and lies in the grid
+// region; both tests are folded into one closed float32 interval per dimension
+// (FramePlan::keep_lo/hi).  Most particles have no shifted image in the region: they take
+// the short path (nothing at all in the symmetric mode, where the unshifted image is the query).
 template <typename T, bool FILL>
 __device__ __forceinline__ void place_images_body(const T* __restrict__ p, const FramePlan& P,
                                                   unsigned* __restrict__ count,
                                                   const unsigned* __restrict__ start,
                                                   Vec4<float>* __restrict__ sorted) {
     float img[3][3];
-    int cell[3][3];
     bool ok[3][3];
+    bool any_shift = false;
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
         const float b = (float)p[d];  // .astype(np.float32): round to nearest even
         const float len = P.shift[d];
+        const float lo = P.keep_lo[d], hi = P.keep_hi[d];
+        const bool shifted = P.nshift[d] == 3;
 #pragma unroll
         for (int v = 0; v < 3; ++v) {
             // v = 0: no shift, 1: -L, 2: +L.  base + v*box in float32 (amep/pbc.py:326)
             const float vf = (v == 0) ? 0.0f : (v == 1 ? -1.0f : 1.0f);
             const float x = __fadd_rn(b, __fmul_rn(vf, len));
-            const double xd = (double)x;
             img[d][v] = x;
-            bool keep = (v == 0) || (P.nshift[d] == 3);
-            keep = keep && (xd < P.win_hi[d]) && (xd > P.win_lo[d]);    // strict window
-            keep = keep && (xd >= P.reg_lo[d]) && (xd <= P.reg_hi[d]);  // grid region
-            ok[d][v] = keep;
-            cell[d][v] = cell_index(xd, P.g0[d], P.inv_h[d], P.n[d]);
+            ok[d][v] = (v == 0 || shifted) && x >= lo && x <= hi;
+            if (v) any_shift = any_shift || ok[d][v];
         }
+    }
+    auto place = [&](int vx, int vy, int vz) {
+        const int cx = cell_index((double)img[0][vx], P.g0[0], P.inv_h[0], P.n[0]);
+        const int cy = cell_index((double)img[1][vy], P.g0[1], P.inv_h[1], P.n[1]);
+        const int cz = cell_index((double)img[2][vz], P.g0[2], P.inv_h[2], P.n[2]);
+        const unsigned c = P.cell_base + (unsigned)((cz * P.n[1] + cy) * P.n[0] + cx);
+        if (!FILL) {
+            atomicAdd(&count[c], 1u);
+        } else {
+            const unsigned slot = start[c] + atomicSub(&count[c], 1u) - 1u;
+            Vec4<float> o;
+            o.x = img[0][vx]; o.y = img[1][vy]; o.z = img[2][vz]; o.w = 0.0f;
+            sorted[slot] = o;
+        }
+    };
+    if (!any_shift) {
+        if (!P.sym && ok[0][0] && ok[1][0] && ok[2][0]) place(0, 0, 0);
+        return;
     }
 #pragma unroll
     for (int vz = 0; vz < 3; ++vz) {
@@ -201,16 +231,7 @@ __device__ __forceinline__ void place_images_body(const T* __restrict__ p, const
             for (int vx = 0; vx < 3; ++vx) {
                 if (!ok[0][vx]) continue;
                 if (P.sym && (vx | vy | vz) == 0) continue;  // the unshifted image is the query itself
-                const unsigned c = P.cell_base +
-                                   (unsigned)((cell[2][vz] * P.n[1] + cell[1][vy]) * P.n[0] + cell[0][vx]);
-                if (!FILL) {
-                    atomicAdd(&count[c], 1u);
-                } else {
-                    const unsigned slot = start[c] + atomicSub(&count[c], 1u) - 1u;
-                    Vec4<float> o;
-                    o.x = img[0][vx]; o.y = img[1][vy]; o.z = img[2][vz]; o.w = 0.0f;
-                    sorted[slot] = o;
-                }
+                place(vx, vy, vz);
             }
         }
     }
@@ -223,8 +244,9 @@ __global__ void __launch_bounds__(256) place_images_kernel(const T* __restrict__
                                                            const unsigned* __restrict__ start,
                                                            Vec4<float>* __restrict__ sorted) {
     const int f = blockIdx.y;
-    const FramePlan& P = plans[f];
-    if (!P.valid) return;
+    if (!plans[f].valid) return;
+    __shared__ int s_words[kPlanHeadWords];
+    const FramePlan& P = stage_plan_head(plans, f, s_words);
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     place_images_body<T, FILL>(pts + ((long long)f * n + i) * 3, P, count, start, sorted);
@@ -244,8 +266,9 @@ __global__ void __launch_bounds__(256) place_self_kernel(const T* __restrict__ p
                                                          Vec4<AT>* __restrict__ qsorted,
                                                          unsigned* __restrict__ qrank) {
     const int f = blockIdx.y;
-    const FramePlan& P = plans[f];
-    if (!P.valid) return;
+    if (!plans[f].valid) return;
+    __shared__ int s_words[kPlanHeadWords];
+    const FramePlan& P = stage_plan_head(plans, f, s_words);
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const T* p = pts + ((long long)f * n + i) * 3;
@@ -277,8 +300,9 @@ __global__ void __launch_bounds__(256) place_points_kernel(const T* __restrict__
                                                            const unsigned* __restrict__ start,
                                                            Vec4<S>* __restrict__ sorted) {
     const int f = blockIdx.y;
-    const FramePlan& P = plans[f];
-    if (!P.valid) return;
+    if (!plans[f].valid) return;
+    __shared__ int s_words[kPlanHeadWords];
+    const FramePlan& P = stage_plan_head(plans, f, s_words);
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const T* p = pts + ((long long)f * n + i) * 3;

@@ -110,6 +110,8 @@ struct FramePlan {
     double win_hi[3];
     double reg_lo[3];  // grid region, inclusive: only images inside are kept
     double reg_hi[3];
+    float keep_lo[3];  // window and region as one closed float32 interval: a float32 image x is
+    float keep_hi[3];  // kept iff keep_lo <= x <= keep_hi (same decisions as the four tests above)
     double dz2c;       // constant dz*dz term of the z-constant kernels
     double bin_e0;     // first edge and 1/width for the bin guess
     double bin_inv_w;
@@ -140,6 +142,27 @@ struct FramePlan {
     signed char row_kx[kMaxRows];
     char pad_[1];
 };
+
+// Smallest float32 f with f >= b (strict: f > b) / largest with f <= b (strict: f < b), as
+// decided in float64 -- turns a float64 comparison of a float32 value into a float32 one.
+inline float float_above(double b, bool strict) {
+    if (b != b) return std::numeric_limits<float>::quiet_NaN();
+    float f = (float)b;
+    while (strict ? !((double)f > b) : !((double)f >= b)) {
+        if (f == std::numeric_limits<float>::infinity()) return std::numeric_limits<float>::quiet_NaN();
+        f = nextafterf(f, INFINITY);
+    }
+    return f;
+}
+inline float float_below(double b, bool strict) {
+    if (b != b) return std::numeric_limits<float>::quiet_NaN();
+    float f = (float)b;
+    while (strict ? !((double)f < b) : !((double)f <= b)) {
+        if (f == -std::numeric_limits<float>::infinity()) return std::numeric_limits<float>::quiet_NaN();
+        f = nextafterf(f, -INFINITY);
+    }
+    return f;
+}
 
 struct PlanInputs {
     const double* box_boundary;  // [3][2] float64 values
@@ -225,6 +248,8 @@ inline bool plan_frame(const PlanInputs& in, int dim, const FrameStats& tgt, con
         P.reg_lo[d] = lo;
         P.reg_hi[d] = hi;
         ext[d] = hi - lo;
+        P.keep_lo[d] = std::max(float_above(P.win_lo[d], true), float_above(lo, false));
+        P.keep_hi[d] = std::min(float_below(P.win_hi[d], true), float_below(hi, false));
     }
 
     // expected number of images in the region (uniform-density estimate)
