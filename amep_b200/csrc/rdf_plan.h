@@ -173,6 +173,7 @@ struct PlanInputs {
     int64_t n_queries;
     int cells_per_cutoff;        // 0 = automatic
     int64_t max_cells;           // upper bound on cells for one frame
+    double task_pairs = 262144.0;  // candidate pairs aimed at per block task
 };
 
 // Image window of pbc_points(width=0.5): (centre - L32, centre + L32), with
@@ -357,7 +358,7 @@ inline bool plan_frame(const PlanInputs& in, int dim, const FrameStats& tgt, con
     // A block task is `run` consecutive query cells; its 8 warps each take one cell (run a
     // multiple of 8) or, for heavy cells, a strided 1/rsplit share of the cell's neighbour rows.
     // Aim at ~2.6e5 candidate pairs per block task.
-    int run = (int)std::min<double>(64.0, std::max(1.0, floor(262144.0 / pairs_per_cell + 0.5)));
+    int run = (int)std::min<double>(256.0, std::max(1.0, floor(in.task_pairs / pairs_per_cell + 0.5)));
     int rsplit = 1;
     if (run >= 8) run = (run / 8) * 8;
     else if (run >= 4) { run = 4; rsplit = 2; }

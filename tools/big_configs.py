@@ -7,7 +7,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from amep_b200 import _core, _lib
 ctx = _lib.context(0); ctx.set_timing(True)
-def timed(c, box, edges, reps=2):
+def timed(c, box, edges, reps=3):
     _core.rdf_histograms(c, box, edges); torch.cuda.synchronize()
     best = 1e9
     for _ in range(reps):
@@ -16,6 +16,24 @@ def timed(c, box, edges, reps=2):
         best = min(best, e0.elapsed_time(e1))
     return hist, best
 g = torch.Generator(device="cuda").manual_seed(3)
+# cfg2 (ii): 2D "ABP-like" clustered, N = 1M, half of the particles in 100 Gaussian blobs (sigma 20), half uniform
+n = 1_000_000; L = float(np.sqrt(n / 0.6366)); nf = 8
+edges = np.linspace(0, 10.0, 501); box = np.array([[0, L], [0, L], [-0.5, 0.5]], dtype=np.float32)
+c = torch.zeros((nf, n, 3), device="cuda", dtype=torch.float32)
+centres = torch.rand((nf, 100, 2), generator=g, device="cuda", dtype=torch.float64) * L
+which = torch.randint(0, 100, (nf, n // 2), generator=g, device="cuda")
+blob = torch.gather(centres, 1, which[..., None].expand(-1, -1, 2)) + torch.randn((nf, n // 2, 2), generator=g, device="cuda", dtype=torch.float64) * 20.0
+c[:, : n // 2, :2] = torch.remainder(blob, L).float()
+c[:, n // 2 :, :2] = (torch.rand((nf, n - n // 2, 2), generator=g, device="cuda", dtype=torch.float64) * L).float()
+del blob, which, centres
+torch.cuda.empty_cache()
+hist, ms = timed(c, box, edges)
+info = ctx.rdf_info(); tot = int(hist.sum().item())
+ctx.set_symmetric(False); h2, ms2 = timed(c[:2], box, edges, reps=1); ctx.set_symmetric(True)
+print(json.dumps(dict(case="cfg2ii_2d_clustered_1M_8frames", ms_per_frame=ms / nf, pairs=tot, pairs_per_s=tot / ms * 1e3,
+                      pair_ms_per_frame=info["pair_kernel_ms"] / nf, build_ms_per_frame=info["build_ms"] / nf, k=info["cells_per_cutoff"],
+                      candidates=info["candidate_pairs"], symmetric_equals_ordered=bool(torch.equal(hist[:2], h2)))), flush=True)
+del c
 # cfg5: 3D uniform rho = 0.8, N = 2^24
 n = 1 << 24; L = float((n / 0.8) ** (1 / 3))
 c = torch.rand((1, n, 3), generator=g, device="cuda", dtype=torch.float32) * L
