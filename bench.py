@@ -351,7 +351,7 @@ def run_gpu(args):
     achieved = pairs_local * args.steps * FLOPS_PER_PAIR_2D / (pair_ms * 1e-3) / 1e12 if pair_ms > 0 else 0.0
     roofline = {
         "bound": "fp32",
-        "kernel": "amepb::pair_kernel<float,float,zconst,smem>",
+        "kernel": "amepb::pair_kernel<float,float,2,true,true> (float32 regime, z constant, shared tables, symmetric walk)",
         "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
         "peak_source": "tools/microbench.cu on this pool's B200 (profiles/microbench_r01.json): FP32 FMUL+FADD "
                        "(non-fused, the bit-exact path may not contract) instruction throughput; "
