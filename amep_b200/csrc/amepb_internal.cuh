@@ -47,6 +47,10 @@ struct amepb_ctx {
     void* pinned = nullptr;  // pinned host scratch (plans, stats read-back)
     size_t pinned_cap = 0;
     amepb_rdf_info rdf_info;
+    // last threshold table built on the host (rdf.cu): edges it belongs to, arithmetic type, values
+    std::vector<double> thr_cache_edges;
+    std::vector<char> thr_cache_values;
+    int thr_cache_f64 = -1;
     int rdf_k_override = 0;
     bool rdf_symmetric = true;
     void* last_stream = nullptr;

@@ -1342,8 +1342,21 @@ static int rdf_sub_batch(amepb_ctx* ctx, const RdfCall& c, int64_t f0, int nf, c
             if (!(fabs(edges[i] - (edges[0] + i * w)) <= 0.01 * w)) uniform = false;
         // pairs below the first counted distance (d <= 1e-3 or d < edges[0]) must round to guess 0
         if (!(w > 0) || !((std::max(1e-3, edges[0]) - edges[0]) / w < 0.45)) uniform = false;
-        if (arith_f64) make_thresholds<double>(edges, nbins, reinterpret_cast<double*>(hthr) + (size_t)tb * (nbins + 1));
-        else make_thresholds<float>(edges, nbins, reinterpret_cast<float*>(hthr) + (size_t)tb * (nbins + 1));
+        // the exact thresholds cost ~0.1 ms of host time per table: reuse the last table when the
+        // edges are the same (every sub-batch of a call, every frame with the same box)
+        char* dst = hthr + (size_t)tb * (nbins + 1) * at_size;
+        const size_t tbytes = (size_t)(nbins + 1) * at_size;
+        const bool hit = ctx->thr_cache_f64 == (arith_f64 ? 1 : 0) && ctx->thr_cache_edges.size() == (size_t)nbins + 1 &&
+                         memcmp(ctx->thr_cache_edges.data(), edges, sizeof(double) * (nbins + 1)) == 0;
+        if (hit) {
+            memcpy(dst, ctx->thr_cache_values.data(), tbytes);
+        } else {
+            if (arith_f64) make_thresholds<double>(edges, nbins, reinterpret_cast<double*>(dst));
+            else make_thresholds<float>(edges, nbins, reinterpret_cast<float*>(dst));
+            ctx->thr_cache_edges.assign(edges, edges + nbins + 1);
+            ctx->thr_cache_values.assign(dst, dst + tbytes);
+            ctx->thr_cache_f64 = arith_f64 ? 1 : 0;
+        }
     }
     {
         const long long pw = (long long)(plan_bytes / sizeof(int)), tw = (long long)((thr_bytes + 3) / sizeof(int));
@@ -1613,10 +1626,22 @@ int amepb_rdf_batch(amepb_ctx* ctx, const void* coords, int coords_dtype, int64_
     } else {
         // Host buffers: double-buffered staging.  The copy of sub-batch i+1 runs on the
         // context's copy stream while sub-batch i is computed on the caller's stream.
-        size_t stage_target = (size_t)192 << 20;
+        size_t stage_target = (size_t)384 << 20;
         if (const char* env = getenv("AMEPB_STAGE_MB")) stage_target = (size_t)std::max(1, atoi(env)) << 20;
         fb = std::min<int64_t>(fb, std::max<int64_t>(1, (int64_t)(stage_target / std::max<size_t>(1, cbytes + obytes))));
-        const int64_t nsub = (nframes + fb - 1) / fb;
+        // sub-batches grow from fb/8 to fb frames: the first copy (not overlapped with anything)
+        // stays short, the later sub-batches amortise their fixed costs (plan, launches)
+        std::vector<std::pair<int64_t, int>> subs;
+        {
+            int64_t f0 = 0, sz = std::max<int64_t>(1, fb / 8);
+            while (f0 < nframes) {
+                const int nf = (int)std::min<int64_t>(sz, nframes - f0);
+                subs.emplace_back(f0, nf);
+                f0 += nf;
+                sz = std::min<int64_t>(fb, sz * 2);
+            }
+        }
+        const int64_t nsub = (int64_t)subs.size();
         int rc = ensure_device(ctx, BUF_STAGE_A, 2 * cbytes * fb);
         if (rc) return rc;
         if (other && (rc = ensure_device(ctx, BUF_STAGE_B, 2 * obytes * fb))) return rc;
@@ -1633,8 +1658,8 @@ int amepb_rdf_batch(amepb_ctx* ctx, const void* coords, int coords_dtype, int64_
         unsigned long long* d_hist = reinterpret_cast<unsigned long long*>(ctx->bufs[BUF_STAGE_OUT].p);
         auto enqueue_copy = [&](int64_t i) -> int {
             const int b = (int)(i & 1);
-            const int64_t f0 = i * fb;
-            const int nf = (int)std::min<int64_t>(fb, nframes - f0);
+            const int64_t f0 = subs[i].first;
+            const int nf = subs[i].second;
             if (i >= 2) AMEPB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_computed[b], 0));
             cudaEvent_t ec0 = timing_event(ctx, ctx->copy_stream);
             AMEPB_CUDA(ctx, cudaMemcpyAsync(stage_a + (size_t)b * cbytes * fb, (const char*)coords + (size_t)f0 * cbytes,
@@ -1659,8 +1684,8 @@ int amepb_rdf_batch(amepb_ctx* ctx, const void* coords, int coords_dtype, int64_
         };
         for (int64_t i = 0; i < nsub; ++i) {
             const int b = (int)(i & 1);
-            const int64_t f0 = i * fb;
-            const int nf = (int)std::min<int64_t>(fb, nframes - f0);
+            const int64_t f0 = subs[i].first;
+            const int nf = subs[i].second;
             const double t0 = now_ms();
             if (i + 1 < nsub && (rc = enqueue_copy(i + 1))) return rc;
             if (trace) fprintf(stderr, "[amepb] sub %lld: enqueue_copy took %.3f ms (host)\n", (long long)i, now_ms() - t0);

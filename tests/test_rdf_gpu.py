@@ -151,6 +151,42 @@ def test_grid_refinement_does_not_change_counts(sc, k):
     np.testing.assert_array_equal(counts3[0], want3)
 
 
+@pytest.mark.parametrize("sym", [True, False])
+def test_dense_cells_query_rounds_and_filter_boundary(sc, sym):
+    """Cells with several hundred particles (k = 1): more than one round of 64 staged queries per
+    cell, neighbour rows longer than the 256-target staging buffer; plus pairs just below and
+    just above the d > 1e-3 filter, with bins narrow enough that the filter sits at 0.4 bin
+    widths (the limit of the dump-slot binning is 0.45; beyond it the general kernel runs)."""
+    from amep_b200 import _lib
+    rng = np.random.default_rng(21)
+    box = np.array([[0, 40], [0, 40], [-0.5, 0.5]], dtype=np.float32)
+    c = _uniform(rng, 8000, box.astype(np.float64), np.float32)
+    c[:, 2] = 0
+    for j, d in enumerate((2e-4, 9e-4, 0.99e-3, 1.01e-3, 1.1e-3, 2.4e-3, 2.6e-3)):   # close partners along x
+        c[4000 + j, :2] = c[j, :2] + np.float32([d, 0])
+    ctx = _lib.context(0)
+    ctx.set_symmetric(sym)
+    try:
+        for k, rmax, nbins in ((1, 8.0, 160), (2, 8.0, 160), (0, 1.25, 500), (0, 1.0, 500)):
+            want, _ = corc.rdf_counts(c, box, rmax=rmax, nbins=nbins)
+            ctx.set_cells_per_cutoff(k)
+            _, _, counts = sc.rdf_frames(c, box, rmax=rmax, nbins=nbins, return_counts=True)
+            np.testing.assert_array_equal(counts[0], want, err_msg=f"k={k} rmax={rmax} nbins={nbins}")
+    finally:
+        ctx.set_cells_per_cutoff(0)
+        ctx.set_symmetric(True)
+    # 3D, dense: 27 rows of ~190 targets per cell at k = 1
+    box3 = np.array([[0, 12], [0, 12], [0, 12]], dtype=np.float32)
+    c3 = _uniform(rng, 6000, box3.astype(np.float64), np.float32)
+    want3, _ = corc.rdf_counts(c3, box3, rmax=4.0, nbins=100)
+    ctx.set_cells_per_cutoff(1)
+    try:
+        _, _, counts3 = sc.rdf_frames(c3, box3, rmax=4.0, nbins=100, return_counts=True)
+    finally:
+        ctx.set_cells_per_cutoff(0)
+    np.testing.assert_array_equal(counts3[0], want3)
+
+
 @pytest.mark.parametrize("case", [c for c in CASES if c[4] is None and (c[2] is np.float32 or not c[6].get("pbc", True))],
                          ids=lambda c: c[0])
 def test_symmetric_and_ordered_evaluation_agree(sc, case):
