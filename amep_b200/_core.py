@@ -255,6 +255,45 @@ def sq_debye(coords, other, q, twod, device=None):
     return out
 
 
+def density_counts(coords, box_boundary, xedges, yedges, pbc=True, device=None):
+    """Particle counts on the grid of ``amep.continuum.hde`` (amepb_density_counts): int32
+    ``[F, ny, nx]`` (a CUDA tensor if the coordinates live on the device, else NumPy).
+
+    ``xedges`` / ``yedges``: the reference's ``np.arange`` bin edges (any float dtype; widened to
+    float64 exactly)."""
+    pc = coords if isinstance(coords, Particles) else Particles(coords)
+    nf = pc.nframes
+    box, box_code = box_array(box_boundary, nf)
+    xe = np.ascontiguousarray(np.asarray(xedges), dtype=np.float64)
+    ye = np.ascontiguousarray(np.asarray(yedges), dtype=np.float64)
+    if xe.ndim != 1 or ye.ndim != 1 or len(xe) < 2 or len(ye) < 2:
+        raise ValueError("bin edges must be one-dimensional with at least two entries")
+    dev_index = _device_of(pc, device)
+    ctx = _lib.context(dev_index)
+    shape = (nf, len(ye) - 1, len(xe) - 1)
+    if pc.on_device:
+        import torch
+        out = torch.empty(shape, dtype=torch.int32, device=pc.tensor.device)
+        optr, space = out.data_ptr(), _lib.DEVICE
+    else:
+        out = np.empty(shape, dtype=np.int32)
+        optr, space = out.ctypes.data, _lib.HOST
+    if nf == 0 or pc.n == 0:
+        if pc.on_device:
+            out.zero_()
+        else:
+            out[...] = 0
+        return out
+    rc = ctx.lib.amepb_density_counts(
+        ctx.handle, ctypes.c_void_p(pc.ptr()), pc.dtype, pc.n, space, nf,
+        box.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), box_code, 1 if pbc else 0,
+        xe.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), len(xe),
+        ye.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), len(ye),
+        ctypes.c_void_p(optr), _stream_for(dev_index, pc.on_device))
+    ctx.check(rc, "amepb_density_counts")
+    return out
+
+
 def sf2d_modes(coords, qpos, nq, accum="c64", chunksize=0, device=None):
     """rho(q) on the sf2d grid (amepb_sf2d_modes) -> complex array ``[F, 2nq, 2nq]``.
 

@@ -1226,6 +1226,13 @@ static int rdf_sub_batch(amepb_ctx* ctx, const RdfCall& c, int64_t f0, int nf, c
     AMEPB_CUDA(ctx, cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * (size_t)nf * nbins, stream));
 
     // ---- stats -> plans ------------------------------------------------------
+    static const bool trace_host = getenv("AMEPB_TRACE") != nullptr;
+    auto host_ms = []() {
+        timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+    };
+    const double th0 = trace_host ? host_ms() : 0.0;
     cudaEvent_t ev_b0 = timing_event(ctx, stream);
     std::vector<FrameStats> tstats, qstats;
     int rc = frame_stats(ctx, d_coords, c.coords_dtype, c.n, nf, tstats, stream, 0);
@@ -1234,6 +1241,7 @@ static int rdf_sub_batch(amepb_ctx* ctx, const RdfCall& c, int64_t f0, int nf, c
         rc = frame_stats(ctx, d_other, c.other_dtype, c.m, nf, qstats, stream, 1);
         if (rc) return rc;
     }
+    const double th1 = trace_host ? host_ms() : 0.0;
     std::vector<FramePlan> plans(nf);
     long long total_cells = 0, total_tasks = 0, total_cap = 0;
     bool all_zconst = true;
@@ -1320,6 +1328,7 @@ static int rdf_sub_batch(amepb_ctx* ctx, const RdfCall& c, int64_t f0, int nf, c
     if (total_cells >= (1ll << 31) || total_cap >= (1ll << 32) || (long long)m * nf >= (1ll << 32))
         return fail(ctx, AMEPB_E_NOMEM, "amepb_rdf_batch: sub-batch too large for 32-bit cell offsets");
 
+    const double th2 = trace_host ? host_ms() : 0.0;
     // ---- thresholds ------------------------------------------------------------
     const int ntables = c.edges_stride ? nf : 1;
     const size_t at_size = arith_f64 ? 8 : 4;
@@ -1492,6 +1501,9 @@ static int rdf_sub_batch(amepb_ctx* ctx, const RdfCall& c, int64_t f0, int nf, c
     if (ev_b1 && ev_p1) ctx->ev_pair.emplace_back(ev_b1, ev_p1);
 
     ctx->rdf_info.cells_per_cutoff = k_used;
+    if (trace_host)
+        fprintf(stderr, "[amepb] host: %d frames: stats+sync %.3f ms, plan %.3f ms, thresholds+launches %.3f ms\n", nf,
+                th1 - th0, th2 - th1, host_ms() - th2);
     return 0;
 }
 

@@ -20,7 +20,7 @@ import logging
 import numpy as np
 
 from . import _core
-from .utils import (available_cpu_count, optimal_chunksize, runningmean,
+from .utils import (available_cpu_count, optimal_chunksize, runningmean, sq_from_sf2d,
                     unit_vector_2D, unit_vector_3D)
 
 _log = logging.getLogger("amep_b200.spatialcor")
@@ -172,9 +172,21 @@ def sfiso_frames(coords, box_boundary, N=None, qmax=20.0, twod=True, mode="std",
         _log.warning("Mode 'fft' does only work for 2d systems. Since twod is False, mode 'std' is used.")
         mode = "std"
     if mode == "fft":
-        raise NotImplementedError(
-            "amep_b200.spatialcor.sfiso: mode 'fft' is not on the B200 hot path yet "
-            "(SURVEY.md section 8f, a next row). Use mode='fast' or mode='std'.")
+        # amep/spatialcor.py:1667-1685: radial average of sf2d(mode='fft')
+        # (the reference overwrites its argument N with len(other_coords), amep/spatialcor.py:1579-1581)
+        S2d, Kx, Ky = sf2d_frames(pc, bb, None if po is pc else po, qmax=qmax, mode="fft",
+                                  Ntot=po.n, accuracy=accuracy)
+        s_rows, q_rows = [], []
+        for f in range(nf):
+            b = bb[f] if per_frame_box else bb
+            dq = 2 * np.pi / np.max(b[:, 1] - b[:, 0])
+            S, q = sq_from_sf2d(S2d[f], Kx[f], Ky[f])
+            keep = (q < qmax) & (q >= dq)
+            s_rows.append(S[keep])
+            q_rows.append(q[keep])
+        if any(len(q) != len(q_rows[0]) for q in q_rows):
+            raise ValueError("sfiso_frames: the box changes the number of q values between frames")
+        return np.stack(s_rows), np.stack(q_rows)
     # q grid per frame (amep/spatialcor.py:1592-1598)
     q_rows, dq_rows = [], []
     for f in range(nf if per_frame_box else 1):
@@ -251,6 +263,83 @@ def _sf2d_chunksize(n, n_other, chunksize, njobs):
     return chunksize
 
 
+
+def _frame_slice(p, f):
+    """Frame ``f`` of a Particles batch as a one-frame batch (no copy)."""
+    return _core.Particles(p.tensor[f:f + 1] if p.on_device else p.array[f:f + 1])
+
+
+def _sf2d_fft_frames(pc, po, same, bb, qmax, Ntot, accuracy):
+    """``sf2d(mode='fft')`` (amep/spatialcor.py:1911-1940): histogram density estimate of the
+    particles (amep/continuum.py:51-139, 300-407; no periodic images: ``hde`` is called with its
+    default ``pbc=False``), 2D FFT, ``S = Re(F_a F_b*)`` with the reference's normalisation
+    (amep/continuum.py:250-281), cropped to ``|q| <= qmax``.
+
+    The integer counts come from ``amepb_density_counts`` (exact ``np.histogram2d`` semantics), the
+    FFT is cuFFT through ``torch.fft`` (library code, like the reference's ``scipy.fft``), the small
+    array arithmetic around it repeats the reference's NumPy expressions one by one."""
+    import torch
+    nf = pc.nframes
+    per_frame_box = bb.ndim == 3
+    dmin = 2 * np.pi / 2 / qmax / (accuracy * 10)
+    dev = pc.tensor.device if pc.on_device else torch.device("cuda", _core._device_of(pc, None))
+    rows = []
+    counts_a = counts_b = None
+    if not per_frame_box:
+        xe = np.arange(bb[0, 0] - 0.5 * dmin, bb[0, 1] + dmin, dmin)
+        ye = np.arange(bb[1, 0] - 0.5 * dmin, bb[1, 1] + dmin, dmin)
+        counts_a = _core.density_counts(pc, bb, xe, ye, pbc=False)
+        counts_b = counts_a if same else _core.density_counts(po, bb, xe, ye, pbc=False)
+    for f in range(nf):
+        b = bb[f] if per_frame_box else bb
+        if per_frame_box:
+            xe = np.arange(b[0, 0] - 0.5 * dmin, b[0, 1] + dmin, dmin)
+            ye = np.arange(b[1, 0] - 0.5 * dmin, b[1, 1] + dmin, dmin)
+            ca = _core.density_counts(_frame_slice(pc, f), b, xe, ye, pbc=False)[0]
+            cb = ca if same else _core.density_counts(_frame_slice(po, f), b, xe, ye, pbc=False)[0]
+        else:
+            ca, cb = counts_a[f], counts_b[f]
+        ca_t = ca if _core._is_torch(ca) else torch.from_numpy(ca).to(dev)
+        cb_t = ca_t if same else (cb if _core._is_torch(cb) else torch.from_numpy(cb).to(dev))
+        # density fields (amep/continuum.py:400-402).  Their sums are taken by NumPy on the host,
+        # on arrays with the reference's memory layout (the transposed view of an [nx, ny]
+        # histogram): int(sum*dx*dy) below truncates a float that sits within rounding of an
+        # integer, so even the order of the pairwise summation has to be the reference's
+        def field(c_t):
+            return np.ascontiguousarray(c_t.cpu().numpy().T).astype(np.float64).T / dmin ** 2
+        d_host = field(ca_t)
+        do_host = d_host if same else field(cb_t)
+        rx, ry = runningmean(xe, 2), runningmean(ye, 2)
+        dx, dy = rx[1] - rx[0], ry[1] - ry[0]
+        sum_a, sum_b = np.sum(d_host), np.sum(do_host)
+        Ni, Nj = int(sum_a * dx * dy), int(sum_b * dx * dy)
+        # FFT of the densities (amep/continuum.py:262-266, norm='backward')
+        fa = torch.fft.fftshift(torch.fft.fft2(ca_t.to(torch.float64) / dmin ** 2))
+        fb = fa if same else torch.fft.fftshift(torch.fft.fft2(cb_t.to(torch.float64) / dmin ** 2))
+        S = torch.real(fa * fb.conj())
+        if Ntot is not None:
+            S = S / float(sum_a) / float(sum_b) * Ni * Nj / Ntot
+        S = S.cpu().numpy()
+        qx = np.fft.fftshift(np.fft.fftfreq(S.shape[0], d=dx)) * 2 * np.pi
+        qy = np.fft.fftshift(np.fft.fftfreq(S.shape[1], d=dy)) * 2 * np.pi
+        Qx, Qy = np.meshgrid(qx, qy)
+        i0, j0 = np.where((Qx == 0.0) & (Qy == 0.0))
+        S[i0, j0] = 0
+        if np.max(Qx) > qmax or np.max(Qy) > qmax:
+            # only the q values in [-qmax, qmax] (amep/spatialcor.py:1922-1935)
+            dqx = Qx[0, 1] - Qx[0, 0]
+            dqy = Qy[1, 0] - Qy[0, 0]
+            nqx, nqy = len(np.arange(dqx, qmax, dqx)), len(np.arange(dqy, qmax, dqy))
+            mask = (np.abs(Qx) <= qmax) & (np.abs(Qy) <= qmax)
+            sx, sy = int(2 * nqx + 1), int(2 * nqy + 1)
+            S, Qx, Qy = S[mask].reshape(sx, sy), Qx[mask].reshape(sx, sy), Qy[mask].reshape(sx, sy)
+        S[S.shape[0] // 2, S.shape[0] // 2] = 0
+        rows.append((S, Qx, Qy))
+    if any(r[0].shape != rows[0][0].shape for r in rows):
+        raise ValueError("sf2d_frames: the box changes the grid between frames")
+    return (np.stack([r[0] for r in rows]), np.stack([r[1] for r in rows]), np.stack([r[2] for r in rows]))
+
+
 def sf2d_frames(coords, box_boundary, other_coords=None, qmax=20.0, njobs=1, mode="std", Ntot=None,
                 accuracy=0.1, chunksize=None, accum="c64", reduce=None, return_modes=False):
     """``sf2d`` for a batch of frames -> ``(S [F, ny, nx], Qx [F, ny, nx], Qy [F, ny, nx])``.
@@ -272,9 +361,7 @@ def sf2d_frames(coords, box_boundary, other_coords=None, qmax=20.0, njobs=1, mod
     if mode not in ["std", "fft"]:
         raise ValueError(f"Mode '{mode}' not available. Available modes are {['std', 'fft']}.")
     if mode == "fft":
-        raise NotImplementedError(
-            "amep_b200.spatialcor.sf2d: mode 'fft' is not on the B200 hot path yet "
-            "(SURVEY.md section 8f, a next row); use mode='std'.")
+        return _sf2d_fft_frames(pc, po, same, bb, qmax, Ntot, accuracy)
     # q axis per frame (amep/spatialcor.py:1849-1857)
     q_rows = []
     for f in range(nf if per_frame_box else 1):

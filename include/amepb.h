@@ -16,6 +16,8 @@
  *   amepb_sq_debye         <- amep/spatialcor.py:1324-1399  __sf_iso_chunk_std
  *   amepb_sf2d_modes       <- amep/spatialcor.py:1690-1719  __sf2d_chunk_std
  *                             amep/spatialcor.py:1876-1907  chunk fan-out + sum
+ *   amepb_density_counts   <- amep/continuum.py:300-407     hde (np.histogram2d of the images),
+ *                             reached by sf2d/sfiso(mode='fft'), amep/spatialcor.py:1911-1940
  *
  * Conventions
  *   - plain C types only; no exceptions cross the boundary;
@@ -172,6 +174,22 @@ int amepb_sq_debye(amepb_ctx* ctx, const void* coords, int dtype, int64_t n,
                    int space, int64_t nframes,
                    const double* q, int64_t q_stride, int32_t nq, int twod,
                    double* out, void* stream);
+
+/*
+ * Particle counts on the grid of the histogram density estimate used by sf2d(mode='fft')
+ * (amep/continuum.py:300-407 hde, called through coords_to_density by amep/spatialcor.py:1918-1920):
+ * periodic images as pbc_points(width=0.5, enforce_nd=2) when pbc != 0 (float32 images, strict
+ * window, amep/pbc.py:270-338), binned like np.histogram2d with explicit edges (bin i holds
+ * edges[i] <= v < edges[i+1], the last bin also its right edge; NaN and outside values dropped).
+ *   xedges, yedges  host float64, strictly increasing, shared by all frames (np.arange values)
+ *   counts          [nframes][nye-1][nxe-1] uint32 in `space` (y-major: the transposed histogram
+ *                   the reference divides by delta**2)
+ * The call returns after the work is complete (it synchronises `stream`).
+ */
+int amepb_density_counts(amepb_ctx* ctx, const void* coords, int dtype, int64_t n, int space,
+                         int64_t nframes, const double* box_boundary, int box_dtype, int pbc,
+                         const double* xedges, int32_t nxe, const double* yedges, int32_t nye,
+                         uint32_t* counts, void* stream);
 
 /*
  * Density modes on the sf2d grid: rho[f][iy][ix] = sum_i exp(-i (qx[ix] x_i + qy[iy] y_i))

@@ -70,6 +70,27 @@ def test_sfiso_fast_bit_exact(name):
     np.testing.assert_array_equal(s, z["S"])
 
 
+FFT_CASES = ["sf2d_fft_f32.npz", "sf2d_fft_f64_cross.npz", "sf2d_fft_f32_offset.npz", "sf2d_fft_lammps_last_f32.npz"]
+
+
+@pytest.mark.parametrize("name", FFT_CASES)
+def test_fft_mode_bit_exact(name):
+    """sf2d / sfiso with mode='fft': density histogram, FFT, normalisation, crop, radial average."""
+    z = _load(name)
+    other = z["other"] if "other" in z.files else None
+    ntot = None if int(z["ntot"]) < 0 else int(z["ntot"])
+    qmax, acc = float(z["qmax"]), float(z["accuracy"])
+    counts, _, _ = orc.density_counts(z["coords"], z["box"], 2 * np.pi / 2 / qmax / (acc * 10))
+    np.testing.assert_array_equal(counts, z["counts"])
+    S, Qx, Qy = orc.sf2d_fft(z["coords"], z["box"], other, qmax, ntot, acc)
+    np.testing.assert_array_equal(S, z["S"])
+    np.testing.assert_array_equal(Qx, z["Qx"])
+    np.testing.assert_array_equal(Qy, z["Qy"])
+    si, qi = orc.sfiso_fft(z["coords"], z["box"], len(z["coords"]), qmax, other, acc)
+    np.testing.assert_array_equal(si, z["S_iso"])
+    np.testing.assert_array_equal(qi, z["q_iso"])
+
+
 @pytest.mark.parametrize("name", ["sfiso_std_2d_f64.npz", "sfiso_std_3d_cross_f32.npz"])
 def test_sfiso_std_debye_bit_exact(name):
     z = _load(name)

@@ -81,8 +81,10 @@ def test_sfiso_modes_and_errors(sc):
     s1, _ = sc.sfiso(c, box, 200, qmax=5.0, twod=True, mode="bogus", num=8)
     s2, _ = sc.sfiso(c, box, 200, qmax=5.0, twod=True, mode="fast", num=8)
     np.testing.assert_array_equal(s1, s2)
-    with pytest.raises(NotImplementedError):
-        sc.sfiso(c, box, 200, qmax=5.0, twod=True, mode="fft")
+    # mode 'fft' needs a 2D system; with twod=False the reference switches to 'std' (:1607-1612)
+    s3, _ = sc.sfiso(c, box, 200, qmax=5.0, twod=False, mode="fft")
+    s4, _ = sc.sfiso(c, box, 200, qmax=5.0, twod=False, mode="std")
+    np.testing.assert_array_equal(s3, s4)
 
 
 @pytest.mark.parametrize("space", ["host", "device"])
@@ -185,6 +187,59 @@ def test_sf2d_square_lattice_bragg_peaks(sc):
         for j in (nq - m, peak):
             off[i, j] = 0
     assert np.max(np.abs(off)) < 1e-9 * m * m + 1e-6
+
+
+FFT_CASES = ["sf2d_fft_f32.npz", "sf2d_fft_f64_cross.npz", "sf2d_fft_f32_offset.npz", "sf2d_fft_lammps_last_f32.npz"]
+
+
+@pytest.mark.parametrize("space", ["host", "device"])
+@pytest.mark.parametrize("name", FFT_CASES)
+def test_fft_mode_golden(sc, name, space):
+    """sf2d / sfiso(mode='fft'): the counts of the density histogram are integers and must be
+    equal; S differs from the reference only by cuFFT vs pocketfft rounding (1e-6 relative)."""
+    from amep_b200 import _core
+    z = np.load(os.path.join(GOLDEN, name))
+    coords, other = z["coords"], (z["other"] if "other" in z.files else None)
+    ntot = None if int(z["ntot"]) < 0 else int(z["ntot"])
+    qmax, acc = float(z["qmax"]), float(z["accuracy"])
+    if space == "device":
+        coords = torch.from_numpy(coords).cuda()
+        other = None if other is None else torch.from_numpy(other).cuda()
+    dmin = 2 * np.pi / 2 / qmax / (acc * 10)
+    _, xe, ye = orc.density_counts(z["coords"], z["box"], dmin)
+    counts = _core.density_counts(coords, z["box"], xe, ye, pbc=False)
+    counts = counts.cpu().numpy() if torch.is_tensor(counts) else counts
+    np.testing.assert_array_equal(counts[0], z["counts"])
+    S, Qx, Qy = sc.sf2d(coords, z["box"], other_coords=other, qmax=qmax, mode="fft", accuracy=acc, Ntot=ntot)
+    np.testing.assert_array_equal(Qx, z["Qx"])
+    np.testing.assert_array_equal(Qy, z["Qy"])
+    _close(S, z["S"], rtol=1e-6, atol_scale=1e-9)
+    si, qi = sc.sfiso(coords, z["box"], len(z["coords"]), qmax=qmax, twod=True, mode="fft", accuracy=acc,
+                      other_coords=other)
+    np.testing.assert_array_equal(qi, z["q_iso"])
+    _close(si, z["S_iso"], rtol=1e-6, atol_scale=1e-9)
+
+
+def test_density_counts_periodic_images_and_edges(sc):
+    """amepb_density_counts with pbc: the images of pbc_points(enforce_nd=2) binned like
+    np.histogram2d (the hde(pbc=True) variant, amep/continuum.py:377-402), float32 and float64."""
+    from amep_b200 import _core
+    rng = np.random.default_rng(41)
+    for dtype in (np.float32, np.float64):
+        box = np.array([[-3, 9], [0, 12], [-0.5, 0.5]], dtype=dtype)
+        c = np.zeros((4000, 3), dtype=dtype)
+        c[:, :2] = rng.uniform([-3, 0], [9, 12], (4000, 2)).astype(dtype)
+        c[0, :2] = (-3, 0)
+        c[1, :2] = (9, 12)
+        xe = np.arange(box[0, 0] - 0.5 * 0.37, box[0, 1] + 0.37, 0.37)
+        ye = np.arange(box[1, 0] - 0.5 * 0.37, box[1, 1] + 0.37, 0.37)
+        img = orc.periodic_images(c, box)                       # 2D: z is constant
+        want = np.histogram2d(img[:, 0], img[:, 1], [xe, ye])[0].T.astype(np.int64)
+        got = _core.density_counts(c, box, xe, ye, pbc=True)
+        np.testing.assert_array_equal(got[0], want)
+        got = _core.density_counts(torch.from_numpy(c).cuda(), box, xe, ye, pbc=True)
+        np.testing.assert_array_equal(got[0].cpu().numpy(), want)
+        assert want.sum() > len(c)                              # images in the margin bins
 
 
 def test_evaluate_sfiso_and_sf2d(sc):
