@@ -677,6 +677,13 @@ __device__ __forceinline__ void sts_f32(unsigned addr, float v) {
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
 
+// float <-> int with the same ordering (for REDUX min/max over a warp)
+__device__ __forceinline__ int float_order(float f) {
+    const int b = __float_as_int(f);
+    return b ^ ((b >> 31) & 0x7fffffff);
+}
+__device__ __forceinline__ float order_float(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
+
 // All staged queries of a warp against the lane's target, float32 regime.  The queries sit in
 // shared memory as (x[2i], x[2i+1], y[2i], y[2i+1]) quads (+ z pairs), padded with NaN to an
 // even count nq2: one broadcast LDS.128 feeds two packed pair evaluations.
@@ -760,9 +767,12 @@ __global__ void __launch_bounds__(kPairThreads, kPairBlocksPerSM) pair_kernel(Pa
     constexpr unsigned kStageComp = ZMODE == 0 ? 3 : 2;
     constexpr unsigned kStageFloats = (kStageCap + kQueryCap) * kStageComp;  // per warp
     // per-warp staging area of the float32 regime, as a shared-space address
-    const unsigned stage_addr = (unsigned)__cvta_generic_to_shared(smem_raw) +
-                                (unsigned)(pair_thr_bytes(nbins, sizeof(AT)) + (((size_t)hist_len * sizeof(unsigned) + 15) & ~(size_t)15)) +
-                                (threadIdx.x >> 5) * (unsigned)(kStageFloats * sizeof(float));
+    unsigned stage_addr = (unsigned)__cvta_generic_to_shared(smem_raw) +
+                          (unsigned)(pair_thr_bytes(nbins, sizeof(AT)) + (((size_t)hist_len * sizeof(unsigned) + 15) & ~(size_t)15)) +
+                          (threadIdx.x >> 5) * (unsigned)(kStageFloats * sizeof(float));
+    // opaque to the compiler: under the 48-register cap it would otherwise re-derive this address
+    // (a dozen instructions) inside the gather loops instead of keeping or spilling one value
+    asm volatile("mov.u32 %0, %0;" : "+r"(stage_addr));
     __shared__ int s_next;
     __shared__ FramePlan s_plan;
     __shared__ long long s_task;
@@ -842,6 +852,8 @@ __global__ void __launch_bounds__(kPairThreads, kPairBlocksPerSM) pair_kernel(Pa
         const int row0 = P.row0;
         const unsigned long long direct_pairs = P.direct_pairs;
         const bool small_ok = direct_pairs >= (unsigned long long)kQueryCap * kStageCap;
+        // squared cutoff of the target culling (float32 regime), less the constant dz*dz of flat frames
+        const float cull_r2 = P.cull_r2 - (ZMODE == 1 ? (float)P.dz2c : 0.0f);
         const int n0 = P.n[0], n1 = P.n[1], n2 = P.n[2];
         const unsigned qrow = P.cell_base + (unsigned)((cz * n1 + cy) * n0);
 
@@ -880,6 +892,9 @@ __global__ void __launch_bounds__(kPairThreads, kPairBlocksPerSM) pair_kernel(Pa
                     const unsigned nqc = min(kQueryCap, qb - qc);
                     const unsigned nq2 = (nqc + 1u) & ~1u;
                     __syncwarp();
+                    // bounding box of the staged queries (NaN coordinates never pair and are left out)
+                    const float finf = __int_as_float(0x7f800000);
+                    float lo[3] = {finf, finf, finf}, hi[3] = {-finf, -finf, -finf};
 #pragma unroll 1
                     for (unsigned i = lane; i < nq2; i += 32) {
                         float x = __int_as_float(0x7fc00000), y = x, z = x;
@@ -891,11 +906,19 @@ __global__ void __launch_bounds__(kPairThreads, kPairBlocksPerSM) pair_kernel(Pa
                                 const float2 v = __ldg(reinterpret_cast<const float2*>(qarr + qc + i));
                                 x = v.x; y = v.y;
                             }
+                            if (x == x) { lo[0] = fminf(lo[0], x); hi[0] = fmaxf(hi[0], x); }
+                            if (y == y) { lo[1] = fminf(lo[1], y); hi[1] = fmaxf(hi[1], y); }
+                            if (ZMODE == 0 && z == z) { lo[2] = fminf(lo[2], z); hi[2] = fmaxf(hi[2], z); }
                         }
                         const unsigned e = sq_xy + (i >> 1) * 16 + (i & 1u) * 4;
                         sts_f32(e, x);
                         sts_f32(e + 8, y);
                         if (ZMODE == 0) sts_f32(sq_z + 4 * i, z);
+                    }
+#pragma unroll
+                    for (int d = 0; d < (ZMODE == 0 ? 3 : 2); ++d) {
+                        lo[d] = order_float(__reduce_min_sync(0xffffffffu, float_order(lo[d])));
+                        hi[d] = order_float(__reduce_max_sync(0xffffffffu, float_order(hi[d])));
                     }
                     unsigned fill = 0, lo_end = 0;
                     auto flush_stage = [&]() {
@@ -917,21 +940,45 @@ __global__ void __launch_bounds__(kPairThreads, kPairBlocksPerSM) pair_kernel(Pa
                         fill = 0;
                         lo_end = 0;
                     };
-                    auto copy_targets = [&](const Vec4<float>* src, unsigned n, unsigned at) {
+                    // Gather n targets into the staging buffer behind position `at`, dropping those
+                    // farther than the cutoff from the box around the staged queries: no query of this
+                    // round can reach them (cull_r2 carries a 1e-4 relative margin, far above the
+                    // float32 rounding of either side).  Returns the new fill level.
+                    auto copy_targets = [&](const Vec4<float>* src, unsigned n, unsigned at, bool cull) -> unsigned {
 #pragma unroll 1
-                        for (unsigned i = lane; i < n; i += 32) {
-                            const unsigned o = 4 * (at + i);
-                            if (ZMODE == 0) {
-                                const Vec4<float> v = load_vec4(src + i);
-                                sts_f32(bx + o, v.x);
-                                sts_f32(by + o, v.y);
-                                sts_f32(bz + o, v.z);
-                            } else {
-                                const float2 v = __ldg(reinterpret_cast<const float2*>(src + i));
-                                sts_f32(bx + o, v.x);
-                                sts_f32(by + o, v.y);
+                        for (unsigned base = 0; base < n; base += 32) {
+                            const unsigned i = base + lane;
+                            float x = 0.f, y = 0.f, z = 0.f;
+                            bool keep = i < n;
+                            if (keep) {
+                                if (ZMODE == 0) {
+                                    const Vec4<float> v = load_vec4(src + i);
+                                    x = v.x; y = v.y; z = v.z;
+                                } else {
+                                    const float2 v = __ldg(reinterpret_cast<const float2*>(src + i));
+                                    x = v.x; y = v.y;
+                                }
+                                if (cull) {
+                                    const float ex = fmaxf(fmaxf(lo[0] - x, x - hi[0]), 0.f);
+                                    const float ey = fmaxf(fmaxf(lo[1] - y, y - hi[1]), 0.f);
+                                    float d2 = ex * ex + ey * ey;
+                                    if (ZMODE == 0) {
+                                        const float ez = fmaxf(fmaxf(lo[2] - z, z - hi[2]), 0.f);
+                                        d2 += ez * ez;
+                                    }
+                                    keep = d2 <= cull_r2;   // false for NaN targets as well
+                                }
                             }
+                            const unsigned m = __ballot_sync(0xffffffffu, keep);
+                            if (keep) {
+                                const unsigned o = 4 * (at + __popc(m & ((1u << lane) - 1u)));
+                                sts_f32(bx + o, x);
+                                sts_f32(by + o, y);
+                                if (ZMODE == 0) sts_f32(bz + o, z);
+                            }
+                            at += __popc(m);
                         }
+                        return at;
                     };
                     for (int eb = 0; eb < E; eb += 32) {
                         const int e = eb + lane;
@@ -980,11 +1027,12 @@ __global__ void __launch_bounds__(kPairThreads, kPairBlocksPerSM) pair_kernel(Pa
                             const unsigned st = __shfl_sync(0xffffffffu, start, src), ln = __shfl_sync(0xffffffffu, len, src);
                             const unsigned fl = __shfl_sync(0xffffffffu, flags, src);
                             const Vec4<float>* arr = ((fl & 2) ? qarr : tarr) + st;
+                            const bool cull = fl != 2;   // the own cell holds the queries themselves
                             if (fill + ln <= kStageCap && small_ok) {  // the usual case: the row fits
-                                copy_targets(arr, ln, fill);
-                                fill += ln;
+                                const unsigned before = fill;
+                                fill = copy_targets(arr, ln, fill, cull);
                                 if (!(fl & 1)) lo_end = fill;
-                                staged += nqc * ln;   // at most kQueryCap * kStageCap
+                                staged += nqc * (fill - before);   // at most kQueryCap * kStageCap
                                 continue;
                             }
                             const unsigned long long npairs = (unsigned long long)nqc * ln;
@@ -995,12 +1043,12 @@ __global__ void __launch_bounds__(kPairThreads, kPairBlocksPerSM) pair_kernel(Pa
                                     (float)dz2c, inv_w, c_magic, (fl & 1) ? 2u : 1u, s_hist, g_hist);
                                 continue;
                             }
-                            staged += npairs;
                             unsigned off = 0;
                             while (off < ln) {
                                 const unsigned n = min(ln - off, kStageCap - fill);
-                                copy_targets(arr + off, n, fill);
-                                fill += n;
+                                const unsigned before = fill;
+                                fill = copy_targets(arr + off, n, fill, cull);
+                                staged += (unsigned long long)nqc * (fill - before);
                                 off += n;
                                 if (!(fl & 1)) lo_end = fill;
                                 if (fill == kStageCap) flush_stage();

@@ -118,6 +118,7 @@ struct FramePlan {
     long long task_begin;  // first block task of this frame
     long long ntasks;
     float shift[3];        // float32 box lengths (amep/pbc.py:300)
+    float cull_r2;         // (largest edge)^2 with a 1e-4 margin: targets farther than this from a query box are skipped
     int n[3];              // cells per dimension
     int nshift[3];         // 3 where images are shifted along the dimension, else 1
     int cq_lo[3];          // query cell range
@@ -370,6 +371,7 @@ inline bool plan_frame(const PlanInputs& in, int dim, const FrameStats& tgt, con
     }
     P.run = run;
     P.rsplit = rsplit;
+    P.cull_r2 = (float)(rc * rc * (1.0 + 1e-4)) * (1.0f + 1e-6f);
     // 32-bit shared-memory counters: a block task has at most run * (2*nrows + 1) warp tasks
     // (rows, the split own row, the ghost pass); warp tasks with more pairs than direct_pairs
     // bypass the shared histogram, so a block task adds fewer than 2^31 increments and the
