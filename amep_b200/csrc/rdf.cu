@@ -762,7 +762,11 @@ __global__ void __launch_bounds__(kPairThreads, kPairBlocksPerSM) pair_kernel(Pa
     // A half has nbins + 2 slots: bin b in slot b + 1, slots 0 and nbins + 1 are dump slots.
     const int half_len = nbins + 2;
     const int hist_len = (SYM ? 2 : 1) * half_len;
-    const unsigned hist_addr = (unsigned)__cvta_generic_to_shared(s_hist);
+    unsigned hist_addr = (unsigned)__cvta_generic_to_shared(s_hist);
+    unsigned thr_base_addr = (unsigned)__cvta_generic_to_shared(s_thr);
+    // (opaque values, see stage_addr below)
+    asm volatile("mov.u32 %0, %0;" : "+r"(hist_addr));
+    asm volatile("mov.u32 %0, %0;" : "+r"(thr_base_addr));
     const unsigned hist2_addr = hist_addr + 4u * (unsigned)half_len;
     constexpr unsigned kStageComp = ZMODE == 0 ? 3 : 2;
     constexpr unsigned kStageFloats = (kStageCap + kQueryCap) * kStageComp;  // per warp
@@ -838,7 +842,7 @@ __global__ void __launch_bounds__(kPairThreads, kPairBlocksPerSM) pair_kernel(Pa
         fa.c_magic = c_magic;
         fa.one = a.one;
         fa.kclamp = (unsigned)(nbins + 1);
-        fa.thr_addr = (unsigned)__cvta_generic_to_shared(s_thr);
+        fa.thr_addr = thr_base_addr;
         unsigned long long* g_hist = a.hist + (long long)f * nbins;
 
         const long long lt = t - P.task_begin;
