@@ -57,8 +57,9 @@ struct amepb_ctx {
     bool sq_attr_harm = false;
     cudaStream_t copy_stream = nullptr;   // host-space staging
     cudaStream_t compute_stream = nullptr; // host-space calls made on the NULL stream
-    cudaEvent_t ev_copied[2] = {nullptr, nullptr};
-    cudaEvent_t ev_computed[2] = {nullptr, nullptr};
+    static constexpr int kStageBuffers = 3;   // host-buffer path: staging buffers in flight
+    cudaEvent_t ev_copied[kStageBuffers] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_computed[kStageBuffers] = {nullptr, nullptr, nullptr};
     bool timing = false;
     std::vector<cudaEvent_t> ev_pool;     // reusable events
     size_t ev_used = 0;

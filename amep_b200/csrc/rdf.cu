@@ -1688,8 +1688,9 @@ int amepb_rdf_batch(amepb_ctx* ctx, const void* coords, int coords_dtype, int64_
             if (rc) return rc;
         }
     } else {
-        // Host buffers: double-buffered staging.  The copy of sub-batch i+1 runs on the
-        // context's copy stream while sub-batch i is computed on the caller's stream.
+        // Host buffers: staging through kStageBuffers device buffers.  The copies of the next two
+        // sub-batches run on the context's copy stream while sub-batch i is computed on the
+        // caller's stream; the extra buffer absorbs the jitter of the host link on shared hosts.
         size_t stage_target = (size_t)384 << 20;
         if (const char* env = getenv("AMEPB_STAGE_MB")) stage_target = (size_t)std::max(1, atoi(env)) << 20;
         fb = std::min<int64_t>(fb, std::max<int64_t>(1, (int64_t)(stage_target / std::max<size_t>(1, cbytes + obytes))));
@@ -1706,13 +1707,14 @@ int amepb_rdf_batch(amepb_ctx* ctx, const void* coords, int coords_dtype, int64_
             }
         }
         const int64_t nsub = (int64_t)subs.size();
-        int rc = ensure_device(ctx, BUF_STAGE_A, 2 * cbytes * fb);
+        constexpr int NB = amepb_ctx::kStageBuffers;
+        int rc = ensure_device(ctx, BUF_STAGE_A, NB * cbytes * fb);
         if (rc) return rc;
-        if (other && (rc = ensure_device(ctx, BUF_STAGE_B, 2 * obytes * fb))) return rc;
+        if (other && (rc = ensure_device(ctx, BUF_STAGE_B, NB * obytes * fb))) return rc;
         if ((rc = ensure_device(ctx, BUF_STAGE_OUT, sizeof(unsigned long long) * (size_t)nframes * nbins))) return rc;
         if (!ctx->copy_stream) {
             AMEPB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-            for (int b = 0; b < 2; ++b) {
+            for (int b = 0; b < NB; ++b) {
                 AMEPB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_copied[b], cudaEventDisableTiming));
                 AMEPB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_computed[b], cudaEventDisableTiming));
             }
@@ -1721,10 +1723,10 @@ int amepb_rdf_batch(amepb_ctx* ctx, const void* coords, int coords_dtype, int64_
         char* stage_b = other ? reinterpret_cast<char*>(ctx->bufs[BUF_STAGE_B].p) : nullptr;
         unsigned long long* d_hist = reinterpret_cast<unsigned long long*>(ctx->bufs[BUF_STAGE_OUT].p);
         auto enqueue_copy = [&](int64_t i) -> int {
-            const int b = (int)(i & 1);
+            const int b = (int)(i % NB);
             const int64_t f0 = subs[i].first;
             const int nf = subs[i].second;
-            if (i >= 2) AMEPB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_computed[b], 0));
+            if (i >= NB) AMEPB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_computed[b], 0));
             cudaEvent_t ec0 = timing_event(ctx, ctx->copy_stream);
             AMEPB_CUDA(ctx, cudaMemcpyAsync(stage_a + (size_t)b * cbytes * fb, (const char*)coords + (size_t)f0 * cbytes,
                                             cbytes * nf, cudaMemcpyHostToDevice, ctx->copy_stream));
@@ -1739,7 +1741,8 @@ int amepb_rdf_batch(amepb_ctx* ctx, const void* coords, int coords_dtype, int64_
         // the copy stream must not start before work already queued on the caller's stream
         // could still be reading the staging buffers of an earlier call
         AMEPB_CUDA(ctx, cudaStreamSynchronize(c.stream));
-        if ((rc = enqueue_copy(0))) return rc;
+        for (int64_t i = 0; i < std::min<int64_t>(NB - 1, nsub); ++i)
+            if ((rc = enqueue_copy(i))) return rc;
         const bool trace = getenv("AMEPB_TRACE") != nullptr;
         auto now_ms = []() {
             timespec ts;
@@ -1747,11 +1750,11 @@ int amepb_rdf_batch(amepb_ctx* ctx, const void* coords, int coords_dtype, int64_
             return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
         };
         for (int64_t i = 0; i < nsub; ++i) {
-            const int b = (int)(i & 1);
+            const int b = (int)(i % NB);
             const int64_t f0 = subs[i].first;
             const int nf = subs[i].second;
             const double t0 = now_ms();
-            if (i + 1 < nsub && (rc = enqueue_copy(i + 1))) return rc;
+            if (i + NB - 1 < nsub && (rc = enqueue_copy(i + NB - 1))) return rc;
             if (trace) fprintf(stderr, "[amepb] sub %lld: enqueue_copy took %.3f ms (host)\n", (long long)i, now_ms() - t0);
             AMEPB_CUDA(ctx, cudaStreamWaitEvent(c.stream, ctx->ev_copied[b], 0));
             rc = rdf_sub_batch(ctx, c, f0, nf, stage_a + (size_t)b * cbytes * fb,
