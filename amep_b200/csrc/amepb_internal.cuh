@@ -47,6 +47,10 @@ struct amepb_ctx {
     void* pinned = nullptr;  // pinned host scratch (plans, stats read-back)
     size_t pinned_cap = 0;
     amepb_rdf_info rdf_info;
+    // per-frame statistics launched ahead for the next sub-batch (rdf.cu: stats prefetch)
+    cudaEvent_t ev_stats = nullptr;
+    int64_t stats_ahead_f0 = -1;   // first frame of the sub-batch whose statistics are in flight, -1: none
+    int stats_ahead_nf = 0;
     // last threshold table built on the host (rdf.cu): edges it belongs to, arithmetic type, values
     std::vector<double> thr_cache_edges;
     std::vector<char> thr_cache_values;

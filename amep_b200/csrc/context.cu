@@ -140,6 +140,7 @@ void amepb_destroy(amepb_ctx* ctx) {
         if (ctx->bufs[i].p) cudaFree(ctx->bufs[i].p);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+    if (ctx->ev_stats) cudaEventDestroy(ctx->ev_stats);
     for (int b = 0; b < amepb_ctx::kStageBuffers; ++b) {
         if (ctx->ev_copied[b]) cudaEventDestroy(ctx->ev_copied[b]);
         if (ctx->ev_computed[b]) cudaEventDestroy(ctx->ev_computed[b]);

@@ -1164,8 +1164,10 @@ static int stats_parts(const amepb_ctx* ctx, int64_t n, int nframes) {
 }
 
 // stats of [nframes][n][3] device array -> host FrameStats[]
-static int frame_stats(amepb_ctx* ctx, const void* pts, int dtype, int64_t n, int nframes,
-                       std::vector<FrameStats>& out, cudaStream_t stream, int slot) {
+// Launch the statistics kernels of `nframes` frames (no synchronisation).  Results land in the
+// context's pinned memory, slot 0: coords, slot 1: other.
+static int frame_stats_launch(amepb_ctx* ctx, const void* pts, int dtype, int64_t n, int nframes,
+                              cudaStream_t stream, int slot) {
     const int nparts = stats_parts(ctx, n, nframes);
     int rc = ensure_device(ctx, BUF_STATS, sizeof(StatsOut) * ((size_t)nframes * nparts * 2 + (size_t)nframes * 2));
     if (rc) return rc;
@@ -1177,10 +1179,13 @@ static int frame_stats(amepb_ctx* ctx, const void* pts, int dtype, int64_t n, in
     StatsOut* h = reinterpret_cast<StatsOut*>(ctx->pinned) + (size_t)slot * nframes;
     StatsOut* d_partial = reinterpret_cast<StatsOut*>(ctx->bufs[BUF_STATS].p) + (size_t)2 * nframes +
                           (size_t)slot * nframes * nparts;
-    if (dtype == AMEPB_F32) rc = launch_stats<float>(ctx, (const float*)pts, n, nframes, d_partial, h, nparts, stream);
-    else rc = launch_stats<double>(ctx, (const double*)pts, n, nframes, d_partial, h, nparts, stream);
-    if (rc) return rc;
-    AMEPB_CUDA(ctx, cudaStreamSynchronize(stream));
+    if (dtype == AMEPB_F32) return launch_stats<float>(ctx, (const float*)pts, n, nframes, d_partial, h, nparts, stream);
+    return launch_stats<double>(ctx, (const double*)pts, n, nframes, d_partial, h, nparts, stream);
+}
+
+// Read the statistics back (the caller has waited for the kernels).
+static void frame_stats_collect(amepb_ctx* ctx, int nframes, std::vector<FrameStats>& out, int slot) {
+    const StatsOut* h = reinterpret_cast<const StatsOut*>(ctx->pinned) + (size_t)slot * nframes;
     out.resize(nframes);
     for (int f = 0; f < nframes; ++f) {
         for (int d = 0; d < 3; ++d) {
@@ -1190,6 +1195,14 @@ static int frame_stats(amepb_ctx* ctx, const void* pts, int dtype, int64_t n, in
             out[f].varies[d] = h[f].varies[d];
         }
     }
+}
+
+static int frame_stats(amepb_ctx* ctx, const void* pts, int dtype, int64_t n, int nframes,
+                       std::vector<FrameStats>& out, cudaStream_t stream, int slot) {
+    int rc = frame_stats_launch(ctx, pts, dtype, n, nframes, stream, slot);
+    if (rc) return rc;
+    AMEPB_CUDA(ctx, cudaStreamSynchronize(stream));
+    frame_stats_collect(ctx, nframes, out, slot);
     return 0;
 }
 
@@ -1260,10 +1273,22 @@ struct RdfCall {
 
 static size_t elem_size(int dtype) { return dtype == AMEPB_F32 ? 4 : 8; }
 
+// The sub-batch after the current one: its statistics kernels are launched ahead of the current
+// pair kernel, so that the host has them (and can plan and enqueue the next build) while the GPU
+// is still busy -- the stream never runs dry waiting for the host.
+struct NextBatch {
+    int64_t f0;
+    int nf;
+    const void* d_coords;
+    const void* d_other;
+    cudaEvent_t ready;   // host-buffer path: the staging copy; prefetch only if it has completed
+};
+
 // One sub-batch: frames [f0, f0+nf) of the call; d_coords / d_other / d_hist
 // are device pointers to this sub-batch's data.
 static int rdf_sub_batch(amepb_ctx* ctx, const RdfCall& c, int64_t f0, int nf, const void* d_coords,
-                         const void* d_other, unsigned long long* d_hist, bool* bad_dim) {
+                         const void* d_other, unsigned long long* d_hist, bool* bad_dim,
+                         const NextBatch* next = nullptr) {
     cudaStream_t stream = c.stream;
     const bool self = (c.other == nullptr);
     const int qdtype = self ? c.coords_dtype : c.other_dtype;
@@ -1287,12 +1312,18 @@ static int rdf_sub_batch(amepb_ctx* ctx, const RdfCall& c, int64_t f0, int nf, c
     const double th0 = trace_host ? host_ms() : 0.0;
     cudaEvent_t ev_b0 = timing_event(ctx, stream);
     std::vector<FrameStats> tstats, qstats;
-    int rc = frame_stats(ctx, d_coords, c.coords_dtype, c.n, nf, tstats, stream, 0);
-    if (rc) return rc;
-    if (!self) {
-        rc = frame_stats(ctx, d_other, c.other_dtype, c.m, nf, qstats, stream, 1);
-        if (rc) return rc;
+    int rc = 0;
+    if (ctx->stats_ahead_f0 == f0 && ctx->stats_ahead_nf == nf && ctx->ev_stats) {
+        // launched ahead of the previous pair kernel
+        AMEPB_CUDA(ctx, cudaEventSynchronize(ctx->ev_stats));
+    } else {
+        if ((rc = frame_stats_launch(ctx, d_coords, c.coords_dtype, c.n, nf, stream, 0))) return rc;
+        if (!self && (rc = frame_stats_launch(ctx, d_other, c.other_dtype, c.m, nf, stream, 1))) return rc;
+        AMEPB_CUDA(ctx, cudaStreamSynchronize(stream));
     }
+    ctx->stats_ahead_f0 = -1;
+    frame_stats_collect(ctx, nf, tstats, 0);
+    if (!self) frame_stats_collect(ctx, nf, qstats, 1);
     const double th1 = trace_host ? host_ms() : 0.0;
     std::vector<FramePlan> plans(nf);
     long long total_cells = 0, total_tasks = 0, total_cap = 0;
@@ -1520,6 +1551,16 @@ static int rdf_sub_batch(amepb_ctx* ctx, const RdfCall& c, int64_t f0, int nf, c
         if (have_targets && (rc = place_targets(true))) return rc;
         if ((rc = place_queries(true))) return rc;
     }
+    // ---- statistics of the next sub-batch, ahead of this sub-batch's pair kernel -------------
+    if (next && next->nf > 0 && (!next->ready || cudaEventQuery(next->ready) == cudaSuccess)) {
+        if (!ctx->ev_stats) AMEPB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_stats, cudaEventDisableTiming));
+        if (next->ready) AMEPB_CUDA(ctx, cudaStreamWaitEvent(stream, next->ready, 0));
+        if ((rc = frame_stats_launch(ctx, next->d_coords, c.coords_dtype, c.n, next->nf, stream, 0))) return rc;
+        if (!self && (rc = frame_stats_launch(ctx, next->d_other, c.other_dtype, c.m, next->nf, stream, 1))) return rc;
+        AMEPB_CUDA(ctx, cudaEventRecord(ctx->ev_stats, stream));
+        ctx->stats_ahead_f0 = next->f0;
+        ctx->stats_ahead_nf = next->nf;
+    }
     cudaEvent_t ev_b1 = timing_event(ctx, stream);
     if (ev_b0 && ev_b1) ctx->ev_build.emplace_back(ev_b0, ev_b1);
 
@@ -1678,14 +1719,33 @@ int amepb_rdf_batch(amepb_ctx* ctx, const void* coords, int coords_dtype, int64_
     fb = std::min<int64_t>(fb, nframes);
 
     bool bad_dim = false;
+    ctx->stats_ahead_f0 = -1;   // nothing in flight from an earlier (possibly failed) call
     if (space == AMEPB_DEVICE) {
         for (int64_t f0 = 0; f0 < nframes; f0 += fb) {
             const int nf = (int)std::min<int64_t>(fb, nframes - f0);
             const void* d_coords = (const char*)coords + (size_t)f0 * cbytes;
             const void* d_other = other ? (const char*)other + (size_t)f0 * obytes : nullptr;
             unsigned long long* d_hist = reinterpret_cast<unsigned long long*>(hist_out) + (size_t)f0 * nbins;
-            int rc = rdf_sub_batch(ctx, c, f0, nf, d_coords, d_other, d_hist, &bad_dim);
+            NextBatch nb;
+            nb.f0 = f0 + nf;
+            nb.nf = (int)std::min<int64_t>(fb, nframes - nb.f0);
+            nb.d_coords = (const char*)coords + (size_t)nb.f0 * cbytes;
+            nb.d_other = other ? (const char*)other + (size_t)nb.f0 * obytes : nullptr;
+            nb.ready = nullptr;
+            int rc = rdf_sub_batch(ctx, c, f0, nf, d_coords, d_other, d_hist, &bad_dim, nb.nf > 0 ? &nb : nullptr);
             if (rc) return rc;
+        }
+        if (getenv("AMEPB_TRACE") && ctx->timing && !ctx->ev_build.empty()) {
+            AMEPB_CUDA(ctx, cudaStreamSynchronize(c.stream));
+            cudaEvent_t t0 = ctx->ev_build[0].first;
+            auto rel = [&](cudaEvent_t e) {
+                float ms = 0;
+                cudaEventElapsedTime(&ms, t0, e);
+                return ms;
+            };
+            for (size_t i = 0; i < ctx->ev_build.size() && i < ctx->ev_pair.size(); ++i)
+                fprintf(stderr, "[amepb] sub %zu: build %.2f-%.2f  pair %.2f-%.2f ms\n", i, rel(ctx->ev_build[i].first),
+                        rel(ctx->ev_build[i].second), rel(ctx->ev_pair[i].first), rel(ctx->ev_pair[i].second));
         }
     } else {
         // Host buffers: staging through kStageBuffers device buffers.  The copies of the next two
@@ -1757,8 +1817,19 @@ int amepb_rdf_batch(amepb_ctx* ctx, const void* coords, int coords_dtype, int64_
             if (i + NB - 1 < nsub && (rc = enqueue_copy(i + NB - 1))) return rc;
             if (trace) fprintf(stderr, "[amepb] sub %lld: enqueue_copy took %.3f ms (host)\n", (long long)i, now_ms() - t0);
             AMEPB_CUDA(ctx, cudaStreamWaitEvent(c.stream, ctx->ev_copied[b], 0));
+            NextBatch nb;
+            nb.nf = 0;
+            if (i + 1 < nsub) {
+                const int b1 = (int)((i + 1) % NB);
+                nb.f0 = subs[i + 1].first;
+                nb.nf = subs[i + 1].second;
+                nb.d_coords = stage_a + (size_t)b1 * cbytes * fb;
+                nb.d_other = other ? stage_b + (size_t)b1 * obytes * fb : nullptr;
+                nb.ready = ctx->ev_copied[b1];
+            }
             rc = rdf_sub_batch(ctx, c, f0, nf, stage_a + (size_t)b * cbytes * fb,
-                               other ? stage_b + (size_t)b * obytes * fb : nullptr, d_hist + (size_t)f0 * nbins, &bad_dim);
+                               other ? stage_b + (size_t)b * obytes * fb : nullptr, d_hist + (size_t)f0 * nbins, &bad_dim,
+                               nb.nf > 0 ? &nb : nullptr);
             if (rc) return rc;
             AMEPB_CUDA(ctx, cudaEventRecord(ctx->ev_computed[b], c.stream));
         }
