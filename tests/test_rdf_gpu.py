@@ -123,6 +123,21 @@ def test_oracle_seeded(sc, case):
     np.testing.assert_array_equal(r[0], ro)
 
 
+@pytest.mark.parametrize("pbc", [True, False])
+@pytest.mark.parametrize("dt_coords,dt_other", [(np.float32, np.float64), (np.float64, np.float32)])
+def test_mixed_dtypes_cross(sc, dt_coords, dt_other, pbc):
+    """coords and other_coords of different dtypes: the arithmetic regime follows NumPy's promotion of
+    ``c - coords`` (amep/spatialcor.py:381), the images stay float32 with pbc."""
+    rng = np.random.default_rng(77)
+    box = np.array([[0, 25], [0, 25], [0, 25]], dtype=np.float64)
+    coords = _uniform(rng, 3000, box, dt_coords)
+    other = _uniform(rng, 1200, box, dt_other)
+    want, _ = orc.rdf_counts(coords, box, other, rmax=4.0, nbins=120, pbc=pbc)
+    _, _, counts = sc.rdf_frames(coords, box, other, rmax=4.0, nbins=120, pbc=pbc, return_counts=True)
+    np.testing.assert_array_equal(counts[0], want)
+    assert want.sum() > 0
+
+
 @pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 6])
 def test_grid_refinement_does_not_change_counts(sc, k):
     from amep_b200 import _lib

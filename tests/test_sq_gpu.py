@@ -269,3 +269,11 @@ def test_evaluate_sfiso_and_sf2d(sc):
     assert ev2.frames.shape[0] == 3 and ev2.frames.shape[1] == 3
     with pytest.raises(NotImplementedError):
         amep_b200.evaluate.SF2d(traj)  # the reference's default is rotate=True: loud, not silent
+    # mode='fft' through the evaluate classes (kwargs reach sf2d / sfiso unchanged)
+    ev3 = amep_b200.evaluate.SF2d(traj, skip=0.0, nav=2, rotate=False, qmax=2.0, mode="fft", accuracy=0.2)
+    idx = orc.frame_indices(nf, 0.0, 2)
+    rows = [orc.sf2d_fft(coords[i], box, qmax=2.0, accuracy=0.2) for i in idx]
+    _close(ev3.avg, np.mean(np.array([r[0] for r in rows]), axis=0), rtol=1e-6, atol_scale=1e-9)
+    ev4 = amep_b200.evaluate.SFiso(traj, skip=0.0, nav=2, qmax=2.0, twod=True, mode="fft", accuracy=0.2)
+    rows = [orc.sfiso_fft(coords[i], box, n, qmax=2.0, accuracy=0.2) for i in idx]
+    _close(ev4.avg, np.mean(np.array([r[0] for r in rows]), axis=0), rtol=1e-6, atol_scale=1e-9)
