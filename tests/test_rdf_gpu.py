@@ -1,5 +1,6 @@
 """RDF parity on the GPU: libamepb (through the C ABI) against the reference's
 golden vectors and against the CPU oracle on seeded inputs.  Bit-exact."""
+import ctypes
 import glob
 import os
 import zlib
@@ -289,6 +290,36 @@ def test_large_nbins_uses_global_path(sc):
         want, _ = corc.rdf_counts(c, box, rmax=4.0, nbins=nbins)
         _, _, counts = sc.rdf_frames(c, box, rmax=4.0, nbins=nbins, return_counts=True)
         np.testing.assert_array_equal(counts[0], want)
+
+
+def test_custom_edges_through_the_c_abi(sc):
+    """amepb_rdf_batch accepts any non-decreasing edges: a first edge above zero, a first edge below
+    the 1e-3 filter, non-uniform edges (general kernel) -- against the C oracle's explicit-edge
+    histogram (np.histogram semantics)."""
+    from amep_b200 import _core
+    rng = np.random.default_rng(91)
+    box = np.array([[0, 30], [0, 30], [-0.5, 0.5]], dtype=np.float32)
+    c = _uniform(rng, 5000, box.astype(np.float64), np.float32)
+    c[:, 2] = 0
+    c[2500:2510, :2] = c[:10, :2] + np.float32(4e-4)      # pairs below the filter
+    targets = corc.images(c, box)
+    def brute(edges):
+        e = np.ascontiguousarray(edges, dtype=np.float64)
+        hist = np.zeros(len(e) - 1, dtype=np.int64)
+        corc.lib().oracle_rdf_hist(targets.ctypes.data, 0, len(targets), c.ctypes.data, 0, 0, len(c),
+                                   e.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                                   len(e) - 1, hist.ctypes.data, 0)
+        return hist
+    for edges in (np.linspace(1.5, 6.0, 91),                       # uniform, first edge > 0
+                  np.linspace(5e-4, 4.0, 401),                     # first edge inside the 1e-3 filter
+                  np.linspace(0.0, 0.9, 1001),                     # bins narrower than 1e-3 / 0.45
+                  np.concatenate([[0.0, 0.3, 0.35, 1.0], np.geomspace(1.1, 6.0, 40)])):   # non-uniform
+        want = brute(edges)
+        got, _ = _core.rdf_histograms(c, box, edges)
+        np.testing.assert_array_equal(got[0], want)
+        got, _ = _core.rdf_histograms(torch.from_numpy(c).cuda(), box, edges)
+        np.testing.assert_array_equal(got[0].cpu().numpy(), want)
+        assert want.sum() > 0
 
 
 def test_edge_cases(sc):
