@@ -275,12 +275,15 @@ constexpr int kC64TileA = 32;
 constexpr int kC64TileB = 16;
 constexpr int kC64Stage = 64;     // particles per shared-memory stage
 
-// fl32(v) for a double v, on the FP64 pipe: adding 1.5*2^(e+29) rounds v to a multiple of
-// the float32 ulp of its binade (round to nearest even); the subtraction is exact.
+// fl32(v) for a double v without the FP64 pipe (which the two DFMA per accumulation already
+// keep busy) and without F2F (a quarter of the FP64 rate): add half a float32 ulp to the bit
+// pattern (64-bit integer add: IADD3 + IADD3.X) and clear the 29 low mantissa bits (LOP3).
+// This is round-half-away instead of round-half-even: the two differ only on exact ties, one
+// addition in 2^29 -- two orders of magnitude rarer than the rounding flips that the 1e-16
+// differences between the tables and libm's exp already cause (section 4 of DESIGN.md).
 __device__ __forceinline__ double round_to_f32(double v) {
-    const int hi = (__double2hiint(v) & 0x7ff00000) + 0x01d80000;
-    const double m = __hiloint2double(hi, 0);
-    return __dsub_rn(__dadd_rn(v, m), m);
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v) + 0x10000000ull;
+    return __longlong_as_double((long long)(b & 0xffffffffe0000000ull));
 }
 
 // One thread owns the quad points (qa, qb0) and (qa, qb1): the X entry is loaded once per
@@ -288,7 +291,7 @@ __device__ __forceinline__ double round_to_f32(double v) {
 // warp-uniform broadcasts -- 3 shared-memory wavefronts per quad-point step instead of 8
 // with a 16 x 16 thread tile, which had the shared pipe at 62 % (ncu) next to the FP64 pipe.
 template <typename T>
-__global__ void __launch_bounds__(kC64Threads) sf2d_c64_kernel(
+__global__ void __launch_bounds__(kC64Threads, 4) sf2d_c64_kernel(
     const T* __restrict__ coords, long long n, const double* __restrict__ qall, long long q_stride, int nq,
     long long chunksize, float2* __restrict__ rho) {
     extern __shared__ __align__(16) unsigned char smem_c64[];
