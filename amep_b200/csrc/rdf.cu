@@ -1754,16 +1754,22 @@ int amepb_rdf_batch(amepb_ctx* ctx, const void* coords, int coords_dtype, int64_
         size_t stage_target = (size_t)384 << 20;
         if (const char* env = getenv("AMEPB_STAGE_MB")) stage_target = (size_t)std::max(1, atoi(env)) << 20;
         fb = std::min<int64_t>(fb, std::max<int64_t>(1, (int64_t)(stage_target / std::max<size_t>(1, cbytes + obytes))));
-        // sub-batches grow from fb/8 to fb frames: the first copy (not overlapped with anything)
-        // stays short, the later sub-batches amortise their fixed costs (plan, launches)
+        // Sub-batches grow slowly (x1.15) from fb/8 to fb frames.  The first copy (not overlapped
+        // with anything) stays short and later sub-batches amortise their fixed costs; the growth
+        // factor follows from the rates: a copy takes about as long as the computation of the same
+        // frames (0.217 vs 0.223 ms per 1M-particle frame), so a sub-batch much larger than its
+        // predecessor would leave the GPU waiting for its copy (a doubling schedule idled 9 %)
         std::vector<std::pair<int64_t, int>> subs;
         {
-            int64_t f0 = 0, sz = std::max<int64_t>(1, fb / 8);
+            int64_t f0 = 0;
+            double sz = (double)std::max<int64_t>(1, fb / 8);
             while (f0 < nframes) {
-                const int nf = (int)std::min<int64_t>(sz, nframes - f0);
-                subs.emplace_back(f0, nf);
+                int64_t nf = std::min<int64_t>((int64_t)(sz + 0.5), nframes - f0);
+                if (nframes - f0 - nf < nf / 2) nf = nframes - f0;   // no tiny last sub-batch
+                nf = std::min<int64_t>(nf, fb);
+                subs.emplace_back(f0, (int)nf);
                 f0 += nf;
-                sz = std::min<int64_t>(fb, sz * 2);
+                sz = std::min<double>((double)fb, std::max(sz + 1.0, sz * 1.15));
             }
         }
         const int64_t nsub = (int64_t)subs.size();
