@@ -1709,8 +1709,15 @@ int amepb_rdf_batch(amepb_ctx* ctx, const void* coords, int coords_dtype, int64_
     const size_t per_frame = (size_t)n * (c.pbc ? 8 : 1) * 32 + (size_t)c.m * 32 +
                              (size_t)std::max<int64_t>(4096, n * 2) * 16 +
                              (space == AMEPB_HOST ? cbytes + obytes : 0);
+    auto wall_ms = []() {
+        timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+    };
+    const double w0 = wall_ms();
     size_t free_b = 0, total_b = 0;
     AMEPB_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+    const double w1 = wall_ms();
     size_t budget = std::min<size_t>((size_t)24 << 30, (free_b + ctx->bufs[BUF_TSORTED].cap) / 3);
     budget = std::max<size_t>(budget, per_frame);
     int64_t fb = (int64_t)std::max<size_t>(1, budget / per_frame);
@@ -1807,6 +1814,7 @@ int amepb_rdf_batch(amepb_ctx* ctx, const void* coords, int coords_dtype, int64_
         // the copy stream must not start before work already queued on the caller's stream
         // could still be reading the staging buffers of an earlier call
         AMEPB_CUDA(ctx, cudaStreamSynchronize(c.stream));
+        const double w2 = wall_ms();
         for (int64_t i = 0; i < std::min<int64_t>(NB - 1, nsub); ++i)
             if ((rc = enqueue_copy(i))) return rc;
         const bool trace = getenv("AMEPB_TRACE") != nullptr;
@@ -1843,8 +1851,24 @@ int amepb_rdf_batch(amepb_ctx* ctx, const void* coords, int coords_dtype, int64_
         // queue behind the next staging copy and stall the stream)
         AMEPB_CUDA(ctx, cudaMemcpyAsync(hist_out, d_hist, sizeof(unsigned long long) * (size_t)nframes * nbins,
                                         cudaMemcpyDeviceToHost, c.stream));
+        const double w3 = wall_ms();
         AMEPB_CUDA(ctx, cudaStreamSynchronize(c.stream));
-        if (trace && ctx->timing && !ctx->ev_build.empty()) {
+        const double w4 = wall_ms();
+        if (const char* slow = getenv("AMEPB_TRACE_SLOW_MS"))
+            if (w4 - w0 > atof(slow))
+                fprintf(stderr, "[amepb] host-buffer call: %.1f ms wall = meminfo %.2f + setup %.2f + loop %.2f + final sync %.2f\n",
+                        w4 - w0, w1 - w0, w2 - w1, w3 - w2, w4 - w3);
+        bool trace_now = trace;
+        if (const char* slow = getenv("AMEPB_TRACE_SLOW_MS")) {
+            // print the timeline only for calls slower than the given time (ms)
+            trace_now = false;
+            if (ctx->timing && !ctx->ev_copy.empty() && !ctx->ev_pair.empty()) {
+                float ms = 0;
+                cudaEventElapsedTime(&ms, ctx->ev_copy[0].first, ctx->ev_pair.back().second);
+                trace_now = ms > atof(slow);
+            }
+        }
+        if (trace_now && ctx->timing && !ctx->ev_build.empty()) {
             cudaEvent_t t0 = ctx->ev_copy.empty() ? ctx->ev_build[0].first : ctx->ev_copy[0].first;
             auto rel = [&](cudaEvent_t e) {
                 float ms = 0;
