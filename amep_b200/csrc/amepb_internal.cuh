@@ -47,6 +47,8 @@ struct amepb_ctx {
     void* pinned = nullptr;  // pinned host scratch (plans, stats read-back)
     size_t pinned_cap = 0;
     amepb_rdf_info rdf_info;
+    // workspace budget of amepb_rdf_batch, queried once per problem shape (rdf.cu)
+    size_t budget_bytes = 0, budget_per_frame = 0;
     // per-frame statistics launched ahead for the next sub-batch (rdf.cu: stats prefetch)
     cudaEvent_t ev_stats = nullptr;
     int64_t stats_ahead_f0 = -1;   // first frame of the sub-batch whose statistics are in flight, -1: none

@@ -1661,11 +1661,32 @@ int amepb_frame_dimension(amepb_ctx* ctx, const void* coords, int dtype, int spa
     return 0;
 }
 
+static int rdf_batch_impl(amepb_ctx* ctx, const void* coords, int coords_dtype, int64_t n, const void* other,
+                          int other_dtype, int64_t m, int space, int64_t nframes, const double* box_boundary,
+                          int box_dtype, const double* edges, int64_t edges_stride, int32_t nbins, int pbc,
+                          uint64_t* hist_out, int32_t* dim_out, void* stream_, bool* budget_was_cached);
+
 int amepb_rdf_batch(amepb_ctx* ctx, const void* coords, int coords_dtype, int64_t n, const void* other,
                     int other_dtype, int64_t m, int space, int64_t nframes, const double* box_boundary,
                     int box_dtype, const double* edges, int64_t edges_stride, int32_t nbins, int pbc,
                     uint64_t* hist_out, int32_t* dim_out, void* stream_) {
     if (!ctx) return AMEPB_E_INVAL;
+    bool cached = false;
+    int rc = rdf_batch_impl(ctx, coords, coords_dtype, n, other, other_dtype, m, space, nframes, box_boundary, box_dtype,
+                            edges, edges_stride, nbins, pbc, hist_out, dim_out, stream_, &cached);
+    if (rc == AMEPB_E_NOMEM && cached) {
+        // the cached workspace budget was stale (the caller allocated device memory in between)
+        ctx->budget_bytes = 0;
+        rc = rdf_batch_impl(ctx, coords, coords_dtype, n, other, other_dtype, m, space, nframes, box_boundary, box_dtype,
+                            edges, edges_stride, nbins, pbc, hist_out, dim_out, stream_, &cached);
+    }
+    return rc;
+}
+
+static int rdf_batch_impl(amepb_ctx* ctx, const void* coords, int coords_dtype, int64_t n, const void* other,
+                          int other_dtype, int64_t m, int space, int64_t nframes, const double* box_boundary,
+                          int box_dtype, const double* edges, int64_t edges_stride, int32_t nbins, int pbc,
+                          uint64_t* hist_out, int32_t* dim_out, void* stream_, bool* budget_was_cached) {
     auto dtype_ok = [](int d) { return d == AMEPB_F32 || d == AMEPB_F64; };
     if (!coords || !box_boundary || !edges || !hist_out)
         return fail(ctx, AMEPB_E_INVAL, "amepb_rdf_batch: NULL pointer argument");
@@ -1715,11 +1736,18 @@ int amepb_rdf_batch(amepb_ctx* ctx, const void* coords, int coords_dtype, int64_
         return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
     };
     const double w0 = wall_ms();
-    size_t free_b = 0, total_b = 0;
-    AMEPB_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+    // The memory budget is queried once per problem shape: cudaMemGetInfo takes a driver-wide
+    // lock and was seen to stall for tens of milliseconds on shared hosts.
+    *budget_was_cached = true;
+    if (ctx->budget_per_frame != per_frame || ctx->budget_bytes == 0) {
+        *budget_was_cached = false;
+        size_t free_b = 0, total_b = 0;
+        AMEPB_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+        ctx->budget_bytes = std::min<size_t>((size_t)24 << 30, (free_b + ctx->bufs[BUF_TSORTED].cap) / 3);
+        ctx->budget_per_frame = per_frame;
+    }
     const double w1 = wall_ms();
-    size_t budget = std::min<size_t>((size_t)24 << 30, (free_b + ctx->bufs[BUF_TSORTED].cap) / 3);
-    budget = std::max<size_t>(budget, per_frame);
+    size_t budget = std::max<size_t>(ctx->budget_bytes, per_frame);
     int64_t fb = (int64_t)std::max<size_t>(1, budget / per_frame);
     fb = std::min<int64_t>(fb, 16384);
     fb = std::min<int64_t>(fb, std::max<int64_t>(1, (int64_t)((1ll << 31) / std::max<int64_t>(1, n * 8))));
