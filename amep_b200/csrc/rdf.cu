@@ -1751,6 +1751,7 @@ static int rdf_batch_impl(amepb_ctx* ctx, const void* coords, int coords_dtype, 
     int64_t fb = (int64_t)std::max<size_t>(1, budget / per_frame);
     fb = std::min<int64_t>(fb, 16384);
     fb = std::min<int64_t>(fb, std::max<int64_t>(1, (int64_t)((1ll << 31) / std::max<int64_t>(1, n * 8))));
+    if (const char* cap = getenv("AMEPB_MAX_FRAMES")) fb = std::min<int64_t>(fb, std::max(1, atoi(cap)));   // tests: force sub-batching
     fb = std::min<int64_t>(fb, nframes);
 
     bool bad_dim = false;
