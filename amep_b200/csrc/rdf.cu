@@ -1351,6 +1351,7 @@ static int rdf_sub_batch(amepb_ctx* ctx, const RdfCall& c, int64_t f0, int nf, c
         in.cells_per_cutoff = ctx->rdf_k_override;
         in.max_cells = std::max<int64_t>(4096, c.n * (c.pbc ? 2 : 1));
         if (const char* tp = getenv("AMEPB_TASK_PAIRS")) in.task_pairs = std::max(1024.0, atof(tp));
+        if (const char* hm = getenv("AMEPB_HEAVY_RUN_MULT")) in.heavy_run_mult = std::max(0, atoi(hm));
         // edges must be usable: finite, non-decreasing
         for (int i = 0; ok && i < nbins; ++i)
             if (!(edges[i] <= edges[i + 1])) ok = false;

@@ -175,6 +175,7 @@ struct PlanInputs {
     int cells_per_cutoff;        // 0 = automatic
     int64_t max_cells;           // upper bound on cells for one frame
     double task_pairs = 262144.0;  // candidate pairs aimed at per block task
+    int heavy_run_mult = 0;        // query cells per block task multiplier when warps share cells (0 = automatic)
 };
 
 // Image window of pbc_points(width=0.5): (centre - L32, centre + L32), with
@@ -368,6 +369,25 @@ inline bool plan_frame(const PlanInputs& in, int dim, const FrameStats& tgt, con
     if (run > P.cq_n[0]) {
         run = P.cq_n[0];
         rsplit = run >= 8 ? 1 : (run >= 4 ? 2 : (run >= 2 ? 4 : 8));
+    }
+    // shared cells: hand out several times more items than warps, so that the dynamic hand-out
+    // inside the task can even out rows of different length before the block barrier
+    // (x4 when the frame still yields thousands of block tasks: 5 % on the 3D configs; fewer,
+    // larger tasks would unbalance the persistent blocks of small frames instead)
+    if (rsplit > 1) {
+        int mult = in.heavy_run_mult;
+        if (mult <= 0) {
+            mult = 1;
+            for (int m = 4; m > 1; m /= 2) {
+                const int r = std::min<int>(P.cq_n[0], run * m);
+                const long long tasks = (long long)((P.cq_n[0] + r - 1) / r) * P.cq_n[1] * P.cq_n[2];
+                if (tasks >= 4096) {
+                    mult = m;
+                    break;
+                }
+            }
+        }
+        run = std::min<int>(P.cq_n[0], run * mult);
     }
     P.run = run;
     P.rsplit = rsplit;
