@@ -145,6 +145,13 @@ static void check_plan(std::mt19937_64& rng, int dim, bool box_f32, const double
                         im.x[d] = b + (float)v[d] * P.shift[d];
                         if (!((double)im.x[d] < P.win_hi[d]) || !((double)im.x[d] > P.win_lo[d])) keep = false;
                     }
+                    // the placement kernels decide with one closed float32 interval per dimension
+                    for (int d = 0; d < 3; ++d) {
+                        const double x = (double)im.x[d];
+                        const bool four = x < P.win_hi[d] && x > P.win_lo[d] && x >= P.reg_lo[d] && x <= P.reg_hi[d];
+                        const bool one = im.x[d] >= P.keep_lo[d] && im.x[d] <= P.keep_hi[d];
+                        CHECK(four == one, "%s: keep interval disagrees for image coordinate %.9g (dim %d)", tag, x, d);
+                    }
                     if (keep) all.push_back(im);
                 }
             }
@@ -291,9 +298,36 @@ static void check_plan(std::mt19937_64& rng, int dim, bool box_f32, const double
     (void)sg;
 }
 
+// float_above / float_below: the float32 neighbours of a float64 bound reproduce the float64
+// comparison for every float32 value (checked on the floats around the bound)
+static void check_float_bounds(std::mt19937_64& rng) {
+    std::uniform_real_distribution<double> U(-1.0, 1.0);
+    const double scales[] = {1e-30, 1e-3, 1.0, 37.5, 1253.3336, 1e6, 1e30};
+    for (double sc : scales)
+        for (int it = 0; it < 2000; ++it) {
+            double b = U(rng) * sc;
+            if (it % 7 == 0) b = (double)(float)b;          // exactly representable bounds too
+            const float ge = float_above(b, false), gt = float_above(b, true);
+            const float le = float_below(b, false), lt = float_below(b, true);
+            float x = (float)b;
+            for (int step = 0; step < 3; ++step) x = nextafterf(x, -INFINITY);
+            for (int step = 0; step < 7; ++step, x = nextafterf(x, INFINITY)) {
+                CHECK(((double)x >= b) == (x >= ge), "float_above(%.17g, false) wrong at %.9g", b, (double)x);
+                CHECK(((double)x > b) == (x >= gt), "float_above(%.17g, true) wrong at %.9g", b, (double)x);
+                CHECK(((double)x <= b) == (x <= le), "float_below(%.17g, false) wrong at %.9g", b, (double)x);
+                CHECK(((double)x < b) == (x <= lt), "float_below(%.17g, true) wrong at %.9g", b, (double)x);
+            }
+        }
+    const double inf = std::numeric_limits<double>::infinity();
+    CHECK(float_above(-inf, true) == -std::numeric_limits<float>::max(), "float_above(-inf, strict)");
+    CHECK(float_below(inf, true) == std::numeric_limits<float>::max(), "float_below(+inf, strict)");
+    CHECK(float_above(-inf, false) == -std::numeric_limits<float>::infinity(), "float_above(-inf)");
+}
+
 int main() {
     std::mt19937_64 rng(12345);
     printf("thresholds\n");
+    check_float_bounds(rng);
     check_thresholds<float>(rng, true, 32.0, 500);
     check_thresholds<float>(rng, false, 10.0, 500);
     check_thresholds<float>(rng, false, 0.05, 500);
