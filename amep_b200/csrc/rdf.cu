@@ -515,15 +515,19 @@ struct PairArgs {
 };
 
 // float32 regime: every warp gathers the neighbourhood of its query cell into a shared buffer
-// of kStageCap targets (x[] | y[] (| z[])) and walks it in full 32-lane passes
-constexpr unsigned kStageCap = 256;   // targets per warp and chunk
-constexpr unsigned kQueryCap = 64;    // queries per warp and chunk
+// of kStageCapF32 targets (x[] | y[] (| z[])) and walks it in full 32-lane passes
+constexpr unsigned kStageCapF32 = 256;   // targets per warp and chunk (float32 regime; half of it in float64)
+constexpr unsigned kQueryCapF32 = 64;    // queries per warp and chunk
 constexpr unsigned kUnitLimit = 1u << 21;                // flush after 2^31 counted pairs (units of 1024)
 constexpr int kPairThreads = 256;
 #ifndef AMEPB_PAIR_BLOCKS
 #define AMEPB_PAIR_BLOCKS 5
 #endif
 constexpr int kPairBlocksPerSM = AMEPB_PAIR_BLOCKS;
+#ifndef AMEPB_PAIR_BLOCKS_F64
+#define AMEPB_PAIR_BLOCKS_F64 5
+#endif
+constexpr int kPairBlocksPerSMF64 = AMEPB_PAIR_BLOCKS_F64;   // float64 arithmetic: register pairs
 
 // ZMODE 0: three coordinates; 1: every z equal, dz*dz is the per-frame constant dz2c;
 // 2: like 1 with dz2c == 0 (s + 0 == s, the addition is dropped)
@@ -676,6 +680,19 @@ __device__ __forceinline__ f32x2 lds_b64(unsigned addr) {
 __device__ __forceinline__ void sts_f32(unsigned addr, float v) {
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_f64(unsigned addr, double v) {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+// staging buffer element of the arithmetic type
+__device__ __forceinline__ float lds_at(unsigned addr, float) { return lds_f32(addr); }
+__device__ __forceinline__ double lds_at(unsigned addr, double) { return lds_f64(addr); }
+__device__ __forceinline__ void sts_at(unsigned addr, float v) { sts_f32(addr, v); }
+__device__ __forceinline__ void sts_at(unsigned addr, double v) { sts_f64(addr, v); }
 
 // float <-> int with the same ordering (for REDUX min/max over a warp)
 __device__ __forceinline__ int float_order(float f) {
@@ -752,7 +769,7 @@ __device__ __forceinline__ void warp_pairs_fast(const Vec4<AT>* __restrict__ qso
 // shifted images ("ghosts", a separate cell-sorted array) are not symmetric in floating point
 // and are evaluated for every ordered (query, ghost) pair.
 template <typename AT, typename NT, int ZMODE, bool SMEM, bool SYM>
-__global__ void __launch_bounds__(kPairThreads, kPairBlocksPerSM) pair_kernel(PairArgs a) {
+__global__ void __launch_bounds__(kPairThreads, (sizeof(AT) == 4 ? kPairBlocksPerSM : kPairBlocksPerSMF64)) pair_kernel(PairArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nbins = a.nbins;
     AT* s_thr = reinterpret_cast<AT*>(smem_raw);  // T[0..nbins+1], see warp_pairs_fast
@@ -769,7 +786,10 @@ __global__ void __launch_bounds__(kPairThreads, kPairBlocksPerSM) pair_kernel(Pa
     asm volatile("mov.u32 %0, %0;" : "+r"(thr_base_addr));
     const unsigned hist2_addr = hist_addr + 4u * (unsigned)half_len;
     constexpr unsigned kStageComp = ZMODE == 0 ? 3 : 2;
-    constexpr unsigned kStageFloats = (kStageCap + kQueryCap) * kStageComp;  // per warp
+    constexpr unsigned kES = (unsigned)sizeof(AT);                             // staged element size
+    constexpr unsigned kStageCap = kStageCapF32 * 4 / kES;                    // same bytes for both types
+    constexpr unsigned kQueryCap = kQueryCapF32 * 4 / kES;
+    constexpr unsigned kStageFloats = (kStageCapF32 + kQueryCapF32) * kStageComp;  // 4-byte words per warp
     // per-warp staging area of the float32 regime, as a shared-space address
     unsigned stage_addr = (unsigned)__cvta_generic_to_shared(smem_raw) +
                           (unsigned)(pair_thr_bytes(nbins, sizeof(AT)) + (((size_t)hist_len * sizeof(unsigned) + 15) & ~(size_t)15)) +
@@ -855,7 +875,7 @@ __global__ void __launch_bounds__(kPairThreads, kPairBlocksPerSM) pair_kernel(Pa
         const int nrows = P.nrows;
         const int row0 = P.row0;
         const unsigned long long direct_pairs = P.direct_pairs;
-        const bool small_ok = direct_pairs >= (unsigned long long)kQueryCap * kStageCap;
+        const bool small_ok = direct_pairs >= (unsigned long long)kQueryCapF32 * kStageCapF32;
         // squared cutoff of the target culling (float32 regime), less the constant dz*dz of flat frames
         const float cull_r2 = P.cull_r2 - (ZMODE == 1 ? (float)P.dz2c : 0.0f);
         const int n0 = P.n[0], n1 = P.n[1], n2 = P.n[2];
@@ -1065,6 +1085,238 @@ __global__ void __launch_bounds__(kPairThreads, kPairBlocksPerSM) pair_kernel(Pa
                     cand += staged + oversize;
                     if (staged) atomicAdd(&s_units, (unsigned)(staged >> 10) + 1u);
                 }
+            } else if constexpr (SMEM) {
+                // ---- float64 regimes: the same staged walk with scalar float64 arithmetic.  (Kept apart from
+                // the float32 block above on purpose: a shared generic version cost the float32 kernels 2 %.)
+                const unsigned bx = stage_addr;                        // targets x[] | y[] (| z[]) of type AT
+                const unsigned by = bx + kES * kStageCap;
+                const unsigned bz = by + kES * kStageCap;              // ZMODE == 0 only
+                // queries: float32: packed pairs, see query_loop_f32; float64: x[] | y[] (| z[])
+                const unsigned sq_xy = bx + kES * kStageCap * kStageComp;
+                const unsigned sq_z = sq_xy + 2 * kES * kQueryCap;     // ZMODE == 0 only
+                const Vec4<AT>* qarr = qsorted;
+                const Vec4<NT>* tarr = tsorted;
+                // entries: [0] own cell (SYM), [1, G] ghost rows (SYM, if any can be near),
+                // then the real rows (SYM: upper half shell) -- weight-1 entries first
+                int G = 0;
+                if (SYM) {
+                    const int kx0 = P.kd[0], ky = P.kd[1], kz = P.kd[2];
+                    const bool gfree = cx - kx0 >= P.gfree_lo[0] && cx + kx0 <= P.gfree_hi[0] && cy - ky >= P.gfree_lo[1] &&
+                                       cy + ky <= P.gfree_hi[1] && cz - kz >= P.gfree_lo[2] && cz + kz <= P.gfree_hi[2];
+                    G = gfree ? 0 : nrows;
+                }
+                const int E = SYM ? 1 + G + (nrows - row0) : nrows;
+                unsigned long long staged = 0, oversize = 0;
+                for (unsigned qc = qa; qc < qb; qc += kQueryCap) {
+                    const unsigned nqc = min(kQueryCap, qb - qc);
+                    const unsigned nq2 = (nqc + 1u) & ~1u;
+                    __syncwarp();
+                    // bounding box of the staged queries in float32, rounded outwards (NaN coordinates
+                    // never pair and are left out)
+                    const float finf = __int_as_float(0x7f800000);
+                    float lo[3] = {finf, finf, finf}, hi[3] = {-finf, -finf, -finf};
+                    auto grow = [&](int d, AT v) {
+                        if (v == v) {
+                            if constexpr (sizeof(AT) == 4) {
+                                lo[d] = fminf(lo[d], v);
+                                hi[d] = fmaxf(hi[d], v);
+                            } else {
+                                lo[d] = fminf(lo[d], __double2float_rd(v));
+                                hi[d] = fmaxf(hi[d], __double2float_ru(v));
+                            }
+                        }
+                    };
+#pragma unroll 1
+                    for (unsigned i = lane; i < nq2; i += 32) {
+                        AT x = (AT)__int_as_float(0x7fc00000), y = x, z = x;
+                        if (i < nqc) {
+                            const Vec4<AT> v = load_query<AT, ZMODE != 0>(qarr + qc + i);
+                            x = v.x; y = v.y; z = v.z;
+                            grow(0, x);
+                            grow(1, y);
+                            if (ZMODE == 0) grow(2, z);
+                        }
+                        if constexpr (sizeof(AT) == 4) {
+                            const unsigned e = sq_xy + (i >> 1) * 16 + (i & 1u) * 4;
+                            sts_f32(e, x);
+                            sts_f32(e + 8, y);
+                            if (ZMODE == 0) sts_f32(sq_z + 4 * i, z);
+                        } else if (i < nqc) {
+                            sts_f64(sq_xy + 8 * i, x);
+                            sts_f64(sq_xy + 8 * kQueryCap + 8 * i, y);
+                            if (ZMODE == 0) sts_f64(sq_z + 8 * i, z);
+                        }
+                    }
+#pragma unroll
+                    for (int d = 0; d < (ZMODE == 0 ? 3 : 2); ++d) {
+                        lo[d] = order_float(__reduce_min_sync(0xffffffffu, float_order(lo[d])));
+                        hi[d] = order_float(__reduce_max_sync(0xffffffffu, float_order(hi[d])));
+                    }
+                    unsigned fill = 0, lo_end = 0;
+                    auto flush_stage = [&]() {
+                        __syncwarp();
+                        for (unsigned g0 = 0; g0 < fill; g0 += 32) {
+                            const unsigned g = g0 + lane;
+                            AT nx = (AT)__int_as_float(0x7fc00000), ny = nx, nz = nx;
+                            if (g < fill) {
+                                nx = lds_at(bx + kES * g, AT());
+                                ny = lds_at(by + kES * g, AT());
+                                if (ZMODE == 0) nz = lds_at(bz + kES * g, AT());
+                            }
+                            // (idle lanes hold NaN targets and end up in a dump slot: without a second
+                            // half that must be the first half's)
+                            const unsigned h_addr = (!SYM || g < lo_end) ? hist_addr : hist2_addr;
+                            if constexpr (sizeof(AT) == 4) {
+                                query_loop_f32<ZMODE>(fa, sq_xy, sq_z, nq2, nx, ny, nz, dz2c, h_addr);
+                            } else {
+#pragma unroll 2
+                                for (unsigned u = 0; u < nqc; ++u) {
+                                    Vec4<double> qv;
+                                    qv.x = lds_f64(sq_xy + 8 * u);
+                                    qv.y = lds_f64(sq_xy + 8 * kQueryCap + 8 * u);
+                                    qv.z = ZMODE == 0 ? lds_f64(sq_z + 8 * u) : 0.0;
+                                    qv.w = 0.0;
+                                    pair_update<double, ZMODE>(qv, nx, ny, nz, dz2c, fa.inv_w, fa.c_magic, fa.kclamp,
+                                                               fa.thr_addr, h_addr);
+                                }
+                            }
+                        }
+                        __syncwarp();
+                        fill = 0;
+                        lo_end = 0;
+                    };
+                    // Gather n targets into the staging buffer behind position `at`, dropping those
+                    // farther than the cutoff from the box around the staged queries: no query of this
+                    // round can reach them (cull_r2 carries a 1e-4 relative margin, far above the
+                    // rounding of either side; the float64 regime tests against the outward-rounded
+                    // float32 box in float64).  Returns the new fill level.
+                    auto copy_targets = [&](auto* src, unsigned n, unsigned at, bool cull) -> unsigned {
+                        typedef decltype(src->x) ST;   // element type of the source array
+#pragma unroll 1
+                        for (unsigned base = 0; base < n; base += 32) {
+                            const unsigned i = base + lane;
+                            AT x = (AT)0, y = (AT)0, z = (AT)0;
+                            bool keep = i < n;
+                            if (keep) {
+                                const Vec4<ST> v = load_query<ST, ZMODE != 0>(src + i);
+                                x = (AT)v.x; y = (AT)v.y; z = (AT)v.z;
+                                if (cull) {
+                                    const AT ex = max(max((AT)lo[0] - x, x - (AT)hi[0]), (AT)0);
+                                    const AT ey = max(max((AT)lo[1] - y, y - (AT)hi[1]), (AT)0);
+                                    AT d2 = ex * ex + ey * ey;
+                                    if (ZMODE == 0) {
+                                        const AT ez = max(max((AT)lo[2] - z, z - (AT)hi[2]), (AT)0);
+                                        d2 += ez * ez;
+                                    }
+                                    keep = d2 <= (AT)cull_r2;   // false for NaN targets as well
+                                }
+                            }
+                            const unsigned m = __ballot_sync(0xffffffffu, keep);
+                            if (keep) {
+                                const unsigned o = kES * (at + __popc(m & ((1u << lane) - 1u)));
+                                sts_at(bx + o, x);
+                                sts_at(by + o, y);
+                                if (ZMODE == 0) sts_at(bz + o, z);
+                            }
+                            at += __popc(m);
+                        }
+                        return at;
+                    };
+                    for (int eb = 0; eb < E; eb += 32) {
+                        const int e = eb + lane;
+                        unsigned start = 0, len = 0, flags = 0;  // flags bit 0: counts twice, bit 1: lives in the query array
+                        if (e < E) {
+                            int r = -1;
+                            if (SYM) {
+                                if (e == 0) {
+                                    flags = 2;
+                                    if (part == 0) {
+                                        start = qa;
+                                        len = qb - qa;
+                                    }
+                                } else if (e <= G) {
+                                    r = e - 1;
+                                    if (rsplit > 1 && r % rsplit != part) r = -1;
+                                } else {
+                                    r = row0 + (e - 1 - G);
+                                    flags = 3;
+                                    if (rsplit > 1 && (r - row0) % rsplit != part) r = -1;
+                                }
+                            } else {
+                                r = e;
+                                if (rsplit > 1 && r % rsplit != part) r = -1;
+                            }
+                            if (r >= 0) {
+                                const int ny = cy + P.row_oy[r], nz = cz + P.row_oz[r];
+                                if (ny >= 0 && ny < n1 && nz >= 0 && nz < n2) {
+                                    const int kx = P.row_kx[r];
+                                    int x_lo = max(cx - kx, 0);
+                                    const int x_hi = min(cx + kx, n0 - 1);
+                                    if (flags == 3 && r == row0) x_lo = cx + 1;  // own row: only the cells to the right
+                                    if (x_lo <= x_hi) {
+                                        const unsigned* starts = (flags & 2) ? a.qstart : a.tstart;
+                                        const unsigned trow = P.cell_base + (unsigned)((nz * n1 + ny) * n0);
+                                        start = __ldg(&starts[trow + x_lo]);
+                                        len = __ldg(&starts[trow + x_hi + 1]) - start;
+                                    }
+                                }
+                            }
+                        }
+                        unsigned todo = __ballot_sync(0xffffffffu, len != 0);
+                        while (todo) {
+                            const int src = __ffs(todo) - 1;
+                            todo &= todo - 1;
+                            const unsigned st = __shfl_sync(0xffffffffu, start, src), ln = __shfl_sync(0xffffffffu, len, src);
+                            const unsigned fl = __shfl_sync(0xffffffffu, flags, src);
+                            const bool from_q = (fl & 2) != 0;   // entries of the symmetric walk that live in the query array
+                            const bool cull = fl != 2;            // the own cell holds the queries themselves
+                            auto gather = [&](unsigned off, unsigned n, unsigned at) -> unsigned {
+                                if constexpr (sizeof(AT) == sizeof(NT)) {   // one array type: one copy of the loop
+                                    const Vec4<AT>* arr = from_q ? qarr : reinterpret_cast<const Vec4<AT>*>(tarr);
+                                    return copy_targets(arr + st + off, n, at, cull);
+                                } else {
+                                    return from_q ? copy_targets(qarr + st + off, n, at, cull)
+                                                  : copy_targets(tarr + st + off, n, at, cull);
+                                }
+                            };
+                            if (fill + ln <= kStageCap && small_ok) {  // the usual case: the row fits
+                                const unsigned before = fill;
+                                fill = gather(0u, ln, fill);
+                                if (!(fl & 1)) lo_end = fill;
+                                staged += nqc * (fill - before);   // at most kQueryCap * kStageCap
+                                continue;
+                            }
+                            const unsigned long long npairs = (unsigned long long)nqc * ln;
+                            if (npairs > direct_pairs) {  // giant cells: straight to the global histogram
+                                oversize += npairs;
+                                if (from_q)
+                                    warp_pairs_general<AT, AT, ZMODE == 0 ? 0 : 1, true>(qarr, qc, qc + nqc, qarr + st, 0u, ln, thr,
+                                                                                         nbins, dz2c, inv_w, c_magic,
+                                                                                         (fl & 1) ? 2u : 1u, s_hist, g_hist);
+                                else
+                                    warp_pairs_general<AT, NT, ZMODE == 0 ? 0 : 1, true>(qarr, qc, qc + nqc, tarr + st, 0u, ln, thr,
+                                                                                         nbins, dz2c, inv_w, c_magic,
+                                                                                         (fl & 1) ? 2u : 1u, s_hist, g_hist);
+                                continue;
+                            }
+                            unsigned off = 0;
+                            while (off < ln) {
+                                const unsigned n = min(ln - off, kStageCap - fill);
+                                const unsigned before = fill;
+                                fill = gather(off, n, fill);
+                                staged += (unsigned long long)nqc * (fill - before);
+                                off += n;
+                                if (!(fl & 1)) lo_end = fill;
+                                if (fill == kStageCap) flush_stage();
+                            }
+                        }
+                    }
+                    if (fill) flush_stage();
+                }
+                if (lane == 0) {
+                    cand += staged + oversize;
+                    if (staged) atomicAdd(&s_units, (unsigned)(staged >> 10) + 1u);
+                }
             } else {
             // pass 0: real targets (SYM: upper half shell, own row to the right, own cell);
             // pass 1 (SYM only): shifted images, all rows, skipped where none can live
@@ -1235,10 +1487,10 @@ static int launch_pairs(amepb_ctx* ctx, const PairArgs& args, int zmode, cudaStr
                           : (zmode == 1 ? pair_kernel<AT, NT, 1, true, SYM> : pair_kernel<AT, NT, 0, true, SYM>);
     else kern = zmode != 0 ? pair_kernel<AT, NT, 1, false, SYM> : pair_kernel<AT, NT, 0, false, SYM>;
     size_t dyn = use_smem ? smem : 16;
-    if (use_smem && sizeof(AT) == 4) {
-        // per-warp staging buffers of the float32 regime (see kStageCap)
+    if (use_smem) {
+        // per-warp staging buffers (see kStageCapF32; the float64 kernels stage half as many elements)
         dyn = ((dyn + 15) & ~(size_t)15) +
-              (size_t)(kPairThreads / 32) * (kStageCap + kQueryCap) * (zmode == 0 ? 3 : 2) * sizeof(float);
+              (size_t)(kPairThreads / 32) * (kStageCapF32 + kQueryCapF32) * (zmode == 0 ? 3 : 2) * sizeof(float);
         AMEPB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     }
     int per_sm = 0;
