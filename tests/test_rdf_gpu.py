@@ -396,16 +396,17 @@ def test_integer_and_noncontiguous_inputs(sc):
     np.testing.assert_array_equal(counts[0], want)
 
 
-def test_full_size_properties(sc):
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64], ids=["f32", "f64"])
+def test_full_size_properties(sc, dtype):
     """Size-independent checks at a size the brute-force oracle cannot reach:
     grid refinements agree with each other bit for bit, the total matches the
     ideal-gas expectation, and a random sample of queries matches the oracle."""
     from amep_b200 import _lib
     n, L, rmax = 400_000, 800.0, 10.0
     g = torch.Generator(device="cuda").manual_seed(5)
-    c = torch.zeros((1, n, 3), device="cuda", dtype=torch.float32)
-    c[0, :, :2] = torch.rand((n, 2), generator=g, device="cuda") * L
-    box = np.array([[0, L], [0, L], [-0.5, 0.5]], dtype=np.float32)
+    c = torch.zeros((1, n, 3), device="cuda", dtype=dtype)
+    c[0, :, :2] = (torch.rand((n, 2), generator=g, device="cuda", dtype=torch.float64) * L).to(dtype)
+    box = np.array([[0, L], [0, L], [-0.5, 0.5]], dtype=np.float32 if dtype == torch.float32 else np.float64)
     ctx = _lib.context(0)
     results = []
     for k in (1, 2, 3):
