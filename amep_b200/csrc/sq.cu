@@ -274,6 +274,7 @@ constexpr int kC64Threads = 256;  // 8 warps: lanes = 32 qx values, each warp 2 
 constexpr int kC64TileA = 32;
 constexpr int kC64TileB = 16;
 constexpr int kC64Stage = 64;     // particles per shared-memory stage
+constexpr size_t kC64ChunkBufferBytes = (size_t)4 << 30;   // chunk sums of the split kernel, per launch
 
 // fl32(v) for a double v without the FP64 pipe (which the two DFMA per accumulation already
 // keep busy) and without F2F (a quarter of the FP64 rate): add half a float32 ulp to the bit
@@ -290,10 +291,14 @@ __device__ __forceinline__ double round_to_f32(double v) {
 // particle and lane (conflict free, 4 wavefronts per warp), the two Y entries are
 // warp-uniform broadcasts -- 3 shared-memory wavefronts per quad-point step instead of 8
 // with a 16 x 16 thread tile, which had the shared pipe at 62 % (ncu) next to the FP64 pipe.
-template <typename T>
+// SPLIT: gridDim.z blocks share the particles of a tile by whole chunks and write every chunk sum
+// (complex64) to chunk_out instead of accumulating the total; sf2d_c64_combine_kernel then adds
+// the chunk sums in chunk order in float32, exactly like the sequential kernel.  Used when a call
+// has too few frames to fill the GPU (one frame of configs[3] is 128 blocks for 148 SMs).
+template <typename T, bool SPLIT>
 __global__ void __launch_bounds__(kC64Threads, 4) sf2d_c64_kernel(
     const T* __restrict__ coords, long long n, const double* __restrict__ qall, long long q_stride, int nq,
-    long long chunksize, float2* __restrict__ rho) {
+    long long chunksize, float2* __restrict__ rho, float4* __restrict__ chunk_out, long long nchunks) {
     extern __shared__ __align__(16) unsigned char smem_c64[];
     double2 (*sX)[kC64TileA] = reinterpret_cast<double2 (*)[kC64TileA]>(smem_c64);
     double2 (*sY)[kC64TileB] = reinterpret_cast<double2 (*)[kC64TileB]>(smem_c64 + sizeof(double2) * kC64Stage * kC64TileA);
@@ -308,20 +313,28 @@ __global__ void __launch_bounds__(kC64Threads, 4) sf2d_c64_kernel(
     // [quad point 0 / 1][pp real, pp imag, mp real, mp imag]
     double acc[2][4] = {{0.0, 0.0, 0.0, 0.0}, {0.0, 0.0, 0.0, 0.0}};
     float tot[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-    long long chunk_end = chunksize < n ? chunksize : n;
+    long long j_lo = 0, j_hi = n, chunk_idx = 0;
+    if (SPLIT) {
+        chunk_idx = nchunks * blockIdx.z / gridDim.z;
+        const long long c_hi = nchunks * (blockIdx.z + 1) / gridDim.z;
+        j_lo = chunk_idx * chunksize;
+        j_hi = c_hi * chunksize < n ? c_hi * chunksize : n;
+    }
+    long long chunk_end = j_lo + chunksize < n ? j_lo + chunksize : n;
+    const int qa_idx = tile_a * kC64TileA + lane;
 
-    for (long long j0 = 0; j0 < n; j0 += kC64Stage) {
+    for (long long j0 = j_lo; j0 < j_hi; j0 += kC64Stage) {
         // tables: 2 X runs and 1 Y run of 16 entries per particle -> 192 of the 256 threads
         if (tid < 3 * kC64Stage) {
             const int jj = tid % kC64Stage, run = tid / kC64Stage;   // run 0,1: X; run 2: Y
             const long long j = j0 + jj;
-            if (j < n) {
+            if (j < j_hi) {
                 if (run < 2) table_run16((double)base[3 * j], q, tile_a * kC64TileA + run * 16, nq, &sX[jj][run * 16], 1);
                 else table_run16((double)base[3 * j + 1], q, tile_b * kC64TileB, nq, &sY[jj][0], 1);
             }
         }
         __syncthreads();
-        const int lim = (int)((n - j0) < kC64Stage ? (n - j0) : kC64Stage);
+        const int lim = (int)((j_hi - j0) < kC64Stage ? (j_hi - j0) : kC64Stage);
         int jj = 0;
         while (jj < lim) {
             // run to the next chunk boundary (or the end of the stage) without per-particle checks
@@ -348,18 +361,27 @@ __global__ void __launch_bounds__(kC64Threads, 4) sf2d_c64_kernel(
             if (j0 + jj == chunk_end) {
                 // rhoq += res : complex64 + complex64 (amep/spatialcor.py:1890-1891)
 #pragma unroll
-                for (int p = 0; p < 2; ++p)
+                for (int p = 0; p < 2; ++p) {
+                    if (SPLIT) {
+                        const int b = tile_b * kC64TileB + 2 * warp + p;
+                        if (qa_idx < nq && b < nq)
+                            chunk_out[(((long long)frame * nchunks + chunk_idx) * nq + b) * nq + qa_idx] =
+                                make_float4((float)acc[p][0], (float)acc[p][1], (float)acc[p][2], (float)acc[p][3]);
+                    }
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
-                        tot[p][c] = __fadd_rn(tot[p][c], (float)acc[p][c]);
+                        if (!SPLIT) tot[p][c] = __fadd_rn(tot[p][c], (float)acc[p][c]);
                         acc[p][c] = 0.0;
                     }
+                }
+                ++chunk_idx;
                 chunk_end = chunk_end + chunksize < n ? chunk_end + chunksize : n;
             }
         }
         __syncthreads();
     }
-    const int a = tile_a * kC64TileA + lane;
+    if (SPLIT) return;
+    const int a = qa_idx;
     const int g = 2 * nq;
     float2* r = rho + (long long)frame * g * g;
 #pragma unroll
@@ -373,6 +395,28 @@ __global__ void __launch_bounds__(kC64Threads, 4) sf2d_c64_kernel(
             r[(long long)iym * g + ixp] = make_float2(tot[p][2], -tot[p][3]);
         }
     }
+}
+
+// Sequential float32 sum of the chunk sums of the SPLIT kernel, in chunk order.
+__global__ void sf2d_c64_combine_kernel(const float4* __restrict__ chunk_out, long long nchunks, int nq, long long nframes,
+                                        float2* __restrict__ rho) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nframes * nq * nq) return;
+    const int a = (int)(i % nq), b = (int)((i / nq) % nq);
+    const long long frame = i / ((long long)nq * nq);
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+    const float4* src = chunk_out + (frame * nchunks * nq + b) * nq + a;
+    for (long long c = 0; c < nchunks; ++c) {
+        const float4 v = src[c * nq * nq];
+        t0 = __fadd_rn(t0, v.x); t1 = __fadd_rn(t1, v.y); t2 = __fadd_rn(t2, v.z); t3 = __fadd_rn(t3, v.w);
+    }
+    const int g = 2 * nq;
+    float2* r = rho + frame * g * g;
+    const int ixp = nq + a, ixm = nq - 1 - a, iyp = nq + b, iym = nq - 1 - b;
+    r[(long long)iyp * g + ixp] = make_float2(t0, t1);
+    r[(long long)iyp * g + ixm] = make_float2(t2, t3);
+    r[(long long)iym * g + ixm] = make_float2(t0, -t1);
+    r[(long long)iym * g + ixp] = make_float2(t2, -t3);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -625,13 +669,22 @@ int amepb_sf2d_modes(amepb_ctx* ctx, const void* coords, int dtype, int space, i
 
     const size_t smem_f64 = sizeof(double2) * kF64Stage * 64 * 2;
     const size_t smem_c64 = sizeof(double2) * kC64Stage * (kC64TileA + kC64TileB);
+    if (accum == AMEPB_ACCUM_C64_REFERENCE) {
+        // frames per launch such that the chunk sums of the split kernel fit their buffer
+        const size_t nchunks = (size_t)((n + chunksize - 1) / chunksize);
+        const size_t per_frame = sizeof(float4) * nchunks * nq * nq;
+        if (nchunks >= 4 && per_frame <= kC64ChunkBufferBytes)
+            fb = std::min<int64_t>(fb, (int64_t)(kC64ChunkBufferBytes / per_frame));
+    }
     if (!ctx->sq_attr_sf2d) {
         AMEPB_CUDA(ctx, cudaFuncSetAttribute(sf2d_f64_kernel<float, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f64));
         AMEPB_CUDA(ctx, cudaFuncSetAttribute(sf2d_f64_kernel<float, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f64));
         AMEPB_CUDA(ctx, cudaFuncSetAttribute(sf2d_f64_kernel<float, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f64));
         AMEPB_CUDA(ctx, cudaFuncSetAttribute(sf2d_f64_kernel<double, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f64));
-        AMEPB_CUDA(ctx, cudaFuncSetAttribute(sf2d_c64_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c64));
-        AMEPB_CUDA(ctx, cudaFuncSetAttribute(sf2d_c64_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c64));
+        AMEPB_CUDA(ctx, cudaFuncSetAttribute(sf2d_c64_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c64));
+        AMEPB_CUDA(ctx, cudaFuncSetAttribute(sf2d_c64_kernel<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c64));
+        AMEPB_CUDA(ctx, cudaFuncSetAttribute(sf2d_c64_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c64));
+        AMEPB_CUDA(ctx, cudaFuncSetAttribute(sf2d_c64_kernel<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c64));
         ctx->sq_attr_sf2d = true;
     }
     // float64 mode: bound the split-K scratch
@@ -698,11 +751,33 @@ int amepb_sf2d_modes(amepb_ctx* ctx, const void* coords, int dtype, int space, i
             AMEPB_LAUNCH_CHECK(ctx);
         } else {
             const int tiles_a = (nq + kC64TileA - 1) / kC64TileA, tiles_b = (nq + kC64TileB - 1) / kC64TileB;
-            dim3 grid((unsigned)(tiles_a * tiles_b), (unsigned)nf);
-            if (dtype == AMEPB_F32)
-                sf2d_c64_kernel<float><<<grid, kC64Threads, smem_c64, stream>>>((const float*)d_coords, n, qf, q_stride, nq, chunksize, reinterpret_cast<float2*>(d_out));
-            else
-                sf2d_c64_kernel<double><<<grid, kC64Threads, smem_c64, stream>>>((const double*)d_coords, n, qf, q_stride, nq, chunksize, reinterpret_cast<float2*>(d_out));
+            // split the particles of every tile by whole chunks over up to 8 blocks (see SPLIT): measured
+            // per-frame time for 1 ... 12 frames of configs[3] is lowest with 8 splits throughout
+            // (28.7 -> 20.4 ms for a single frame, 20.5 -> 19.7 ms for 8), tools/sf2d_split_sweep.py
+            const long long nchunks = (n + chunksize - 1) / chunksize;
+            long long ksplit_c = 1;
+            if (nchunks >= 4 && getenv("AMEPB_SF2D_NO_SPLIT") == nullptr &&
+                sizeof(float4) * (size_t)nf * nchunks * nq * nq <= kC64ChunkBufferBytes)
+                ksplit_c = std::min<long long>(8, nchunks / 2);
+            if (const char* ks = getenv("AMEPB_SF2D_SPLIT")) ksplit_c = std::max<long long>(1, std::min<long long>(atoi(ks), nchunks / 2));
+            if (ksplit_c > 1) {
+                if ((rc = ensure_device(ctx, BUF_SQ_B, sizeof(float4) * (size_t)nf * nchunks * nq * nq))) return rc;
+                float4* d_chunks = reinterpret_cast<float4*>(ctx->bufs[BUF_SQ_B].p);
+                dim3 grid((unsigned)(tiles_a * tiles_b), (unsigned)nf, (unsigned)ksplit_c);
+                if (dtype == AMEPB_F32)
+                    sf2d_c64_kernel<float, true><<<grid, kC64Threads, smem_c64, stream>>>((const float*)d_coords, n, qf, q_stride, nq, chunksize, reinterpret_cast<float2*>(d_out), d_chunks, nchunks);
+                else
+                    sf2d_c64_kernel<double, true><<<grid, kC64Threads, smem_c64, stream>>>((const double*)d_coords, n, qf, q_stride, nq, chunksize, reinterpret_cast<float2*>(d_out), d_chunks, nchunks);
+                AMEPB_LAUNCH_CHECK(ctx);
+                const long long total = (long long)nf * nq * nq;
+                sf2d_c64_combine_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(d_chunks, nchunks, nq, nf, reinterpret_cast<float2*>(d_out));
+            } else {
+                dim3 grid((unsigned)(tiles_a * tiles_b), (unsigned)nf);
+                if (dtype == AMEPB_F32)
+                    sf2d_c64_kernel<float, false><<<grid, kC64Threads, smem_c64, stream>>>((const float*)d_coords, n, qf, q_stride, nq, chunksize, reinterpret_cast<float2*>(d_out), nullptr, nchunks);
+                else
+                    sf2d_c64_kernel<double, false><<<grid, kC64Threads, smem_c64, stream>>>((const double*)d_coords, n, qf, q_stride, nq, chunksize, reinterpret_cast<float2*>(d_out), nullptr, nchunks);
+            }
             AMEPB_LAUNCH_CHECK(ctx);
             cudaEvent_t ev1 = timing_event(ctx, stream);
             if (ev0 && ev1) ctx->ev_sq.emplace_back(ev0, ev1);
