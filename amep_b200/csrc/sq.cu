@@ -273,7 +273,7 @@ __global__ void sf2d_f64_finish_kernel(const double* __restrict__ partial, int k
 constexpr int kC64Threads = 256;  // 8 warps: lanes = 32 qx values, each warp 2 qy values
 constexpr int kC64TileA = 32;
 constexpr int kC64TileB = 16;
-constexpr int kC64Stage = 64;     // particles per shared-memory stage
+constexpr int kC64Stage = 32;     // particles per shared-memory stage (two stages resident)
 constexpr size_t kC64ChunkBufferBytes = (size_t)4 << 30;   // chunk sums of the split kernel, per launch
 
 // fl32(v) for a double v without the FP64 pipe (which the two DFMA per accumulation already
@@ -291,6 +291,22 @@ __device__ __forceinline__ double round_to_f32(double v) {
 // particle and lane (conflict free, 4 wavefronts per warp), the two Y entries are
 // warp-uniform broadcasts -- 3 shared-memory wavefronts per quad-point step instead of 8
 // with a 16 x 16 thread tile, which had the shared pipe at 62 % (ncu) next to the FP64 pipe.
+// Tables of one stage (2 X runs and 1 Y run of 16 entries per particle -> 3 * kC64Stage threads).
+// Not inlined on purpose: the double-precision sincos would otherwise inflate the register
+// allocation of the accumulation loop it is interleaved with.
+template <typename T>
+__device__ __noinline__ void c64_build_stage(const T* __restrict__ base, const double* __restrict__ q, long long j0,
+                                             long long j_hi, int xa0, int ya0, int nq, double2* __restrict__ bX,
+                                             double2* __restrict__ bY) {
+    const int tid = threadIdx.x;
+    if (tid >= 3 * kC64Stage) return;
+    const int jj = tid % kC64Stage, run = tid / kC64Stage;   // run 0,1: X; run 2: Y
+    const long long j = j0 + jj;
+    if (j >= j_hi) return;
+    if (run < 2) table_run16((double)base[3 * j], q, xa0 + run * 16, nq, bX + jj * kC64TileA + run * 16, 1);
+    else table_run16((double)base[3 * j + 1], q, ya0, nq, bY + jj * kC64TileB, 1);
+}
+
 // SPLIT: gridDim.z blocks share the particles of a tile by whole chunks and write every chunk sum
 // (complex64) to chunk_out instead of accumulating the total; sf2d_c64_combine_kernel then adds
 // the chunk sums in chunk order in float32, exactly like the sequential kernel.  Used when a call
@@ -300,8 +316,7 @@ __global__ void __launch_bounds__(kC64Threads, 4) sf2d_c64_kernel(
     const T* __restrict__ coords, long long n, const double* __restrict__ qall, long long q_stride, int nq,
     long long chunksize, float2* __restrict__ rho, float4* __restrict__ chunk_out, long long nchunks) {
     extern __shared__ __align__(16) unsigned char smem_c64[];
-    double2 (*sX)[kC64TileA] = reinterpret_cast<double2 (*)[kC64TileA]>(smem_c64);
-    double2 (*sY)[kC64TileB] = reinterpret_cast<double2 (*)[kC64TileB]>(smem_c64 + sizeof(double2) * kC64Stage * kC64TileA);
+    constexpr size_t kBufBytes = sizeof(double2) * kC64Stage * (kC64TileA + kC64TileB);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tiles_a = (nq + kC64TileA - 1) / kC64TileA;
     const int tile_a = blockIdx.x % tiles_a, tile_b = blockIdx.x / tiles_a;
@@ -323,17 +338,18 @@ __global__ void __launch_bounds__(kC64Threads, 4) sf2d_c64_kernel(
     long long chunk_end = j_lo + chunksize < n ? j_lo + chunksize : n;
     const int qa_idx = tile_a * kC64TileA + lane;
 
-    for (long long j0 = j_lo; j0 < j_hi; j0 += kC64Stage) {
-        // tables: 2 X runs and 1 Y run of 16 entries per particle -> 192 of the 256 threads
-        if (tid < 3 * kC64Stage) {
-            const int jj = tid % kC64Stage, run = tid / kC64Stage;   // run 0,1: X; run 2: Y
-            const long long j = j0 + jj;
-            if (j < j_hi) {
-                if (run < 2) table_run16((double)base[3 * j], q, tile_a * kC64TileA + run * 16, nq, &sX[jj][run * 16], 1);
-                else table_run16((double)base[3 * j + 1], q, tile_b * kC64TileB, nq, &sY[jj][0], 1);
-            }
-        }
-        __syncthreads();
+    auto buf_x = [&](int b) { return reinterpret_cast<double2*>(smem_c64 + b * kBufBytes); };
+    auto buf_y = [&](int b) { return reinterpret_cast<double2*>(smem_c64 + b * kBufBytes + sizeof(double2) * kC64Stage * kC64TileA); };
+    c64_build_stage<T>(base, q, j_lo, j_hi, tile_a * kC64TileA, tile_b * kC64TileB, nq, buf_x(0), buf_y(0));
+    __syncthreads();
+    int cur = 0;
+    for (long long j0 = j_lo; j0 < j_hi; j0 += kC64Stage, cur ^= 1) {
+        // the tables of the next stage are built by three of the eight warps before they join the
+        // accumulation of this stage; one barrier per stage
+        if (j0 + kC64Stage < j_hi)
+            c64_build_stage<T>(base, q, j0 + kC64Stage, j_hi, tile_a * kC64TileA, tile_b * kC64TileB, nq, buf_x(cur ^ 1), buf_y(cur ^ 1));
+        const double2 (*sX)[kC64TileA] = reinterpret_cast<const double2 (*)[kC64TileA]>(buf_x(cur));
+        const double2 (*sY)[kC64TileB] = reinterpret_cast<const double2 (*)[kC64TileB]>(buf_y(cur));
         const int lim = (int)((j_hi - j0) < kC64Stage ? (j_hi - j0) : kC64Stage);
         int jj = 0;
         while (jj < lim) {
@@ -668,7 +684,7 @@ int amepb_sf2d_modes(amepb_ctx* ctx, const void* coords, int dtype, int space, i
     const double* d_q = reinterpret_cast<const double*>(ctx->bufs[BUF_SQ_A].p);
 
     const size_t smem_f64 = sizeof(double2) * kF64Stage * 64 * 2;
-    const size_t smem_c64 = sizeof(double2) * kC64Stage * (kC64TileA + kC64TileB);
+    const size_t smem_c64 = 2 * sizeof(double2) * kC64Stage * (kC64TileA + kC64TileB);
     if (accum == AMEPB_ACCUM_C64_REFERENCE) {
         // frames per launch such that the chunk sums of the split kernel fit their buffer
         const size_t nchunks = (size_t)((n + chunksize - 1) / chunksize);
