@@ -294,6 +294,67 @@ def density_counts(coords, box_boundary, xedges, yedges, pbc=True, device=None):
     return out
 
 
+def pcf2d_counts(coords, other, center, center_f32, rot, xedges, yedges, device=None):
+    """Pair counts on the (dx, dy) grid of ``amep.spatialcor.pcf2d`` (amepb_pcf2d_counts): int64
+    ``[F, nx, ny]`` (a CUDA tensor if the coordinates live on the device, else NumPy).
+
+    ``other=None`` means the same particles (equal indices are skipped).  ``center``: float64
+    ``[F, 3]``; ``rot``: ``None`` or float64 ``[F, 3]`` = (flag, cos, sin); ``xedges`` / ``yedges``:
+    ``[nx+1]`` / ``[ny+1]`` shared by all frames, or ``[F, nx+1]`` / ``[F, ny+1]``."""
+    pc = coords if isinstance(coords, Particles) else Particles(coords)
+    same = other is None
+    po = pc if same else (other if isinstance(other, Particles) else Particles(other, "other_coords"))
+    nf = pc.nframes
+    if po.nframes != nf:
+        raise ValueError("coords and other_coords hold different numbers of frames")
+    if po.on_device != pc.on_device:
+        raise ValueError("coords and other_coords must both be NumPy arrays or both CUDA tensors")
+    xe = np.asarray(xedges, dtype=np.float64)
+    ye = np.asarray(yedges, dtype=np.float64)
+    if xe.ndim != ye.ndim or xe.ndim not in (1, 2) or xe.shape[-1] < 2 or ye.shape[-1] < 2:
+        raise ValueError("bin edges must be [nx+1] / [ny+1] or [F, nx+1] / [F, ny+1] with at least two entries")
+    nxe, nye = xe.shape[-1], ye.shape[-1]
+    stride = 0
+    if xe.ndim == 2:
+        if len(xe) != nf or len(ye) != nf:
+            raise ValueError("per-frame bin edges need one row per frame")
+        stride = max(nxe, nye)
+        xpad = np.zeros((nf, stride)); xpad[:, :nxe] = xe
+        ypad = np.zeros((nf, stride)); ypad[:, :nye] = ye
+        xe, ye = xpad, ypad
+    xe = np.ascontiguousarray(xe)
+    ye = np.ascontiguousarray(ye)
+    cen = np.ascontiguousarray(np.broadcast_to(np.asarray(center, dtype=np.float64), (nf, 3)))
+    rot_ptr = None
+    if rot is not None:
+        rot = np.ascontiguousarray(np.broadcast_to(np.asarray(rot, dtype=np.float64), (nf, 3)))
+        rot_ptr = rot.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+    dev_index = _device_of(pc, device)
+    ctx = _lib.context(dev_index)
+    shape = (nf, nxe - 1, nye - 1)
+    if pc.on_device:
+        import torch
+        out = torch.empty(shape, dtype=torch.int64, device=pc.tensor.device)
+        optr, space = out.data_ptr(), _lib.DEVICE
+    else:
+        out = np.empty(shape, dtype=np.int64)
+        optr, space = out.ctypes.data, _lib.HOST
+    if nf == 0 or pc.n == 0 or po.n == 0:
+        if pc.on_device:
+            out.zero_()
+        else:
+            out[...] = 0
+        return out
+    rc = ctx.lib.amepb_pcf2d_counts(
+        ctx.handle, ctypes.c_void_p(pc.ptr()), pc.dtype, pc.n, ctypes.c_void_p(po.ptr()), po.dtype, po.n,
+        1 if same else 0, space, nf, cen.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), 1 if center_f32 else 0,
+        rot_ptr, xe.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), nxe,
+        ye.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), nye, stride,
+        ctypes.c_void_p(optr), _stream_for(dev_index, pc.on_device))
+    ctx.check(rc, "amepb_pcf2d_counts")
+    return out
+
+
 def sf2d_modes(coords, qpos, nq, accum="c64", chunksize=0, device=None):
     """rho(q) on the sf2d grid (amepb_sf2d_modes) -> complex array ``[F, 2nq, 2nq]``.
 

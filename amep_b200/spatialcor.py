@@ -1,8 +1,8 @@
 """Drop-in for the RDF / S(q) functions of ``amep.spatialcor`` (AMEP 1.3.0).
 
 Same signatures, argument meaning and error behaviour as
-``amep.spatialcor.rdf`` (amep/spatialcor.py:421-649), ``sfiso`` (:1451-1687) and
-``sf2d`` (:1722-1940).  The per-particle work runs in libamepb's sm_100a
+``amep.spatialcor.rdf`` (amep/spatialcor.py:421-649), ``sfiso`` (:1451-1687),
+``sf2d`` (:1722-1940) and ``pcf2d`` (:726-926).  The per-particle work runs in libamepb's sm_100a
 kernels; what stays on the host is the parameter prologue (bin edges, q grid,
 unit vectors) and the normalisation epilogue, written as the same NumPy
 expressions as the reference because they define output dtype and rounding
@@ -25,7 +25,7 @@ from .utils import (available_cpu_count, optimal_chunksize, runningmean, sq_from
 
 _log = logging.getLogger("amep_b200.spatialcor")
 
-__all__ = ["rdf", "sfiso", "sf2d", "rdf_frames", "sfiso_frames", "sf2d_frames"]
+__all__ = ["rdf", "sfiso", "sf2d", "pcf2d", "rdf_frames", "sfiso_frames", "sf2d_frames", "pcf2d_frames"]
 
 
 def _box_numpy(box_boundary):
@@ -409,3 +409,94 @@ def sf2d(coords, box_boundary, other_coords=None, qmax=20.0, njobs=1, mode="std"
     s, qx, qy = sf2d_frames(coords, box_boundary, other_coords, qmax=qmax, njobs=njobs, mode=mode,
                             Ntot=Ntot, accuracy=accuracy, chunksize=chunksize, accum=accum)
     return s[0], qx[0], qy[0]
+
+
+# =============================================================================
+# PCF2D
+# =============================================================================
+def _pcf2d_angle(psi):
+    """Angle that orients the x axis along ``psi`` (amep/spatialcor.py:866-872)."""
+    angle = 0.0
+    if psi is not None:
+        ex = np.array([1, 0])
+        angle = np.arccos(np.dot(ex, psi) / np.sqrt(psi[0] ** 2 + psi[1] ** 2))
+        if psi[1] < 0:
+            angle = 2 * np.pi - angle
+    return angle
+
+
+def _zero_last_column(data):
+    """``coords[:,-1] = 0.0`` (amep/spatialcor.py:846-848): the reference flattens the caller's
+    arrays in place, and so does this."""
+    if isinstance(data, _core.Particles):
+        data = data.tensor if data.on_device else data.array
+    data[..., -1] = 0.0
+
+
+def pcf2d_frames(coords, box_boundary, other_coords=None, nxbins=None, nybins=None, rmax=None,
+                 psi=None):
+    """``pcf2d`` for a batch of frames ``[F, N, 3]`` in one library call.
+
+    ``box_boundary``: ``(3,2)`` or ``(F,3,2)``; ``psi``: ``None``, ``(2,)`` or ``(F,2)``.  Returns
+    ``(g [F, nx, ny], X [F, ny, nx], Y [F, ny, nx])``: per frame what ``amep.spatialcor.pcf2d``
+    returns.  The bin edges follow each frame's box when ``rmax`` is None."""
+    same = other_coords is None
+    _zero_last_column(coords)
+    if not same:
+        _zero_last_column(other_coords)
+    pc = coords if isinstance(coords, _core.Particles) else _core.Particles(coords)
+    po = pc if same else (other_coords if isinstance(other_coords, _core.Particles)
+                          else _core.Particles(other_coords, "other_coords"))
+    nf = pc.nframes
+    bb_all = _box_numpy(box_boundary)
+    if nxbins is None:
+        nxbins = 500
+    if nybins is None:
+        nybins = 500
+    if psi is not None:
+        psi = np.asarray(psi)
+    xbins_all, ybins_all, centers, rots, boxes = [], [], [], [], []
+    for f in range(nf):
+        bb = bb_all[f] if bb_all.ndim == 3 else bb_all
+        box = bb[:, 1] - bb[:, 0]
+        # divide by 2*np.sqrt(2) to allow averaging with rotation (amep/spatialcor.py:857-861;
+        # the floor division is the reference's)
+        r = max(box) // (2 * np.sqrt(2)) if rmax is None else rmax
+        angle = _pcf2d_angle(None if psi is None else (psi[f] if psi.ndim == 2 else psi))
+        xbins_all.append(np.linspace(-r, r, nxbins + 1))
+        ybins_all.append(np.linspace(-r, r, nybins + 1))
+        centers.append(np.mean(bb, axis=1))
+        theta = -angle
+        rots.append((1.0 if angle != 0.0 else 0.0, np.cos(theta), np.sin(theta)))
+        boxes.append(box)
+    center_f32 = nf > 0 and centers[0].dtype == np.float32
+    counts = _core.pcf2d_counts(
+        pc, None if same else po, np.array(centers, dtype=np.float64).reshape(nf, 3), center_f32,
+        np.array(rots, dtype=np.float64).reshape(nf, 3) if any(r[0] for r in rots) else None,
+        np.array(xbins_all, dtype=np.float64).reshape(nf, nxbins + 1),
+        np.array(ybins_all, dtype=np.float64).reshape(nf, nybins + 1))
+    if _core._is_torch(counts):
+        counts = counts.cpu().numpy()
+    g, xs, ys = [], [], []
+    for f in range(nf):
+        xbins, ybins, box = xbins_all[f], ybins_all[f], boxes[f]
+        hist = counts[f].astype(float)
+        # normalization (amep/spatialcor.py:914-926)
+        area = (xbins[1:] - xbins[:-1])[:, None] * (ybins[1:] - ybins[:-1])
+        density = pc.n / (box[0] * box[1])
+        g.append(hist / area / density / po.n)
+        X, Y = np.meshgrid(runningmean(xbins, 2), runningmean(ybins, 2))
+        xs.append(X)
+        ys.append(Y)
+    return np.array(g), np.array(xs), np.array(ys)
+
+
+def pcf2d(coords, box_boundary, other_coords=None, nxbins=None, nybins=None, rmax=None, psi=None,
+          njobs=1, pbc=True, verbose=False, chunksize=None):
+    """2D pair correlation function g(x, y) of one frame; contract of ``amep.spatialcor.pcf2d``
+    (amep/spatialcor.py:726-926), including what the reference actually does with its arguments:
+    plain difference vectors ``other_coords[n] - coords`` without minimum image (``pbc`` is
+    accepted and has no effect, amep/spatialcor.py:700-713), the last column of the caller's
+    arrays set to zero in place (:846-848) and ``rmax = max(box)//(2*sqrt(2))`` by default (:861)."""
+    g, X, Y = pcf2d_frames(coords, box_boundary, other_coords, nxbins=nxbins, nybins=nybins, rmax=rmax, psi=psi)
+    return g[0], X[0], Y[0]

@@ -18,6 +18,8 @@
  *                             amep/spatialcor.py:1876-1907  chunk fan-out + sum
  *   amepb_density_counts   <- amep/continuum.py:300-407     hde (np.histogram2d of the images),
  *                             reached by sf2d/sfiso(mode='fft'), amep/spatialcor.py:1911-1940
+ *   amepb_pcf2d_counts     <- amep/spatialcor.py:652-723    __dhist2d (difference vectors, rotation,
+ *                             np.histogram2d) and the chunk fan-out + sum of pcf2d, :886-912
  *
  * Conventions
  *   - plain C types only; no exceptions cross the boundary;
@@ -190,6 +192,30 @@ int amepb_density_counts(amepb_ctx* ctx, const void* coords, int dtype, int64_t 
                          int64_t nframes, const double* box_boundary, int box_dtype, int pbc,
                          const double* xedges, int32_t nxe, const double* yedges, int32_t nye,
                          uint32_t* counts, void* stream);
+
+/*
+ * Pair counts on the (dx, dy) grid of spatialcor.pcf2d (amep/spatialcor.py:652-723 __dhist2d,
+ * summed over all chunks as amep/spatialcor.py:886-912 does): for every row o of `other` and every
+ * row c of `coords` (skipping equal indices when same != 0) the difference o - c in the promoted
+ * dtype of the two arrays -- no minimum image, exactly like the reference, whose pbc_diff calls
+ * are commented out -- optionally rotated about the box centre (amep/utils.py:581-652: subtract the
+ * centre, multiply by R(-angle) in float64, add the centre), binned like np.histogram2d with
+ * explicit edges (bin i holds edges[i] <= v < edges[i+1], the last bin also its right edge).
+ *   center      host float64 [nframes][3]: np.mean(box_boundary, axis=1) widened to float64;
+ *               center_f32 != 0 says that it was float32 (then "diff - centre" of float32
+ *               differences is a float32 subtraction, as NumPy's promotion makes it)
+ *   rot         NULL (no rotation) or host float64 [nframes][3] = (flag, cos(-angle), sin(-angle)):
+ *               flag != 0 where the reference's `angle != 0.0` holds
+ *   xedges, yedges  host float64, strictly increasing; shared by all frames (edge_stride = 0) or
+ *               one set per frame, edge_stride doubles apart
+ *   counts      [nframes][nxe-1][nye-1] uint64 in `space` (x-major like np.histogram2d)
+ * The call returns after the work is complete (it synchronises `stream`).
+ */
+int amepb_pcf2d_counts(amepb_ctx* ctx, const void* coords, int dtype, int64_t n, const void* other,
+                       int other_dtype, int64_t m, int same, int space, int64_t nframes,
+                       const double* center, int center_f32, const double* rot, const double* xedges,
+                       int32_t nxe, const double* yedges, int32_t nye, int64_t edge_stride,
+                       uint64_t* counts, void* stream);
 
 /*
  * Density modes on the sf2d grid: rho[f][iy][ix] = sum_i exp(-i (qx[ix] x_i + qy[iy] y_i))

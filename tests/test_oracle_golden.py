@@ -175,3 +175,35 @@ def test_c_oracle_sf2d_bit_exact(name):
     s, qx, qy = corc.sf2d_std(z["coords"], z["box"], other, qmax=float(z["qmax"]),
                               chunksize=None if cs < 0 else cs)
     np.testing.assert_array_equal(s, z["S"])
+
+
+PCF2D_CASES = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "pcf2d_*.npz")))
+
+
+def pcf2d_kwargs(z):
+    kw = {}
+    if int(z["nxbins"]) >= 0:
+        kw["nxbins"] = int(z["nxbins"])
+    if int(z["nybins"]) >= 0:
+        kw["nybins"] = int(z["nybins"])
+    if not np.isnan(float(z["rmax"])):
+        kw["rmax"] = float(z["rmax"])
+    if "psi" in z.files:
+        kw["psi"] = z["psi"]
+    return kw
+
+
+@pytest.mark.parametrize("name", PCF2D_CASES)
+def test_pcf2d_bit_exact(name):
+    """pcf2d: integer pair counts, g(x, y) and the bin-centre grids, bit for bit."""
+    assert len(PCF2D_CASES) == 6
+    z = _load(name)
+    other = z["other"] if "other" in z.files else None
+    kw = pcf2d_kwargs(z)
+    counts, _, _ = orc.pcf2d_counts(z["coords"], z["box"], other, **kw)
+    np.testing.assert_array_equal(counts, z["counts"])
+    g, X, Y = orc.pcf2d(z["coords"], z["box"], other, **kw)
+    assert g.dtype == z["g"].dtype
+    np.testing.assert_array_equal(g, z["g"])
+    np.testing.assert_array_equal(X, z["X"])
+    np.testing.assert_array_equal(Y, z["Y"])

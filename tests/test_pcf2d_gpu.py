@@ -1,0 +1,130 @@
+"""pcf2d parity on the GPU: spatialcor.pcf2d through the C ABI against the reference's golden
+vectors and the CPU oracle.  The pair counts are integers: bit-exact; g(x, y), X and Y are the
+reference's NumPy expressions on those counts: bit-exact as well."""
+import glob
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+import amep_oracle as orc
+from conftest import GOLDEN
+from test_oracle_golden import pcf2d_kwargs
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+PCF2D_CASES = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "pcf2d_*.npz")))
+
+
+@pytest.fixture(scope="module")
+def sc():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import amep_b200
+    return amep_b200.spatialcor
+
+
+def _rng(tag):
+    return np.random.default_rng(zlib.crc32(tag.encode()))
+
+
+@pytest.mark.parametrize("space", ["host", "device"])
+@pytest.mark.parametrize("name", PCF2D_CASES)
+def test_pcf2d_golden(sc, name, space):
+    z = np.load(os.path.join(GOLDEN, name))
+    coords = z["coords"].copy()
+    other = z["other"].copy() if "other" in z.files else None
+    if space == "device":
+        coords = torch.from_numpy(coords).cuda()
+        other = None if other is None else torch.from_numpy(other).cuda()
+    g, X, Y = sc.pcf2d(coords, z["box"], other_coords=other, **pcf2d_kwargs(z))
+    assert g.dtype == z["g"].dtype and g.shape == z["g"].shape
+    np.testing.assert_array_equal(g, z["g"])
+    np.testing.assert_array_equal(X, z["X"])
+    np.testing.assert_array_equal(Y, z["Y"])
+    # the reference flattens the caller's arrays in place (amep/spatialcor.py:846-848)
+    last = coords[:, -1].cpu().numpy() if space == "device" else coords[:, -1]
+    assert not last.any()
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("rot", [False, True])
+def test_pcf2d_counts_vs_oracle_ragged(sc, dtype, rot):
+    """Sizes that are no multiple of the query tile (256) or the target stage (1024), several
+    target splits, default 500 x 500 grid."""
+    from amep_b200 import _core
+    rng = _rng(f"pcf2d-ragged-{np.dtype(dtype).name}-{rot}")
+    n, m = 2311, 777
+    box = np.array([[0, 40], [0, 40], [-0.5, 0.5]], dtype=dtype)
+    c = np.zeros((n, 3), dtype=dtype)
+    c[:, :2] = rng.uniform(0, 40, (n, 2)).astype(dtype)
+    o = np.zeros((m, 3), dtype=dtype)
+    o[:, :2] = rng.uniform(0, 40, (m, 2)).astype(dtype)
+    psi = np.array([-0.4, 0.6]) if rot else None
+    want, xb, yb = orc.pcf2d_counts(c, box, o, psi=psi)
+    g, X, Y = sc.pcf2d(c.copy(), box, other_coords=o.copy(), psi=psi)
+    gw, Xw, Yw = orc.pcf2d(c, box, o, psi=psi)
+    assert want.sum() > 0
+    np.testing.assert_array_equal(g, gw)
+    np.testing.assert_array_equal(X, Xw)
+    # same particles: the equal-index pair is the only one left out
+    want_s, _, _ = orc.pcf2d_counts(c, box, None, nxbins=64, nybins=48, rmax=11.0, psi=psi)
+    cen = np.mean(box, axis=1)
+    r = None
+    if rot:
+        ang = np.arccos(psi[0] / np.sqrt(psi[0] ** 2 + psi[1] ** 2))
+        r = np.array([[1.0, np.cos(-ang), np.sin(-ang)]])
+    got_s = _core.pcf2d_counts(torch.from_numpy(c).cuda(), None, cen.astype(np.float64)[None], cen.dtype == np.float32, r,
+                               np.linspace(-11.0, 11.0, 65), np.linspace(-11.0, 11.0, 49))
+    np.testing.assert_array_equal(got_s[0].cpu().numpy(), want_s)
+
+
+def test_pcf2d_frames_batch_matches_single_frames(sc):
+    """Several frames with their own boxes (own default rmax, own edges) and orientations in one
+    library call give what frame-by-frame calls give."""
+    rng = _rng("pcf2d-frames")
+    nf, n = 3, 900
+    boxes = np.array([[[0, 30 + 4 * f], [0, 30 + 4 * f], [-0.5, 0.5]] for f in range(nf)], dtype=np.float32)
+    c = np.zeros((nf, n, 3), dtype=np.float32)
+    for f in range(nf):
+        c[f, :, :2] = rng.uniform(0, 30 + 4 * f, (n, 2)).astype(np.float32)
+    psi = np.array([[0.2, 0.9], [1.0, 0.0], [-0.3, -0.8]])
+    g, X, Y = sc.pcf2d_frames(torch.from_numpy(c).cuda(), boxes, nxbins=50, nybins=30, psi=psi)
+    assert g.shape == (nf, 50, 30) and X.shape == (nf, 30, 50)
+    for f in range(nf):
+        g1, X1, Y1 = sc.pcf2d(c[f].copy(), boxes[f], nxbins=50, nybins=30, psi=psi[f])
+        gw, Xw, Yw = orc.pcf2d(c[f], boxes[f], None, 50, 30, None, psi[f])
+        np.testing.assert_array_equal(g[f], g1)
+        np.testing.assert_array_equal(g[f], gw)
+        np.testing.assert_array_equal(X[f], Xw)
+        np.testing.assert_array_equal(Y[f], Yw)
+
+
+def test_pcf2d_sum_rule_large(sc):
+    """Size-independent property at a size the oracle cannot reach: with a window that covers
+    every difference vector the counts add up to N*(N-1), and g(x, y) = g(-x, -y) for the same
+    particles (every pair is seen from both ends)."""
+    from amep_b200 import _core
+    rng = _rng("pcf2d-large")
+    n = 60000
+    c = torch.zeros((n, 3), dtype=torch.float32)
+    c[:, :2] = torch.from_numpy(rng.uniform(0, 100, (n, 2)).astype(np.float32))
+    edges = np.linspace(-128.0, 128.0, 257)
+    counts = _core.pcf2d_counts(c.cuda(), None, np.array([[50.0, 50.0, 0.0]]), True, None, edges, edges)[0].cpu().numpy()
+    assert counts.sum() == n * (n - 1)
+    # exact float32 differences are antisymmetric, bins are [lo, hi): only differences that sit
+    # exactly on an edge land one bin off the mirror image
+    mirror = counts[::-1, ::-1]
+    assert np.abs(counts - mirror).sum() <= 1e-4 * counts.sum()
+
+
+def test_pcf2d_invalid_arguments(sc):
+    from amep_b200 import _core, _lib
+    c = torch.zeros((10, 3), dtype=torch.float32).cuda()
+    with pytest.raises(_lib.AmepbError):
+        _core.pcf2d_counts(c, None, np.zeros((1, 3)), True, None, np.array([0.0, 1.0, 1.0]), np.array([0.0, 1.0]))
+    with pytest.raises(ValueError):
+        _core.pcf2d_counts(c, None, np.zeros((1, 3)), True, None, np.array([0.0]), np.array([0.0, 1.0]))
