@@ -27,6 +27,7 @@
 #include <vector>
 
 #include "amepb_internal.cuh"
+#include "rdf_plan.h"
 
 namespace amepb {
 
@@ -35,7 +36,10 @@ struct Pcf2dFrame {
     double r00, r01;   // first row of R(-angle):  cos, -sin
     double r10, r11;   // second row:              sin,  cos
     int rotate;        // angle != 0
-    int pad;
+    // float32 prefilter for float32 differences.  No rotation: the closed float32 interval that is
+    // equivalent to the float64 test against the outer edges; rotation: squared radius about the
+    // centre that holds the whole window (conservative: never rejects a pair that bins)
+    float fxlo, fxhi, fylo, fyhi, fr2;
 };
 
 constexpr int kPcfThreads = 256;
@@ -61,7 +65,9 @@ __global__ void __launch_bounds__(kPcfThreads) pcf2d_kernel(const TC* __restrict
                                                             const double* __restrict__ xedges, int nxe,
                                                             const double* __restrict__ yedges, int nye,
                                                             long long edge_stride, long long per_split,
+                                                            const float* __restrict__ thr,
                                                             unsigned long long* __restrict__ counts) {
+    extern __shared__ float s_thr[];   // float32 thresholds of the x edges, then of the y edges
     __shared__ D sx[kPcfStage], sy[kPcfStage];
     __shared__ Pcf2dFrame F;
     const int f = blockIdx.z;
@@ -78,8 +84,18 @@ __global__ void __launch_bounds__(kPcfThreads) pcf2d_kernel(const TC* __restrict
     const bool live = qi < m;
     const D qx = live ? (D)of[qi * 3 + 0] : (D)0, qy = live ? (D)of[qi * 3 + 1] : (D)0;
     const long long t_lo = (long long)blockIdx.y * per_split, t_hi = min(n, t_lo + per_split);
+    // float32 differences without rotation: binning against float32 thresholds (thr[k] = smallest
+    // float32 >= edges[k], so "v >= edges[k]" in float64 is "v >= thr[k]" in float32)
+    const bool use_thr = sizeof(D) == 4 && thr != nullptr;
+    if (use_thr) {
+        const float* tf = thr + (long long)f * (nxe + nye);
+        for (int i = threadIdx.x; i < nxe + nye; i += kPcfThreads) s_thr[i] = tf[i];
+    }
     __syncthreads();
     const bool rotate = F.rotate != 0;
+    const float* tx = s_thr;
+    const float* ty = s_thr + nxe;
+    const float finv_dx = (float)inv_dx, finv_dy = (float)inv_dy;
     for (long long t0 = t_lo; t0 < t_hi; t0 += kPcfStage) {
         const int cnt = (int)min((long long)kPcfStage, t_hi - t0);
         __syncthreads();
@@ -100,6 +116,26 @@ __global__ void __launch_bounds__(kPcfThreads) pcf2d_kernel(const TC* __restrict
                 dy = __dsub_rn(qy, sy[i]);
             }
             double x, y;
+            if constexpr (sizeof(D) == 4) {
+                if (!rotate) {
+                    if (!(dx >= F.fxlo) || !(dx <= F.fxhi) || !(dy >= F.fylo) || !(dy <= F.fyhi)) continue;
+                    if (use_thr) {
+                        if (i == skip) continue;
+                        // guess from the uniform spacing, then settle against the thresholds
+                        int bx = min(max(__float2int_rd((dx - F.fxlo) * finv_dx), 0), nxe - 2);
+                        int by = min(max(__float2int_rd((dy - F.fylo) * finv_dy), 0), nye - 2);
+                        while (dx < tx[bx]) --bx;
+                        while (bx < nxe - 2 && dx >= tx[bx + 1]) ++bx;
+                        while (dy < ty[by]) --by;
+                        while (by < nye - 2 && dy >= ty[by + 1]) ++by;
+                        atomicAdd(&grid[(size_t)bx * (nye - 1) + by], 1ULL);
+                        continue;
+                    }
+                } else {
+                    const float ux = dx - (float)F.cx, uy = dy - (float)F.cy;
+                    if (!(ux * ux + uy * uy <= F.fr2)) continue;
+                }
+            }
             if (!rotate) {
                 x = (double)dx;
                 y = (double)dy;
@@ -128,16 +164,16 @@ __global__ void __launch_bounds__(kPcfThreads) pcf2d_kernel(const TC* __restrict
 template <typename TC, typename TO>
 static void launch_pcf2d(dim3 grid, cudaStream_t stream, bool center_f32, const void* coords, long long n,
                          const void* other, long long m, int same, const Pcf2dFrame* frames, const double* xe, int nxe,
-                         const double* ye, int nye, long long edge_stride, long long per_split,
-                         unsigned long long* counts) {
+                         const double* ye, int nye, long long edge_stride, long long per_split, const float* thr,
+                         size_t smem, unsigned long long* counts) {
     constexpr bool both_f32 = sizeof(TC) == 4 && sizeof(TO) == 4;
     if constexpr (both_f32) {
         if (center_f32)
-            pcf2d_kernel<TC, TO, float, true><<<grid, kPcfThreads, 0, stream>>>((const TC*)coords, n, (const TO*)other, m, same, frames, xe, nxe, ye, nye, edge_stride, per_split, counts);
+            pcf2d_kernel<TC, TO, float, true><<<grid, kPcfThreads, smem, stream>>>((const TC*)coords, n, (const TO*)other, m, same, frames, xe, nxe, ye, nye, edge_stride, per_split, thr, counts);
         else
-            pcf2d_kernel<TC, TO, float, false><<<grid, kPcfThreads, 0, stream>>>((const TC*)coords, n, (const TO*)other, m, same, frames, xe, nxe, ye, nye, edge_stride, per_split, counts);
+            pcf2d_kernel<TC, TO, float, false><<<grid, kPcfThreads, smem, stream>>>((const TC*)coords, n, (const TO*)other, m, same, frames, xe, nxe, ye, nye, edge_stride, per_split, thr, counts);
     } else {
-        pcf2d_kernel<TC, TO, double, false><<<grid, kPcfThreads, 0, stream>>>((const TC*)coords, n, (const TO*)other, m, same, frames, xe, nxe, ye, nye, edge_stride, per_split, counts);
+        pcf2d_kernel<TC, TO, double, false><<<grid, kPcfThreads, smem, stream>>>((const TC*)coords, n, (const TO*)other, m, same, frames, xe, nxe, ye, nye, edge_stride, per_split, thr, counts);
     }
 }
 
@@ -194,7 +230,12 @@ extern "C" int amepb_pcf2d_counts(amepb_ctx* ctx, const void* coords, int dtype,
     const size_t fbytes = (sizeof(Pcf2dFrame) * (size_t)nframes + 15) & ~(size_t)15;
     const size_t estride = edge_stride ? (size_t)edge_stride : (size_t)std::max(nxe, nye);
     const size_t ebytes = sizeof(double) * estride * nedge_sets;
-    const size_t pbytes = fbytes + 2 * ebytes;
+    // float32 thresholds of the edges, per frame (x then y), used by the float32 kernels when they
+    // fit shared memory beside the target stage
+    const bool all_f32 = dtype == AMEPB_F32 && other_dtype == AMEPB_F32;
+    const bool with_thr = all_f32 && (size_t)nxe + nye <= 6144;
+    const size_t tbytes = with_thr ? ((sizeof(float) * (size_t)nframes * (nxe + nye) + 15) & ~(size_t)15) : 0;
+    const size_t pbytes = fbytes + 2 * ebytes + tbytes;
     if ((rc = ensure_pinned(ctx, pbytes))) return rc;
     if ((rc = ensure_device(ctx, BUF_SQ_A, pbytes))) return rc;
     char* hp = reinterpret_cast<char*>(ctx->pinned);
@@ -210,12 +251,35 @@ extern "C" int amepb_pcf2d_counts(amepb_ctx* ctx, const void* coords, int dtype,
         F.r01 = -s;
         F.r10 = s;
         F.r11 = c;
+        const double* xe = xedges + f * edge_stride;
+        const double* ye = yedges + f * edge_stride;
+        F.fxlo = float_above(xe[0], false);      // dx >= xlo in float64  <=>  dx >= fxlo in float32
+        F.fxhi = float_below(xe[nxe - 1], false);
+        F.fylo = float_above(ye[0], false);
+        F.fyhi = float_below(ye[nye - 1], false);
+        // |R v| = |v|: the rotated vector lies in the window only if |diff - centre| is at most
+        // the distance from the centre to the farthest window corner (plus float32 slack: the
+        // prefilter subtracts a float32-rounded centre and rounds its products)
+        const double ax = std::max(fabs(xe[0] - F.cx), fabs(xe[nxe - 1] - F.cx));
+        const double ay = std::max(fabs(ye[0] - F.cy), fabs(ye[nye - 1] - F.cy));
+        const double rad = sqrt(ax * ax + ay * ay) * (1.0 + 1e-5) + 1e-5 * (fabs(F.cx) + fabs(F.cy)) + 1e-30;
+        F.fr2 = float_above(rad * rad, false);
     }
     double* hxe = reinterpret_cast<double*>(hp + fbytes);
     double* hye = reinterpret_cast<double*>(hp + fbytes + ebytes);
     for (int64_t f = 0; f < nedge_sets; ++f) {
         memcpy(hxe + f * estride, xedges + f * edge_stride, sizeof(double) * nxe);
         memcpy(hye + f * estride, yedges + f * edge_stride, sizeof(double) * nye);
+    }
+    if (with_thr) {
+        float* ht = reinterpret_cast<float*>(hp + fbytes + 2 * ebytes);
+        for (int64_t f = 0; f < nframes; ++f) {
+            const double* xe = xedges + f * edge_stride;
+            const double* ye = yedges + f * edge_stride;
+            float* t = ht + f * (nxe + nye);
+            for (int i = 0; i < nxe; ++i) t[i] = float_above(xe[i], false);
+            for (int i = 0; i < nye; ++i) t[nxe + i] = float_above(ye[i], false);
+        }
     }
     char* dp = reinterpret_cast<char*>(ctx->bufs[BUF_SQ_A].p);
     AMEPB_CUDA(ctx, cudaMemcpyAsync(dp, hp, pbytes, cudaMemcpyHostToDevice, stream));
@@ -224,6 +288,8 @@ extern "C" int amepb_pcf2d_counts(amepb_ctx* ctx, const void* coords, int dtype,
     const double* d_xe = reinterpret_cast<const double*>(dp + fbytes);
     const double* d_ye = reinterpret_cast<const double*>(dp + fbytes + ebytes);
     const long long dev_stride = edge_stride ? (long long)estride : 0;
+    const float* d_thr = with_thr ? reinterpret_cast<const float*>(dp + fbytes + 2 * ebytes) : nullptr;
+    const size_t smem = with_thr ? sizeof(float) * ((size_t)nxe + nye) : 0;
 
     // query tiles x target splits x frames: at least ~4 blocks per SM when the system allows it
     const long long qtiles = (m + kPcfThreads - 1) / kPcfThreads;
@@ -237,13 +303,13 @@ extern "C" int amepb_pcf2d_counts(amepb_ctx* ctx, const void* coords, int dtype,
     const dim3 grid((unsigned)qtiles, (unsigned)tsplit, (unsigned)nframes);
     const bool cf32 = center_f32 != 0;
     if (dtype == AMEPB_F32 && other_dtype == AMEPB_F32)
-        launch_pcf2d<float, float>(grid, stream, cf32, d_coords, n, d_other, m, same, d_frames, d_xe, nxe, d_ye, nye, dev_stride, per_split, d_counts);
+        launch_pcf2d<float, float>(grid, stream, cf32, d_coords, n, d_other, m, same, d_frames, d_xe, nxe, d_ye, nye, dev_stride, per_split, d_thr, smem, d_counts);
     else if (dtype == AMEPB_F32)
-        launch_pcf2d<float, double>(grid, stream, cf32, d_coords, n, d_other, m, same, d_frames, d_xe, nxe, d_ye, nye, dev_stride, per_split, d_counts);
+        launch_pcf2d<float, double>(grid, stream, cf32, d_coords, n, d_other, m, same, d_frames, d_xe, nxe, d_ye, nye, dev_stride, per_split, d_thr, smem, d_counts);
     else if (other_dtype == AMEPB_F32)
-        launch_pcf2d<double, float>(grid, stream, cf32, d_coords, n, d_other, m, same, d_frames, d_xe, nxe, d_ye, nye, dev_stride, per_split, d_counts);
+        launch_pcf2d<double, float>(grid, stream, cf32, d_coords, n, d_other, m, same, d_frames, d_xe, nxe, d_ye, nye, dev_stride, per_split, d_thr, smem, d_counts);
     else
-        launch_pcf2d<double, double>(grid, stream, cf32, d_coords, n, d_other, m, same, d_frames, d_xe, nxe, d_ye, nye, dev_stride, per_split, d_counts);
+        launch_pcf2d<double, double>(grid, stream, cf32, d_coords, n, d_other, m, same, d_frames, d_xe, nxe, d_ye, nye, dev_stride, per_split, d_thr, smem, d_counts);
     AMEPB_LAUNCH_CHECK(ctx);
     if (space == AMEPB_HOST) {
         AMEPB_CUDA(ctx, cudaMemcpyAsync(counts, d_counts, gbytes, cudaMemcpyDeviceToHost, stream));
