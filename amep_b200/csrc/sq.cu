@@ -163,15 +163,18 @@ __device__ __forceinline__ void table_run16(double x, const double* __restrict__
 // ---------------------------------------------------------------------------------------
 constexpr int kF64Threads = 256;   // 8 warps x 32 lanes, 2 x 8 quad points per thread: 64 x 64 tile
 constexpr int kF64Stage = 32;      // particles per shared-memory stage
+constexpr int kF64Row = 65;        // 64 table entries per particle and axis + 1 of padding
 
 template <typename T, int UNROLL>
 __global__ void __launch_bounds__(kF64Threads, 1) sf2d_f64_kernel(
     const T* __restrict__ coords, long long n, const double* __restrict__ qall, long long q_stride, int nq,
     int ksplit, double* __restrict__ partial) {
-    // shared: X[stage][64], Y[stage][64] as double2 (64 KB, dynamic)
+    // shared: X[stage][64 + 1], Y[stage][64 + 1] as double2 (65 KB, dynamic)
     extern __shared__ __align__(16) unsigned char smem_f64[];
-    double2 (*sX)[64] = reinterpret_cast<double2 (*)[64]>(smem_f64);
-    double2 (*sY)[64] = reinterpret_cast<double2 (*)[64]>(smem_f64 + sizeof(double2) * kF64Stage * 64);
+    // (rows padded by one entry: the builder's lanes hold different particles, a row apart, and
+    // would otherwise all store to the same four banks)
+    double2 (*sX)[kF64Row] = reinterpret_cast<double2 (*)[kF64Row]>(smem_f64);
+    double2 (*sY)[kF64Row] = reinterpret_cast<double2 (*)[kF64Row]>(smem_f64 + sizeof(double2) * kF64Stage * kF64Row);
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;   // lanes: qx = lane, lane + 32; warp: 8 consecutive qy
     const int tiles = (nq + 63) / 64;
@@ -273,6 +276,10 @@ __global__ void sf2d_f64_finish_kernel(const double* __restrict__ partial, int k
 constexpr int kC64Threads = 256;  // 8 warps: lanes = 32 qx values, each warp 2 qy values
 constexpr int kC64TileA = 32;
 constexpr int kC64TileB = 16;
+// rows of the shared tables are padded by one entry: the builder's lanes hold different particles
+// (row stride apart) and would otherwise all store to the same four banks
+constexpr int kC64RowA = kC64TileA + 1;
+constexpr int kC64RowB = kC64TileB + 1;
 constexpr int kC64Stage = 32;     // particles per shared-memory stage (two stages resident)
 constexpr size_t kC64ChunkBufferBytes = (size_t)4 << 30;   // chunk sums of the split kernel, per launch
 
@@ -303,8 +310,8 @@ __device__ __noinline__ void c64_build_stage(const T* __restrict__ base, const d
     const int jj = tid % kC64Stage, run = tid / kC64Stage;   // run 0,1: X; run 2: Y
     const long long j = j0 + jj;
     if (j >= j_hi) return;
-    if (run < 2) table_run16((double)base[3 * j], q, xa0 + run * 16, nq, bX + jj * kC64TileA + run * 16, 1);
-    else table_run16((double)base[3 * j + 1], q, ya0, nq, bY + jj * kC64TileB, 1);
+    if (run < 2) table_run16((double)base[3 * j], q, xa0 + run * 16, nq, bX + jj * kC64RowA + run * 16, 1);
+    else table_run16((double)base[3 * j + 1], q, ya0, nq, bY + jj * kC64RowB, 1);
 }
 
 // SPLIT: gridDim.z blocks share the particles of a tile by whole chunks and write every chunk sum
@@ -316,7 +323,7 @@ __global__ void __launch_bounds__(kC64Threads, 4) sf2d_c64_kernel(
     const T* __restrict__ coords, long long n, const double* __restrict__ qall, long long q_stride, int nq,
     long long chunksize, float2* __restrict__ rho, float4* __restrict__ chunk_out, long long nchunks) {
     extern __shared__ __align__(16) unsigned char smem_c64[];
-    constexpr size_t kBufBytes = sizeof(double2) * kC64Stage * (kC64TileA + kC64TileB);
+    constexpr size_t kBufBytes = sizeof(double2) * kC64Stage * (kC64RowA + kC64RowB);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tiles_a = (nq + kC64TileA - 1) / kC64TileA;
     const int tile_a = blockIdx.x % tiles_a, tile_b = blockIdx.x / tiles_a;
@@ -339,7 +346,7 @@ __global__ void __launch_bounds__(kC64Threads, 4) sf2d_c64_kernel(
     const int qa_idx = tile_a * kC64TileA + lane;
 
     auto buf_x = [&](int b) { return reinterpret_cast<double2*>(smem_c64 + b * kBufBytes); };
-    auto buf_y = [&](int b) { return reinterpret_cast<double2*>(smem_c64 + b * kBufBytes + sizeof(double2) * kC64Stage * kC64TileA); };
+    auto buf_y = [&](int b) { return reinterpret_cast<double2*>(smem_c64 + b * kBufBytes + sizeof(double2) * kC64Stage * kC64RowA); };
     c64_build_stage<T>(base, q, j_lo, j_hi, tile_a * kC64TileA, tile_b * kC64TileB, nq, buf_x(0), buf_y(0));
     __syncthreads();
     int cur = 0;
@@ -348,8 +355,8 @@ __global__ void __launch_bounds__(kC64Threads, 4) sf2d_c64_kernel(
         // accumulation of this stage; one barrier per stage
         if (j0 + kC64Stage < j_hi)
             c64_build_stage<T>(base, q, j0 + kC64Stage, j_hi, tile_a * kC64TileA, tile_b * kC64TileB, nq, buf_x(cur ^ 1), buf_y(cur ^ 1));
-        const double2 (*sX)[kC64TileA] = reinterpret_cast<const double2 (*)[kC64TileA]>(buf_x(cur));
-        const double2 (*sY)[kC64TileB] = reinterpret_cast<const double2 (*)[kC64TileB]>(buf_y(cur));
+        const double2 (*sX)[kC64RowA] = reinterpret_cast<const double2 (*)[kC64RowA]>(buf_x(cur));
+        const double2 (*sY)[kC64RowB] = reinterpret_cast<const double2 (*)[kC64RowB]>(buf_y(cur));
         const int lim = (int)((j_hi - j0) < kC64Stage ? (j_hi - j0) : kC64Stage);
         int jj = 0;
         while (jj < lim) {
@@ -683,8 +690,8 @@ int amepb_sf2d_modes(amepb_ctx* ctx, const void* coords, int dtype, int space, i
     AMEPB_CUDA(ctx, cudaMemcpyAsync(ctx->bufs[BUF_SQ_A].p, ctx->pinned, q_count * sizeof(double), cudaMemcpyHostToDevice, stream));
     const double* d_q = reinterpret_cast<const double*>(ctx->bufs[BUF_SQ_A].p);
 
-    const size_t smem_f64 = sizeof(double2) * kF64Stage * 64 * 2;
-    const size_t smem_c64 = 2 * sizeof(double2) * kC64Stage * (kC64TileA + kC64TileB);
+    const size_t smem_f64 = sizeof(double2) * kF64Stage * kF64Row * 2;
+    const size_t smem_c64 = 2 * sizeof(double2) * kC64Stage * (kC64RowA + kC64RowB);
     if (accum == AMEPB_ACCUM_C64_REFERENCE) {
         // frames per launch such that the chunk sums of the split kernel fit their buffer
         const size_t nchunks = (size_t)((n + chunksize - 1) / chunksize);
