@@ -24,6 +24,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <cmath>
+#include <type_traits>
 #include <vector>
 
 #include "amepb_internal.cuh"
@@ -57,7 +59,82 @@ __device__ __forceinline__ int pcf_bin_of(double v, const double* __restrict__ e
     return g;
 }
 
+// Bins one difference vector exactly as the reference does (see the header comment).
 // D: dtype of other_coords[n] - coords;  CF32: the centre is float32 (only matters if D is float)
+template <typename D, bool CF32>
+struct PairBinner {
+    const Pcf2dFrame* F;
+    const double* xe;
+    const double* ye;
+    const float* tx;   // float32 thresholds of the x / y edges in shared memory (use_thr)
+    const float* ty;
+    double xlo, xhi, ylo, yhi, inv_dx, inv_dy;
+    float finv_dx, finv_dy;
+    int nxe, nye;
+    bool rotate, use_thr;
+
+    __device__ __forceinline__ void init(const Pcf2dFrame* frame, const double* xedges, int nxe_, const double* yedges,
+                                         int nye_, const float* s_thr, bool with_thr) {
+        F = frame; xe = xedges; ye = yedges; nxe = nxe_; nye = nye_;
+        xlo = xe[0]; xhi = xe[nxe - 1]; ylo = ye[0]; yhi = ye[nye - 1];
+        inv_dx = (double)(nxe - 1) / (xhi - xlo);
+        inv_dy = (double)(nye - 1) / (yhi - ylo);
+        finv_dx = (float)inv_dx; finv_dy = (float)inv_dy;
+        tx = s_thr; ty = s_thr + nxe;
+        rotate = frame->rotate != 0;
+        use_thr = sizeof(D) == 4 && with_thr;
+    }
+
+    __device__ __forceinline__ bool bins(D dx, D dy, int& bx, int& by) const {
+        double x, y;
+        if constexpr (sizeof(D) == 4) {
+            if (!rotate) {
+                if (!(dx >= F->fxlo) || !(dx <= F->fxhi) || !(dy >= F->fylo) || !(dy <= F->fyhi)) return false;
+                if (use_thr) {
+                    // float32 differences without rotation: "v >= edges[k]" in float64 is
+                    // "v >= thr[k]" in float32 (thr[k] = smallest float32 >= edges[k]); guess from
+                    // the uniform spacing, then settle against the thresholds
+                    bx = min(max(__float2int_rd((dx - F->fxlo) * finv_dx), 0), nxe - 2);
+                    by = min(max(__float2int_rd((dy - F->fylo) * finv_dy), 0), nye - 2);
+                    while (dx < tx[bx]) --bx;
+                    while (bx < nxe - 2 && dx >= tx[bx + 1]) ++bx;
+                    while (dy < ty[by]) --by;
+                    while (by < nye - 2 && dy >= ty[by + 1]) ++by;
+                    return true;
+                }
+            } else {
+                const float ux = dx - (float)F->cx, uy = dy - (float)F->cy;
+                if (!(ux * ux + uy * uy <= F->fr2)) return false;
+            }
+        }
+        if (!rotate) {
+            x = (double)dx;
+            y = (double)dy;
+        } else {
+            double vx, vy;
+            if constexpr (sizeof(D) == 4 && CF32) {
+                vx = (double)__fsub_rn(dx, (float)F->cx);
+                vy = (double)__fsub_rn(dy, (float)F->cy);
+            } else {
+                vx = __dsub_rn((double)dx, F->cx);
+                vy = __dsub_rn((double)dy, F->cy);
+            }
+            x = __dadd_rn(__dadd_rn(__dmul_rn(F->r00, vx), __dmul_rn(F->r01, vy)), F->cx);
+            y = __dadd_rn(__dadd_rn(__dmul_rn(F->r10, vx), __dmul_rn(F->r11, vy)), F->cy);
+        }
+        if (!(x >= xlo) || !(x <= xhi) || !(y >= ylo) || !(y <= yhi)) return false;
+        bx = pcf_bin_of(x, xe, nxe, inv_dx);
+        by = pcf_bin_of(y, ye, nye, inv_dy);
+        return bx >= 0 && by >= 0;
+    }
+};
+
+template <typename D>
+__device__ __forceinline__ D pcf_sub(D a, D b) {
+    if constexpr (sizeof(D) == 4) return __fsub_rn(a, b);
+    else return __dsub_rn(a, b);
+}
+
 template <typename TC, typename TO, typename D, bool CF32>
 __global__ void __launch_bounds__(kPcfThreads) pcf2d_kernel(const TC* __restrict__ coords, long long n,
                                                             const TO* __restrict__ other, long long m, int same,
@@ -73,10 +150,10 @@ __global__ void __launch_bounds__(kPcfThreads) pcf2d_kernel(const TC* __restrict
     const int f = blockIdx.z;
     if (threadIdx.x < sizeof(Pcf2dFrame) / sizeof(int))
         reinterpret_cast<int*>(&F)[threadIdx.x] = reinterpret_cast<const int*>(frames + f)[threadIdx.x];
-    const double* xe = xedges + (long long)f * edge_stride;
-    const double* ye = yedges + (long long)f * edge_stride;
-    const double xlo = xe[0], xhi = xe[nxe - 1], ylo = ye[0], yhi = ye[nye - 1];
-    const double inv_dx = (double)(nxe - 1) / (xhi - xlo), inv_dy = (double)(nye - 1) / (yhi - ylo);
+    if (sizeof(D) == 4 && thr != nullptr) {
+        const float* tf = thr + (long long)f * (nxe + nye);
+        for (int i = threadIdx.x; i < nxe + nye; i += kPcfThreads) s_thr[i] = tf[i];
+    }
     const TC* cf = coords + (long long)f * n * 3;
     const TO* of = other + (long long)f * m * 3;
     unsigned long long* grid = counts + (size_t)f * (nxe - 1) * (nye - 1);
@@ -84,18 +161,9 @@ __global__ void __launch_bounds__(kPcfThreads) pcf2d_kernel(const TC* __restrict
     const bool live = qi < m;
     const D qx = live ? (D)of[qi * 3 + 0] : (D)0, qy = live ? (D)of[qi * 3 + 1] : (D)0;
     const long long t_lo = (long long)blockIdx.y * per_split, t_hi = min(n, t_lo + per_split);
-    // float32 differences without rotation: binning against float32 thresholds (thr[k] = smallest
-    // float32 >= edges[k], so "v >= edges[k]" in float64 is "v >= thr[k]" in float32)
-    const bool use_thr = sizeof(D) == 4 && thr != nullptr;
-    if (use_thr) {
-        const float* tf = thr + (long long)f * (nxe + nye);
-        for (int i = threadIdx.x; i < nxe + nye; i += kPcfThreads) s_thr[i] = tf[i];
-    }
     __syncthreads();
-    const bool rotate = F.rotate != 0;
-    const float* tx = s_thr;
-    const float* ty = s_thr + nxe;
-    const float finv_dx = (float)inv_dx, finv_dy = (float)inv_dy;
+    PairBinner<D, CF32> B;
+    B.init(&F, xedges + (long long)f * edge_stride, nxe, yedges + (long long)f * edge_stride, nye, s_thr, thr != nullptr);
     for (long long t0 = t_lo; t0 < t_hi; t0 += kPcfStage) {
         const int cnt = (int)min((long long)kPcfStage, t_hi - t0);
         __syncthreads();
@@ -107,56 +175,190 @@ __global__ void __launch_bounds__(kPcfThreads) pcf2d_kernel(const TC* __restrict
         if (!live) continue;
         const int skip = (same && qi >= t0 && qi < t0 + cnt) ? (int)(qi - t0) : -1;
         for (int i = 0; i < cnt; ++i) {
-            D dx, dy;
-            if constexpr (sizeof(D) == 4) {
-                dx = __fsub_rn(qx, sx[i]);
-                dy = __fsub_rn(qy, sy[i]);
-            } else {
-                dx = __dsub_rn(qx, sx[i]);
-                dy = __dsub_rn(qy, sy[i]);
-            }
-            double x, y;
-            if constexpr (sizeof(D) == 4) {
-                if (!rotate) {
-                    if (!(dx >= F.fxlo) || !(dx <= F.fxhi) || !(dy >= F.fylo) || !(dy <= F.fyhi)) continue;
-                    if (use_thr) {
-                        if (i == skip) continue;
-                        // guess from the uniform spacing, then settle against the thresholds
-                        int bx = min(max(__float2int_rd((dx - F.fxlo) * finv_dx), 0), nxe - 2);
-                        int by = min(max(__float2int_rd((dy - F.fylo) * finv_dy), 0), nye - 2);
-                        while (dx < tx[bx]) --bx;
-                        while (bx < nxe - 2 && dx >= tx[bx + 1]) ++bx;
-                        while (dy < ty[by]) --by;
-                        while (by < nye - 2 && dy >= ty[by + 1]) ++by;
-                        atomicAdd(&grid[(size_t)bx * (nye - 1) + by], 1ULL);
-                        continue;
-                    }
-                } else {
-                    const float ux = dx - (float)F.cx, uy = dy - (float)F.cy;
-                    if (!(ux * ux + uy * uy <= F.fr2)) continue;
-                }
-            }
-            if (!rotate) {
-                x = (double)dx;
-                y = (double)dy;
-                if (!(x >= xlo) || !(x <= xhi) || !(y >= ylo) || !(y <= yhi)) continue;
-            } else {
-                double vx, vy;
-                if constexpr (sizeof(D) == 4 && CF32) {
-                    vx = (double)__fsub_rn(dx, (float)F.cx);
-                    vy = (double)__fsub_rn(dy, (float)F.cy);
-                } else {
-                    vx = __dsub_rn((double)dx, F.cx);
-                    vy = __dsub_rn((double)dy, F.cy);
-                }
-                x = __dadd_rn(__dadd_rn(__dmul_rn(F.r00, vx), __dmul_rn(F.r01, vy)), F.cx);
-                y = __dadd_rn(__dadd_rn(__dmul_rn(F.r10, vx), __dmul_rn(F.r11, vy)), F.cy);
-                if (!(x >= xlo) || !(x <= xhi) || !(y >= ylo) || !(y <= yhi)) continue;
-            }
+            int bx, by;
+            if (!B.bins(pcf_sub<D>(qx, sx[i]), pcf_sub<D>(qy, sy[i]), bx, by)) continue;
             if (i == skip) continue;
-            const int bx = pcf_bin_of(x, xe, nxe, inv_dx);
-            const int by = pcf_bin_of(y, ye, nye, inv_dy);
-            if (bx >= 0 && by >= 0) atomicAdd(&grid[(size_t)bx * (nye - 1) + by], 1ULL);
+            atomicAdd(&grid[(size_t)bx * (nye - 1) + by], 1ULL);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Cell-sorted walk with a shared-memory window of the grid.
+//
+// With a wide window (the default rmax bins half of all pairs) the kernel above is bound by its
+// global atomics (~1e11/s).  Here both particle sets are counting-sorted into square cells of side
+// cs; the differences of a (query cell, target cell) pair span 2 cs per axis -- kPcfWin bins at
+// most by the choice of cs, also after the rotation -- so a block counts a cell pair in a
+// kPcfWin x kPcfWin window of 32-bit shared-memory counters and adds the non-zero ones to the
+// grid afterwards: W^2 global atomics per cell pair instead of one per binned pair.  The bins
+// themselves come from PairBinner on the original coordinate values (sorting only permutes), and
+// a pair whose bin falls outside the window (the window origin is computed approximately) is
+// added to the grid directly, so the counts do not depend on the cell geometry.
+// ---------------------------------------------------------------------------------------
+constexpr int kPcfWin = 96;
+
+struct PcfCellPlan {
+    float x0, y0, cs, inv_cs;   // cell (i, j) covers [x0 + i cs, x0 + (i+1) cs) x [y0 + j cs, ...)
+    int gx, gy;
+};
+
+template <typename D> struct PcfVec2 { using type = float2; };
+template <> struct PcfVec2<double> { using type = double2; };
+
+__device__ __forceinline__ int pcf_float_order(float f) {
+    const int i = __float_as_int(f);
+    return i ^ ((i >> 31) & 0x7fffffff);
+}
+
+// bbox[0..3] = ordered-int min x, min y, max x, max y over the finite coordinates
+template <typename T>
+__global__ void pcf_bbox_kernel(const T* __restrict__ pts, long long n, int* __restrict__ bbox) {
+    float lox = INFINITY, loy = INFINITY, hix = -INFINITY, hiy = -INFINITY;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float x = (float)pts[3 * i], y = (float)pts[3 * i + 1];
+        if (isfinite(x)) { lox = fminf(lox, x); hix = fmaxf(hix, x); }
+        if (isfinite(y)) { loy = fminf(loy, y); hiy = fmaxf(hiy, y); }
+    }
+    const int a = __reduce_min_sync(0xffffffffu, pcf_float_order(lox));
+    const int b = __reduce_min_sync(0xffffffffu, pcf_float_order(loy));
+    const int c = __reduce_max_sync(0xffffffffu, pcf_float_order(hix));
+    const int d = __reduce_max_sync(0xffffffffu, pcf_float_order(hiy));
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&bbox[0], a); atomicMin(&bbox[1], b); atomicMax(&bbox[2], c); atomicMax(&bbox[3], d);
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ int pcf_cell_of(const T* __restrict__ p, const PcfCellPlan& P) {
+    // any deterministic assignment is correct (see above); non-finite values go to cell 0
+    const float x = (float)p[0], y = (float)p[1];
+    int cx = isfinite(x) ? (int)((x - P.x0) * P.inv_cs) : 0;
+    int cy = isfinite(y) ? (int)((y - P.y0) * P.inv_cs) : 0;
+    cx = min(max(cx, 0), P.gx - 1);
+    cy = min(max(cy, 0), P.gy - 1);
+    return cy * P.gx + cx;
+}
+
+template <typename T>
+__global__ void pcf_cell_count_kernel(const T* __restrict__ pts, long long n, PcfCellPlan P, int* __restrict__ count) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) atomicAdd(&count[pcf_cell_of(pts + 3 * i, P)], 1);
+}
+
+// start[c] = exclusive prefix sum of count (start[ncell] = n), count zeroed for use as a cursor
+__global__ void pcf_cell_scan_kernel(int* __restrict__ count, int* __restrict__ start, int ncell) {
+    __shared__ int s_part[1024];
+    const int tid = threadIdx.x;
+    const int per = (ncell + 1023) / 1024;
+    const int lo = min(tid * per, ncell), hi = min(lo + per, ncell);
+    int sum = 0;
+    for (int c = lo; c < hi; ++c) sum += count[c];
+    s_part[tid] = sum;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+        const int v = tid >= off ? s_part[tid - off] : 0;
+        __syncthreads();
+        s_part[tid] += v;
+        __syncthreads();
+    }
+    int run = s_part[tid] - sum;
+    for (int c = lo; c < hi; ++c) {
+        const int v = count[c];
+        start[c] = run;
+        run += v;
+        count[c] = 0;
+    }
+    if (tid == 1023) start[ncell] = s_part[1023];
+}
+
+template <typename T, typename D>
+__global__ void pcf_cell_scatter_kernel(const T* __restrict__ pts, long long n, PcfCellPlan P,
+                                        const int* __restrict__ start, int* __restrict__ cursor,
+                                        typename PcfVec2<D>::type* __restrict__ sorted, int* __restrict__ sidx) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int c = pcf_cell_of(pts + 3 * i, P);
+    const int pos = start[c] + atomicAdd(&cursor[c], 1);
+    typename PcfVec2<D>::type v;
+    v.x = (D)pts[3 * i];
+    v.y = (D)pts[3 * i + 1];
+    sorted[pos] = v;
+    sidx[pos] = (int)i;
+}
+
+template <typename D, bool CF32>
+__global__ void __launch_bounds__(kPcfThreads) pcf2d_cells_kernel(
+    const typename PcfVec2<D>::type* __restrict__ qs, const int* __restrict__ qidx, const int* __restrict__ qstart,
+    const typename PcfVec2<D>::type* __restrict__ ts, const int* __restrict__ tidx, const int* __restrict__ tstart,
+    PcfCellPlan P, int same, const Pcf2dFrame* __restrict__ frame, const double* __restrict__ xe, int nxe,
+    const double* __restrict__ ye, int nye, const float* __restrict__ thr, unsigned long long* __restrict__ grid) {
+    extern __shared__ unsigned s_dyn[];              // window, then the float32 thresholds
+    unsigned* win = s_dyn;
+    float* s_thr = reinterpret_cast<float*>(s_dyn + kPcfWin * kPcfWin);
+    __shared__ Pcf2dFrame F;
+    if (threadIdx.x < sizeof(Pcf2dFrame) / sizeof(int))
+        reinterpret_cast<int*>(&F)[threadIdx.x] = reinterpret_cast<const int*>(frame)[threadIdx.x];
+    if (sizeof(D) == 4 && thr != nullptr)
+        for (int i = threadIdx.x; i < nxe + nye; i += kPcfThreads) s_thr[i] = thr[i];
+    const int qc = blockIdx.x, ncell = P.gx * P.gy;
+    const int q0 = qstart[qc], nqc = qstart[qc + 1] - q0;
+    if (nqc == 0) return;
+    __syncthreads();
+    PairBinner<D, CF32> B;
+    B.init(&F, xe, nxe, ye, nye, s_thr, thr != nullptr);
+    const int qcx = qc % P.gx, qcy = qc / P.gx;
+    const double qxlo = (double)P.x0 + (double)qcx * P.cs, qylo = (double)P.y0 + (double)qcy * P.cs;
+    for (int tc = blockIdx.y; tc < ncell; tc += gridDim.y) {
+        const int t0 = tstart[tc], ntc = tstart[tc + 1] - t0;
+        if (ntc == 0) continue;
+        // differences of this cell pair (one cell side of slack: clamped and rounded members)
+        const int tcx = tc % P.gx, tcy = tc / P.gx;
+        const double txlo = (double)P.x0 + (double)tcx * P.cs, tylo = (double)P.y0 + (double)tcy * P.cs;
+        const bool edge_cell = qcx == 0 || qcy == 0 || qcx == P.gx - 1 || qcy == P.gy - 1 || tcx == 0 || tcy == 0 ||
+                               tcx == P.gx - 1 || tcy == P.gy - 1;
+        double dlo[2] = {qxlo - (txlo + P.cs), qylo - (tylo + P.cs)};
+        double dhi[2] = {qxlo + P.cs - txlo, qylo + P.cs - tylo};
+        double wxlo, wxhi, wylo, wyhi;
+        if (!B.rotate) {
+            wxlo = dlo[0]; wxhi = dhi[0]; wylo = dlo[1]; wyhi = dhi[1];
+        } else {
+            wxlo = wylo = INFINITY; wxhi = wyhi = -INFINITY;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const double vx = ((k & 1) ? dhi[0] : dlo[0]) - F.cx, vy = ((k & 2) ? dhi[1] : dlo[1]) - F.cy;
+                const double x = F.r00 * vx + F.r01 * vy + F.cx, y = F.r10 * vx + F.r11 * vy + F.cy;
+                wxlo = fmin(wxlo, x); wxhi = fmax(wxhi, x); wylo = fmin(wylo, y); wyhi = fmax(wyhi, y);
+            }
+        }
+        // cells on the rim also hold whatever lies outside the grid: no geometric statement there
+        if (!edge_cell) {
+            const double slack_x = 2.0 / B.inv_dx, slack_y = 2.0 / B.inv_dy;
+            if (wxhi + slack_x < B.xlo || wxlo - slack_x > B.xhi || wyhi + slack_y < B.ylo || wylo - slack_y > B.yhi) continue;
+        }
+        const int bx0 = max(0, (int)floor((wxlo - B.xlo) * B.inv_dx) - 1);
+        const int by0 = max(0, (int)floor((wylo - B.ylo) * B.inv_dy) - 1);
+        const bool priv = (unsigned long long)nqc * (unsigned long long)ntc < 0xffffffffull;
+        __syncthreads();
+        for (int i = threadIdx.x; i < kPcfWin * kPcfWin; i += kPcfThreads) win[i] = 0u;
+        __syncthreads();
+        for (int q = threadIdx.x; q < nqc; q += kPcfThreads) {
+            const typename PcfVec2<D>::type qv = qs[q0 + q];
+            const int skip = same ? qidx[q0 + q] : -1;
+            for (int i = 0; i < ntc; ++i) {
+                const typename PcfVec2<D>::type tv = ts[t0 + i];
+                int bx, by;
+                if (!B.bins(pcf_sub<D>(qv.x, tv.x), pcf_sub<D>(qv.y, tv.y), bx, by)) continue;
+                if (same && tidx[t0 + i] == skip) continue;
+                const unsigned lx = (unsigned)(bx - bx0), ly = (unsigned)(by - by0);
+                if (priv && lx < (unsigned)kPcfWin && ly < (unsigned)kPcfWin) atomicAdd(&win[lx * kPcfWin + ly], 1u);
+                else atomicAdd(&grid[(size_t)bx * (nye - 1) + by], 1ULL);
+            }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < kPcfWin * kPcfWin; i += kPcfThreads) {
+            const unsigned v = win[i];
+            if (v) atomicAdd(&grid[(size_t)(bx0 + i / kPcfWin) * (nye - 1) + (by0 + i % kPcfWin)], (unsigned long long)v);
         }
     }
 }
@@ -175,6 +377,110 @@ static void launch_pcf2d(dim3 grid, cudaStream_t stream, bool center_f32, const 
     } else {
         pcf2d_kernel<TC, TO, double, false><<<grid, kPcfThreads, smem, stream>>>((const TC*)coords, n, (const TO*)other, m, same, frames, xe, nxe, ye, nye, edge_stride, per_split, thr, counts);
     }
+}
+
+__global__ void pcf_bbox_init_kernel(int* bbox) {
+    bbox[0] = bbox[1] = pcf_float_order(INFINITY);
+    bbox[2] = bbox[3] = pcf_float_order(-INFINITY);
+}
+
+inline float pcf_order_to_float(int i) {
+    i ^= (i >> 31) & 0x7fffffff;
+    float f;
+    memcpy(&f, &i, sizeof f);
+    return f;
+}
+
+// Sorts one particle set into the cells of P: sorted positions (as D), original indices, cell starts.
+template <typename T, typename D>
+static int pcf_sort_cells(amepb_ctx* ctx, cudaStream_t stream, const T* pts, long long n, const PcfCellPlan& P,
+                          int buf_sorted, int buf_idx, int buf_count, int buf_start) {
+    const int ncell = P.gx * P.gy;
+    int rc;
+    if ((rc = ensure_device(ctx, buf_sorted, sizeof(typename PcfVec2<D>::type) * (size_t)n))) return rc;
+    if ((rc = ensure_device(ctx, buf_idx, sizeof(int) * (size_t)n))) return rc;
+    if ((rc = ensure_device(ctx, buf_count, sizeof(int) * (size_t)ncell))) return rc;
+    if ((rc = ensure_device(ctx, buf_start, sizeof(int) * ((size_t)ncell + 1)))) return rc;
+    int* count = reinterpret_cast<int*>(ctx->bufs[buf_count].p);
+    int* start = reinterpret_cast<int*>(ctx->bufs[buf_start].p);
+    AMEPB_CUDA(ctx, cudaMemsetAsync(count, 0, sizeof(int) * (size_t)ncell, stream));
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    pcf_cell_count_kernel<T><<<blocks, 256, 0, stream>>>(pts, n, P, count);
+    pcf_cell_scan_kernel<<<1, 1024, 0, stream>>>(count, start, ncell);
+    pcf_cell_scatter_kernel<T, D><<<blocks, 256, 0, stream>>>(
+        pts, n, P, start, count, reinterpret_cast<typename PcfVec2<D>::type*>(ctx->bufs[buf_sorted].p),
+        reinterpret_cast<int*>(ctx->bufs[buf_idx].p));
+    AMEPB_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+// One frame through the cell-sorted walk.  Returns 0 when done, 1 when the frame does not
+// qualify (the caller then uses pcf2d_kernel), < 0 / cudaError on failure.
+template <typename TC, typename TO>
+static int pcf2d_cells_frame(amepb_ctx* ctx, cudaStream_t stream, const TC* coords, long long n, const TO* other,
+                             long long m, int same, bool center_f32, const Pcf2dFrame& hF, const Pcf2dFrame* d_frame,
+                             const double* h_xe, const double* d_xe, int nxe, const double* h_ye, const double* d_ye,
+                             int nye, const float* d_thr, double min_occupancy, int* h_bbox,
+                             unsigned long long* d_grid) {
+    using D = typename std::conditional<sizeof(TC) == 4 && sizeof(TO) == 4, float, double>::type;
+    if (n >= (1LL << 31) || m >= (1LL << 31)) return 1;
+    int rc;
+    if ((rc = ensure_device(ctx, BUF_MISC, 64))) return rc;
+    int* d_bbox = reinterpret_cast<int*>(ctx->bufs[BUF_MISC].p);
+    pcf_bbox_init_kernel<<<1, 1, 0, stream>>>(d_bbox);
+    const unsigned rblocks = (unsigned)std::min<long long>((n + 255) / 256, 4LL * ctx->sm_count);
+    pcf_bbox_kernel<TC><<<rblocks, 256, 0, stream>>>(coords, n, d_bbox);
+    if (!same) {
+        const unsigned oblocks = (unsigned)std::min<long long>((m + 255) / 256, 4LL * ctx->sm_count);
+        pcf_bbox_kernel<TO><<<oblocks, 256, 0, stream>>>(other, m, d_bbox);
+    }
+    AMEPB_LAUNCH_CHECK(ctx);
+    AMEPB_CUDA(ctx, cudaMemcpyAsync(h_bbox, d_bbox, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    AMEPB_CUDA(ctx, cudaStreamSynchronize(stream));
+    const float lox = pcf_order_to_float(h_bbox[0]), loy = pcf_order_to_float(h_bbox[1]);
+    const float hix = pcf_order_to_float(h_bbox[2]), hiy = pcf_order_to_float(h_bbox[3]);
+    if (!(lox <= hix) || !(loy <= hiy) || !std::isfinite(lox) || !std::isfinite(hix) || !std::isfinite(loy) ||
+        !std::isfinite(hiy))
+        return 1;
+    // cell side: the differences of a cell pair span 2 cs per axis, (|cos| + |sin|) times that after
+    // the rotation, and have to fit the window with a few bins to spare
+    const double bwx = (h_xe[nxe - 1] - h_xe[0]) / (nxe - 1), bwy = (h_ye[nye - 1] - h_ye[0]) / (nye - 1);
+    const double spread = hF.rotate ? fabs(hF.r00) + fabs(hF.r10) : 1.0;
+    if (!(spread >= 1.0 - 1e-9) || !(spread <= 1.5)) return 1;   // NaN angle: nothing bins anyway
+    const double cs = 0.5 * (kPcfWin - 6) * std::min(bwx, bwy) / spread;
+    const double ex = (double)hix - lox, ey = (double)hiy - loy;
+    if (!(cs > 0.0) || ex / cs > 4096.0 || ey / cs > 4096.0) return 1;
+    PcfCellPlan P;
+    P.x0 = lox; P.y0 = loy; P.cs = (float)cs; P.inv_cs = (float)(1.0 / cs);
+    P.gx = (int)(ex / cs) + 1; P.gy = (int)(ey / cs) + 1;
+    const long long ncell = (long long)P.gx * P.gy;
+    if (ncell > 65536 || (double)n / ncell < min_occupancy || (double)m / ncell < min_occupancy) return 1;
+    if ((rc = pcf_sort_cells<TC, D>(ctx, stream, coords, n, P, BUF_TSORTED, BUF_QRANK, BUF_TCOUNT, BUF_TSTART))) return rc;
+    if (!same)
+        if ((rc = pcf_sort_cells<TO, D>(ctx, stream, other, m, P, BUF_QSORTED, BUF_SCAN, BUF_QCOUNT, BUF_QSTART))) return rc;
+    using V = typename PcfVec2<D>::type;
+    const V* ts = reinterpret_cast<const V*>(ctx->bufs[BUF_TSORTED].p);
+    const int* tidx = reinterpret_cast<const int*>(ctx->bufs[BUF_QRANK].p);
+    const int* tstart = reinterpret_cast<const int*>(ctx->bufs[BUF_TSTART].p);
+    const V* qs = same ? ts : reinterpret_cast<const V*>(ctx->bufs[BUF_QSORTED].p);
+    const int* qidx = same ? tidx : reinterpret_cast<const int*>(ctx->bufs[BUF_SCAN].p);
+    const int* qstart = same ? tstart : reinterpret_cast<const int*>(ctx->bufs[BUF_QSTART].p);
+    // thresholds only while they fit the default 48 KB of dynamic shared memory beside the window
+    const bool with_thr = d_thr != nullptr && (size_t)nxe + nye <= 2048;
+    const size_t smem = sizeof(unsigned) * kPcfWin * kPcfWin + (with_thr ? sizeof(float) * ((size_t)nxe + nye) : 0);
+    const long long ysplit = std::max(1LL, std::min<long long>({(8LL * ctx->sm_count + ncell - 1) / ncell, ncell, 64LL}));
+    const dim3 grid((unsigned)ncell, (unsigned)ysplit);
+    const float* thr = with_thr ? d_thr : nullptr;
+    if constexpr (sizeof(D) == 4) {
+        if (center_f32)
+            pcf2d_cells_kernel<float, true><<<grid, kPcfThreads, smem, stream>>>(qs, qidx, qstart, ts, tidx, tstart, P, same, d_frame, d_xe, nxe, d_ye, nye, thr, d_grid);
+        else
+            pcf2d_cells_kernel<float, false><<<grid, kPcfThreads, smem, stream>>>(qs, qidx, qstart, ts, tidx, tstart, P, same, d_frame, d_xe, nxe, d_ye, nye, thr, d_grid);
+    } else {
+        pcf2d_cells_kernel<double, false><<<grid, kPcfThreads, smem, stream>>>(qs, qidx, qstart, ts, tidx, tstart, P, same, d_frame, d_xe, nxe, d_ye, nye, nullptr, d_grid);
+    }
+    AMEPB_LAUNCH_CHECK(ctx);
+    return 0;
 }
 
 }  // namespace amepb
@@ -236,7 +542,8 @@ extern "C" int amepb_pcf2d_counts(amepb_ctx* ctx, const void* coords, int dtype,
     const bool with_thr = all_f32 && (size_t)nxe + nye <= 6144;
     const size_t tbytes = with_thr ? ((sizeof(float) * (size_t)nframes * (nxe + nye) + 15) & ~(size_t)15) : 0;
     const size_t pbytes = fbytes + 2 * ebytes + tbytes;
-    if ((rc = ensure_pinned(ctx, pbytes))) return rc;
+    const size_t bbox_off = (pbytes + 63) & ~(size_t)63;   // bounding-box read-back of the cell-sorted walk
+    if ((rc = ensure_pinned(ctx, bbox_off + 64))) return rc;
     if ((rc = ensure_device(ctx, BUF_SQ_A, pbytes))) return rc;
     char* hp = reinterpret_cast<char*>(ctx->pinned);
     memset(hp, 0, pbytes);
@@ -291,25 +598,66 @@ extern "C" int amepb_pcf2d_counts(amepb_ctx* ctx, const void* coords, int dtype,
     const float* d_thr = with_thr ? reinterpret_cast<const float*>(dp + fbytes + 2 * ebytes) : nullptr;
     const size_t smem = with_thr ? sizeof(float) * ((size_t)nxe + nye) : 0;
 
-    // query tiles x target splits x frames: at least ~4 blocks per SM when the system allows it
-    const long long qtiles = (m + kPcfThreads - 1) / kPcfThreads;
-    const long long want = 4LL * ctx->sm_count;
-    long long tsplit = (want + qtiles * nframes - 1) / (qtiles * nframes);
-    const long long max_split = (n + kPcfStage - 1) / kPcfStage;
-    tsplit = std::max(1LL, std::min({tsplit, max_split, 65535LL}));
-    long long per_split = (n + tsplit - 1) / tsplit;
-    per_split = (per_split + kPcfStage - 1) / kPcfStage * kPcfStage;
-    tsplit = (n + per_split - 1) / per_split;
-    const dim3 grid((unsigned)qtiles, (unsigned)tsplit, (unsigned)nframes);
     const bool cf32 = center_f32 != 0;
-    if (dtype == AMEPB_F32 && other_dtype == AMEPB_F32)
-        launch_pcf2d<float, float>(grid, stream, cf32, d_coords, n, d_other, m, same, d_frames, d_xe, nxe, d_ye, nye, dev_stride, per_split, d_thr, smem, d_counts);
-    else if (dtype == AMEPB_F32)
-        launch_pcf2d<float, double>(grid, stream, cf32, d_coords, n, d_other, m, same, d_frames, d_xe, nxe, d_ye, nye, dev_stride, per_split, d_thr, smem, d_counts);
-    else if (other_dtype == AMEPB_F32)
-        launch_pcf2d<double, float>(grid, stream, cf32, d_coords, n, d_other, m, same, d_frames, d_xe, nxe, d_ye, nye, dev_stride, per_split, d_thr, smem, d_counts);
-    else
-        launch_pcf2d<double, double>(grid, stream, cf32, d_coords, n, d_other, m, same, d_frames, d_xe, nxe, d_ye, nye, dev_stride, per_split, d_thr, smem, d_counts);
+    // frames [f0, f0 + nf) through pcf2d_kernel: query tiles x target splits x frames, at least
+    // ~4 blocks per SM when the system allows it
+    auto launch_direct = [&](int64_t f0, int64_t nf) {
+        const long long qtiles = (m + kPcfThreads - 1) / kPcfThreads;
+        const long long want = 4LL * ctx->sm_count;
+        long long tsplit = (want + qtiles * nf - 1) / (qtiles * nf);
+        const long long max_split = (n + kPcfStage - 1) / kPcfStage;
+        tsplit = std::max(1LL, std::min({tsplit, max_split, 65535LL}));
+        long long per_split = (n + tsplit - 1) / tsplit;
+        per_split = (per_split + kPcfStage - 1) / kPcfStage * kPcfStage;
+        tsplit = (n + per_split - 1) / per_split;
+        const dim3 grid((unsigned)qtiles, (unsigned)tsplit, (unsigned)nf);
+        const char* c0 = reinterpret_cast<const char*>(d_coords) + (size_t)f0 * n * 3 * (dtype == AMEPB_F32 ? 4 : 8);
+        const char* o0 = reinterpret_cast<const char*>(d_other) + (size_t)f0 * m * 3 * (other_dtype == AMEPB_F32 ? 4 : 8);
+        const Pcf2dFrame* fr = d_frames + f0;
+        const double* xe0 = d_xe + f0 * dev_stride;
+        const double* ye0 = d_ye + f0 * dev_stride;
+        const float* th0 = d_thr ? d_thr + f0 * (nxe + nye) : nullptr;
+        unsigned long long* g0 = d_counts + (size_t)f0 * (nxe - 1) * (nye - 1);
+        if (dtype == AMEPB_F32 && other_dtype == AMEPB_F32)
+            launch_pcf2d<float, float>(grid, stream, cf32, c0, n, o0, m, same, fr, xe0, nxe, ye0, nye, dev_stride, per_split, th0, smem, g0);
+        else if (dtype == AMEPB_F32)
+            launch_pcf2d<float, double>(grid, stream, cf32, c0, n, o0, m, same, fr, xe0, nxe, ye0, nye, dev_stride, per_split, th0, smem, g0);
+        else if (other_dtype == AMEPB_F32)
+            launch_pcf2d<double, float>(grid, stream, cf32, c0, n, o0, m, same, fr, xe0, nxe, ye0, nye, dev_stride, per_split, th0, smem, g0);
+        else
+            launch_pcf2d<double, double>(grid, stream, cf32, c0, n, o0, m, same, fr, xe0, nxe, ye0, nye, dev_stride, per_split, th0, smem, g0);
+    };
+    // Large systems: cell-sorted walk with a shared-memory window, frame by frame (each frame
+    // needs its bounding box on the host).  AMEPB_PCF2D_CELLS=0 disables it, =1 drops the
+    // occupancy requirement (tests).
+    const char* cells_env = getenv("AMEPB_PCF2D_CELLS");
+    const int cells_mode = cells_env ? atoi(cells_env) : -1;
+    const bool try_cells = cells_mode != 0 && (cells_mode == 1 || (double)n * (double)m >= 2.5e9);
+    if (!try_cells) {
+        launch_direct(0, nframes);
+    } else {
+        const double min_occ = cells_mode == 1 ? 0.0 : 128.0;
+        for (int64_t f = 0; f < nframes; ++f) {
+            const char* c0 = reinterpret_cast<const char*>(d_coords) + (size_t)f * n * 3 * (dtype == AMEPB_F32 ? 4 : 8);
+            const char* o0 = reinterpret_cast<const char*>(d_other) + (size_t)f * m * 3 * (other_dtype == AMEPB_F32 ? 4 : 8);
+            const double* hxf = hxe + f * (edge_stride ? estride : 0);
+            const double* hyf = hye + f * (edge_stride ? estride : 0);
+            const float* th0 = d_thr ? d_thr + f * (nxe + nye) : nullptr;
+            unsigned long long* g0 = d_counts + (size_t)f * (nxe - 1) * (nye - 1);
+            int* h_bbox = reinterpret_cast<int*>(hp + bbox_off);
+            int r;
+            if (dtype == AMEPB_F32 && other_dtype == AMEPB_F32)
+                r = pcf2d_cells_frame<float, float>(ctx, stream, (const float*)c0, n, (const float*)o0, m, same, cf32, hf[f], d_frames + f, hxf, d_xe + f * dev_stride, nxe, hyf, d_ye + f * dev_stride, nye, th0, min_occ, h_bbox, g0);
+            else if (dtype == AMEPB_F32)
+                r = pcf2d_cells_frame<float, double>(ctx, stream, (const float*)c0, n, (const double*)o0, m, same, cf32, hf[f], d_frames + f, hxf, d_xe + f * dev_stride, nxe, hyf, d_ye + f * dev_stride, nye, th0, min_occ, h_bbox, g0);
+            else if (other_dtype == AMEPB_F32)
+                r = pcf2d_cells_frame<double, float>(ctx, stream, (const double*)c0, n, (const float*)o0, m, same, cf32, hf[f], d_frames + f, hxf, d_xe + f * dev_stride, nxe, hyf, d_ye + f * dev_stride, nye, th0, min_occ, h_bbox, g0);
+            else
+                r = pcf2d_cells_frame<double, double>(ctx, stream, (const double*)c0, n, (const double*)o0, m, same, cf32, hf[f], d_frames + f, hxf, d_xe + f * dev_stride, nxe, hyf, d_ye + f * dev_stride, nye, th0, min_occ, h_bbox, g0);
+            if (r == 1) launch_direct(f, 1);
+            else if (r != 0) return r;
+        }
+    }
     AMEPB_LAUNCH_CHECK(ctx);
     if (space == AMEPB_HOST) {
         AMEPB_CUDA(ctx, cudaMemcpyAsync(counts, d_counts, gbytes, cudaMemcpyDeviceToHost, stream));

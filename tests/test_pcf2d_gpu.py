@@ -31,9 +31,17 @@ def _rng(tag):
     return np.random.default_rng(zlib.crc32(tag.encode()))
 
 
+@pytest.fixture(params=["direct", "cells"])
+def walk(request, monkeypatch):
+    """Both pair walks of the library: the direct kernel (what small systems get) and the
+    cell-sorted walk with the shared-memory window, forced here at any size."""
+    monkeypatch.setenv("AMEPB_PCF2D_CELLS", "1" if request.param == "cells" else "0")
+    return request.param
+
+
 @pytest.mark.parametrize("space", ["host", "device"])
 @pytest.mark.parametrize("name", PCF2D_CASES)
-def test_pcf2d_golden(sc, name, space):
+def test_pcf2d_golden(sc, name, space, walk):
     z = np.load(os.path.join(GOLDEN, name))
     coords = z["coords"].copy()
     other = z["other"].copy() if "other" in z.files else None
@@ -52,7 +60,7 @@ def test_pcf2d_golden(sc, name, space):
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("rot", [False, True])
-def test_pcf2d_counts_vs_oracle_ragged(sc, dtype, rot):
+def test_pcf2d_counts_vs_oracle_ragged(sc, dtype, rot, walk):
     """Sizes that are no multiple of the query tile (256) or the target stage (1024), several
     target splits, default 500 x 500 grid."""
     from amep_b200 import _core
@@ -82,7 +90,7 @@ def test_pcf2d_counts_vs_oracle_ragged(sc, dtype, rot):
     np.testing.assert_array_equal(got_s[0].cpu().numpy(), want_s)
 
 
-def test_pcf2d_frames_batch_matches_single_frames(sc):
+def test_pcf2d_frames_batch_matches_single_frames(sc, walk):
     """Several frames with their own boxes (own default rmax, own edges) and orientations in one
     library call give what frame-by-frame calls give."""
     rng = _rng("pcf2d-frames")
@@ -103,7 +111,7 @@ def test_pcf2d_frames_batch_matches_single_frames(sc):
         np.testing.assert_array_equal(Y[f], Yw)
 
 
-def test_pcf2d_sum_rule_large(sc):
+def test_pcf2d_sum_rule_large(sc, walk):
     """Size-independent property at a size the oracle cannot reach: with a window that covers
     every difference vector the counts add up to N*(N-1), and g(x, y) = g(-x, -y) for the same
     particles (every pair is seen from both ends)."""
@@ -128,3 +136,27 @@ def test_pcf2d_invalid_arguments(sc):
         _core.pcf2d_counts(c, None, np.zeros((1, 3)), True, None, np.array([0.0, 1.0, 1.0]), np.array([0.0, 1.0]))
     with pytest.raises(ValueError):
         _core.pcf2d_counts(c, None, np.zeros((1, 3)), True, None, np.array([0.0]), np.array([0.0, 1.0]))
+
+
+def test_pcf2d_cells_equal_direct_clustered_and_outliers(sc, monkeypatch):
+    """The two walks agree bit for bit on a frame that stresses the cell geometry: a dense blob,
+    far outliers, NaN / inf rows, coincident particles, rotation, fine bins (many cells)."""
+    from amep_b200 import _core
+    rng = _rng("pcf2d-cells-clustered")
+    n = 6000
+    c = np.zeros((n, 3), dtype=np.float32)
+    c[:, :2] = rng.uniform(0, 50, (n, 2))
+    c[:2000, :2] = rng.normal(25.0, 0.7, (2000, 2))
+    c[10, :2] = (4000.0, -3000.0)
+    c[11, :2] = (np.nan, 3.0)
+    c[12, :2] = (7.0, np.inf)
+    c[13] = c[14]
+    edges_x, edges_y = np.linspace(-3.0, 3.0, 241), np.linspace(-2.0, 2.5, 131)
+    cen = np.array([[25.0, 25.0, 0.0]])
+    for rot in (None, np.array([[1.0, np.cos(-1.1), np.sin(-1.1)]])):
+        out = {}
+        for mode in ("0", "1"):
+            monkeypatch.setenv("AMEPB_PCF2D_CELLS", mode)
+            out[mode] = _core.pcf2d_counts(torch.from_numpy(c).cuda(), None, cen, True, rot, edges_x, edges_y)[0].cpu().numpy()
+        assert out["0"].sum() > 0
+        np.testing.assert_array_equal(out["0"], out["1"])
