@@ -71,6 +71,7 @@ struct amepb_ctx {
     size_t ev_used = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pair, ev_build, ev_sq, ev_copy;
     bool sq_attr_sf2d = false;
+    bool pcf_attr = false;   // dynamic shared-memory opt-in of the pcf2d cell kernels set
 };
 
 namespace amepb {

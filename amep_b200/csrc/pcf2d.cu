@@ -42,18 +42,26 @@ struct Pcf2dFrame {
     // equivalent to the float64 test against the outer edges; rotation: squared radius about the
     // centre that holds the whole window (conservative: never rejects a pair that bins)
     float fxlo, fxhi, fylo, fyhi, fr2;
+    // both edge arrays are uniform to within 0.2 bin widths and their float32 thresholds strictly
+    // increase: the bin guessed from the spacing is off by at most one
+    int uniform;
+    // float32 copies of the rotation and the centre, and the margin within which the float32
+    // evaluation of a rotated difference is guaranteed to lie of the float64 one (see bins())
+    float fr00, fr01, fr10, fr11, fcx, fcy, fmargin;
 };
 
 constexpr int kPcfThreads = 256;
 constexpr int kPcfStage = 1024;
+constexpr size_t kPcfStageEdges = 2048;   // edges (x + y) up to this many are staged in shared memory
 
 // index of the bin holding v, or -1 (np.histogramdd semantics)
-__device__ __forceinline__ int pcf_bin_of(double v, const double* __restrict__ e, int ne, double inv_d) {
+__device__ __forceinline__ int pcf_bin_of(double v, const double* __restrict__ e, int ne, double inv_d, bool uniform) {
     const double lo = e[0], hi = e[ne - 1];
     if (!(v >= lo) || !(v <= hi)) return -1;
     if (v == hi) return ne - 2;
     int g = __double2int_rd((v - lo) * inv_d);
     g = min(max(g, 0), ne - 2);
+    if (uniform) return g + (int)(g < ne - 2 && v >= e[g + 1]) - (int)(v < e[g]);   // off by one at most
     while (v < e[g]) --g;
     while (v >= e[g + 1]) ++g;
     return g;
@@ -96,6 +104,11 @@ struct PairBinner {
                     // the uniform spacing, then settle against the thresholds
                     bx = min(max(__float2int_rd((dx - F->fxlo) * finv_dx), 0), nxe - 2);
                     by = min(max(__float2int_rd((dy - F->fylo) * finv_dy), 0), nye - 2);
+                    if (F->uniform) {
+                        bx += (int)(bx < nxe - 2 && dx >= tx[bx + 1]) - (int)(dx < tx[bx]);
+                        by += (int)(by < nye - 2 && dy >= ty[by + 1]) - (int)(dy < ty[by]);
+                        return true;
+                    }
                     while (dx < tx[bx]) --bx;
                     while (bx < nxe - 2 && dx >= tx[bx + 1]) ++bx;
                     while (dy < ty[by]) --by;
@@ -103,8 +116,27 @@ struct PairBinner {
                     return true;
                 }
             } else {
-                const float ux = dx - (float)F->cx, uy = dy - (float)F->cy;
+                const float ux = dx - F->fcx, uy = dy - F->fcy;
                 if (!(ux * ux + uy * uy <= F->fr2)) return false;
+                if (use_thr) {
+                    // Rotation in float32 first: the result lies within fmargin of the float64 value
+                    // the reference bins (|error| <= 4e-7 (|ux| + |uy|) + 2.5e-7 (|cx| + |cy|), the
+                    // margin is 1e-6 of their largest possible sum plus two ulps of the largest
+                    // edge).  A value farther than that from the thresholds of its bin, or from the
+                    // edge range, is decided here; the rest (about 4 margin / bin width of the
+                    // pairs) takes the float64 path below.
+                    const float xa = fmaf(F->fr00, ux, F->fr01 * uy) + F->fcx;
+                    const float ya = fmaf(F->fr10, ux, F->fr11 * uy) + F->fcy;
+                    const float mg = F->fmargin;
+                    if (xa < F->fxlo - mg || xa > F->fxhi + mg || ya < F->fylo - mg || ya > F->fyhi + mg) return false;
+                    const int kx = min(max(__float2int_rd((xa - F->fxlo) * finv_dx), 0), nxe - 2);
+                    const int ky = min(max(__float2int_rd((ya - F->fylo) * finv_dy), 0), nye - 2);
+                    if (xa - tx[kx] > mg && tx[kx + 1] - xa > mg && ya - ty[ky] > mg && ty[ky + 1] - ya > mg) {
+                        bx = kx;
+                        by = ky;
+                        return true;
+                    }
+                }
             }
         }
         if (!rotate) {
@@ -123,8 +155,8 @@ struct PairBinner {
             y = __dadd_rn(__dadd_rn(__dmul_rn(F->r10, vx), __dmul_rn(F->r11, vy)), F->cy);
         }
         if (!(x >= xlo) || !(x <= xhi) || !(y >= ylo) || !(y <= yhi)) return false;
-        bx = pcf_bin_of(x, xe, nxe, inv_dx);
-        by = pcf_bin_of(y, ye, nye, inv_dy);
+        bx = pcf_bin_of(x, xe, nxe, inv_dx, F->uniform != 0);
+        by = pcf_bin_of(y, ye, nye, inv_dy, F->uniform != 0);
         return bx >= 0 && by >= 0;
     }
 };
@@ -142,14 +174,22 @@ __global__ void __launch_bounds__(kPcfThreads) pcf2d_kernel(const TC* __restrict
                                                             const double* __restrict__ xedges, int nxe,
                                                             const double* __restrict__ yedges, int nye,
                                                             long long edge_stride, long long per_split,
-                                                            const float* __restrict__ thr,
+                                                            const float* __restrict__ thr, int stage,
                                                             unsigned long long* __restrict__ counts) {
-    extern __shared__ float s_thr[];   // float32 thresholds of the x edges, then of the y edges
+    // stage != 0: the x and y edges (float64), then their float32 thresholds (thr != nullptr)
+    extern __shared__ double s_edges[];
+    float* s_thr = reinterpret_cast<float*>(s_edges + (stage ? nxe + nye : 0));
     __shared__ D sx[kPcfStage], sy[kPcfStage];
     __shared__ Pcf2dFrame F;
     const int f = blockIdx.z;
     if (threadIdx.x < sizeof(Pcf2dFrame) / sizeof(int))
         reinterpret_cast<int*>(&F)[threadIdx.x] = reinterpret_cast<const int*>(frames + f)[threadIdx.x];
+    const double* xe_f = xedges + (long long)f * edge_stride;
+    const double* ye_f = yedges + (long long)f * edge_stride;
+    if (stage) {
+        for (int i = threadIdx.x; i < nxe; i += kPcfThreads) s_edges[i] = xe_f[i];
+        for (int i = threadIdx.x; i < nye; i += kPcfThreads) s_edges[nxe + i] = ye_f[i];
+    }
     if (sizeof(D) == 4 && thr != nullptr) {
         const float* tf = thr + (long long)f * (nxe + nye);
         for (int i = threadIdx.x; i < nxe + nye; i += kPcfThreads) s_thr[i] = tf[i];
@@ -163,7 +203,7 @@ __global__ void __launch_bounds__(kPcfThreads) pcf2d_kernel(const TC* __restrict
     const long long t_lo = (long long)blockIdx.y * per_split, t_hi = min(n, t_lo + per_split);
     __syncthreads();
     PairBinner<D, CF32> B;
-    B.init(&F, xedges + (long long)f * edge_stride, nxe, yedges + (long long)f * edge_stride, nye, s_thr, thr != nullptr);
+    B.init(&F, stage ? s_edges : xe_f, nxe, stage ? s_edges + nxe : ye_f, nye, s_thr, thr != nullptr);
     for (long long t0 = t_lo; t0 < t_hi; t0 += kPcfStage) {
         const int cnt = (int)min((long long)kPcfStage, t_hi - t0);
         __syncthreads();
@@ -292,10 +332,17 @@ __global__ void __launch_bounds__(kPcfThreads) pcf2d_cells_kernel(
     const typename PcfVec2<D>::type* __restrict__ qs, const int* __restrict__ qidx, const int* __restrict__ qstart,
     const typename PcfVec2<D>::type* __restrict__ ts, const int* __restrict__ tidx, const int* __restrict__ tstart,
     PcfCellPlan P, int same, const Pcf2dFrame* __restrict__ frame, const double* __restrict__ xe, int nxe,
-    const double* __restrict__ ye, int nye, const float* __restrict__ thr, unsigned long long* __restrict__ grid) {
-    extern __shared__ unsigned s_dyn[];              // window, then the float32 thresholds
+    const double* __restrict__ ye, int nye, const float* __restrict__ thr, int stage,
+    unsigned long long* __restrict__ grid) {
+    // window, then (stage != 0) the float64 edges and (thr != nullptr) their float32 thresholds
+    extern __shared__ __align__(8) unsigned s_dyn[];
     unsigned* win = s_dyn;
-    float* s_thr = reinterpret_cast<float*>(s_dyn + kPcfWin * kPcfWin);
+    double* s_edges = reinterpret_cast<double*>(s_dyn + kPcfWin * kPcfWin);
+    float* s_thr = reinterpret_cast<float*>(s_edges + (stage ? nxe + nye : 0));
+    if (stage) {
+        for (int i = threadIdx.x; i < nxe; i += kPcfThreads) s_edges[i] = xe[i];
+        for (int i = threadIdx.x; i < nye; i += kPcfThreads) s_edges[nxe + i] = ye[i];
+    }
     __shared__ Pcf2dFrame F;
     if (threadIdx.x < sizeof(Pcf2dFrame) / sizeof(int))
         reinterpret_cast<int*>(&F)[threadIdx.x] = reinterpret_cast<const int*>(frame)[threadIdx.x];
@@ -306,7 +353,7 @@ __global__ void __launch_bounds__(kPcfThreads) pcf2d_cells_kernel(
     if (nqc == 0) return;
     __syncthreads();
     PairBinner<D, CF32> B;
-    B.init(&F, xe, nxe, ye, nye, s_thr, thr != nullptr);
+    B.init(&F, stage ? s_edges : xe, nxe, stage ? s_edges + nxe : ye, nye, s_thr, thr != nullptr);
     const int qcx = qc % P.gx, qcy = qc / P.gx;
     const double qxlo = (double)P.x0 + (double)qcx * P.cs, qylo = (double)P.y0 + (double)qcy * P.cs;
     for (int tc = blockIdx.y; tc < ncell; tc += gridDim.y) {
@@ -367,15 +414,15 @@ template <typename TC, typename TO>
 static void launch_pcf2d(dim3 grid, cudaStream_t stream, bool center_f32, const void* coords, long long n,
                          const void* other, long long m, int same, const Pcf2dFrame* frames, const double* xe, int nxe,
                          const double* ye, int nye, long long edge_stride, long long per_split, const float* thr,
-                         size_t smem, unsigned long long* counts) {
+                         int stage, size_t smem, unsigned long long* counts) {
     constexpr bool both_f32 = sizeof(TC) == 4 && sizeof(TO) == 4;
     if constexpr (both_f32) {
         if (center_f32)
-            pcf2d_kernel<TC, TO, float, true><<<grid, kPcfThreads, smem, stream>>>((const TC*)coords, n, (const TO*)other, m, same, frames, xe, nxe, ye, nye, edge_stride, per_split, thr, counts);
+            pcf2d_kernel<TC, TO, float, true><<<grid, kPcfThreads, smem, stream>>>((const TC*)coords, n, (const TO*)other, m, same, frames, xe, nxe, ye, nye, edge_stride, per_split, thr, stage, counts);
         else
-            pcf2d_kernel<TC, TO, float, false><<<grid, kPcfThreads, smem, stream>>>((const TC*)coords, n, (const TO*)other, m, same, frames, xe, nxe, ye, nye, edge_stride, per_split, thr, counts);
+            pcf2d_kernel<TC, TO, float, false><<<grid, kPcfThreads, smem, stream>>>((const TC*)coords, n, (const TO*)other, m, same, frames, xe, nxe, ye, nye, edge_stride, per_split, thr, stage, counts);
     } else {
-        pcf2d_kernel<TC, TO, double, false><<<grid, kPcfThreads, smem, stream>>>((const TC*)coords, n, (const TO*)other, m, same, frames, xe, nxe, ye, nye, edge_stride, per_split, thr, counts);
+        pcf2d_kernel<TC, TO, double, false><<<grid, kPcfThreads, smem, stream>>>((const TC*)coords, n, (const TO*)other, m, same, frames, xe, nxe, ye, nye, edge_stride, per_split, thr, stage, counts);
     }
 }
 
@@ -466,18 +513,27 @@ static int pcf2d_cells_frame(amepb_ctx* ctx, cudaStream_t stream, const TC* coor
     const int* qidx = same ? tidx : reinterpret_cast<const int*>(ctx->bufs[BUF_SCAN].p);
     const int* qstart = same ? tstart : reinterpret_cast<const int*>(ctx->bufs[BUF_QSTART].p);
     // thresholds only while they fit the default 48 KB of dynamic shared memory beside the window
-    const bool with_thr = d_thr != nullptr && (size_t)nxe + nye <= 2048;
-    const size_t smem = sizeof(unsigned) * kPcfWin * kPcfWin + (with_thr ? sizeof(float) * ((size_t)nxe + nye) : 0);
+    const int stage = (size_t)nxe + nye <= kPcfStageEdges ? 1 : 0;
+    const bool with_thr = d_thr != nullptr && stage;
+    const size_t smem = sizeof(unsigned) * kPcfWin * kPcfWin +
+                        (stage ? sizeof(double) * ((size_t)nxe + nye) : 0) + (with_thr ? sizeof(float) * ((size_t)nxe + nye) : 0);
     const long long ysplit = std::max(1LL, std::min<long long>({(8LL * ctx->sm_count + ncell - 1) / ncell, ncell, 64LL}));
     const dim3 grid((unsigned)ncell, (unsigned)ysplit);
     const float* thr = with_thr ? d_thr : nullptr;
+    if (!ctx->pcf_attr) {
+        const int cap = (int)(sizeof(unsigned) * kPcfWin * kPcfWin + (sizeof(double) + sizeof(float)) * kPcfStageEdges);
+        AMEPB_CUDA(ctx, cudaFuncSetAttribute(pcf2d_cells_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+        AMEPB_CUDA(ctx, cudaFuncSetAttribute(pcf2d_cells_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+        AMEPB_CUDA(ctx, cudaFuncSetAttribute(pcf2d_cells_kernel<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+        ctx->pcf_attr = true;
+    }
     if constexpr (sizeof(D) == 4) {
         if (center_f32)
-            pcf2d_cells_kernel<float, true><<<grid, kPcfThreads, smem, stream>>>(qs, qidx, qstart, ts, tidx, tstart, P, same, d_frame, d_xe, nxe, d_ye, nye, thr, d_grid);
+            pcf2d_cells_kernel<float, true><<<grid, kPcfThreads, smem, stream>>>(qs, qidx, qstart, ts, tidx, tstart, P, same, d_frame, d_xe, nxe, d_ye, nye, thr, stage, d_grid);
         else
-            pcf2d_cells_kernel<float, false><<<grid, kPcfThreads, smem, stream>>>(qs, qidx, qstart, ts, tidx, tstart, P, same, d_frame, d_xe, nxe, d_ye, nye, thr, d_grid);
+            pcf2d_cells_kernel<float, false><<<grid, kPcfThreads, smem, stream>>>(qs, qidx, qstart, ts, tidx, tstart, P, same, d_frame, d_xe, nxe, d_ye, nye, thr, stage, d_grid);
     } else {
-        pcf2d_cells_kernel<double, false><<<grid, kPcfThreads, smem, stream>>>(qs, qidx, qstart, ts, tidx, tstart, P, same, d_frame, d_xe, nxe, d_ye, nye, nullptr, d_grid);
+        pcf2d_cells_kernel<double, false><<<grid, kPcfThreads, smem, stream>>>(qs, qidx, qstart, ts, tidx, tstart, P, same, d_frame, d_xe, nxe, d_ye, nye, nullptr, stage, d_grid);
     }
     AMEPB_LAUNCH_CHECK(ctx);
     return 0;
@@ -539,7 +595,8 @@ extern "C" int amepb_pcf2d_counts(amepb_ctx* ctx, const void* coords, int dtype,
     // float32 thresholds of the edges, per frame (x then y), used by the float32 kernels when they
     // fit shared memory beside the target stage
     const bool all_f32 = dtype == AMEPB_F32 && other_dtype == AMEPB_F32;
-    const bool with_thr = all_f32 && (size_t)nxe + nye <= 6144;
+    const int stage = (size_t)nxe + nye <= kPcfStageEdges ? 1 : 0;
+    const bool with_thr = all_f32 && stage;
     const size_t tbytes = with_thr ? ((sizeof(float) * (size_t)nframes * (nxe + nye) + 15) & ~(size_t)15) : 0;
     const size_t pbytes = fbytes + 2 * ebytes + tbytes;
     const size_t bbox_off = (pbytes + 63) & ~(size_t)63;   // bounding-box read-back of the cell-sorted walk
@@ -548,6 +605,7 @@ extern "C" int amepb_pcf2d_counts(amepb_ctx* ctx, const void* coords, int dtype,
     char* hp = reinterpret_cast<char*>(ctx->pinned);
     memset(hp, 0, pbytes);
     Pcf2dFrame* hf = reinterpret_cast<Pcf2dFrame*>(hp);
+    const bool no_f32rot = getenv("AMEPB_PCF2D_NO_F32ROT") != nullptr;   // diagnostics / tests
     for (int64_t f = 0; f < nframes; ++f) {
         Pcf2dFrame& F = hf[f];
         F.cx = center[f * 3 + 0];
@@ -571,6 +629,20 @@ extern "C" int amepb_pcf2d_counts(amepb_ctx* ctx, const void* coords, int dtype,
         const double ay = std::max(fabs(ye[0] - F.cy), fabs(ye[nye - 1] - F.cy));
         const double rad = sqrt(ax * ax + ay * ay) * (1.0 + 1e-5) + 1e-5 * (fabs(F.cx) + fabs(F.cy)) + 1e-30;
         F.fr2 = float_above(rad * rad, false);
+        F.fr00 = (float)F.r00; F.fr01 = (float)F.r01; F.fr10 = (float)F.r10; F.fr11 = (float)F.r11;
+        F.fcx = (float)F.cx; F.fcy = (float)F.cy;
+        const double emax = std::max(std::max(fabs(xe[0]), fabs(xe[nxe - 1])), std::max(fabs(ye[0]), fabs(ye[nye - 1])));
+        F.fmargin = float_above(1.01e-6 * (2.002 * sqrt((double)F.fr2) + fabs(F.cx) + fabs(F.cy)) + 2.5e-7 * emax + 1e-30, false);
+        if (no_f32rot) F.fmargin = INFINITY;   // nothing is decided in float32: every pair takes the float64 path
+        auto uniform_axis = [](const double* e, int ne) {
+            const double w = (e[ne - 1] - e[0]) / (ne - 1);
+            for (int k = 0; k < ne; ++k) {
+                if (!(fabs(e[k] - (e[0] + k * w)) <= 0.2 * w)) return false;
+                if (k > 0 && !(float_above(e[k - 1], false) < float_above(e[k], false))) return false;
+            }
+            return true;
+        };
+        F.uniform = uniform_axis(xe, nxe) && uniform_axis(ye, nye) ? 1 : 0;
     }
     double* hxe = reinterpret_cast<double*>(hp + fbytes);
     double* hye = reinterpret_cast<double*>(hp + fbytes + ebytes);
@@ -596,7 +668,7 @@ extern "C" int amepb_pcf2d_counts(amepb_ctx* ctx, const void* coords, int dtype,
     const double* d_ye = reinterpret_cast<const double*>(dp + fbytes + ebytes);
     const long long dev_stride = edge_stride ? (long long)estride : 0;
     const float* d_thr = with_thr ? reinterpret_cast<const float*>(dp + fbytes + 2 * ebytes) : nullptr;
-    const size_t smem = with_thr ? sizeof(float) * ((size_t)nxe + nye) : 0;
+    const size_t smem = (stage ? sizeof(double) * ((size_t)nxe + nye) : 0) + (with_thr ? sizeof(float) * ((size_t)nxe + nye) : 0);
 
     const bool cf32 = center_f32 != 0;
     // frames [f0, f0 + nf) through pcf2d_kernel: query tiles x target splits x frames, at least
@@ -619,13 +691,13 @@ extern "C" int amepb_pcf2d_counts(amepb_ctx* ctx, const void* coords, int dtype,
         const float* th0 = d_thr ? d_thr + f0 * (nxe + nye) : nullptr;
         unsigned long long* g0 = d_counts + (size_t)f0 * (nxe - 1) * (nye - 1);
         if (dtype == AMEPB_F32 && other_dtype == AMEPB_F32)
-            launch_pcf2d<float, float>(grid, stream, cf32, c0, n, o0, m, same, fr, xe0, nxe, ye0, nye, dev_stride, per_split, th0, smem, g0);
+            launch_pcf2d<float, float>(grid, stream, cf32, c0, n, o0, m, same, fr, xe0, nxe, ye0, nye, dev_stride, per_split, th0, stage, smem, g0);
         else if (dtype == AMEPB_F32)
-            launch_pcf2d<float, double>(grid, stream, cf32, c0, n, o0, m, same, fr, xe0, nxe, ye0, nye, dev_stride, per_split, th0, smem, g0);
+            launch_pcf2d<float, double>(grid, stream, cf32, c0, n, o0, m, same, fr, xe0, nxe, ye0, nye, dev_stride, per_split, th0, stage, smem, g0);
         else if (other_dtype == AMEPB_F32)
-            launch_pcf2d<double, float>(grid, stream, cf32, c0, n, o0, m, same, fr, xe0, nxe, ye0, nye, dev_stride, per_split, th0, smem, g0);
+            launch_pcf2d<double, float>(grid, stream, cf32, c0, n, o0, m, same, fr, xe0, nxe, ye0, nye, dev_stride, per_split, th0, stage, smem, g0);
         else
-            launch_pcf2d<double, double>(grid, stream, cf32, c0, n, o0, m, same, fr, xe0, nxe, ye0, nye, dev_stride, per_split, th0, smem, g0);
+            launch_pcf2d<double, double>(grid, stream, cf32, c0, n, o0, m, same, fr, xe0, nxe, ye0, nye, dev_stride, per_split, th0, stage, smem, g0);
     };
     // Large systems: cell-sorted walk with a shared-memory window, frame by frame (each frame
     // needs its bounding box on the host).  AMEPB_PCF2D_CELLS=0 disables it, =1 drops the

@@ -160,3 +160,81 @@ def test_pcf2d_cells_equal_direct_clustered_and_outliers(sc, monkeypatch):
             out[mode] = _core.pcf2d_counts(torch.from_numpy(c).cuda(), None, cen, True, rot, edges_x, edges_y)[0].cpu().numpy()
         assert out["0"].sum() > 0
         np.testing.assert_array_equal(out["0"], out["1"])
+
+
+def test_pcf2d_nonuniform_edges(walk):
+    """Arbitrary increasing edges through the C ABI (the reference only makes uniform ones): the
+    threshold search cannot rely on the spacing; checked against np.histogram2d on the float32
+    differences."""
+    from amep_b200 import _core
+    rng = _rng("pcf2d-nonuniform")
+    n = 1500
+    c = np.zeros((n, 3), dtype=np.float32)
+    c[:, :2] = rng.uniform(0, 20, (n, 2)).astype(np.float32)
+    xe = np.concatenate([[-6.0], -6.0 + np.cumsum(rng.uniform(0.01, 0.6, 40))])
+    ye = np.concatenate([[-4.0], -4.0 + np.cumsum(rng.uniform(0.05, 0.3, 55))])
+    got = _core.pcf2d_counts(torch.from_numpy(c).cuda(), None, np.array([[10.0, 10.0, 0.0]]), True, None, xe, ye)[0].cpu().numpy()
+    dx = (c[:, None, 0] - c[None, :, 0])
+    dy = (c[:, None, 1] - c[None, :, 1])
+    off = ~np.eye(n, dtype=bool)
+    want = np.histogram2d(dx[off], dy[off], [xe, ye])[0].astype(np.int64)
+    np.testing.assert_array_equal(got, want)
+
+
+@pytest.mark.parametrize("rot", [False, True])
+def test_pcf2d_many_bins_unstaged_edges(sc, rot, walk):
+    """More edges than the kernels stage in shared memory (x + y > 2048): bins are searched in
+    the global edge arrays."""
+    rng = _rng(f"pcf2d-manybins-{rot}")
+    n = 900
+    box = np.array([[0, 25], [0, 25], [-0.5, 0.5]], dtype=np.float32)
+    c = np.zeros((n, 3), dtype=np.float32)
+    c[:, :2] = rng.uniform(0, 25, (n, 2)).astype(np.float32)
+    psi = np.array([0.6, 0.2]) if rot else None
+    g, X, Y = sc.pcf2d(c.copy(), box, nxbins=1100, nybins=1030, rmax=6.0, psi=psi)
+    gw, Xw, Yw = orc.pcf2d(c, box, None, 1100, 1030, 6.0, psi)
+    np.testing.assert_array_equal(g, gw)
+    np.testing.assert_array_equal(Y, Yw)
+
+
+@pytest.mark.parametrize("box_dtype", [np.float32, np.float64])
+def test_pcf2d_rotated_dense_vs_oracle(sc, box_dtype):
+    """2e7 binned pairs with rotation on narrow bins: the float32 evaluation that decides most
+    rotated pairs must never disagree with the float64 binning of the reference.  (The box is
+    centred on the origin: the reference rotates the *difference vectors* about the box centre,
+    which moves them out of the window for any other box.)"""
+    rng = _rng(f"pcf2d-rot-dense-{np.dtype(box_dtype).name}")
+    n = 8000
+    box = np.array([[-30, 30], [-30, 30], [-0.5, 0.5]], dtype=box_dtype)
+    c = np.zeros((n, 3), dtype=np.float32)
+    c[:, :2] = rng.uniform(-30, 30, (n, 2)).astype(np.float32)
+    psi = np.array([-0.35, -0.61])
+    g, X, Y = sc.pcf2d(c.copy(), box, nxbins=400, nybins=380, rmax=20.0, psi=psi)
+    want, _, _ = orc.pcf2d_counts(c, box, None, 400, 380, 20.0, psi)
+    gw, _, _ = orc.pcf2d(c, box, None, 400, 380, 20.0, psi)
+    assert want.sum() > 1e7
+    np.testing.assert_array_equal(g, gw)
+
+
+@pytest.mark.parametrize("centre", [(0.0, 0.0), (0.37, -0.21)])
+def test_pcf2d_rotated_float32_decisions_equal_float64(sc, monkeypatch, centre, walk):
+    """1e9 rotated pairs: deciding bins in float32 where the error margin allows gives the same
+    counts as sending every pair through the float64 path (AMEPB_PCF2D_NO_F32ROT)."""
+    from amep_b200 import _core
+    rng = _rng(f"pcf2d-rot-f32-{centre}")
+    n = 32000
+    c = torch.zeros((n, 3), dtype=torch.float32)
+    c[:, :2] = torch.from_numpy(rng.uniform(-40, 40, (n, 2)).astype(np.float32))
+    c = c.cuda()
+    edges = np.linspace(-25.0, 25.0, 501)
+    cen = np.array([[centre[0], centre[1], 0.0]])
+    rot = np.array([[1.0, np.cos(-2.2), np.sin(-2.2)]])
+    out = {}
+    for mode in ("fast", "f64"):
+        if mode == "f64":
+            monkeypatch.setenv("AMEPB_PCF2D_NO_F32ROT", "1")
+        else:
+            monkeypatch.delenv("AMEPB_PCF2D_NO_F32ROT", raising=False)
+        out[mode] = _core.pcf2d_counts(c, None, cen, True, rot, edges, edges)[0].cpu().numpy()
+    assert out["fast"].sum() > 2e8
+    np.testing.assert_array_equal(out["fast"], out["f64"])
