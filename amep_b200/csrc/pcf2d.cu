@@ -69,7 +69,7 @@ __device__ __forceinline__ int pcf_bin_of(double v, const double* __restrict__ e
 
 // Bins one difference vector exactly as the reference does (see the header comment).
 // D: dtype of other_coords[n] - coords;  CF32: the centre is float32 (only matters if D is float)
-template <typename D, bool CF32>
+template <typename D, bool CF32, bool ROT>
 struct PairBinner {
     const Pcf2dFrame* F;
     const double* xe;
@@ -78,8 +78,11 @@ struct PairBinner {
     const float* ty;
     double xlo, xhi, ylo, yhi, inv_dx, inv_dy;
     float finv_dx, finv_dy;
+    // prefilter bounds and the float32 rotation in registers (the reject path is the hot one)
+    float fxlo, fxhi, fylo, fyhi, fcx, fcy, fr2, fr00, fr01, fr10, fr11, fmargin;
     int nxe, nye;
-    bool rotate, use_thr;
+    static constexpr bool rotate = ROT;   // the frame's `angle != 0`, resolved at compile time
+    bool use_thr, uniform;
 
     __device__ __forceinline__ void init(const Pcf2dFrame* frame, const double* xedges, int nxe_, const double* yedges,
                                          int nye_, const float* s_thr, bool with_thr) {
@@ -89,22 +92,25 @@ struct PairBinner {
         inv_dy = (double)(nye - 1) / (yhi - ylo);
         finv_dx = (float)inv_dx; finv_dy = (float)inv_dy;
         tx = s_thr; ty = s_thr + nxe;
-        rotate = frame->rotate != 0;
+        uniform = frame->uniform != 0;
+        fxlo = frame->fxlo; fxhi = frame->fxhi; fylo = frame->fylo; fyhi = frame->fyhi;
+        fcx = frame->fcx; fcy = frame->fcy; fr2 = frame->fr2;
+        fr00 = frame->fr00; fr01 = frame->fr01; fr10 = frame->fr10; fr11 = frame->fr11; fmargin = frame->fmargin;
         use_thr = sizeof(D) == 4 && with_thr;
     }
 
     __device__ __forceinline__ bool bins(D dx, D dy, int& bx, int& by) const {
         double x, y;
         if constexpr (sizeof(D) == 4) {
-            if (!rotate) {
-                if (!(dx >= F->fxlo) || !(dx <= F->fxhi) || !(dy >= F->fylo) || !(dy <= F->fyhi)) return false;
+            if constexpr (!ROT) {
+                if (!(dx >= fxlo) || !(dx <= fxhi) || !(dy >= fylo) || !(dy <= fyhi)) return false;
                 if (use_thr) {
                     // float32 differences without rotation: "v >= edges[k]" in float64 is
                     // "v >= thr[k]" in float32 (thr[k] = smallest float32 >= edges[k]); guess from
                     // the uniform spacing, then settle against the thresholds
-                    bx = min(max(__float2int_rd((dx - F->fxlo) * finv_dx), 0), nxe - 2);
-                    by = min(max(__float2int_rd((dy - F->fylo) * finv_dy), 0), nye - 2);
-                    if (F->uniform) {
+                    bx = min(max(__float2int_rd((dx - fxlo) * finv_dx), 0), nxe - 2);
+                    by = min(max(__float2int_rd((dy - fylo) * finv_dy), 0), nye - 2);
+                    if (uniform) {
                         bx += (int)(bx < nxe - 2 && dx >= tx[bx + 1]) - (int)(dx < tx[bx]);
                         by += (int)(by < nye - 2 && dy >= ty[by + 1]) - (int)(dy < ty[by]);
                         return true;
@@ -116,8 +122,8 @@ struct PairBinner {
                     return true;
                 }
             } else {
-                const float ux = dx - F->fcx, uy = dy - F->fcy;
-                if (!(ux * ux + uy * uy <= F->fr2)) return false;
+                const float ux = dx - fcx, uy = dy - fcy;
+                if (!(ux * ux + uy * uy <= fr2)) return false;
                 if (use_thr) {
                     // Rotation in float32 first: the result lies within fmargin of the float64 value
                     // the reference bins (|error| <= 4e-7 (|ux| + |uy|) + 2.5e-7 (|cx| + |cy|), the
@@ -125,12 +131,12 @@ struct PairBinner {
                     // edge).  A value farther than that from the thresholds of its bin, or from the
                     // edge range, is decided here; the rest (about 4 margin / bin width of the
                     // pairs) takes the float64 path below.
-                    const float xa = fmaf(F->fr00, ux, F->fr01 * uy) + F->fcx;
-                    const float ya = fmaf(F->fr10, ux, F->fr11 * uy) + F->fcy;
-                    const float mg = F->fmargin;
-                    if (xa < F->fxlo - mg || xa > F->fxhi + mg || ya < F->fylo - mg || ya > F->fyhi + mg) return false;
-                    const int kx = min(max(__float2int_rd((xa - F->fxlo) * finv_dx), 0), nxe - 2);
-                    const int ky = min(max(__float2int_rd((ya - F->fylo) * finv_dy), 0), nye - 2);
+                    const float xa = fmaf(fr00, ux, fr01 * uy) + fcx;
+                    const float ya = fmaf(fr10, ux, fr11 * uy) + fcy;
+                    const float mg = fmargin;
+                    if (xa < fxlo - mg || xa > fxhi + mg || ya < fylo - mg || ya > fyhi + mg) return false;
+                    const int kx = min(max(__float2int_rd((xa - fxlo) * finv_dx), 0), nxe - 2);
+                    const int ky = min(max(__float2int_rd((ya - fylo) * finv_dy), 0), nye - 2);
                     if (xa - tx[kx] > mg && tx[kx + 1] - xa > mg && ya - ty[ky] > mg && ty[ky + 1] - ya > mg) {
                         bx = kx;
                         by = ky;
@@ -139,7 +145,7 @@ struct PairBinner {
                 }
             }
         }
-        if (!rotate) {
+        if constexpr (!ROT) {
             x = (double)dx;
             y = (double)dy;
         } else {
@@ -155,8 +161,8 @@ struct PairBinner {
             y = __dadd_rn(__dadd_rn(__dmul_rn(F->r10, vx), __dmul_rn(F->r11, vy)), F->cy);
         }
         if (!(x >= xlo) || !(x <= xhi) || !(y >= ylo) || !(y <= yhi)) return false;
-        bx = pcf_bin_of(x, xe, nxe, inv_dx, F->uniform != 0);
-        by = pcf_bin_of(y, ye, nye, inv_dy, F->uniform != 0);
+        bx = pcf_bin_of(x, xe, nxe, inv_dx, uniform);
+        by = pcf_bin_of(y, ye, nye, inv_dy, uniform);
         return bx >= 0 && by >= 0;
     }
 };
@@ -167,7 +173,7 @@ __device__ __forceinline__ D pcf_sub(D a, D b) {
     else return __dsub_rn(a, b);
 }
 
-template <typename TC, typename TO, typename D, bool CF32>
+template <typename TC, typename TO, typename D, bool CF32, bool ROT>
 __global__ void __launch_bounds__(kPcfThreads) pcf2d_kernel(const TC* __restrict__ coords, long long n,
                                                             const TO* __restrict__ other, long long m, int same,
                                                             const Pcf2dFrame* __restrict__ frames,
@@ -202,7 +208,7 @@ __global__ void __launch_bounds__(kPcfThreads) pcf2d_kernel(const TC* __restrict
     const D qx = live ? (D)of[qi * 3 + 0] : (D)0, qy = live ? (D)of[qi * 3 + 1] : (D)0;
     const long long t_lo = (long long)blockIdx.y * per_split, t_hi = min(n, t_lo + per_split);
     __syncthreads();
-    PairBinner<D, CF32> B;
+    PairBinner<D, CF32, ROT> B;
     B.init(&F, stage ? s_edges : xe_f, nxe, stage ? s_edges + nxe : ye_f, nye, s_thr, thr != nullptr);
     for (long long t0 = t_lo; t0 < t_hi; t0 += kPcfStage) {
         const int cnt = (int)min((long long)kPcfStage, t_hi - t0);
@@ -327,7 +333,7 @@ __global__ void pcf_cell_scatter_kernel(const T* __restrict__ pts, long long n, 
     sidx[pos] = (int)i;
 }
 
-template <typename D, bool CF32>
+template <typename D, bool CF32, bool ROT>
 __global__ void __launch_bounds__(kPcfThreads) pcf2d_cells_kernel(
     const typename PcfVec2<D>::type* __restrict__ qs, const int* __restrict__ qidx, const int* __restrict__ qstart,
     const typename PcfVec2<D>::type* __restrict__ ts, const int* __restrict__ tidx, const int* __restrict__ tstart,
@@ -352,7 +358,7 @@ __global__ void __launch_bounds__(kPcfThreads) pcf2d_cells_kernel(
     const int q0 = qstart[qc], nqc = qstart[qc + 1] - q0;
     if (nqc == 0) return;
     __syncthreads();
-    PairBinner<D, CF32> B;
+    PairBinner<D, CF32, ROT> B;
     B.init(&F, stage ? s_edges : xe, nxe, stage ? s_edges + nxe : ye, nye, s_thr, thr != nullptr);
     const int qcx = qc % P.gx, qcy = qc / P.gx;
     const double qxlo = (double)P.x0 + (double)qcx * P.cs, qylo = (double)P.y0 + (double)qcy * P.cs;
@@ -367,7 +373,7 @@ __global__ void __launch_bounds__(kPcfThreads) pcf2d_cells_kernel(
         double dlo[2] = {qxlo - (txlo + P.cs), qylo - (tylo + P.cs)};
         double dhi[2] = {qxlo + P.cs - txlo, qylo + P.cs - tylo};
         double wxlo, wxhi, wylo, wyhi;
-        if (!B.rotate) {
+        if (!ROT) {
             wxlo = dlo[0]; wxhi = dhi[0]; wylo = dlo[1]; wyhi = dhi[1];
         } else {
             wxlo = wylo = INFINITY; wxhi = wyhi = -INFINITY;
@@ -410,20 +416,32 @@ __global__ void __launch_bounds__(kPcfThreads) pcf2d_cells_kernel(
     }
 }
 
-template <typename TC, typename TO>
-static void launch_pcf2d(dim3 grid, cudaStream_t stream, bool center_f32, const void* coords, long long n,
-                         const void* other, long long m, int same, const Pcf2dFrame* frames, const double* xe, int nxe,
-                         const double* ye, int nye, long long edge_stride, long long per_split, const float* thr,
-                         int stage, size_t smem, unsigned long long* counts) {
+template <typename TC, typename TO, bool ROT>
+static void launch_pcf2d_rot(dim3 grid, cudaStream_t stream, bool center_f32, const void* coords, long long n,
+                             const void* other, long long m, int same, const Pcf2dFrame* frames, const double* xe,
+                             int nxe, const double* ye, int nye, long long edge_stride, long long per_split,
+                             const float* thr, int stage, size_t smem, unsigned long long* counts) {
     constexpr bool both_f32 = sizeof(TC) == 4 && sizeof(TO) == 4;
     if constexpr (both_f32) {
         if (center_f32)
-            pcf2d_kernel<TC, TO, float, true><<<grid, kPcfThreads, smem, stream>>>((const TC*)coords, n, (const TO*)other, m, same, frames, xe, nxe, ye, nye, edge_stride, per_split, thr, stage, counts);
+            pcf2d_kernel<TC, TO, float, true, ROT><<<grid, kPcfThreads, smem, stream>>>((const TC*)coords, n, (const TO*)other, m, same, frames, xe, nxe, ye, nye, edge_stride, per_split, thr, stage, counts);
         else
-            pcf2d_kernel<TC, TO, float, false><<<grid, kPcfThreads, smem, stream>>>((const TC*)coords, n, (const TO*)other, m, same, frames, xe, nxe, ye, nye, edge_stride, per_split, thr, stage, counts);
+            pcf2d_kernel<TC, TO, float, false, ROT><<<grid, kPcfThreads, smem, stream>>>((const TC*)coords, n, (const TO*)other, m, same, frames, xe, nxe, ye, nye, edge_stride, per_split, thr, stage, counts);
     } else {
-        pcf2d_kernel<TC, TO, double, false><<<grid, kPcfThreads, smem, stream>>>((const TC*)coords, n, (const TO*)other, m, same, frames, xe, nxe, ye, nye, edge_stride, per_split, thr, stage, counts);
+        pcf2d_kernel<TC, TO, double, false, ROT><<<grid, kPcfThreads, smem, stream>>>((const TC*)coords, n, (const TO*)other, m, same, frames, xe, nxe, ye, nye, edge_stride, per_split, thr, stage, counts);
     }
+}
+
+// all frames of one launch share `rot` (the kernels resolve it at compile time)
+template <typename TC, typename TO>
+static void launch_pcf2d(bool rot, dim3 grid, cudaStream_t stream, bool center_f32, const void* coords, long long n,
+                         const void* other, long long m, int same, const Pcf2dFrame* frames, const double* xe, int nxe,
+                         const double* ye, int nye, long long edge_stride, long long per_split, const float* thr,
+                         int stage, size_t smem, unsigned long long* counts) {
+    if (rot)
+        launch_pcf2d_rot<TC, TO, true>(grid, stream, center_f32, coords, n, other, m, same, frames, xe, nxe, ye, nye, edge_stride, per_split, thr, stage, smem, counts);
+    else
+        launch_pcf2d_rot<TC, TO, false>(grid, stream, center_f32, coords, n, other, m, same, frames, xe, nxe, ye, nye, edge_stride, per_split, thr, stage, smem, counts);
 }
 
 __global__ void pcf_bbox_init_kernel(int* bbox) {
@@ -522,19 +540,24 @@ static int pcf2d_cells_frame(amepb_ctx* ctx, cudaStream_t stream, const TC* coor
     const float* thr = with_thr ? d_thr : nullptr;
     if (!ctx->pcf_attr) {
         const int cap = (int)(sizeof(unsigned) * kPcfWin * kPcfWin + (sizeof(double) + sizeof(float)) * kPcfStageEdges);
-        AMEPB_CUDA(ctx, cudaFuncSetAttribute(pcf2d_cells_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
-        AMEPB_CUDA(ctx, cudaFuncSetAttribute(pcf2d_cells_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
-        AMEPB_CUDA(ctx, cudaFuncSetAttribute(pcf2d_cells_kernel<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+        AMEPB_CUDA(ctx, cudaFuncSetAttribute(pcf2d_cells_kernel<float, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+        AMEPB_CUDA(ctx, cudaFuncSetAttribute(pcf2d_cells_kernel<float, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+        AMEPB_CUDA(ctx, cudaFuncSetAttribute(pcf2d_cells_kernel<float, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+        AMEPB_CUDA(ctx, cudaFuncSetAttribute(pcf2d_cells_kernel<float, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+        AMEPB_CUDA(ctx, cudaFuncSetAttribute(pcf2d_cells_kernel<double, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+        AMEPB_CUDA(ctx, cudaFuncSetAttribute(pcf2d_cells_kernel<double, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
         ctx->pcf_attr = true;
     }
+    const bool rot = hF.rotate != 0;
+#define AMEPB_PCF_CELLS(DT, CF, RT, THR) \
+    pcf2d_cells_kernel<DT, CF, RT><<<grid, kPcfThreads, smem, stream>>>(qs, qidx, qstart, ts, tidx, tstart, P, same, d_frame, d_xe, nxe, d_ye, nye, THR, stage, d_grid)
     if constexpr (sizeof(D) == 4) {
-        if (center_f32)
-            pcf2d_cells_kernel<float, true><<<grid, kPcfThreads, smem, stream>>>(qs, qidx, qstart, ts, tidx, tstart, P, same, d_frame, d_xe, nxe, d_ye, nye, thr, stage, d_grid);
-        else
-            pcf2d_cells_kernel<float, false><<<grid, kPcfThreads, smem, stream>>>(qs, qidx, qstart, ts, tidx, tstart, P, same, d_frame, d_xe, nxe, d_ye, nye, thr, stage, d_grid);
+        if (center_f32) { if (rot) AMEPB_PCF_CELLS(float, true, true, thr); else AMEPB_PCF_CELLS(float, true, false, thr); }
+        else { if (rot) AMEPB_PCF_CELLS(float, false, true, thr); else AMEPB_PCF_CELLS(float, false, false, thr); }
     } else {
-        pcf2d_cells_kernel<double, false><<<grid, kPcfThreads, smem, stream>>>(qs, qidx, qstart, ts, tidx, tstart, P, same, d_frame, d_xe, nxe, d_ye, nye, nullptr, stage, d_grid);
+        if (rot) AMEPB_PCF_CELLS(double, false, true, nullptr); else AMEPB_PCF_CELLS(double, false, false, nullptr);
     }
+#undef AMEPB_PCF_CELLS
     AMEPB_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -673,7 +696,7 @@ extern "C" int amepb_pcf2d_counts(amepb_ctx* ctx, const void* coords, int dtype,
     const bool cf32 = center_f32 != 0;
     // frames [f0, f0 + nf) through pcf2d_kernel: query tiles x target splits x frames, at least
     // ~4 blocks per SM when the system allows it
-    auto launch_direct = [&](int64_t f0, int64_t nf) {
+    auto launch_direct_run = [&](int64_t f0, int64_t nf, bool rot_run) {
         const long long qtiles = (m + kPcfThreads - 1) / kPcfThreads;
         const long long want = 4LL * ctx->sm_count;
         long long tsplit = (want + qtiles * nf - 1) / (qtiles * nf);
@@ -691,13 +714,23 @@ extern "C" int amepb_pcf2d_counts(amepb_ctx* ctx, const void* coords, int dtype,
         const float* th0 = d_thr ? d_thr + f0 * (nxe + nye) : nullptr;
         unsigned long long* g0 = d_counts + (size_t)f0 * (nxe - 1) * (nye - 1);
         if (dtype == AMEPB_F32 && other_dtype == AMEPB_F32)
-            launch_pcf2d<float, float>(grid, stream, cf32, c0, n, o0, m, same, fr, xe0, nxe, ye0, nye, dev_stride, per_split, th0, stage, smem, g0);
+            launch_pcf2d<float, float>(rot_run, grid, stream, cf32, c0, n, o0, m, same, fr, xe0, nxe, ye0, nye, dev_stride, per_split, th0, stage, smem, g0);
         else if (dtype == AMEPB_F32)
-            launch_pcf2d<float, double>(grid, stream, cf32, c0, n, o0, m, same, fr, xe0, nxe, ye0, nye, dev_stride, per_split, th0, stage, smem, g0);
+            launch_pcf2d<float, double>(rot_run, grid, stream, cf32, c0, n, o0, m, same, fr, xe0, nxe, ye0, nye, dev_stride, per_split, th0, stage, smem, g0);
         else if (other_dtype == AMEPB_F32)
-            launch_pcf2d<double, float>(grid, stream, cf32, c0, n, o0, m, same, fr, xe0, nxe, ye0, nye, dev_stride, per_split, th0, stage, smem, g0);
+            launch_pcf2d<double, float>(rot_run, grid, stream, cf32, c0, n, o0, m, same, fr, xe0, nxe, ye0, nye, dev_stride, per_split, th0, stage, smem, g0);
         else
-            launch_pcf2d<double, double>(grid, stream, cf32, c0, n, o0, m, same, fr, xe0, nxe, ye0, nye, dev_stride, per_split, th0, stage, smem, g0);
+            launch_pcf2d<double, double>(rot_run, grid, stream, cf32, c0, n, o0, m, same, fr, xe0, nxe, ye0, nye, dev_stride, per_split, th0, stage, smem, g0);
+    };
+    // consecutive frames with the same `angle != 0` share a launch
+    auto launch_direct = [&](int64_t f0, int64_t nf) {
+        int64_t a = f0;
+        while (a < f0 + nf) {
+            int64_t b = a + 1;
+            while (b < f0 + nf && hf[b].rotate == hf[a].rotate) ++b;
+            launch_direct_run(a, b - a, hf[a].rotate != 0);
+            a = b;
+        }
     };
     // Large systems: cell-sorted walk with a shared-memory window, frame by frame (each frame
     // needs its bounding box on the host).  AMEPB_PCF2D_CELLS=0 disables it, =1 drops the
