@@ -127,13 +127,13 @@ struct PairBinner {
                 if (use_thr) {
                     // Rotation in float32 first: the result lies within fmargin of the float64 value
                     // the reference bins (|error| <= 4e-7 (|ux| + |uy|) + 2.5e-7 (|cx| + |cy|), the
-                    // margin is 1e-6 of their largest possible sum plus two ulps of the largest
+                    // margin is 1.01e-6 (|ux| + |uy| + |cx| + |cy|) plus two ulps of the largest
                     // edge).  A value farther than that from the thresholds of its bin, or from the
                     // edge range, is decided here; the rest (about 4 margin / bin width of the
                     // pairs) takes the float64 path below.
                     const float xa = fmaf(fr00, ux, fr01 * uy) + fcx;
                     const float ya = fmaf(fr10, ux, fr11 * uy) + fcy;
-                    const float mg = fmargin;
+                    const float mg = fmaf(1.01e-6f, fabsf(ux) + fabsf(uy), fmargin);
                     if (xa < fxlo - mg || xa > fxhi + mg || ya < fylo - mg || ya > fyhi + mg) return false;
                     const int kx = min(max(__float2int_rd((xa - fxlo) * finv_dx), 0), nxe - 2);
                     const int ky = min(max(__float2int_rd((ya - fylo) * finv_dy), 0), nye - 2);
@@ -655,7 +655,8 @@ extern "C" int amepb_pcf2d_counts(amepb_ctx* ctx, const void* coords, int dtype,
         F.fr00 = (float)F.r00; F.fr01 = (float)F.r01; F.fr10 = (float)F.r10; F.fr11 = (float)F.r11;
         F.fcx = (float)F.cx; F.fcy = (float)F.cy;
         const double emax = std::max(std::max(fabs(xe[0]), fabs(xe[nxe - 1])), std::max(fabs(ye[0]), fabs(ye[nye - 1])));
-        F.fmargin = float_above(1.01e-6 * (2.002 * sqrt((double)F.fr2) + fabs(F.cx) + fabs(F.cy)) + 2.5e-7 * emax + 1e-30, false);
+        // constant part of the margin; bins() adds 1.01e-6 (|ux| + |uy|) per pair
+        F.fmargin = float_above(1.01e-6 * (fabs(F.cx) + fabs(F.cy)) + 2.5e-7 * emax + 1e-30, false);
         if (no_f32rot) F.fmargin = INFINITY;   // nothing is decided in float32: every pair takes the float64 path
         auto uniform_axis = [](const double* e, int ne) {
             const double w = (e[ne - 1] - e[0]) / (ne - 1);
