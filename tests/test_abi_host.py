@@ -41,6 +41,8 @@ def test_no_cpu_fallback_without_gpu():
     import amep_b200
     with pytest.raises(amep_b200.AmepbError):
         amep_b200.spatialcor.rdf(np.random.rand(10, 3), np.array([[0, 1], [0, 1], [0, 1.0]]))
+    with pytest.raises(amep_b200.AmepbError):
+        amep_b200.spatialcor.pcf2d(np.random.rand(10, 3), np.array([[0, 1], [0, 1], [0, 1.0]]), rmax=0.4, nxbins=8, nybins=8)
 
 
 def test_product_never_imports_the_oracle():
