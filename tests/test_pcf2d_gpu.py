@@ -140,18 +140,18 @@ def test_pcf2d_invalid_arguments(sc):
 
 def test_pcf2d_cells_equal_direct_clustered_and_outliers(sc, monkeypatch):
     """The two walks agree bit for bit on a frame that stresses the cell geometry: a dense blob,
-    far outliers, NaN / inf rows, coincident particles, rotation, fine bins (many cells)."""
+    a far outlier (most cells empty), NaN / inf rows, coincident particles, rotation."""
     from amep_b200 import _core
     rng = _rng("pcf2d-cells-clustered")
     n = 6000
     c = np.zeros((n, 3), dtype=np.float32)
     c[:, :2] = rng.uniform(0, 50, (n, 2))
     c[:2000, :2] = rng.normal(25.0, 0.7, (2000, 2))
-    c[10, :2] = (4000.0, -3000.0)
+    c[10, :2] = (400.0, -300.0)        # stretches the cell grid to ~20 x 16 mostly empty cells
     c[11, :2] = (np.nan, 3.0)
     c[12, :2] = (7.0, np.inf)
     c[13] = c[14]
-    edges_x, edges_y = np.linspace(-3.0, 3.0, 241), np.linspace(-2.0, 2.5, 131)
+    edges_x, edges_y = np.linspace(-30.0, 30.0, 121), np.linspace(-20.0, 25.0, 91)
     cen = np.array([[25.0, 25.0, 0.0]])
     for rot in (None, np.array([[1.0, np.cos(-1.1), np.sin(-1.1)]])):
         out = {}
