@@ -1,4 +1,4 @@
-"""Drop-in for ``amep.evaluate.RDF`` / ``SFiso`` / ``SF2d`` (AMEP 1.3.0).
+"""Drop-in for ``amep.evaluate.RDF`` / ``SFiso`` / ``SF2d`` / ``PCF2d`` (AMEP 1.3.0).
 
 Same constructor arguments and result properties as amep/evaluate.py:406-609
 (RDF), :1183-1522 (SF2d) and :1525-1838 (SFiso).  Where the reference maps a
@@ -17,11 +17,11 @@ import numpy as np
 
 from . import _core, dist
 from .base import BaseEvaluation
-from .spatialcor import rdf_frames, sf2d_frames, sfiso_frames
+from .spatialcor import pcf2d_frames, rdf_frames, sf2d_frames, sfiso_frames
 from .trajectory import TensorTrajectory
 from .utils import evaluated_indices
 
-__all__ = ["RDF", "SFiso", "SF2d"]
+__all__ = ["RDF", "SFiso", "SF2d", "PCF2d"]
 
 
 def _gather(traj, indices, ptype):
@@ -263,6 +263,87 @@ class SF2d(_FrameAverage):
     @property
     def qy(self):
         return self._qy
+
+    @property
+    def frames(self):
+        return self._frames
+
+    @property
+    def times(self):
+        return self._times
+
+    @property
+    def avg(self):
+        return self._avg
+
+    @property
+    def indices(self):
+        return self._indices
+
+
+class PCF2d(_FrameAverage):
+    """Two-dimensional pair correlation function g(x, y), time-averaged (amep/evaluate.py:612-752).
+
+    The reference orients every frame along its mean hexagonal order parameter,
+    ``psi = np.mean(psi_k(frame.coords(), frame.box, k=6))`` (amep/evaluate.py:730-735), before it
+    calls ``pcf2d``.  That psi_6 prologue is the same next row that ``SF2d(rotate=True)`` waits
+    for, so the orientation is an argument here: ``psi`` is an array
+    ``[len(traj), 2]`` of (Re psi_6, Im psi_6) per trajectory frame, or a callable
+    ``frame -> (re, im)``.  Without it the class *raises* instead of silently returning the
+    unrotated function; ``psi=False`` asks for exactly that (no rotation).  Everything else --
+    frame selection, ``ptype`` / ``other``, the keyword arguments of ``pcf2d``, the average -- is
+    the reference's."""
+
+    def __init__(self, traj, skip: float = 0.0, nav: int = 10, ptype=None, other=None,
+                 max_workers=1, psi=None, distributed=None, group=None, **kwargs) -> None:
+        super().__init__()
+        self.name = "pcf2d"
+        if psi is None:
+            raise NotImplementedError(
+                "amep_b200.evaluate.PCF2d: the psi_6 orientation prologue (amep/evaluate.py:730-735) is a "
+                "next row of the scope table; pass psi=[len(traj), 2] (or a callable frame -> (re, im)), "
+                "or psi=False for no rotation")
+        for ignored in ("verbose", "njobs", "chunksize", "pbc"):
+            kwargs.pop(ignored, None)
+        idx = self._select(traj, skip, nav)
+        nsel = len(idx)
+        lo, hi, ws = _local_block(nsel, distributed, group)
+        g = X = Y = None
+        if hi > lo:
+            coords, box = _gather(traj, idx[lo:hi], ptype)
+            other_coords = None if other is None else _gather(traj, idx[lo:hi], other)[0]
+            if psi is False:
+                psi_rows = None
+            elif callable(psi):
+                psi_rows = np.array([np.asarray(psi(f), dtype=np.float64) for f in traj[np.asarray(idx[lo:hi])]])
+            else:
+                psi_rows = np.asarray(psi, dtype=np.float64)[np.asarray(idx[lo:hi])]
+            # pcf2d zeroes the last column of what it is given in place (amep/spatialcor.py:846-848);
+            # in the reference that hits the fresh array frame.coords() returns, here the stacks
+            # may be views of the trajectory, so the side effect is switched off
+            g, X, Y = pcf2d_frames(coords, box, other_coords, psi=psi_rows, zero_last_column=False, **kwargs)
+        if ws > 1:
+            if g is None:
+                raise ValueError("PCF2d: more ranks than selected frames")
+            if g.shape[1:] != X.shape[1:]:
+                raise ValueError("PCF2d: nxbins and nybins must be equal (the reference's np.array(results) "
+                                 "needs g and the bin-centre grids to have one shape)")
+            local = np.zeros((hi - lo, 3) + g.shape[1:])
+            local[:, 0], local[:, 1], local[:, 2] = g, X, Y
+            table = dist.assemble_rows(local, lo, nsel, group)
+            g, X, Y = table[:, 0], table[:, 1], table[:, 2]
+        res = self._finish(traj, [(g[f], X[f], Y[f]) for f in range(nsel)])
+        self._avg = res[0]
+        self._x = res[1]
+        self._y = res[2]
+
+    @property
+    def x(self):
+        return self._x
+
+    @property
+    def y(self):
+        return self._y
 
     @property
     def frames(self):

@@ -434,16 +434,19 @@ def _zero_last_column(data):
 
 
 def pcf2d_frames(coords, box_boundary, other_coords=None, nxbins=None, nybins=None, rmax=None,
-                 psi=None):
+                 psi=None, zero_last_column=True):
     """``pcf2d`` for a batch of frames ``[F, N, 3]`` in one library call.
 
     ``box_boundary``: ``(3,2)`` or ``(F,3,2)``; ``psi``: ``None``, ``(2,)`` or ``(F,2)``.  Returns
     ``(g [F, nx, ny], X [F, ny, nx], Y [F, ny, nx])``: per frame what ``amep.spatialcor.pcf2d``
-    returns.  The bin edges follow each frame's box when ``rmax`` is None."""
+    returns.  The bin edges follow each frame's box when ``rmax`` is None.  ``zero_last_column=False``
+    leaves the inputs untouched (``evaluate.PCF2d`` works on views of the trajectory)."""
     same = other_coords is None
-    _zero_last_column(coords)
-    if not same:
-        _zero_last_column(other_coords)
+    if zero_last_column:
+        # the reference's side effect on the caller's arrays; the kernel never reads that column
+        _zero_last_column(coords)
+        if not same:
+            _zero_last_column(other_coords)
     pc = coords if isinstance(coords, _core.Particles) else _core.Particles(coords)
     po = pc if same else (other_coords if isinstance(other_coords, _core.Particles)
                           else _core.Particles(other_coords, "other_coords"))

@@ -15,6 +15,11 @@ torch = pytest.importorskip("torch")
 import torch.multiprocessing as mp  # noqa: E402
 
 
+def orc_pcf2d(coords, box, psi):
+    import amep_oracle as orc
+    return orc.pcf2d(coords, box, None, 12, 12, 3.0, psi)
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -36,6 +41,18 @@ def _oracle_rdf_frames(coords, box, other_coords=None, nbins=None, rmax=None, mo
         g_rows.append(g), r_rows.append(r), h_rows.append(hist)
     out = (np.array(g_rows), np.array(r_rows))
     return out + (np.array(h_rows),) if return_counts else out
+
+
+def _oracle_pcf2d_frames(coords, box, other_coords=None, nxbins=None, nybins=None, rmax=None, psi=None,
+                         zero_last_column=True):
+    import amep_oracle as orc
+    coords = np.asarray(coords)
+    out = []
+    for f in range(coords.shape[0]):
+        b = box[f] if np.ndim(box) == 3 else box
+        o = None if other_coords is None else np.asarray(other_coords)[f]
+        out.append(orc.pcf2d(coords[f], b, o, nxbins, nybins, rmax, None if psi is None else psi[f]))
+    return tuple(np.array([r[k] for r in out]) for k in range(3))
 
 
 def _worker(rank, world, port, tmpdir):
@@ -69,6 +86,20 @@ def _worker(rank, world, port, tmpdir):
     ev1 = evaluate.RDF(traj, skip=0.0, nav=1, nbins=50)
     solo, _ = _oracle_rdf_frames(z["coords"][ev1.indices], z["box"], nbins=50)
     assert np.array_equal(ev1.avg, solo[0])
+    # (3) evaluate.PCF2d: frames sharded, one all-reduce, average as average_func does
+    evaluate.pcf2d_frames = _oracle_pcf2d_frames
+    rng = np.random.default_rng(77)
+    pc = np.zeros((5, 150, 3), dtype=np.float32)
+    pc[:, :, :2] = rng.uniform(-6, 6, (5, 150, 2)).astype(np.float32)
+    pc[:, :, 2] = 0.25
+    pbox = np.array([[-6, 6], [-6, 6], [-0.5, 0.5]], dtype=np.float32)
+    psi = rng.normal(size=(5, 2))
+    ptraj = amep_b200.TensorTrajectory(pc.copy(), pbox)
+    evp = evaluate.PCF2d(ptraj, skip=0.0, nav=4, psi=psi, nxbins=12, nybins=12, rmax=3.0)
+    want = [orc_pcf2d(pc[i], pbox, psi[i]) for i in evp.indices]
+    assert np.array_equal(evp.avg, np.mean(np.array([w[0] for w in want]), axis=0))
+    assert np.array_equal(evp.x, want[0][1]) and np.array_equal(evp.y, want[0][2])
+    assert evp.frames.shape == (len(evp.indices), 3, 12, 12)
     np.save(os.path.join(tmpdir, f"ok{rank}.npy"), np.array([1]))
     dist.destroy_process_group()
 

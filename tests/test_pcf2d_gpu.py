@@ -238,3 +238,37 @@ def test_pcf2d_rotated_float32_decisions_equal_float64(sc, monkeypatch, centre, 
         out[mode] = _core.pcf2d_counts(c, None, cen, True, rot, edges, edges)[0].cpu().numpy()
     assert out["fast"].sum() > 2e8
     np.testing.assert_array_equal(out["fast"], out["f64"])
+
+
+def test_evaluate_pcf2d(sc):
+    """evaluate.PCF2d: frame selection and average of the reference's average_func, orientation
+    supplied by the caller (array, callable, or False), loud without it; the trajectory is not
+    modified."""
+    import amep_b200
+    rng = _rng("evaluate-pcf2d")
+    nf, n = 6, 400
+    c = np.zeros((nf, n, 3), dtype=np.float32)
+    c[:, :, :2] = rng.uniform(-8, 8, (nf, n, 2)).astype(np.float32)
+    c[:, :, 2] = 0.125
+    box = np.array([[-8, 8], [-8, 8], [-0.5, 0.5]], dtype=np.float32)
+    psi = rng.normal(size=(nf, 2))
+    for dev in ("numpy", "cuda"):
+        data = c.copy() if dev == "numpy" else torch.from_numpy(c.copy()).cuda()
+        traj = amep_b200.TensorTrajectory(data, box)
+        with pytest.raises(NotImplementedError):
+            amep_b200.evaluate.PCF2d(traj)
+        ev = amep_b200.evaluate.PCF2d(traj, skip=0.2, nav=3, psi=psi, nxbins=24, nybins=24, rmax=5.0, njobs=4)
+        want = [orc.pcf2d(c[i], box, None, 24, 24, 5.0, psi[i]) for i in ev.indices]
+        np.testing.assert_array_equal(ev.avg, np.mean(np.array([w[0] for w in want]), axis=0))
+        # x, y are means over the frames too (np.mean(np.array(results), axis=0), amep/utils.py:184-186)
+        np.testing.assert_array_equal(ev.x, np.mean(np.array([w[1] for w in want]), axis=0))
+        np.testing.assert_array_equal(ev.y, np.mean(np.array([w[2] for w in want]), axis=0))
+        np.testing.assert_array_equal(ev.frames[:, 0], np.array([w[0] for w in want]))
+        ev2 = amep_b200.evaluate.PCF2d(traj, skip=0.2, nav=3, psi=lambda frame: psi[2], nxbins=24, nybins=24, rmax=5.0)
+        want2 = [orc.pcf2d(c[i], box, None, 24, 24, 5.0, psi[2]) for i in ev2.indices]
+        np.testing.assert_array_equal(ev2.avg, np.mean(np.array([w[0] for w in want2]), axis=0))
+        ev3 = amep_b200.evaluate.PCF2d(traj, skip=0.0, nav=2, psi=False, nxbins=16, nybins=16, rmax=4.0)
+        want3 = [orc.pcf2d(c[i], box, None, 16, 16, 4.0, None) for i in ev3.indices]
+        np.testing.assert_array_equal(ev3.avg, np.mean(np.array([w[0] for w in want3]), axis=0))
+        z = data[:, :, 2].cpu().numpy() if dev == "cuda" else data[:, :, 2]
+        assert np.all(z == 0.125)
