@@ -243,6 +243,7 @@ __global__ void __launch_bounds__(kPcfThreads) pcf2d_kernel(const TC* __restrict
 // added to the grid directly, so the counts do not depend on the cell geometry.
 // ---------------------------------------------------------------------------------------
 constexpr int kPcfWin = 96;
+constexpr int kPcfCellStage = 512;   // targets of a cell per shared-memory stage
 
 struct PcfCellPlan {
     float x0, y0, cs, inv_cs;   // cell (i, j) covers [x0 + i cs, x0 + (i+1) cs) x [y0 + j cs, ...)
@@ -350,6 +351,8 @@ __global__ void __launch_bounds__(kPcfThreads) pcf2d_cells_kernel(
         for (int i = threadIdx.x; i < nye; i += kPcfThreads) s_edges[nxe + i] = ye[i];
     }
     __shared__ Pcf2dFrame F;
+    __shared__ typename PcfVec2<D>::type s_tv[kPcfCellStage];
+    __shared__ int s_ti[kPcfCellStage];
     if (threadIdx.x < sizeof(Pcf2dFrame) / sizeof(int))
         reinterpret_cast<int*>(&F)[threadIdx.x] = reinterpret_cast<const int*>(frame)[threadIdx.x];
     if (sizeof(D) == 4 && thr != nullptr)
@@ -395,17 +398,27 @@ __global__ void __launch_bounds__(kPcfThreads) pcf2d_cells_kernel(
         __syncthreads();
         for (int i = threadIdx.x; i < kPcfWin * kPcfWin; i += kPcfThreads) win[i] = 0u;
         __syncthreads();
-        for (int q = threadIdx.x; q < nqc; q += kPcfThreads) {
-            const typename PcfVec2<D>::type qv = qs[q0 + q];
-            const int skip = same ? qidx[q0 + q] : -1;
-            for (int i = 0; i < ntc; ++i) {
-                const typename PcfVec2<D>::type tv = ts[t0 + i];
-                int bx, by;
-                if (!B.bins(pcf_sub<D>(qv.x, tv.x), pcf_sub<D>(qv.y, tv.y), bx, by)) continue;
-                if (same && tidx[t0 + i] == skip) continue;
-                const unsigned lx = (unsigned)(bx - bx0), ly = (unsigned)(by - by0);
-                if (priv && lx < (unsigned)kPcfWin && ly < (unsigned)kPcfWin) atomicAdd(&win[lx * kPcfWin + ly], 1u);
-                else atomicAdd(&grid[(size_t)bx * (nye - 1) + by], 1ULL);
+        // targets of the cell staged through shared memory (read by all threads at once)
+        for (int c0 = 0; c0 < ntc; c0 += kPcfCellStage) {
+            const int cnt = min(kPcfCellStage, ntc - c0);
+            if (c0 > 0) __syncthreads();
+            for (int i = threadIdx.x; i < cnt; i += kPcfThreads) {
+                s_tv[i] = ts[t0 + c0 + i];
+                s_ti[i] = same ? tidx[t0 + c0 + i] : -1;
+            }
+            __syncthreads();
+            for (int q = threadIdx.x; q < nqc; q += kPcfThreads) {
+                const typename PcfVec2<D>::type qv = qs[q0 + q];
+                const int skip = same ? qidx[q0 + q] : -2;
+                for (int i = 0; i < cnt; ++i) {
+                    const typename PcfVec2<D>::type tv = s_tv[i];
+                    int bx, by;
+                    if (!B.bins(pcf_sub<D>(qv.x, tv.x), pcf_sub<D>(qv.y, tv.y), bx, by)) continue;
+                    if (s_ti[i] == skip) continue;
+                    const unsigned lx = (unsigned)(bx - bx0), ly = (unsigned)(by - by0);
+                    if (priv && lx < (unsigned)kPcfWin && ly < (unsigned)kPcfWin) atomicAdd(&win[lx * kPcfWin + ly], 1u);
+                    else atomicAdd(&grid[(size_t)bx * (nye - 1) + by], 1ULL);
+                }
             }
         }
         __syncthreads();
