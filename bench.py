@@ -453,6 +453,29 @@ def sq_section(torch, dist, _core, ctx, dev, world, rank):
                         + ("complex64 accumulation in the reference's order" if accum == "c64" else "float64 accumulation"),
             "terms_per_s": nf2 * n2 * g * g * world / (ms * 1e-3), "ms": ms, "kernel_ms": ctx.last_kernel_ms(),
             "dtype": "f64 (rounded to f32 per add)" if accum == "c64" else "f64"}
+    del c2
+    # pcf2d (widened row): 2D, density 1, 500 x 500 grid; the reference's default
+    # window (half of all pairs bin) with an orientation, and a narrow window.  Never allowed to
+    # break the headline line.
+    try:
+        npc = 100_000
+        Lp = float(np.sqrt(npc))
+        cp = torch.zeros((1, npc, 3), device=dev, dtype=torch.float32)
+        # box centred on the origin: the reference rotates the difference vectors about the box centre
+        cp[:, :, :2] = (torch.rand((1, npc, 2), generator=gen, device=dev, dtype=torch.float32) - 0.5) * Lp
+        boxp = np.array([[-Lp / 2, Lp / 2], [-Lp / 2, Lp / 2], [-0.5, 0.5]], dtype=np.float32)
+        for tag, kw in (("default_window_rotated", dict(psi=np.array([0.8, 0.3]))), ("rmax10", dict(rmax=10.0))):
+            def run_pcf2d():
+                res["g"] = sc.pcf2d_frames(cp, boxp, zero_last_column=False, **kw)[0]
+            ms = timed(run_pcf2d, reps=2)
+            area = (2.0 * (Lp // (2 * np.sqrt(2)) if "rmax" not in kw else kw["rmax"]) / 500) ** 2
+            binned = float(np.sum(res["g"][0]) * area * npc)   # undo the normalisation: g = hist / area / (N / L^2) / N
+            out["pcf2d_" + tag] = {
+                "workload": f"2D uniform N={npc}, density 1, 500x500 (dx, dy) grid, 1 frame per GPU, " + tag,
+                "pair_evals_per_s": npc * (npc - 1) * world / (ms * 1e-3), "binned_pairs_per_s": binned * world / (ms * 1e-3),
+                "ms": ms, "dtype": "f32 differences, exact np.histogram2d binning"}
+    except Exception as exc:  # noqa: BLE001
+        out["pcf2d"] = {"error": repr(exc)}
     return out
 
 
