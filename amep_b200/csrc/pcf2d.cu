@@ -16,10 +16,18 @@
 // Everything after the counts (bin areas, density, N_other, bin centres) is array arithmetic
 // on the grid and stays with the caller.
 //
-// Layout: one thread per query particle (a row of other_coords), targets (rows of coords) staged
-// through shared memory 1024 at a time and read by all threads at once (broadcast); the targets
-// are split over blockIdx.y so that small systems still fill the SMs; counts are 64-bit and
-// added with global atomics (a 500 x 500 grid does not fit shared memory).
+// Two pair walks share one binning routine (PairBinner) and give identical counts:
+//   * pcf2d_kernel (direct): one thread per query particle (a row of other_coords), targets (rows
+//     of coords) staged through shared memory 1024 at a time and read by all threads at once
+//     (broadcast); the targets are split over blockIdx.y so that small systems still fill the
+//     SMs; counts are 64-bit and added with global atomics (a 500 x 500 grid does not fit shared
+//     memory).  Best when few pairs bin (narrow window).
+//   * pcf2d_cells_kernel (large systems, wide window): both sets counting-sorted into cells, a
+//     block counts a (query cell, target cell) pair in a shared-memory window of the grid; see the
+//     comment above that kernel.
+// The rotation flag is a template parameter (all frames of a launch share it); float32
+// differences are decided in float32 wherever that provably agrees with the float64 arithmetic
+// of the reference (thresholds for unrotated pairs, an error margin for rotated ones).
 #include <math.h>
 #include <string.h>
 
