@@ -89,11 +89,30 @@ def box_array(box_boundary, nframes):
     return np.ascontiguousarray(b, dtype=np.float64), code
 
 
+def to_numpy(x):
+    """Host NumPy view / copy of a NumPy array or (CUDA) tensor."""
+    if _is_torch(x):
+        return x.detach().cpu().numpy()
+    return np.asarray(x)
+
+
+def current_device() -> int:
+    """The calling process' current CUDA device (one process per GPU sets it once with
+    ``torch.cuda.set_device``); 0 when torch has no say."""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            return int(torch.cuda.current_device())
+    except Exception:  # pragma: no cover
+        pass
+    return 0
+
+
 def _device_of(p: Particles, device):
     if p.on_device:
         return p.tensor.device.index if p.tensor.device.index is not None else 0
     if device is None:
-        return 0
+        return current_device()
     if isinstance(device, int):
         return device
     import torch
@@ -108,13 +127,14 @@ def _stream_for(dev_index, on_device):
     return ctypes.c_void_p(torch.cuda.current_stream(dev_index).cuda_stream)
 
 
-def rdf_histograms(coords, box_boundary, edges, other=None, pbc=True, device=None, out=None):
+def rdf_histograms(coords, box_boundary, edges, other=None, pbc=True, device=None, out=None, shard=None):
     """Integer pair histograms for a batch of frames (amepb_rdf_batch).
 
     Returns ``(hist, dims)``: ``hist`` int64 ``[F, nbins]`` (a CUDA tensor if the
     coordinates live on the device, else a NumPy array), ``dims`` int32 ``[F]``.
     Raises ValueError for frames that are neither 2D nor 3D (as the reference,
-    amep/pbc.py:290-294).
+    amep/pbc.py:290-294).  ``shard=(index, count)``: evaluate only this share of every frame's
+    query cell runs (amepb_rdf_set_shard); the histograms of all shares add up to the full one.
     """
     pc = coords if isinstance(coords, Particles) else Particles(coords)
     po = None
@@ -152,17 +172,23 @@ def rdf_histograms(coords, box_boundary, edges, other=None, pbc=True, device=Non
             out = np.empty((nf, nbins), dtype=np.int64)
         hist_ptr = out.ctypes.data
         space = _lib.HOST
-    rc = ctx.lib.amepb_rdf_batch(
-        ctx.handle,
-        ctypes.c_void_p(pc.ptr()), pc.dtype, pc.n,
-        ctypes.c_void_p(po.ptr()) if po is not None else None,
-        po.dtype if po is not None else 0, po.n if po is not None else 0,
-        space, nf,
-        box.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), box_code,
-        e.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), stride, nbins,
-        1 if pbc else 0,
-        ctypes.c_void_p(hist_ptr), dims.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
-        _stream_for(dev_index, pc.on_device))
+    if shard is not None:
+        ctx.set_shard(*shard)
+    try:
+        rc = ctx.lib.amepb_rdf_batch(
+            ctx.handle,
+            ctypes.c_void_p(pc.ptr()), pc.dtype, pc.n,
+            ctypes.c_void_p(po.ptr()) if po is not None else None,
+            po.dtype if po is not None else 0, po.n if po is not None else 0,
+            space, nf,
+            box.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), box_code,
+            e.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), stride, nbins,
+            1 if pbc else 0,
+            ctypes.c_void_p(hist_ptr), dims.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+            _stream_for(dev_index, pc.on_device))
+    finally:
+        if shard is not None:
+            ctx.set_shard(0, 1)
     if rc == _lib.E_DIMENSION:
         raise ValueError(ctx.error())
     ctx.check(rc, "amepb_rdf_batch")

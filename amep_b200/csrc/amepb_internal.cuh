@@ -44,8 +44,12 @@ struct amepb_ctx {
     std::string err;
     int64_t launches = 0;
     DevBuf bufs[BUF_COUNT];
-    void* pinned = nullptr;  // pinned host scratch (plans, stats read-back)
+    void* pinned = nullptr;  // pinned host scratch (plans, stats read-back, small tables)
     size_t pinned_cap = 0;
+    // recorded after the last asynchronous device read of `pinned` (upload kernel / H2D copy);
+    // every host write to `pinned` waits for it first (pinned_host_acquire)
+    cudaEvent_t ev_pinned = nullptr;
+    bool pinned_in_flight = false;
     amepb_rdf_info rdf_info;
     // workspace budget of amepb_rdf_batch, queried once per problem shape (rdf.cu)
     size_t budget_bytes = 0, budget_per_frame = 0;
@@ -59,6 +63,7 @@ struct amepb_ctx {
     int thr_cache_f64 = -1;
     int rdf_k_override = 0;
     bool rdf_symmetric = true;
+    int rdf_shard_index = 0, rdf_shard_count = 1;   // amepb_rdf_set_shard
     void* last_stream = nullptr;
     bool sq_attr_harm = false;
     cudaStream_t copy_stream = nullptr;   // host-space staging
@@ -80,6 +85,11 @@ int fail(amepb_ctx* ctx, int code, const char* fmt, ...);
 int fail_cuda(amepb_ctx* ctx, cudaError_t e, const char* what, const char* file, int line);
 int ensure_device(amepb_ctx* ctx, int which, size_t bytes);
 int ensure_pinned(amepb_ctx* ctx, size_t bytes);
+// The pinned scratch block is shared by asynchronous consumers.  Host code calls
+// pinned_host_acquire() before it writes into ctx->pinned (blocks until the last recorded device
+// read has run) and pinned_device_release() right after it has enqueued a device read of it.
+int pinned_host_acquire(amepb_ctx* ctx);
+int pinned_device_release(amepb_ctx* ctx, cudaStream_t stream);
 
 cudaEvent_t timing_event(amepb_ctx* ctx, cudaStream_t stream);  // records and returns an event (or nullptr)
 double timing_total_ms(amepb_ctx* ctx, std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& spans);

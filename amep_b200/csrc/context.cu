@@ -52,9 +52,27 @@ int ensure_device(amepb_ctx* ctx, int which, size_t bytes) {
     return 0;
 }
 
+int pinned_host_acquire(amepb_ctx* ctx) {
+    if (ctx->pinned_in_flight && ctx->ev_pinned) {
+        AMEPB_CUDA(ctx, cudaEventSynchronize(ctx->ev_pinned));
+        ctx->pinned_in_flight = false;
+    }
+    return 0;
+}
+
+int pinned_device_release(amepb_ctx* ctx, cudaStream_t stream) {
+    if (!ctx->ev_pinned) AMEPB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_pinned, cudaEventDisableTiming));
+    AMEPB_CUDA(ctx, cudaEventRecord(ctx->ev_pinned, stream));
+    ctx->pinned_in_flight = true;
+    return 0;
+}
+
 int ensure_pinned(amepb_ctx* ctx, size_t bytes) {
     if (ctx->pinned_cap >= bytes && ctx->pinned) return 0;
     if (ctx->pinned) {
+        // a queued device read of the old block must have run before it is freed
+        int rc = pinned_host_acquire(ctx);
+        if (rc) return rc;
         AMEPB_CUDA(ctx, cudaFreeHost(ctx->pinned));
         ctx->pinned = nullptr;
         ctx->pinned_cap = 0;
@@ -141,6 +159,7 @@ void amepb_destroy(amepb_ctx* ctx) {
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->ev_stats) cudaEventDestroy(ctx->ev_stats);
+    if (ctx->ev_pinned) cudaEventDestroy(ctx->ev_pinned);
     for (int b = 0; b < amepb_ctx::kStageBuffers; ++b) {
         if (ctx->ev_copied[b]) cudaEventDestroy(ctx->ev_copied[b]);
         if (ctx->ev_computed[b]) cudaEventDestroy(ctx->ev_computed[b]);

@@ -121,6 +121,7 @@ extern "C" int amepb_density_counts(amepb_ctx* ctx, const void* coords, int dtyp
     const size_t pbytes = fbytes + sizeof(double) * ((size_t)nxe + nye);
     if ((rc = ensure_pinned(ctx, pbytes))) return rc;
     if ((rc = ensure_device(ctx, BUF_SQ_A, pbytes))) return rc;
+    if ((rc = pinned_host_acquire(ctx))) return rc;   // an earlier call may still be reading the block
     char* hp = reinterpret_cast<char*>(ctx->pinned);
     DensityFrame* hf = reinterpret_cast<DensityFrame*>(hp);
     for (int64_t f = 0; f < nframes; ++f) {

@@ -646,6 +646,7 @@ extern "C" int amepb_pcf2d_counts(amepb_ctx* ctx, const void* coords, int dtype,
     const size_t bbox_off = (pbytes + 63) & ~(size_t)63;   // bounding-box read-back of the cell-sorted walk
     if ((rc = ensure_pinned(ctx, bbox_off + 64))) return rc;
     if ((rc = ensure_device(ctx, BUF_SQ_A, pbytes))) return rc;
+    if ((rc = pinned_host_acquire(ctx))) return rc;   // an earlier call may still be reading the block
     char* hp = reinterpret_cast<char*>(ctx->pinned);
     memset(hp, 0, pbytes);
     Pcf2dFrame* hf = reinterpret_cast<Pcf2dFrame*>(hp);

@@ -512,6 +512,7 @@ struct PairArgs {
     int nframes;
     int uniform;                    // every edge table is uniform (linspace-like) and fit for the one-comparison binning
     float one;                      // 1.0f, opaque to the compiler (see add2_unfused)
+    int shard_index, shard_count;   // this launch takes the block tasks t with t % shard_count == shard_index
 };
 
 // float32 regime: every warp gathers the neighbourhood of its query cell into a shared buffer
@@ -813,7 +814,7 @@ __global__ void __launch_bounds__(kPairThreads, (sizeof(AT) == 4 ? kPairBlocksPe
 
     for (;;) {
         if (tid == 0) {
-            s_task = (long long)atomicAdd(&a.counters[0], 1ull);
+            s_task = (long long)atomicAdd(&a.counters[0], 1ull) * a.shard_count + a.shard_index;
             s_next = blockDim.x >> 5;
             const int fl = s_units >= kUnitLimit;
             s_flush = fl;
@@ -1451,7 +1452,9 @@ static void frame_stats_collect(amepb_ctx* ctx, int nframes, std::vector<FrameSt
 
 static int frame_stats(amepb_ctx* ctx, const void* pts, int dtype, int64_t n, int nframes,
                        std::vector<FrameStats>& out, cudaStream_t stream, int slot) {
-    int rc = frame_stats_launch(ctx, pts, dtype, n, nframes, stream, slot);
+    int rc = pinned_host_acquire(ctx);
+    if (rc) return rc;
+    rc = frame_stats_launch(ctx, pts, dtype, n, nframes, stream, slot);
     if (rc) return rc;
     AMEPB_CUDA(ctx, cudaStreamSynchronize(stream));
     frame_stats_collect(ctx, nframes, out, slot);
@@ -1497,7 +1500,7 @@ static int launch_pairs(amepb_ctx* ctx, const PairArgs& args, int zmode, cudaStr
     AMEPB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kPairThreads, dyn));
     if (per_sm < 1) per_sm = 1;
     long long blocks = (long long)ctx->sm_count * per_sm;
-    blocks = std::max<long long>(1, std::min<long long>(blocks, args.total_tasks));
+    blocks = std::max<long long>(1, std::min<long long>(blocks, (args.total_tasks + args.shard_count - 1) / args.shard_count));
     kern<<<(unsigned)blocks, kPairThreads, dyn, stream>>>(args);
     AMEPB_LAUNCH_CHECK(ctx);
     return 0;
@@ -1569,6 +1572,8 @@ static int rdf_sub_batch(amepb_ctx* ctx, const RdfCall& c, int64_t f0, int nf, c
         // launched ahead of the previous pair kernel
         AMEPB_CUDA(ctx, cudaEventSynchronize(ctx->ev_stats));
     } else {
+        // the statistics land in the pinned block: no read queued by an earlier call may be pending
+        if ((rc = pinned_host_acquire(ctx))) return rc;
         if ((rc = frame_stats_launch(ctx, d_coords, c.coords_dtype, c.n, nf, stream, 0))) return rc;
         if (!self && (rc = frame_stats_launch(ctx, d_other, c.other_dtype, c.m, nf, stream, 1))) return rc;
         AMEPB_CUDA(ctx, cudaStreamSynchronize(stream));
@@ -1613,7 +1618,8 @@ static int rdf_sub_batch(amepb_ctx* ctx, const RdfCall& c, int64_t f0, int nf, c
         P.cell_base = (unsigned)total_cells;
         P.task_begin = total_tasks;
         if (P.valid) {
-            const bool zc = !ts.varies[2] && !qs.varies[2];
+            // (with z images -- dimension 3, e.g. a single target particle -- dz is not one constant)
+            const bool zc = !ts.varies[2] && !qs.varies[2] && !(c.pbc && P.nshift[2] == 3);
             all_zconst = all_zconst && zc;
             if (zc) {
                 if (arith_f64) {
@@ -1676,6 +1682,9 @@ static int rdf_sub_batch(amepb_ctx* ctx, const RdfCall& c, int64_t f0, int nf, c
     if (rc) return rc;
     rc = ensure_device(ctx, BUF_THR, thr_bytes);
     if (rc) return rc;
+    // (the statistics of this sub-batch were read above, after every earlier read of the block on
+    // this stream had run; a read queued by another call on another stream is waited for here)
+    if ((rc = pinned_host_acquire(ctx))) return rc;
     char* hp = reinterpret_cast<char*>(ctx->pinned);
     memcpy(hp, plans.data(), plan_bytes);
     char* hthr = hp + ((plan_bytes + 15) & ~(size_t)15);
@@ -1711,6 +1720,7 @@ static int rdf_sub_batch(amepb_ctx* ctx, const RdfCall& c, int64_t f0, int nf, c
         upload_kernel<<<(unsigned)std::min<long long>(64, (tw + 255) / 256), 256, 0, stream>>>(
             reinterpret_cast<int*>(ctx->bufs[BUF_THR].p), reinterpret_cast<const int*>(hthr), tw);
         AMEPB_LAUNCH_CHECK(ctx);
+        if ((rc = pinned_device_release(ctx, stream))) return rc;
     }
     const FramePlan* d_plans = reinterpret_cast<const FramePlan*>(ctx->bufs[BUF_PLANS].p);
 
@@ -1833,6 +1843,8 @@ static int rdf_sub_batch(amepb_ctx* ctx, const RdfCall& c, int64_t f0, int nf, c
     args.nframes = nf;
     args.uniform = uniform ? 1 : 0;
     args.one = 1.0f;
+    args.shard_index = ctx->rdf_shard_index;
+    args.shard_count = ctx->rdf_shard_count;
     int zmode = all_zconst ? 2 : 0;
     for (int f = 0; f < nf && zmode == 2; ++f)
         if (plans[f].valid && plans[f].dz2c != 0.0) zmode = 1;
@@ -1862,6 +1874,13 @@ extern "C" {
 int amepb_rdf_set_symmetric(amepb_ctx* ctx, int enable) {
     if (!ctx) return AMEPB_E_INVAL;
     ctx->rdf_symmetric = enable != 0;
+    return 0;
+}
+
+int amepb_rdf_set_shard(amepb_ctx* ctx, int index, int count) {
+    if (!ctx || count < 1 || index < 0 || index >= count) return AMEPB_E_INVAL;
+    ctx->rdf_shard_index = index;
+    ctx->rdf_shard_count = count;
     return 0;
 }
 

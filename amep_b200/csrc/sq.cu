@@ -578,9 +578,11 @@ int amepb_sq_harmonics(amepb_ctx* ctx, const void* coords, int dtype, int space,
     if (rc) return rc;
     rc = ensure_device(ctx, BUF_SQ_A, kv_count * sizeof(double));
     if (rc) return rc;
+    if ((rc = pinned_host_acquire(ctx))) return rc;
     memcpy(ctx->pinned, kvec, kv_count * sizeof(double));
     AMEPB_CUDA(ctx, cudaMemcpyAsync(ctx->bufs[BUF_SQ_A].p, ctx->pinned, kv_count * sizeof(double),
                                     cudaMemcpyHostToDevice, stream));
+    if ((rc = pinned_device_release(ctx, stream))) return rc;
     const double* d_kvec = reinterpret_cast<const double*>(ctx->bufs[BUF_SQ_A].p);
 
     const long long tile_particles = (long long)kHarmThreads * kHarmP;
@@ -686,8 +688,10 @@ int amepb_sf2d_modes(amepb_ctx* ctx, const void* coords, int dtype, int space, i
     int rc = ensure_pinned(ctx, q_count * sizeof(double));
     if (rc) return rc;
     if ((rc = ensure_device(ctx, BUF_SQ_A, q_count * sizeof(double)))) return rc;
+    if ((rc = pinned_host_acquire(ctx))) return rc;
     memcpy(ctx->pinned, q, q_count * sizeof(double));
     AMEPB_CUDA(ctx, cudaMemcpyAsync(ctx->bufs[BUF_SQ_A].p, ctx->pinned, q_count * sizeof(double), cudaMemcpyHostToDevice, stream));
+    if ((rc = pinned_device_release(ctx, stream))) return rc;
     const double* d_q = reinterpret_cast<const double*>(ctx->bufs[BUF_SQ_A].p);
 
     const size_t smem_f64 = sizeof(double2) * kF64Stage * kF64Row * 2;
@@ -855,8 +859,10 @@ int amepb_sq_debye(amepb_ctx* ctx, const void* coords, int dtype, int64_t n, con
     const size_t q_count = (size_t)(q_stride ? nframes * q_stride : nq);
     if ((rc = ensure_pinned(ctx, q_count * sizeof(double)))) return rc;
     if ((rc = ensure_device(ctx, BUF_SQ_A, q_count * sizeof(double)))) return rc;
+    if ((rc = pinned_host_acquire(ctx))) return rc;
     memcpy(ctx->pinned, q, q_count * sizeof(double));
     AMEPB_CUDA(ctx, cudaMemcpyAsync(ctx->bufs[BUF_SQ_A].p, ctx->pinned, q_count * sizeof(double), cudaMemcpyHostToDevice, stream));
+    if ((rc = pinned_device_release(ctx, stream))) return rc;
     const double* d_q = reinterpret_cast<const double*>(ctx->bufs[BUF_SQ_A].p);
 
     const long long tiles = ((n + kDebyeThreads - 1) / kDebyeThreads) * ((m + kDebyeTileB - 1) / kDebyeTileB);

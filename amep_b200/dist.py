@@ -53,3 +53,52 @@ def assemble_rows(local_rows, lo: int, total_rows: int, group=None):
     else:
         dist.all_reduce(table, op=dist.ReduceOp.SUM, group=group)
     return table.cpu().numpy()
+
+
+def _to_backend_tensor(array, group):
+    import torch
+    import torch.distributed as dist
+    t = array if isinstance(array, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(array))
+    if dist.get_backend(group) == "nccl" and not t.is_cuda:
+        t = t.cuda()
+    return t
+
+
+def all_reduce_sum(array, group=None):
+    """Element-wise sum of a NumPy array / tensor over the ranks -> NumPy array (one all-reduce)."""
+    import torch
+    import torch.distributed as dist
+    t = _to_backend_tensor(array, group).clone()
+    if t.is_complex():
+        dist.all_reduce(torch.view_as_real(t), op=dist.ReduceOp.SUM, group=group)
+    else:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t.cpu().numpy()
+
+
+def agree_shape(shape, group=None, max_dims: int = 8):
+    """The one shape all ranks that have one (``shape`` not None) share; ranks without work pass
+    None and learn it.  Decided by two MAX all-reduces, so that a rank with an empty shard neither
+    raises on its own nor leaves the others waiting in a collective."""
+    import torch
+    import torch.distributed as dist
+    pad = torch.zeros(max_dims + 1, dtype=torch.int64)
+    if shape is not None:
+        if len(shape) > max_dims:
+            raise ValueError("agree_shape: too many dimensions")
+        pad[0] = len(shape)
+        for i, s in enumerate(shape):
+            pad[1 + i] = int(s)
+    pad = _to_backend_tensor(pad, group)
+    dist.all_reduce(pad, op=dist.ReduceOp.MAX, group=group)
+    pad = pad.cpu().tolist()
+    return tuple(int(x) for x in pad[1:1 + int(pad[0])])
+
+
+def all_true(flag: bool, group=None) -> bool:
+    """Logical AND of ``flag`` over the ranks."""
+    import torch
+    import torch.distributed as dist
+    t = _to_backend_tensor(torch.tensor([0 if flag else 1], dtype=torch.int64), group)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return int(t.item()) == 0

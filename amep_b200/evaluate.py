@@ -1,79 +1,248 @@
 """Drop-in for ``amep.evaluate.RDF`` / ``SFiso`` / ``SF2d`` / ``PCF2d`` (AMEP 1.3.0).
 
 Same constructor arguments and result properties as amep/evaluate.py:406-609
-(RDF), :1183-1522 (SF2d) and :1525-1838 (SFiso).  Where the reference maps a
-per-frame function over the selected frames with ``average_func``
-(amep/utils.py:80-187), these classes select the same frames, hand all of them
-to the batched kernels in one call, shard them over the ranks of a
+(RDF), :612-752 (PCF2d), :1183-1522 (SF2d) and :1525-1838 (SFiso).  Where the
+reference maps a per-frame function over the selected frames with ``average_func``
+(amep/utils.py:80-187), these classes select the same frames, hand them to the
+batched kernels in a few large calls, shard them over the ranks of a
 ``torch.distributed`` job when there is one, and average exactly like
 ``np.mean(np.array(results), axis=0)``.
+
+Data path.  A ``TensorTrajectory`` (arrays already in host memory or HBM) is read in
+place.  Any other trajectory object (the reference's ``ParticleTrajectory``: one HDF5
+read per ``frame.coords()`` call, amep/base.py:941-979) is *streamed*: a producer thread
+pulls the next block of frames into a pinned staging buffer while the GPU works on the
+current one (``_streamed_batches``), so wall time is max(read, compute) rather than the
+sum and host memory stays at a few staging buffers instead of the whole selection.
+
+Multi-GPU.  Frames are the unit of sharding (contiguous blocks per rank, one
+all-reduce).  With fewer selected frames than ranks the RDF is sharded *inside* the
+frame instead (every rank holds the frame, ``amepb_rdf_set_shard`` deals out the query
+cell runs, the integer histograms add up exactly) -- the split the reference makes over
+query chunks (amep/spatialcor.py:587-600).
 
 ``max_workers``, ``njobs`` and ``chunksize`` (except sf2d's, which is part of
 the result) are accepted for compatibility and have no effect.
 """
 from __future__ import annotations
 
+import queue
+import threading
+
 import numpy as np
 
 from . import _core, dist
 from .base import BaseEvaluation
+from .order import psi6_orientation, rotated_periodic_crop
 from .spatialcor import pcf2d_frames, rdf_frames, sf2d_frames, sfiso_frames
 from .trajectory import TensorTrajectory
 from .utils import evaluated_indices
 
 __all__ = ["RDF", "SFiso", "SF2d", "PCF2d"]
 
+# bytes of coordinates per streamed block (per species); three staging buffers are in flight
+STREAM_BLOCK_BYTES = 256 << 20
 
-def _gather(traj, indices, ptype):
-    """Coordinates ``[F, n, 3]`` and boxes of the selected frames."""
+
+# =============================================================================
+# frame access
+# =============================================================================
+def _same_box(boxes):
+    first = boxes[0]
+    if all(b.dtype == first.dtype and np.array_equal(b, first) for b in boxes):
+        return first
+    return np.stack(boxes)
+
+
+def _pinned_empty(shape, dtype):
+    """Host staging buffer, page-locked when a CUDA device is there (the library's copies from it
+    then run asynchronously at full link speed)."""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            tdt = {np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64}[np.dtype(dtype)]
+            return torch.empty(tuple(shape), dtype=tdt).pin_memory().numpy()
+    except Exception:  # pragma: no cover - no torch / no pinned memory: plain pages still work
+        pass
+    return np.empty(shape, dtype=dtype)
+
+
+def _streamed_batches(traj, indices, ptype, other, want_other, block_bytes=None):
+    """Blocks of frames of a generic trajectory: ``(coords [f,n,3], other or None, box)``.
+
+    The reference reads frame after frame inside its serial loop (amep/utils.py:156-158, one
+    ``h5py.File`` open + decompression per ``frame.coords()``, amep/base.py:941-979).  Here a
+    producer thread fills the next staging buffer while the caller computes on the current one."""
+    frames = traj[np.asarray(indices)]
+    if len(frames) == 0:
+        return
+    first = frames[0].coords(ptype=ptype)
+    if _core._is_torch(first):
+        # frames that are tensors already (possibly in HBM): nothing to stream
+        import torch
+        coords = torch.stack([f.coords(ptype=ptype) for f in frames])
+        oc = torch.stack([f.coords(ptype=other) for f in frames]) if want_other else None
+        yield coords, oc, _same_box([np.asarray(f.box) for f in frames])
+        return
+    first = np.asarray(first)
+    if first.dtype not in (np.float32, np.float64):
+        first = first.astype(np.float64)
+    shape_c, dtype_c = first.shape, first.dtype
+    shape_o = dtype_o = None
+    per_frame = first.nbytes
+    if want_other:
+        fo = np.asarray(frames[0].coords(ptype=other))
+        if fo.dtype not in (np.float32, np.float64):
+            fo = fo.astype(np.float64)
+        shape_o, dtype_o = fo.shape, fo.dtype
+        per_frame = max(per_frame, fo.nbytes)
+    block = int(max(1, min(len(frames), (block_bytes or STREAM_BLOCK_BYTES) // max(1, per_frame))))
+    nbuf = 3 if len(frames) > 2 * block else (2 if len(frames) > block else 1)
+    bufs_c = [_pinned_empty((block,) + shape_c, dtype_c) for _ in range(nbuf)]
+    bufs_o = [_pinned_empty((block,) + shape_o, dtype_o) for _ in range(nbuf)] if want_other else None
+    free, ready = queue.Queue(), queue.Queue(maxsize=nbuf)
+    for b in range(nbuf):
+        free.put(b)
+    stop = threading.Event()
+
+    def producer():
+        try:
+            for lo in range(0, len(frames), block):
+                b = free.get()
+                if stop.is_set():
+                    return
+                hi = min(len(frames), lo + block)
+                boxes = []
+                for k, fr in enumerate(frames[lo:hi]):
+                    c = np.asarray(fr.coords(ptype=ptype))
+                    if c.shape != shape_c:
+                        raise ValueError("the number of selected particles changes between frames; "
+                                         "evaluate such trajectories frame by frame with amep_b200.spatialcor")
+                    bufs_c[b][k] = c
+                    if want_other:
+                        o = np.asarray(fr.coords(ptype=other))
+                        if o.shape != shape_o:
+                            raise ValueError("the number of selected particles changes between frames; "
+                                             "evaluate such trajectories frame by frame with amep_b200.spatialcor")
+                        bufs_o[b][k] = o
+                    boxes.append(np.asarray(fr.box))
+                ready.put((b, hi - lo, boxes))
+            ready.put(None)
+        except BaseException as exc:  # noqa: BLE001 - handed to the consumer
+            ready.put(exc)
+
+    thread = threading.Thread(target=producer, name="amep_b200-frame-reader", daemon=True)
+    thread.start()
+    try:
+        while True:
+            item = ready.get()
+            if item is None:
+                break
+            if isinstance(item, BaseException):
+                raise item
+            b, nf, boxes = item
+            yield bufs_c[b][:nf], (bufs_o[b][:nf] if want_other else None), _same_box(boxes)
+            free.put(b)   # the consumer has finished with this buffer (library calls are complete on return)
+    finally:
+        stop.set()
+        free.put(0)       # unblock a producer waiting for a buffer
+        thread.join(timeout=10)
+
+
+def _frame_batches(traj, indices, ptype, other, want_other):
+    """``(coords, other_coords or None, box)`` blocks covering ``indices`` in order."""
+    if len(indices) == 0:
+        return
     if isinstance(traj, TensorTrajectory):
         try:
-            return traj.stack(indices, ptype)
+            coords, box = traj.stack(indices, ptype)
+            oc = traj.stack(indices, other)[0] if want_other else None
+            yield coords, oc, box
+            return
         except ValueError:
             pass
-    frames = traj[np.asarray(indices)]
-    coords = [f.coords(ptype=ptype) for f in frames]
-    boxes = [np.asarray(f.box) for f in frames]
-    if len({tuple(c.shape) for c in coords}) != 1:
-        raise ValueError("the number of selected particles changes between frames; "
-                         "evaluate such trajectories frame by frame with amep_b200.spatialcor")
-    if _core._is_torch(coords[0]):
-        import torch
-        stack = torch.stack(list(coords))
-    else:
-        stack = np.stack([np.asarray(c) for c in coords])
-    same_box = all(b.dtype == boxes[0].dtype and np.array_equal(b, boxes[0]) for b in boxes)
-    return stack, (boxes[0] if same_box else np.stack(boxes))
+    yield from _streamed_batches(traj, indices, ptype, other, want_other)
 
 
-def _local_block(nsel, distributed, group):
-    rank, ws = dist.world(group)
-    if distributed is False or ws == 1:
-        return 0, nsel, 1
-    lo, hi = dist.shard_bounds(nsel, rank, ws)
-    return lo, hi, ws
+def _gather(traj, indices, ptype):
+    """Coordinates ``[F, n, 3]`` and boxes of the selected frames in one piece."""
+    parts = list(_frame_batches(traj, indices, ptype, None, False))
+    if len(parts) == 1:
+        return parts[0][0].copy() if not isinstance(traj, TensorTrajectory) and not _core._is_torch(parts[0][0]) \
+            else parts[0][0], parts[0][2]
+    raise RuntimeError("unreachable: _gather is only used on single-block selections")
 
 
-def _box_rows(box, lo, hi):
-    return box[lo:hi] if np.ndim(box) == 3 else box
+# =============================================================================
+# sharding
+# =============================================================================
+class _Shard:
+    """What this rank evaluates: frames ``[lo, hi)`` of the selection, or -- ``intra`` -- all of
+    them with a 1/ws share of the work inside every frame."""
+
+    def __init__(self, nsel, distributed, group, allow_intra=False):
+        self.rank, self.ws = dist.world(group)
+        self.group = group
+        if distributed is False:
+            self.rank, self.ws = 0, 1
+        self.nsel = nsel
+        self.intra = allow_intra and self.ws > 1 and nsel < self.ws
+        if self.ws == 1 or self.intra:
+            self.lo, self.hi = 0, nsel
+        else:
+            self.lo, self.hi = dist.shard_bounds(nsel, self.rank, self.ws)
+
+    def all_sum(self, array):
+        """Sum a NumPy array / tensor over the ranks (identity for one rank) -> NumPy."""
+        if self.ws == 1:
+            return array.cpu().numpy() if _core._is_torch(array) else np.asarray(array)
+        return dist.all_reduce_sum(array, self.group)
+
+    def tail_shape(self, local):
+        """Shape of one row, agreed between ranks some of which may hold no frame."""
+        return dist.agree_shape(None if local is None else tuple(local.shape[1:]), self.group)
+
+    def assemble(self, local, dtype=np.float64):
+        """Rows of all ranks -> ``[nsel, ...]`` (zero rows + one all-reduce; exact)."""
+        if self.ws == 1 or self.intra:
+            return local
+        tail = self.tail_shape(local)
+        rows = np.zeros((self.hi - self.lo,) + tail, dtype=dtype)
+        if local is not None and self.hi > self.lo:
+            rows[...] = local
+        return dist.assemble_rows(rows, self.lo, self.nsel, self.group)
+
+
+def _mean_of_copies(v, n):
+    """``np.mean`` over ``n`` identical rows ``v`` as average_func computes it (amep/utils.py:186):
+    a sequential float64 sum along the frame axis, divided by ``n`` -- not always ``v`` itself."""
+    v = np.asarray(v, dtype=np.float64)
+    acc = v.copy()
+    for _ in range(n - 1):
+        acc = acc + v
+    return acc / n
 
 
 class _FrameAverage(BaseEvaluation):
-    """Common frame selection / sharding / averaging."""
+    """Common frame selection / averaging."""
 
     def _select(self, traj, skip, nav):
         self._indices = evaluated_indices(len(traj), skip, nav)
+        self._times = np.asarray(traj.times)[self._indices]
         return self._indices
 
-    def _finish(self, traj, per_frame):
-        """``per_frame``: list (one entry per selected frame) of tuples of arrays;
-        mirrors amep/utils.py:184-186."""
-        evaluated = np.array(per_frame)
-        self._frames = evaluated
-        self._times = np.asarray(traj.times)[self._indices]
-        return np.mean(evaluated, axis=0)
+    @property
+    def times(self):
+        return self._times
+
+    @property
+    def indices(self):
+        return self._indices
 
 
+# =============================================================================
+# RDF
+# =============================================================================
 class RDF(_FrameAverage):
     """Radial pair distribution function, time-averaged over frames
     (contract of amep/evaluate.py:406-609)."""
@@ -86,33 +255,26 @@ class RDF(_FrameAverage):
         kwargs.pop("chunksize", None)
         kwargs.pop("verbose", None)
         idx = self._select(traj, skip, nav)
-        nsel = len(idx)
-        lo, hi, ws = _local_block(nsel, distributed, group)
-        counts = None
-        nbins = None
-        if hi > lo:
-            coords, box = _gather(traj, idx[lo:hi], ptype)
-            other_coords = None if other is None else _gather(traj, idx[lo:hi], other)[0]
-            g, r, counts = rdf_frames(coords, box, other_coords, return_counts=True, **kwargs)
-            nbins = g.shape[1]
-        if ws > 1:
-            # one all-reduce over [nsel, 2, nbins] float64 rows: g and r of every frame
-            # (rows of other ranks are zero, so the sum is exact), plus the counts
-            import torch
-            nb = torch.tensor([0 if nbins is None else nbins])
-            if torch.distributed.get_backend(group) == "nccl":
-                nb = nb.cuda()
-            torch.distributed.all_reduce(nb, op=torch.distributed.ReduceOp.MAX, group=group)
-            nbins = int(nb.item())
-            local = np.zeros((hi - lo, 3, nbins))
-            if hi > lo:
-                local[:, 0], local[:, 1], local[:, 2] = g, r, counts
-            table = dist.assemble_rows(local, lo, nsel, group)
-            g, r, counts = table[:, 0], table[:, 1], table[:, 2].astype(np.int64)
-        self._counts = counts
-        res = self._finish(traj, [(g[f], r[f]) for f in range(nsel)])
-        self._avg = res[0]
-        self._r = res[1]
+        sh = _Shard(len(idx), distributed, group, allow_intra=True)
+        rows = []   # (g, r, counts) per block
+        extra = {}
+        if sh.intra:
+            # fewer frames than ranks: every rank evaluates its share of the query cells of every
+            # frame; the integer histograms are summed before the normalisation
+            extra = dict(shard=(sh.rank, sh.ws), reduce=sh.all_sum)
+        for coords, other_coords, box in _frame_batches(traj, idx[sh.lo:sh.hi], ptype, other, other is not None):
+            rows.append(rdf_frames(coords, box, other_coords, return_counts=True, **extra, **kwargs))
+        local = None
+        if rows:
+            g, r, counts = (np.concatenate([p[k] for p in rows]) for k in range(3))
+            local = np.stack([g, r, counts.astype(np.float64)], axis=1)   # counts < 2^53: exact
+        table = sh.assemble(local)
+        # np.array(results) of the reference: (nav, 2, nbins)
+        self._frames = np.ascontiguousarray(table[:, :2])
+        self._counts = table[:, 2].astype(np.int64)
+        avg = np.mean(self._frames, axis=0)   # amep/utils.py:186
+        self._avg = avg[0]
+        self._r = avg[1]
 
     @property
     def r(self):
@@ -125,17 +287,9 @@ class RDF(_FrameAverage):
         return self._frames
 
     @property
-    def times(self):
-        return self._times
-
-    @property
     def avg(self):
         """Time-averaged g(r)."""
         return self._avg
-
-    @property
-    def indices(self):
-        return self._indices
 
     @property
     def counts(self):
@@ -143,6 +297,9 @@ class RDF(_FrameAverage):
         return self._counts
 
 
+# =============================================================================
+# isotropic S(q)
+# =============================================================================
 class SFiso(_FrameAverage):
     """Isotropic static structure factor, time-averaged (amep/evaluate.py:1525-1838)."""
 
@@ -156,19 +313,19 @@ class SFiso(_FrameAverage):
             raise TypeError("amep_b200.evaluate.SFiso: field trajectories are not on the B200 hot path "
                             "(SURVEY.md section 8f)")
         idx = self._select(traj, skip, nav)
-        nsel = len(idx)
-        lo, hi, ws = _local_block(nsel, distributed, group)
-        s = q = None
-        if hi > lo:
-            coords, box = _gather(traj, idx[lo:hi], ptype)
-            other_coords = None if other is None else _gather(traj, idx[lo:hi], other)[0]
-            s, q = sfiso_frames(coords, box, None, qmax=qmax, twod=twod, mode=mode,
-                                other_coords=other_coords, accuracy=accuracy, num=num)
-        if ws > 1:
-            s, q = _assemble_pair(s, q, lo, hi, nsel, group)
-        res = self._finish(traj, [(s[f], q[f]) for f in range(nsel)])
-        self._avg = res[0]
-        self._q = res[1]
+        sh = _Shard(len(idx), distributed, group)
+        rows = []
+        for coords, other_coords, box in _frame_batches(traj, idx[sh.lo:sh.hi], ptype, other, other is not None):
+            rows.append(sfiso_frames(coords, box, None, qmax=qmax, twod=twod, mode=mode,
+                                     other_coords=other_coords, accuracy=accuracy, num=num))
+        local = None
+        if rows:
+            s, q = (np.concatenate([p[k] for p in rows]) for k in range(2))
+            local = np.stack([s, q], axis=1)
+        self._frames = sh.assemble(local)
+        avg = np.mean(self._frames, axis=0)
+        self._avg = avg[0]
+        self._q = avg[1]
 
     @property
     def q(self):
@@ -179,44 +336,25 @@ class SFiso(_FrameAverage):
         return self._frames
 
     @property
-    def times(self):
-        return self._times
-
-    @property
     def avg(self):
         return self._avg
 
-    @property
-    def indices(self):
-        return self._indices
 
-
-def _assemble_pair(a, b, lo, hi, nsel, group):
-    """All-reduce two equally shaped per-frame float arrays as one table."""
-    import torch
-    shape = torch.tensor(list(a.shape[1:]) if a is not None else [0] * 8)[:8]
-    pad = torch.zeros(8, dtype=torch.int64)
-    pad[:len(shape)] = shape
-    ndim = torch.tensor([0 if a is None else a.ndim - 1])
-    if torch.distributed.get_backend(group) == "nccl":
-        pad, ndim = pad.cuda(), ndim.cuda()
-    torch.distributed.all_reduce(pad, op=torch.distributed.ReduceOp.MAX, group=group)
-    torch.distributed.all_reduce(ndim, op=torch.distributed.ReduceOp.MAX, group=group)
-    tail = tuple(int(x) for x in pad[:int(ndim.item())].tolist())
-    local = np.zeros((hi - lo, 2) + tail)
-    if hi > lo:
-        local[:, 0], local[:, 1] = a, b
-    table = dist.assemble_rows(local, lo, nsel, group)
-    return table[:, 0], table[:, 1]
-
-
+# =============================================================================
+# 2D S(q)
+# =============================================================================
 class SF2d(_FrameAverage):
     """Two-dimensional static structure factor, time-averaged (amep/evaluate.py:1183-1522).
 
-    ``rotate`` defaults to True as in the reference (a psi_6 alignment prologue,
-    amep/evaluate.py:1349-1377).  That prologue is a next row of the scope table
-     and not built yet, so the default *raises* instead of silently
-    computing the unrotated structure factor: pass ``rotate=False`` explicitly."""
+    ``rotate=True`` (the reference's default) aligns every frame with its mean hexagonal order
+    parameter first (amep/evaluate.py:1349-1377): psi_6 from the six nearest neighbours
+    (``amep_b200.order.psi6_orientation``, sm_100a kernel), rotation of the periodic images about
+    the box centre and crop to the box (``rotated_periodic_crop``).
+
+    Memory: per-frame results are kept as float32 ``S`` rows (what ``sf2d`` returns) plus one pair
+    of q grids; the reference's ``(nav, 3, ny, nx)`` float64 array is only materialised when
+    ``frames`` is read.  Under ``torch.distributed`` only the frame *sum* is all-reduced for
+    ``avg``; ``frames`` gathers the rows on demand (a collective: read it on every rank)."""
 
     def __init__(self, traj, skip: float = 0.0, nav: int = 10, ptype=None, other=None,
                  rotate: bool = True, ftype=None, max_workers=1, distributed=None, group=None,
@@ -226,35 +364,63 @@ class SF2d(_FrameAverage):
         if ftype is not None or type(traj).__name__ == "FieldTrajectory":
             raise TypeError("amep_b200.evaluate.SF2d: field trajectories are not on the B200 hot path "
                             "(SURVEY.md section 8f)")
-        if rotate:
-            raise NotImplementedError(
-                "amep_b200.evaluate.SF2d: rotate=True (psi_6 alignment, amep/evaluate.py:1349-1377) "
-                "is a next row of the scope table; pass rotate=False")
         kwargs.pop("verbose", None)
         idx = self._select(traj, skip, nav)
+        sh = self._shard = _Shard(len(idx), distributed, group)
+        s_rows, qx_rows, qy_rows = [], [], []
+        # the reference always passes other_coords, so rho is evaluated twice
+        # (amep/evaluate.py:1380-1394); identical arrays give identical sums,
+        # so one evaluation serves both when ptype == other
+        want_other = other != ptype
+        for coords, other_coords, box in _frame_batches(traj, idx[sh.lo:sh.hi], ptype, other, want_other):
+            if rotate:
+                # the crop changes the particle number from frame to frame: one library call per frame
+                for f in range(coords.shape[0]):
+                    b = box[f] if np.ndim(box) == 3 else box
+                    c = _core.to_numpy(coords[f])
+                    theta = psi6_orientation(c, b)
+                    c = rotated_periodic_crop(c, b, theta)
+                    o = None
+                    if want_other:
+                        o = rotated_periodic_crop(_core.to_numpy(other_coords[f]), b, theta)
+                    s, qx, qy = sf2d_frames(c[None], b, None if o is None else o[None], **kwargs)
+                    s_rows.append(s), qx_rows.append(qx), qy_rows.append(qy)
+            else:
+                s, qx, qy = sf2d_frames(coords, box, other_coords, compact_grids=True, **kwargs)
+                s_rows.append(s), qx_rows.append(qx), qy_rows.append(qy)
+        self._s = np.concatenate(s_rows) if s_rows else None            # [local frames, ny, nx], as returned by sf2d
+        qx = np.concatenate(qx_rows) if qx_rows else None               # [local frames or 1, ny, nx]
+        qy = np.concatenate(qy_rows) if qy_rows else None
+        if qx is not None and len(qx) > 1 and all(np.array_equal(qx[0], g) for g in qx[1:]) \
+                and all(np.array_equal(qy[0], g) for g in qy[1:]):
+            qx, qy = qx[:1], qy[:1]
+        self._qx_rows, self._qy_rows = qx, qy
+        self._frames = None
         nsel = len(idx)
-        lo, hi, ws = _local_block(nsel, distributed, group)
-        s = qx = qy = None
-        if hi > lo:
-            coords, box = _gather(traj, idx[lo:hi], ptype)
-            # the reference always passes other_coords, so rho is evaluated twice
-            # (amep/evaluate.py:1380-1394); identical arrays give identical sums,
-            # so one evaluation serves both when ptype == other
-            other_coords = None if other == ptype else _gather(traj, idx[lo:hi], other)[0]
-            s, qx, qy = sf2d_frames(coords, box, other_coords, **kwargs)
-            s = s.astype(np.float64)  # np.array((S, qx, qy)) upcasts the float32 S
-        if ws > 1:
-            import torch
-            local = np.zeros((hi - lo, 3) + (() if s is None else s.shape[1:]))
-            if s is None:
-                raise ValueError("SF2d: more ranks than selected frames")
-            local[:, 0], local[:, 1], local[:, 2] = s, qx, qy
-            table = dist.assemble_rows(local, lo, nsel, group)
-            s, qx, qy = table[:, 0], table[:, 1], table[:, 2]
-        res = self._finish(traj, [(s[f], qx[f], qy[f]) for f in range(nsel)])
-        self._avg = res[0]
-        self._qx = res[1]
-        self._qy = res[2]
+        # ---- average (np.mean(np.array(results), axis=0): sequential float64 sums over the frames)
+        shared_grid = qx is None or len(qx) == 1
+        if sh.ws > 1:
+            shared_grid = bool(dist.all_true(shared_grid, group))
+        if sh.ws == 1:
+            self._avg = np.mean(self._s, axis=0, dtype=np.float64)
+        else:
+            tail = sh.tail_shape(self._s)
+            part = np.zeros(tail) if self._s is None or len(self._s) == 0 else np.sum(self._s, axis=0, dtype=np.float64)
+            self._avg = sh.all_sum(part) / nsel
+        if shared_grid:
+            if sh.ws > 1:   # ranks without frames take the grids from rank 0's block
+                tail = sh.tail_shape(qx)
+                gx = qx[0] if (qx is not None and sh.lo == 0 and sh.hi > 0) else np.zeros(tail)
+                gy = qy[0] if (qy is not None and sh.lo == 0 and sh.hi > 0) else np.zeros(tail)
+                both = sh.all_sum(np.stack([gx, gy]))
+                self._qx_rows, self._qy_rows = both[0][None], both[1][None]
+            # the grids are meshgrids of one axis: average the axis, then rebuild
+            ax = _mean_of_copies(self._qx_rows[0][0, :], nsel)
+            ay = _mean_of_copies(self._qy_rows[0][:, 0], nsel)
+            self._qx, self._qy = np.meshgrid(ax, ay)
+        else:
+            fr = self.frames
+            self._qx, self._qy = np.mean(fr[:, 1], axis=0), np.mean(fr[:, 2], axis=0)
 
     @property
     def qx(self):
@@ -266,76 +432,85 @@ class SF2d(_FrameAverage):
 
     @property
     def frames(self):
+        """``(S, Qx, Qy)`` of every evaluated frame, shape ``(nav, 3, ny, nx)`` float64 -- built on
+        first access (12.6 GB for 2000 frames of a 512 x 512 grid; a collective under
+        ``torch.distributed``)."""
+        if self._frames is None:
+            sh = self._shard
+            s = None if self._s is None else self._s.astype(np.float64)   # np.array((S, qx, qy)) upcasts the float32 S
+            s = sh.assemble(s)
+            nsel = sh.nsel
+            out = np.empty((nsel, 3) + s.shape[1:])
+            out[:, 0] = s
+            if len(self._qx_rows) == 1:
+                out[:, 1], out[:, 2] = self._qx_rows[0], self._qy_rows[0]
+            else:
+                out[:, 1], out[:, 2] = sh.assemble(self._qx_rows), sh.assemble(self._qy_rows)
+            self._frames = out
         return self._frames
-
-    @property
-    def times(self):
-        return self._times
 
     @property
     def avg(self):
         return self._avg
 
-    @property
-    def indices(self):
-        return self._indices
 
-
+# =============================================================================
+# PCF2d
+# =============================================================================
 class PCF2d(_FrameAverage):
     """Two-dimensional pair correlation function g(x, y), time-averaged (amep/evaluate.py:612-752).
 
-    The reference orients every frame along its mean hexagonal order parameter,
-    ``psi = np.mean(psi_k(frame.coords(), frame.box, k=6))`` (amep/evaluate.py:730-735), before it
-    calls ``pcf2d``.  That psi_6 prologue is the same next row that ``SF2d(rotate=True)`` waits
-    for, so the orientation is an argument here: ``psi`` is an array
-    ``[len(traj), 2]`` of (Re psi_6, Im psi_6) per trajectory frame, or a callable
-    ``frame -> (re, im)``.  Without it the class *raises* instead of silently returning the
-    unrotated function; ``psi=False`` asks for exactly that (no rotation).  Everything else --
-    frame selection, ``ptype`` / ``other``, the keyword arguments of ``pcf2d``, the average -- is
-    the reference's."""
+    Like the reference, every frame is oriented along its mean hexagonal order parameter,
+    ``psi = np.mean(psi_k(frame.coords(), frame.box, k=6))`` (amep/evaluate.py:730-735), computed by
+    ``amep_b200.order.psi6_mean`` (sm_100a kernel).  Extension: ``psi`` may be given -- an array
+    ``[len(traj), 2]`` of (Re psi_6, Im psi_6) per trajectory frame or a callable
+    ``frame -> (re, im)`` -- and ``psi=False`` switches the rotation off."""
 
     def __init__(self, traj, skip: float = 0.0, nav: int = 10, ptype=None, other=None,
                  max_workers=1, psi=None, distributed=None, group=None, **kwargs) -> None:
         super().__init__()
         self.name = "pcf2d"
-        if psi is None:
-            raise NotImplementedError(
-                "amep_b200.evaluate.PCF2d: the psi_6 orientation prologue (amep/evaluate.py:730-735) is a "
-                "next row of the scope table; pass psi=[len(traj), 2] (or a callable frame -> (re, im)), "
-                "or psi=False for no rotation")
         for ignored in ("verbose", "njobs", "chunksize", "pbc"):
             kwargs.pop(ignored, None)
         idx = self._select(traj, skip, nav)
-        nsel = len(idx)
-        lo, hi, ws = _local_block(nsel, distributed, group)
-        g = X = Y = None
-        if hi > lo:
-            coords, box = _gather(traj, idx[lo:hi], ptype)
-            other_coords = None if other is None else _gather(traj, idx[lo:hi], other)[0]
+        sh = _Shard(len(idx), distributed, group)
+        rows = []
+        done = 0
+        for coords, other_coords, box in _frame_batches(traj, idx[sh.lo:sh.hi], ptype, other, other is not None):
+            nf = coords.shape[0]
+            block = np.asarray(idx[sh.lo + done:sh.lo + done + nf])
+            done += nf
             if psi is False:
                 psi_rows = None
+            elif psi is None:
+                # amep/evaluate.py:730-735: psi_6 of *all* particles of the frame
+                if ptype is None:
+                    allc = coords
+                else:
+                    allc = _gather(traj, block, None)[0]
+                from .order import psi6_mean
+                psi_rows = np.array([psi6_mean(_core.to_numpy(allc[f]), box[f] if np.ndim(box) == 3 else box)
+                                     for f in range(nf)], dtype=np.float64)
             elif callable(psi):
-                psi_rows = np.array([np.asarray(psi(f), dtype=np.float64) for f in traj[np.asarray(idx[lo:hi])]])
+                psi_rows = np.array([np.asarray(psi(f), dtype=np.float64) for f in traj[block]])
             else:
-                psi_rows = np.asarray(psi, dtype=np.float64)[np.asarray(idx[lo:hi])]
+                psi_rows = np.asarray(psi, dtype=np.float64)[block]
             # pcf2d zeroes the last column of what it is given in place (amep/spatialcor.py:846-848);
             # in the reference that hits the fresh array frame.coords() returns, here the stacks
             # may be views of the trajectory, so the side effect is switched off
-            g, X, Y = pcf2d_frames(coords, box, other_coords, psi=psi_rows, zero_last_column=False, **kwargs)
-        if ws > 1:
-            if g is None:
-                raise ValueError("PCF2d: more ranks than selected frames")
+            rows.append(pcf2d_frames(coords, box, other_coords, psi=psi_rows, zero_last_column=False, **kwargs))
+        local = None
+        if rows:
+            g, X, Y = (np.concatenate([p[k] for p in rows]) for k in range(3))
             if g.shape[1:] != X.shape[1:]:
                 raise ValueError("PCF2d: nxbins and nybins must be equal (the reference's np.array(results) "
                                  "needs g and the bin-centre grids to have one shape)")
-            local = np.zeros((hi - lo, 3) + g.shape[1:])
-            local[:, 0], local[:, 1], local[:, 2] = g, X, Y
-            table = dist.assemble_rows(local, lo, nsel, group)
-            g, X, Y = table[:, 0], table[:, 1], table[:, 2]
-        res = self._finish(traj, [(g[f], X[f], Y[f]) for f in range(nsel)])
-        self._avg = res[0]
-        self._x = res[1]
-        self._y = res[2]
+            local = np.stack([g, X, Y], axis=1)
+        self._frames = sh.assemble(local)
+        avg = np.mean(self._frames, axis=0)
+        self._avg = avg[0]
+        self._x = avg[1]
+        self._y = avg[2]
 
     @property
     def x(self):
@@ -350,13 +525,5 @@ class PCF2d(_FrameAverage):
         return self._frames
 
     @property
-    def times(self):
-        return self._times
-
-    @property
     def avg(self):
         return self._avg
-
-    @property
-    def indices(self):
-        return self._indices

@@ -62,13 +62,14 @@ def _rdf_normalise(hist, bins, box, n, n_other, dim):
 
 
 def rdf_frames(coords, box_boundary, other_coords=None, nbins=None, rmax=None, mode="diff",
-               pbc=True, return_counts=False, reduce=None):
+               pbc=True, return_counts=False, reduce=None, shard=None):
     """``rdf`` for a batch of frames ``[F, N, 3]`` in one library call.
 
     ``box_boundary``: ``(3,2)`` or ``(F,3,2)``.  Returns ``(g [F, nbins], r [F, nbins])``
     (plus the int64 counts with ``return_counts=True``).  ``reduce`` is an
     optional callable applied to the device/host histogram before the epilogue
-    (the multi-GPU all-reduce hooks in here)."""
+    (the multi-GPU all-reduce hooks in here); ``shard=(index, count)`` evaluates only that
+    share of the query cells of every frame (intra-frame sharding, amepb_rdf_set_shard)."""
     if mode not in ["diff", "kdtree"]:
         raise ValueError(
             f"amep.spatialcor.rdf: Invalid mode '{mode}'. Available modes "
@@ -94,20 +95,42 @@ def rdf_frames(coords, box_boundary, other_coords=None, nbins=None, rmax=None, m
         edges = np.asarray(e, dtype=np.float64)
     if np.any(np.diff(edges, axis=-1) < 0):
         raise ValueError("`bins` must increase monotonically, when an array")
-    hist, dims = _core.rdf_histograms(pc, bb, edges, other=po, pbc=pbc)
+    hist, dims = _core.rdf_histograms(pc, bb, edges, other=po, pbc=pbc, shard=shard)
+    if mode == "kdtree" and pbc:
+        # the reference's kdtree mode counts one minimum-image distance per pair
+        # (amep/pbc.py:632-655), 'diff' every image inside the pbc_points window: the two differ
+        # beyond half the shortest periodic box length
+        lengths = np.broadcast_to(bb[..., 1] - bb[..., 0], (nf, 3))
+        short = min(float(np.min(lengths[f, :max(2, int(dims[f]))])) for f in range(nf)) if nf else np.inf
+        if float(np.max(edges)) > 0.5 * short:
+            _log.warning("amep_b200.spatialcor.rdf: mode='kdtree' is evaluated like mode='diff' (every periodic "
+                         "image inside the pbc_points window); beyond rmax = min(box)/2 = %g the reference's "
+                         "kdtree mode (minimum image only) counts fewer pairs than this result.", 0.5 * short)
     if reduce is not None:
         hist = reduce(hist)
     if _core._is_torch(hist):
         hist = hist.cpu().numpy()
     n, n_other = pc.n, (pc.n if po is None else po.n)
-    g_rows, r_rows = [], []
-    for f in range(nf):
-        b = bb[f] if per_frame_box else bb
-        box = b[:, 1] - b[:, 0]
-        g, r = _rdf_normalise(hist[f], edge_list[f], box, n, n_other, int(dims[f]))
-        g_rows.append(g)
-        r_rows.append(r)
-    g_all, r_all = np.array(g_rows), np.array(r_rows)
+    if not per_frame_box and nf > 0:
+        # one box, one set of edges: the reference's per-frame expression
+        # hist / shell / density / Nother is elementwise, so evaluating it on all rows at once
+        # gives the same bits as the frame loop (tests/test_abi_host.py pins that)
+        box = bb[:, 1] - bb[:, 0]
+        g_all, r_row = _rdf_normalise(hist, e, box, n, n_other, int(dims[0]))
+        for dim in np.unique(dims):   # frames of another dimensionality (rare): their own shells
+            if dim != dims[0]:
+                rows = np.flatnonzero(dims == dim)
+                g_all[rows] = _rdf_normalise(hist[rows], e, box, n, n_other, int(dim))[0]
+        r_all = np.broadcast_to(r_row, (nf, nb)).copy()
+    else:
+        g_rows, r_rows = [], []
+        for f in range(nf):
+            b = bb[f]
+            box = b[:, 1] - b[:, 0]
+            g, r = _rdf_normalise(hist[f], edge_list[f], box, n, n_other, int(dims[f]))
+            g_rows.append(g)
+            r_rows.append(r)
+        g_all, r_all = np.array(g_rows), np.array(r_rows)
     if return_counts:
         return g_all, r_all, hist
     return g_all, r_all
@@ -341,7 +364,8 @@ def _sf2d_fft_frames(pc, po, same, bb, qmax, Ntot, accuracy):
 
 
 def sf2d_frames(coords, box_boundary, other_coords=None, qmax=20.0, njobs=1, mode="std", Ntot=None,
-                accuracy=0.1, chunksize=None, accum="c64", reduce=None, return_modes=False):
+                accuracy=0.1, chunksize=None, accum="c64", reduce=None, return_modes=False,
+                compact_grids=False, verbose=False):
     """``sf2d`` for a batch of frames -> ``(S [F, ny, nx], Qx [F, ny, nx], Qy [F, ny, nx])``.
 
     ``accum='c64'`` reproduces the reference's complex64 running sums (order and
@@ -394,6 +418,9 @@ def sf2d_frames(coords, box_boundary, other_coords=None, qmax=20.0, njobs=1, mod
         qy_rows.append(gy)
     if per_frame_box:
         qx_all, qy_all = np.stack(qx_rows), np.stack(qy_rows)
+    elif compact_grids:
+        # one box: one pair of grids for all frames, ``[1, ny, nx]`` (evaluate.SF2d)
+        qx_all, qy_all = qx_rows[0][None], qy_rows[0][None]
     else:
         qx_all = np.broadcast_to(qx_rows[0], (nf,) + qx_rows[0].shape).copy()
         qy_all = np.broadcast_to(qy_rows[0], (nf,) + qy_rows[0].shape).copy()

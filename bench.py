@@ -5,7 +5,7 @@
     python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host cores
 
 A *step* is one pass of the hot path over one batch of synthetic frames.
-Workload at every N (weak scaling, frames sharded over ranks, one NCCL
+Headline workload at every N (weak scaling, frames sharded over ranks, one NCCL
 all-reduce of the per-frame histograms): BASELINE.json configs[1], "2D active
 Brownian particles, 1M particles, RDF rmax=10 sigma, nbins=500" -- uniform
 positions at packing fraction 0.5 (rho = 0.6366, L = 1253.3), `--frames` frames
@@ -15,16 +15,20 @@ repeated).
 One JSON line on stdout (rank 0):
   value      in-range ordered pair evaluations per second (sum of all histogram
              counts / time), inputs resident in HBM, all ranks, all-reduce included
-  e2e        the same metric through the C ABI with HOST (pinned) buffers:
-             host->device copies of the coordinates and device->host of the
-             histograms inside the timed region
+  e2e        the same metric through the public API, evaluate.RDF(trajectory over PINNED
+             HOST arrays): host->device copies of every frame, kernels, device->host of the
+             histograms, the NumPy normalisation and the frame average inside the timed region
   roofline   the pair kernel (dominant launch): algorithmic flops (5 per in-range
              2D pair: 2 SUB, 2 MUL, 1 ADD -- SURVEY.md 8d) over its CUDA-event time,
-             against the FP32 non-FMA instruction peak measured by tools/microbench
+             against the FP32 FFMA peak measured by tools/microbench (`frac`); the
+             non-fused FMUL+FADD rate the bit-exact arithmetic is limited to is `frac_unfused`
   cpu_baseline  the C restatement of the reference algorithm (oracle/rdf_oracle.c,
              brute force over all periodic images like amep/spatialcor.py:348-388)
              on the host cores, on a bounded sample of the same frame
-  sq         S(q) particle*q terms per second for sfiso(mode='fast') and sf2d(mode='std')
+  strong     BASELINE.json configs[4]: 3D uniform 16.7M particles, 64 frames in total split
+             over the N ranks (strong scaling), RDF rmax=10, one all-reduce of the histograms
+  sq         S(q) particle*q terms per second for sfiso(mode='fast') and sf2d(mode='std'), each
+             with the FP64-pipe roofline of its kernel and a CPU baseline (C oracle, host cores)
 """
 import argparse
 import json
@@ -57,7 +61,11 @@ def parse_args():
     ap.add_argument("--impl", default="amep_b200", choices=["amep_b200", "reference"])
     ap.add_argument("--particles", type=int, default=1_000_000)
     ap.add_argument("--frames", type=int, default=1000, help="frames per GPU and step")
-    ap.add_argument("--e2e-frames", type=int, default=256, help="frames per GPU of the host-buffer leg")
+    ap.add_argument("--e2e-frames", type=int, default=0,
+                    help="frames per GPU of the end-to-end leg (0 = all --frames, bounded by host memory)")
+    ap.add_argument("--strong-frames", type=int, default=64, help="total frames of the strong-scaling section")
+    ap.add_argument("--strong-particles", type=int, default=1 << 24)
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling section (configs[4])")
     ap.add_argument("--cpu-queries", type=int, default=0, help="query sample of the CPU baseline (0 = auto)")
     ap.add_argument("--no-sq", action="store_true", help="skip the S(q) section")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline")
@@ -291,15 +299,48 @@ def run_gpu(args):
     pairs_local = int(local_rows.sum().item()) if world == 1 else int(table[rank * nf:(rank + 1) * nf].sum().item())
     value = total_pairs * args.steps / (elapsed_ms * 1e-3)
 
-    # ---- e2e: host (pinned) buffers through the C ABI ----------------------------------
-    ef = max(1, min(args.e2e_frames, nf))
-    host = torch.empty((ef, n, 3), dtype=torch.float32).pin_memory()
+    # ---- e2e: the public API, evaluate.RDF over a trajectory of PINNED HOST arrays ------------
+    # Every rank holds its own block of a global trajectory (ShardView); evaluate.RDF selects all
+    # frames, takes this rank's contiguous block, streams it host -> device through the library's
+    # staging pipeline, reads the histograms back, normalises, assembles the rows of all ranks
+    # with one all-reduce and averages -- all inside the timed region.
+    import amep_b200
+    ef = nf if args.e2e_frames <= 0 else max(1, min(args.e2e_frames, nf))
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+        # all ranks of this node pin memory at the same time: stay below a third of what is free
+        ef = int(max(1, min(ef, avail / 3 / max(1, world) // (n * 12))))
+    except Exception:
+        pass
+    host = torch.empty((ef, n, 3), dtype=torch.float32, pin_memory=True)
     host.copy_(coords[:ef])
+    torch.cuda.synchronize()
     host_np = host.numpy()
-    hist_host = torch.empty((ef, NBINS), dtype=torch.int64).pin_memory()
-    hist_np = hist_host.numpy()
+
+    class ShardView(amep_b200.TensorTrajectory):
+        """Global trajectory of ef * world frames of which this process holds [rank*ef, (rank+1)*ef)."""
+
+        def __init__(self):
+            super().__init__(host_np, box)
+            self.steps = np.arange(ef * world)
+            self.times = self.steps.astype(float)
+
+        def __len__(self):
+            return ef * world
+
+        def stack(self, indices, ptype=None):
+            idx = np.asarray(indices) - rank * ef
+            assert len(idx) == 0 or (idx[0] >= 0 and idx[-1] < ef), "frame outside this rank's block"
+            return super().stack(idx, ptype)
+
+    traj = ShardView()
+
+    def e2e_step():
+        return amep_b200.evaluate.RDF(traj, skip=0.0, nav=ef * world, rmax=RMAX, nbins=NBINS)
+
     for _ in range(2):
-        _core.rdf_histograms(host_np, box, edges, out=hist_np, device=local)
+        ev = e2e_step()
     # raw pinned host->device copy rate of the same buffer (the floor of any host-buffer path)
     scratch = torch.empty_like(coords[:ef])
     torch.cuda.synchronize()
@@ -309,6 +350,16 @@ def run_gpu(args):
     h1.record()
     torch.cuda.synchronize()
     h2d_gbs = host.numel() * 4 / (h0.elapsed_time(h1) * 1e-3) / 1e9
+    # the same with every rank copying at once: what the platform gives N concurrent streams
+    barrier()
+    h0.record()
+    scratch.copy_(host, non_blocking=True)
+    h1.record()
+    torch.cuda.synchronize()
+    tcc = torch.tensor([h0.elapsed_time(h1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tcc, op=dist.ReduceOp.MAX)
+    h2d_gbs_concurrent = host.numel() * 4 / (float(tcc.item()) * 1e-3) / 1e9
     del scratch
     barrier()
     t0 = time.perf_counter()
@@ -316,23 +367,31 @@ def run_gpu(args):
     e2e_step_ms = []
     for _ in range(e2e_steps):
         ts = time.perf_counter()
-        _core.rdf_histograms(host_np, box, edges, out=hist_np, device=local)   # returns when hist_np is complete
+        ev = e2e_step()               # returns when frames / avg are complete on the host
         e2e_step_ms.append(round((time.perf_counter() - ts) * 1e3, 3))
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-    pe = torch.tensor([float(hist_np.sum())], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        dist.all_reduce(pe, op=dist.ReduceOp.SUM)
-    e2e_value = float(pe.item()) * e2e_steps / float(te.item())
-    np.testing.assert_array_equal(hist_np, local_rows[:ef].cpu().numpy())   # both paths agree bit for bit
-    del host, hist_host
+    e2e_pairs = float(ev.counts.sum())                      # all ranks' frames (assembled table)
+    e2e_value = e2e_pairs * e2e_steps / float(te.item())
+    # both paths agree bit for bit
+    np.testing.assert_array_equal(ev.counts[rank * ef:(rank + 1) * ef], local_rows[:ef].cpu().numpy())
+    e2e_floor_s = ef * n * 12 / (h2d_gbs_concurrent * 1e9)
+    del host, traj, ev
+
+    del coords, table
+    torch.cuda.empty_cache()
+    # ---- strong scaling: BASELINE.json configs[4] ----------------------------------------
+    strong = None
+    if not args.no_strong:
+        strong = strong_section(args, torch, dist, _core, ctx, dev, world, rank, barrier)
 
     # ---- S(q) ------------------------------------------------------------------------
     sq = None
     if not args.no_sq:
-        sq = sq_section(torch, dist, _core, ctx, dev, world, rank)
+        sq = sq_section(args, torch, dist, _core, ctx, dev, world, rank, peaks_file())
 
     if rank != 0:
         if world > 1:
@@ -340,31 +399,39 @@ def run_gpu(args):
         return
 
     # ---- roofline of the pair kernel -----------------------------------------------------
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "profiles", "microbench_r01.json")))
-    except Exception:
-        pass
-    fp32_peak = float(peaks.get("fp32_mul_add_unfused_tflops", 35.9))   # TFLOP/s, 1 flop per instruction
+    peaks = peaks_file()
+    ffma_peak = float(peaks.get("fp32_ffma_tflops", 69.2))                 # TFLOP/s, 2 flops per FFMA
+    unfused_peak = float(peaks.get("fp32_mul_add_unfused_tflops", 35.9))   # TFLOP/s, 1 flop per instruction
     launches_pair = args.steps * info["sub_batches"]
     pair_ms_avg = pair_ms / max(1, launches_pair)
     achieved = pairs_local * args.steps * FLOPS_PER_PAIR_2D / (pair_ms * 1e-3) / 1e12 if pair_ms > 0 else 0.0
     roofline = {
         "bound": "fp32",
         "kernel": "amepb::pair_kernel<float,float,2,true,true> (float32 regime, z constant, shared tables, symmetric walk)",
-        "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
-        "peak_source": "tools/microbench.cu on this pool's B200 (profiles/microbench_r01.json): FP32 FMUL+FADD "
-                       "(non-fused, the bit-exact path may not contract) instruction throughput; "
-                       "MEASURED_PEAKS.json has no CUDA-core peak",
+        "achieved": achieved, "peak": ffma_peak, "unit": "TFLOP/s", "frac": achieved / ffma_peak,
+        "peak_source": "FP32 FFMA throughput measured with tools/microbench.cu on this pool's B200 "
+                       "(profiles/microbench_r01.json; theoretical 148 SM x 128 x 2 x 1.965 GHz = 74.5); "
+                       "MEASURED_PEAKS.json has no CUDA-core peak (SURVEY.md 8d)",
+        "frac_unfused": achieved / unfused_peak, "peak_unfused": unfused_peak,
+        "peak_unfused_note": "FMUL+FADD instruction rate: the bit-exact arithmetic (every product rounded, no "
+                             "contraction) cannot use FFMA for the distance itself",
         "flops_per_unit": FLOPS_PER_PAIR_2D, "units_per_launch": pairs_local / max(1, info["sub_batches"]),
         "avg_launch_ms": pair_ms_avg, "share_of_step": pair_ms / elapsed_ms,
         "candidate_pairs_per_s": info["candidate_pairs"] * args.steps / (pair_ms * 1e-3) if pair_ms > 0 else 0.0,
         "traffic": (peaks["pair_kernel_dram_bytes_per_frame"] * nf / max(1, info["sub_batches"])
                     if "pair_kernel_dram_bytes_per_frame" in peaks else None),
         "traffic_source": peaks.get("pair_kernel_dram_source"),
-        "hbm_gbs_peak": json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs")
-        if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0,
+        "hbm_gbs_peak": hbm_peak(),
+        "cell_build": {
+            "bound": "hbm", "unit": "GB/s", "peak": hbm_peak(),
+            "algorithmic_bytes_per_frame": 28 * n + 4 * info["cells"] / max(1, info["frames"]),
+            "ms_per_frame": build_ms / args.steps / nf,
+            "achieved": (28 * n + 4 * info["cells"] / max(1, info["frames"])) / (build_ms / args.steps / nf * 1e-3) / 1e9
+            if build_ms > 0 else None,
+            "note": "stats + count + scan + fill; 28 B/particle + 4 B/cell (SURVEY.md 8d)"},
     }
+    if roofline["cell_build"]["achieved"]:
+        roofline["cell_build"]["frac"] = roofline["cell_build"]["achieved"] / hbm_peak()
 
     cpu = None
     if not args.no_cpu and world == 1:
@@ -384,20 +451,153 @@ def run_gpu(args):
         "config": workload_config(args, world),
         "e2e": {"value": e2e_value, "unit": "pair-evals/s", "h2d_bytes_per_step": ef * n * 12 * world,
                 "d2h_bytes_per_step": ef * NBINS * 8 * world, "frames_per_gpu": ef,
-                "pinned_h2d_copy_gbs": h2d_gbs,
-                "h2d_floor_ms_per_frame": n * 12 / (h2d_gbs * 1e9) * 1e3, "step_ms": e2e_step_ms},
+                "api": "amep_b200.evaluate.RDF(TensorTrajectory over pinned host arrays, nav=all frames): H2D of "
+                       "every frame, kernels, D2H of the histograms, NumPy normalisation, all-reduce of the rows, "
+                       "frame average",
+                "pinned_h2d_copy_gbs": h2d_gbs, "pinned_h2d_copy_gbs_all_ranks_at_once": h2d_gbs_concurrent,
+                "h2d_floor_ms_per_frame": n * 12 / (h2d_gbs * 1e9) * 1e3,
+                "platform_floor": {"value": e2e_pairs / max(e2e_floor_s, 1e-9), "unit": "pair-evals/s",
+                                   "note": "pairs / time of the bare pinned H2D copies of the same frames with all "
+                                           "ranks copying concurrently (no kernel, no epilogue)"},
+                "frac_of_platform_floor": e2e_value / (e2e_pairs / max(e2e_floor_s, 1e-9)),
+                "step_ms": e2e_step_ms},
         "gpu_launches": int(agg[0].item()),
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
         "ms_per_frame": elapsed_ms / args.steps / nf, "pair_kernel_ms_per_frame": pair_ms / args.steps / nf,
         "build_ms_per_frame": build_ms / args.steps / nf,
-        "cells_per_cutoff": info["cells_per_cutoff"], "sq": sq,
+        "cells_per_cutoff": info["cells_per_cutoff"], "strong": strong, "sq": sq,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def sq_section(torch, dist, _core, ctx, dev, world, rank):
+def peaks_file():
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "microbench_r01.json")))
+    except Exception:
+        return {}
+
+
+def hbm_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6650.0   # fallback of /opt/skills/guides/B200_PROFILING.md
+
+
+def strong_section(args, torch, dist, _core, ctx, dev, world, rank, barrier):
+    """BASELINE.json configs[4]: 3D uniform rho = 0.8, 2^24 particles, 64 frames in total, RDF rmax = 10,
+    nbins = 500.  The frames are split over the ranks (contiguous blocks; fewer frames than ranks
+    would shard inside the frame), one all-reduce of the [64, 500] histogram table per step."""
+    from amep_b200 import dist as adist
+    n, total = args.strong_particles, args.strong_frames
+    rho = 0.8
+    L = float((n / rho) ** (1.0 / 3.0))
+    box = np.array([[0, L], [0, L], [0, L]], dtype=np.float32)
+    edges = np.linspace(0.0, RMAX, NBINS + 1)
+    intra = total < world
+    lo, hi = (0, total) if intra else adist.shard_bounds(total, rank, world)
+    nloc = hi - lo
+    coords = torch.empty((max(nloc, 1), n, 3), device=dev, dtype=torch.float32)
+    for f in range(nloc):      # frame f of the global trajectory has the same content on any rank count
+        gen = torch.Generator(device=dev).manual_seed(50_000 + lo + f)
+        coords[f] = (torch.rand((n, 3), generator=gen, device=dev, dtype=torch.float64) * L).float()
+    table = torch.zeros((total, NBINS), dtype=torch.int64, device=dev)
+    rows = table[lo:hi]
+
+    def step():
+        if world > 1:
+            table.zero_()
+        if nloc:
+            _core.rdf_histograms(coords[:nloc], box, edges, out=rows, shard=(rank, world) if intra else None)
+        if world > 1:
+            dist.all_reduce(table, op=dist.ReduceOp.SUM)
+
+    steps, warm = max(1, min(args.steps, 3)), 1
+    for _ in range(warm):
+        step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pair_ms = build_ms = 0.0
+    e0.record()
+    for _ in range(steps):
+        step()
+        if nloc:
+            info = ctx.rdf_info()
+            pair_ms += info["pair_kernel_ms"]
+            build_ms += info["build_ms"]
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    pairs = int(table.sum().item())
+    checksum = int((table.sum(dim=0) * torch.arange(1, NBINS + 1, device=dev)).sum().item() % (1 << 61))
+    expect = total * n * rho * 4.0 / 3.0 * np.pi * RMAX ** 3
+    out = {"workload": f"BASELINE.json configs[4]: 3D uniform rho=0.8, N={n}, {total} frames in total split over "
+                       f"{world} GPU(s), RDF rmax=10, nbins=500, float32 regime",
+           "scaling": "strong", "value": pairs / (ms * 1e-3), "unit": "pair-evals/s", "ms_per_step": ms,
+           "steps": steps, "warmup": warm, "frames_total": total, "frames_this_rank": nloc,
+           "pairs_per_step": pairs, "ideal_gas_expectation": expect, "rel_dev_from_ideal_gas": (pairs - expect) / expect,
+           "histogram_checksum": checksum,
+           "pair_kernel_ms_per_frame_rank0": pair_ms / steps / max(1, nloc), "build_ms_per_frame_rank0": build_ms / steps / max(1, nloc),
+           "flops_per_pair": 8,
+           "pair_kernel_tflops_rank0": (pairs / total * nloc * 8 / (pair_ms / steps * 1e-3) / 1e12) if pair_ms > 0 else None}
+    del coords, table
+    torch.cuda.empty_cache()
+    return out
+
+
+def sq_cpu_baselines(threads):
+    """The reference's S(q) inner loops (C restatement in oracle/rdf_oracle.c) on the host cores, on
+    bounded samples: __sf2d_chunk_std (amep/spatialcor.py:1690-1719, complex64 running sums) on a
+    slice of the configs[3] grid, and __sf_iso_chunk_fast (amep/spatialcor.py:1402-1448) on one
+    direction of the 3D case."""
+    import ctypes
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import c_oracle as corc
+    out = {}
+    rng = np.random.default_rng(4)
+    # sf2d: 65 536 particles of configs[3] against a slice of the 512 x 512 grid
+    n, L = 65_536, 512.0
+    c = np.zeros((n, 3), dtype=np.float32)
+    c[:, :2] = rng.uniform(0, L, (n, 2)).astype(np.float32)
+    box = np.array([[0, L], [0, L], [-0.5, 0.5]], dtype=np.float32)
+    qmax = 256.5 * 2 * np.pi / 512.0
+    npts = 512 * threads
+    t0 = time.perf_counter()
+    corc.sf2d_modes(c, box, qmax, 715, nthreads=threads, grid_slice=(0, npts))
+    dt = time.perf_counter() - t0
+    if dt < 3.0:     # aim at a few seconds
+        npts = int(min(512 * 512, npts * 4.0 / max(dt, 1e-3)))
+        npts = max(threads, npts // threads * threads)
+        t0 = time.perf_counter()
+        corc.sf2d_modes(c, box, qmax, 715, nthreads=threads, grid_slice=(0, npts))
+        dt = time.perf_counter() - t0
+    out["sf2d_std"] = {"value": n * npts / dt, "unit": "particle*q terms/s", "cores": threads, "kind": "port",
+                       "sample": f"{n} particles x {npts} points of the 512x512 grid of configs[3], complex64 running sums "
+                                 f"in the reference's order (sincos in float64 per term), {dt:.1f} s"}
+    # sfiso fast: one direction, 544 q values, 3D
+    n3 = 262_144
+    L3 = float((n3 / 0.8) ** (1 / 3))
+    c3 = rng.uniform(0, L3, (n3, 3)).astype(np.float32)
+    q = np.ascontiguousarray(np.arange(1, 545) * (2 * np.pi / 171.0))
+    u = np.ascontiguousarray(np.array([0.6, 0.0, 0.8]))
+    sums = np.empty((len(q), 2))
+    dp = ctypes.POINTER(ctypes.c_double)
+    t0 = time.perf_counter()
+    corc.lib().oracle_sfiso_sums(c3.ctypes.data, 0, n3, u.ctypes.data_as(dp), q.ctypes.data_as(dp), len(q),
+                                 sums.ctypes.data_as(dp), threads)
+    dt = time.perf_counter() - t0
+    out["sfiso_fast"] = {"value": n3 * len(q) / dt, "unit": "particle*q terms/s", "cores": threads, "kind": "port",
+                         "sample": f"{n3} particles x {len(q)} q values x 1 direction (float64 cos and sin per term, as "
+                                   f"amep/spatialcor.py:1440-1444), {dt:.1f} s"}
+    return out
+
+
+def sq_section(args, torch, dist, _core, ctx, dev, world, rank, peaks):
     """S(q) throughput: particle*q terms per second, reference-equivalent term counts
     (SURVEY.md 8d): sfiso fast = N * nq * n_directions; sf2d = N * nx * ny."""
     from amep_b200 import spatialcor as sc
@@ -433,9 +633,23 @@ def sq_section(torch, dist, _core, ctx, dev, world, rank):
         res["s"], res["q"] = sc.sfiso_frames(c3, box3, None, qmax=20.0, twod=False, mode="fast", num=8)
     ms = timed(run_sfiso)
     nq = res["q"].shape[1]
+    dfma_instr_peak = float(peaks.get("fp64_dfma_tflops", 33.9)) / 2 * 1e12     # FP64-pipe instructions per second
+
+    def fp64_roofline(kernel, instr, kernel_ms, what):
+        rate = instr / (kernel_ms * 1e-3) if kernel_ms > 0 else 0.0
+        return {"bound": "fp64 pipe", "kernel": kernel, "achieved": rate / 1e12, "peak": dfma_instr_peak / 1e12,
+                "unit": "T FP64-pipe instructions/s", "frac": rate / dfma_instr_peak, "instructions_per_launch_set": instr,
+                "counted": what, "kernel_ms": kernel_ms,
+                "peak_source": "DFMA rate measured with tools/microbench.cu (profiles/microbench_r01.json: "
+                               "33.9 TFLOP/s = 16.9 T DFMA/s; theoretical 148 x 64 x 1.965 GHz = 18.6 T/s)"}
+
+    kms = ctx.last_kernel_ms()
     out["sfiso_fast"] = {"workload": f"3D uniform rho=0.8, N={n3}, qmax=20, num=8 (nq={nq}, 32 directions, 13 unique), {nf3} frames per GPU",
-                         "terms_per_s": nf3 * n3 * nq * 32 * world / (ms * 1e-3), "ms": ms, "kernel_ms": ctx.last_kernel_ms(),
-                         "unique_terms_per_s": nf3 * n3 * nq * 13 * world / (ms * 1e-3), "dtype": "f64"}
+                         "terms_per_s": nf3 * n3 * nq * 32 * world / (ms * 1e-3), "ms": ms, "kernel_ms": kms,
+                         "unique_terms_per_s": nf3 * n3 * nq * 13 * world / (ms * 1e-3), "dtype": "f64",
+                         "roofline": fp64_roofline("amepb::harmonics_kernel<float>", nf3 * n3 * nq * 13 * 4.0, kms,
+                                                   "2 DFMA + 2 DADD per (particle, harmonic, unique direction): Chebyshev "
+                                                   "recurrence for cos and sin")}
     del c3
     # sf2d(mode='std'), configs[3]: 256k particles, 512 x 512 q grid
     n2, L2, nf2 = 262_144, 512.0, 8
@@ -448,11 +662,20 @@ def sq_section(torch, dist, _core, ctx, dev, world, rank):
             res["s2"] = sc.sf2d_frames(c2, box2, qmax=qmax2, accum=accum)[0]
         ms = timed(run_sf2d, reps=2)
         g = res["s2"].shape[1]
+        kms = ctx.last_kernel_ms()
+        per_point = 2.0 if accum == "c64" else 1.0
         out["sf2d_std_" + accum] = {
             "workload": f"configs[3]: 2D uniform N={n2}, {g}x{g} q grid, {nf2} frames per GPU, "
                         + ("complex64 accumulation in the reference's order" if accum == "c64" else "float64 accumulation"),
-            "terms_per_s": nf2 * n2 * g * g * world / (ms * 1e-3), "ms": ms, "kernel_ms": ctx.last_kernel_ms(),
-            "dtype": "f64 (rounded to f32 per add)" if accum == "c64" else "f64"}
+            "terms_per_s": nf2 * n2 * g * g * world / (ms * 1e-3), "ms": ms, "kernel_ms": kms,
+            "dtype": "f64 (rounded to f32 per add)" if accum == "c64" else "f64",
+            "roofline": fp64_roofline("amepb::sf2d_c64_kernel<float>" if accum == "c64" else "amepb::sf2d_f64_kernel<float>",
+                                      nf2 * n2 * g * g * per_point, kms,
+                                      "8 DFMA per particle and quadruple of grid points (+-qx, +-qy) = 2 per grid point: every "
+                                      "running sum is rounded to float32 after each term, so real and imaginary parts of both "
+                                      "sign combinations are separate chains" if accum == "c64" else
+                                      "4 DFMA per particle and quadruple of grid points = 1 per grid point (separable "
+                                      "cos/sin products; SURVEY's 8 flops per unique term overstate this formulation)")}
     del c2
     # pcf2d (widened row): 2D, density 1, 500 x 500 grid; the reference's default
     # window (half of all pairs bin) with an orientation, and a narrow window.  Never allowed to
@@ -487,6 +710,12 @@ def sq_section(torch, dist, _core, ctx, dev, world, rank):
                 "ms": ms, "dtype": "f32 differences, exact np.histogram2d binning"}
     except Exception as exc:  # noqa: BLE001
         out["pcf2d"] = {"error": repr(exc)}
+    if world == 1 and rank == 0 and not args.no_cpu:
+        try:
+            threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+            out["cpu_baseline"] = sq_cpu_baselines(threads)
+        except Exception as exc:  # noqa: BLE001
+            out["cpu_baseline"] = {"error": repr(exc)}
     return out
 
 

@@ -146,6 +146,14 @@ int amepb_rdf_set_cells_per_cutoff(amepb_ctx* ctx, int k);
  * The counts are identical either way. */
 int amepb_rdf_set_symmetric(amepb_ctx* ctx, int enable);
 
+/* Intra-frame sharding (default 0 of 1): later amepb_rdf_batch calls on this context evaluate only
+ * the scheduling units (runs of query cells) u with u % count == index.  Every in-range pair
+ * belongs to exactly one unit, so the uint64 histograms of the `count` shards of the same call
+ * -- one per GPU, each holding a copy of the frames -- add up to the full histogram exactly.
+ * This is the split the reference makes over query chunks inside one frame
+ * (amep/spatialcor.py:587-600), used when there are fewer frames than GPUs. */
+int amepb_rdf_set_shard(amepb_ctx* ctx, int index, int count);
+
 /*
  * Harmonic density modes along given wave vectors:
  *   out[f][d][h] = ( sum_i cos((h+1) k_d . r_i),  sum_i sin((h+1) k_d . r_i) )

@@ -29,18 +29,49 @@ def _free_port():
 
 
 def _oracle_rdf_frames(coords, box, other_coords=None, nbins=None, rmax=None, mode="diff", pbc=True,
-                       return_counts=False, reduce=None):
+                       return_counts=False, reduce=None, shard=None):
+    """Stand-in for spatialcor.rdf_frames on the CPU oracle.  ``shard=(i, c)`` keeps every c-th query
+    (the library deals out query cell runs instead; either way the shares add up to the full
+    histogram), ``reduce`` is applied to the counts before the normalisation."""
     import amep_oracle as orc
     coords = np.asarray(coords)
-    g_rows, r_rows, h_rows = [], [], []
+    h_rows, e_rows = [], []
     for f in range(coords.shape[0]):
         b = box[f] if np.ndim(box) == 3 else box
         o = None if other_coords is None else np.asarray(other_coords)[f]
+        if shard is not None:
+            o = (coords[f] if o is None else o)[shard[0]::shard[1]]
         hist, edges = orc.rdf_counts(coords[f], b, o, nbins=nbins, rmax=rmax, pbc=pbc)
-        g, r = orc.rdf_normalise(hist, edges, coords[f], b, len(coords[f]) if o is None else len(o))
-        g_rows.append(g), r_rows.append(r), h_rows.append(hist)
+        h_rows.append(hist), e_rows.append(edges)
+    hists = np.array(h_rows)
+    if reduce is not None:
+        hists = reduce(hists)
+    g_rows, r_rows = [], []
+    for f in range(coords.shape[0]):
+        b = box[f] if np.ndim(box) == 3 else box
+        nq = len(coords[f]) if other_coords is None else len(np.asarray(other_coords)[f])
+        g, r = orc.rdf_normalise(hists[f], e_rows[f], coords[f], b, nq)
+        g_rows.append(g), r_rows.append(r)
     out = (np.array(g_rows), np.array(r_rows))
-    return out + (np.array(h_rows),) if return_counts else out
+    return out + (hists,) if return_counts else out
+
+
+def _oracle_sfiso_frames(coords, box, N=None, qmax=20.0, twod=True, mode="fast", other_coords=None,
+                         accuracy=0.5, num=8, reduce=None):
+    import amep_oracle as orc
+    coords = np.asarray(coords)
+    rows = [orc.sfiso_fast(coords[f], box, qmax=qmax, twod=twod, num=num) for f in range(coords.shape[0])]
+    return np.array([r[0] for r in rows]), np.array([r[1] for r in rows])
+
+
+def _oracle_sf2d_frames(coords, box, other_coords=None, qmax=20.0, compact_grids=False, **kw):
+    import amep_oracle as orc
+    coords = np.asarray(coords)
+    rows = [orc.sf2d_std(coords[f], box, qmax=qmax) for f in range(coords.shape[0])]
+    s = np.array([r[0] for r in rows])
+    if compact_grids:
+        return s, rows[0][1][None], rows[0][2][None]
+    return s, np.array([r[1] for r in rows]), np.array([r[2] for r in rows])
 
 
 def _oracle_pcf2d_frames(coords, box, other_coords=None, nxbins=None, nybins=None, rmax=None, psi=None,
@@ -82,10 +113,28 @@ def _worker(rank, world, port, tmpdir):
     assert np.array_equal(ev.indices, z["indices"])
     assert np.array_equal(ev.frames, z["frames"])
     assert np.array_equal(ev.avg, z["avg"][0]) and np.array_equal(ev.r, z["avg"][1])
-    # more ranks than work for one of them: nav=1
+    # fewer frames than ranks (nav=1): the frame is sharded *inside* (every rank a share of the
+    # queries, integer histograms summed before the normalisation) -- same bits as one rank
     ev1 = evaluate.RDF(traj, skip=0.0, nav=1, nbins=50)
-    solo, _ = _oracle_rdf_frames(z["coords"][ev1.indices], z["box"], nbins=50)
-    assert np.array_equal(ev1.avg, solo[0])
+    solo, _, solo_counts = _oracle_rdf_frames(z["coords"][ev1.indices], z["box"], nbins=50, return_counts=True)
+    assert np.array_equal(ev1.avg, solo[0]) and np.array_equal(ev1.counts, solo_counts)
+    # (2b) SFiso / SF2d: contiguous frame blocks, rows assembled by one all-reduce; with nav=1 one
+    # rank has no frame at all and must neither raise nor leave the other waiting
+    evaluate.sfiso_frames = _oracle_sfiso_frames
+    evaluate.sf2d_frames = _oracle_sf2d_frames
+    small = amep_b200.TensorTrajectory(z["coords"][:, :200], z["box"])
+    for nav in (3, 1):
+        es = evaluate.SFiso(small, skip=0.0, nav=nav, qmax=2.0, num=4)
+        rows = [_oracle_sfiso_frames(z["coords"][i:i + 1, :200], z["box"], qmax=2.0, num=4) for i in es.indices]
+        want = np.array([(r[0][0], r[1][0]) for r in rows])
+        assert np.array_equal(es.frames, want) and np.array_equal(es.avg, np.mean(want, axis=0)[0])
+        e2 = evaluate.SF2d(small, skip=0.0, nav=nav, qmax=1.0, rotate=False)
+        rows = [_oracle_sf2d_frames(z["coords"][i:i + 1, :200], z["box"], qmax=1.0) for i in e2.indices]
+        want = np.array([(r[0][0], r[1][0], r[2][0]) for r in rows])
+        mean = np.mean(want, axis=0)
+        assert np.allclose(e2.avg, mean[0], rtol=1e-13, atol=0)          # partial sums per rank: last-bit freedom
+        assert np.array_equal(e2.qx, mean[1]) and np.array_equal(e2.qy, mean[2])
+        assert np.array_equal(e2.frames, want)                            # gathered on demand, exact
     # (3) evaluate.PCF2d: frames sharded, one all-reduce, average as average_func does
     evaluate.pcf2d_frames = _oracle_pcf2d_frames
     rng = np.random.default_rng(77)

@@ -461,3 +461,55 @@ def test_evaluate_rdf_particle_types_and_cross(sc):
         rows = [orc.rdf(coords[i][types == 1], box, coords[i][types == 2], rmax=4.0, nbins=80) for i in idx]
         np.testing.assert_array_equal(ev.frames, np.array(rows))
         np.testing.assert_array_equal(ev.avg, np.mean(np.array(rows), axis=0)[0])
+
+
+def test_single_target_particle_with_z_images(sc):
+    """One target particle is three-dimensional for dimension() (amep/utils.py:1650-1651), so its
+    images are shifted along z as well; with z constant in both sets the z-constant fast path must
+    not be taken: images at z +- Lz count at sqrt(dxy^2 + Lz^2)."""
+    rng = np.random.default_rng(61)
+    for dtype in (np.float32, np.float64):
+        box = np.array([[0, 9], [0, 9], [0, 4]], dtype=dtype)
+        tracer = np.array([[4.5, 4.0, 0.7]], dtype=dtype)          # z off the box centre
+        bath = rng.uniform(0, 9, (500, 3)).astype(dtype)
+        bath[:, 2] = 0.7                                            # constant z in the query set too
+        for rmax in (4.4, 6.5):                                     # below and above Lz
+            want, _ = orc.rdf_counts(tracer, box, bath, rmax=rmax, nbins=60)
+            _, _, counts = sc.rdf_frames(tracer, box, bath, rmax=rmax, nbins=60, return_counts=True)
+            np.testing.assert_array_equal(counts[0], want)
+            assert want.sum() > 0
+
+
+def test_back_to_back_calls_do_not_clobber_the_parameter_block(sc, monkeypatch):
+    """The pinned parameter block of a context is shared by asynchronous consumers (plans and
+    thresholds of the RDF sub-batches, k / q tables of the S(q) calls).  Device-space calls return
+    without synchronising; a following call must not overwrite parameters that are still queued
+    behind earlier work.  A long kernel keeps the stream busy while RDF (several
+    sub-batches) and sq_harmonics calls with different tables are issued back to back."""
+    from amep_b200 import _core
+    rng = np.random.default_rng(62)
+    nf, n, L = 12, 4000, 30.0
+    box = np.array([[0, L], [0, L], [0, L]], dtype=np.float32)
+    c = torch.from_numpy(rng.uniform(0, L, (nf, n, 3)).astype(np.float32)).cuda()
+    edges_a, edges_b = np.linspace(0.0, 3.0, 101), np.linspace(0.0, 2.0, 81)
+    kv_a = np.array([[0.21, 0.0, 0.0], [0.0, 0.4, 0.1]])
+    kv_b = np.array([[0.05, 0.3, 0.0], [0.3, 0.1, 0.2]])
+    # references: every call alone, synchronised
+    ref = {}
+    ref["ra"] = _core.rdf_histograms(c, box, edges_a)[0].cpu()
+    ref["rb"] = _core.rdf_histograms(c, box, edges_b)[0].cpu()
+    ref["ha"] = _core.sq_harmonics(c, kv_a, 40).cpu()
+    ref["hb"] = _core.sq_harmonics(c, kv_b, 40).cpu()
+    torch.cuda.synchronize()
+    monkeypatch.setenv("AMEPB_MAX_FRAMES", "4")          # three sub-batches per RDF call
+    busy = torch.empty((8192, 8192), device="cuda")
+    for _ in range(3):
+        for _ in range(6):
+            busy = (busy @ busy).clamp_(-1, 1)           # ~tens of ms of queued work ahead of the calls
+        ra = _core.rdf_histograms(c, box, edges_a)[0]
+        ha = _core.sq_harmonics(c, kv_a, 40)
+        rb = _core.rdf_histograms(c, box, edges_b)[0]
+        hb = _core.sq_harmonics(c, kv_b, 40)
+        torch.cuda.synchronize()
+        assert torch.equal(ra.cpu(), ref["ra"]) and torch.equal(rb.cpu(), ref["rb"])
+        assert torch.equal(ha.cpu(), ref["ha"]) and torch.equal(hb.cpu(), ref["hb"])
