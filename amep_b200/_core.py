@@ -414,3 +414,75 @@ def sf2d_modes(coords, qpos, nq, accum="c64", chunksize=0, device=None):
         ctypes.c_void_p(optr), _stream_for(dev_index, pc.on_device))
     ctx.check(rc, "amepb_sf2d_modes")
     return out
+
+
+def psi_k(coords, box_boundary, k=6, want_neighbors=False, device=None):
+    """``amep.order.psi_k`` of one 2D frame (amepb_psi_k) -> complex array ``[n]`` (complex64 for
+    float32 coordinates, like NumPy's arithmetic in the reference), optionally the neighbour ids
+    ``[n, k]``.  Raises ValueError where the reference does: a particle with an image of itself
+    among its neighbours makes the reference's id array ragged (amep/order.py:1340-1348, 1486)."""
+    pc = coords if isinstance(coords, Particles) else Particles(coords)
+    if pc.nframes != 1:
+        raise ValueError("psi_k takes one frame")
+    n = pc.n
+    box, box_code = box_array(box_boundary, 1)
+    dev_index = _device_of(pc, device)
+    ctx = _lib.context(dev_index)
+    f32 = pc.dtype == _lib.F32
+    if pc.on_device:
+        import torch
+        out = torch.empty((n, 2), dtype=torch.float32 if f32 else torch.float64, device=pc.tensor.device)
+        nb = torch.empty((n, k), dtype=torch.int32, device=pc.tensor.device) if want_neighbors else None
+        optr, nptr, space = out.data_ptr(), (nb.data_ptr() if nb is not None else None), _lib.DEVICE
+    else:
+        out = np.empty((n, 2), dtype=np.float32 if f32 else np.float64)
+        nb = np.empty((n, k), dtype=np.int32) if want_neighbors else None
+        optr, nptr, space = out.ctypes.data, (nb.ctypes.data if nb is not None else None), _lib.HOST
+    bad = ctypes.c_int64(0)
+    rc = ctx.lib.amepb_psi_k(ctx.handle, ctypes.c_void_p(pc.ptr()), pc.dtype, n, space,
+                             box.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), box_code, int(k),
+                             ctypes.c_void_p(optr), ctypes.c_void_p(nptr) if nptr else None, ctypes.byref(bad),
+                             _stream_for(dev_index, pc.on_device))
+    ctx.check(rc, "amepb_psi_k")
+    if bad.value:
+        raise ValueError("setting an array element with a sequence. The requested array has an inhomogeneous shape: "
+                         f"{bad.value} particle(s) have a periodic image of themselves (or fewer than k images) among "
+                         "their k nearest neighbours (amep/order.py:1340-1348)")
+    host = to_numpy(out)
+    psi = host.view(np.complex64 if f32 else np.complex128).reshape(n)
+    if want_neighbors:
+        return psi, to_numpy(nb).astype(np.int64)
+    return psi
+
+
+def rotate_crop(coords, box_boundary, dim, cos_sin, device=None):
+    """``in_box(rotate_coords(pbc_points(coords, box), angle, center), box)`` of one frame
+    (amepb_rotate_crop) -> float64 ``[m, 3]`` in the memory space of ``coords``."""
+    pc = coords if isinstance(coords, Particles) else Particles(coords)
+    if pc.nframes != 1:
+        raise ValueError("rotate_crop takes one frame")
+    n = pc.n
+    box, box_code = box_array(box_boundary, 1)
+    dev_index = _device_of(pc, device)
+    ctx = _lib.context(dev_index)
+    rot = np.ascontiguousarray(np.asarray(cos_sin, dtype=np.float64).reshape(2))
+    count = ctypes.c_int64(0)
+    space = _lib.DEVICE if pc.on_device else _lib.HOST
+    stream = _stream_for(dev_index, pc.on_device)
+    args = (ctx.handle, ctypes.c_void_p(pc.ptr()), pc.dtype, n, space,
+            box.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), box_code, int(dim),
+            rot.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+    rc = ctx.lib.amepb_rotate_crop(*args, None, 0, ctypes.byref(count), stream)
+    ctx.check(rc, "amepb_rotate_crop")
+    m = int(count.value)
+    if pc.on_device:
+        import torch
+        out = torch.empty((m, 3), dtype=torch.float64, device=pc.tensor.device)
+        optr = out.data_ptr()
+    else:
+        out = np.empty((m, 3), dtype=np.float64)
+        optr = out.ctypes.data
+    if m:
+        rc = ctx.lib.amepb_rotate_crop(*args, ctypes.c_void_p(optr), m, ctypes.byref(count), stream)
+        ctx.check(rc, "amepb_rotate_crop")
+    return out

@@ -33,6 +33,9 @@ enum {
     BUF_STAGE_OUT,     // host-space staging: results
     BUF_SQ_A,          // S(q) workspaces
     BUF_SQ_B,
+    BUF_ORD_A,         // order.cu: cell counters / block counters
+    BUF_ORD_B,         // order.cu: cell offsets / block offsets
+    BUF_ORD_C,         // order.cu: images in cell order
     BUF_COUNT
 };
 
@@ -94,6 +97,10 @@ int pinned_device_release(amepb_ctx* ctx, cudaStream_t stream);
 cudaEvent_t timing_event(amepb_ctx* ctx, cudaStream_t stream);  // records and returns an event (or nullptr)
 double timing_total_ms(amepb_ctx* ctx, std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& spans);
 void timing_reset(amepb_ctx* ctx);
+
+// shared by rdf.cu and order.cu
+// exclusive prefix sum of `len` counters (device arrays, in != out), on `stream`
+int exclusive_scan(amepb_ctx* ctx, const unsigned* in, unsigned* out, long long len, cudaStream_t stream);
 
 struct DeviceGuard {
     int prev = -1;

@@ -237,6 +237,12 @@ __device__ __forceinline__ void place_images_body(const T* __restrict__ p, const
     }
 }
 
+// Particles per thread of the placement kernels.  A thread loads all of them first and then issues
+// its cell-counter atomics / offset gathers back to back, so that several L2 round trips are in
+// flight per thread: with one particle per thread the kernels were latency bound (long-scoreboard
+// stalls of 10-12 per issue, 21-27 % of the HBM rate; profiles/r01_place_v8_ncu_summary.txt).
+constexpr int kPlaceILP = 4;
+
 template <typename T, bool FILL>
 __global__ void __launch_bounds__(256) place_images_kernel(const T* __restrict__ pts, long long n,
                                                            const FramePlan* __restrict__ plans,
@@ -247,9 +253,12 @@ __global__ void __launch_bounds__(256) place_images_kernel(const T* __restrict__
     if (!plans[f].valid) return;
     __shared__ int s_words[kPlanHeadWords];
     const FramePlan& P = stage_plan_head(plans, f, s_words);
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    place_images_body<T, FILL>(pts + ((long long)f * n + i) * 3, P, count, start, sorted);
+    const long long i0 = (long long)blockIdx.x * (blockDim.x * kPlaceILP) + threadIdx.x;
+#pragma unroll
+    for (int u = 0; u < kPlaceILP; ++u) {
+        const long long i = i0 + (long long)u * blockDim.x;
+        if (i < n) place_images_body<T, FILL>(pts + ((long long)f * n + i) * 3, P, count, start, sorted);
+    }
 }
 
 // Self RDF with periodic images: queries and images of one particle in a single pass over the
@@ -269,25 +278,54 @@ __global__ void __launch_bounds__(256) place_self_kernel(const T* __restrict__ p
     if (!plans[f].valid) return;
     __shared__ int s_words[kPlanHeadWords];
     const FramePlan& P = stage_plan_head(plans, f, s_words);
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const T* p = pts + ((long long)f * n + i) * 3;
-    AT v[3];
-    int c[3];
+    const long long i0 = (long long)blockIdx.x * (blockDim.x * kPlaceILP) + threadIdx.x;
+    const T* fbase = pts + (long long)f * n * 3;
+    unsigned* frank = qrank + (long long)f * n;
+    AT v[kPlaceILP][3];
+    unsigned cc[kPlaceILP], aux[kPlaceILP];
+    bool have[kPlaceILP];
+    // (1) all loads of the thread's particles (consecutive threads read consecutive records)
 #pragma unroll
-    for (int d = 0; d < 3; ++d) {
-        v[d] = (AT)p[d];
-        c[d] = cell_index((double)v[d], P.g0[d], P.inv_h[d], P.n[d]);
+    for (int u = 0; u < kPlaceILP; ++u) {
+        const long long i = i0 + (long long)u * blockDim.x;
+        have[u] = i < n;
+        const T* p = fbase + (have[u] ? i : 0) * 3;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) v[u][d] = (AT)p[d];
+        if (FILL) aux[u] = have[u] ? frank[i] : 0u;
     }
-    const unsigned cc = P.cell_base + (unsigned)((c[2] * P.n[1] + c[1]) * P.n[0] + c[0]);
-    if (!FILL) {
-        qrank[(long long)f * n + i] = atomicAdd(&qcount[cc], 1u);
-    } else {
-        Vec4<AT> o;
-        o.x = v[0]; o.y = v[1]; o.z = v[2]; o.w = (AT)0;
-        qsorted[qstart[cc] + qrank[(long long)f * n + i]] = o;
+    // (2) cells, then the dependent L2 accesses back to back
+#pragma unroll
+    for (int u = 0; u < kPlaceILP; ++u) {
+        int c[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) c[d] = cell_index((double)v[u][d], P.g0[d], P.inv_h[d], P.n[d]);
+        cc[u] = P.cell_base + (unsigned)((c[2] * P.n[1] + c[1]) * P.n[0] + c[0]);
     }
-    place_images_body<T, FILL>(p, P, tcount, tstart, tsorted);
+#pragma unroll
+    for (int u = 0; u < kPlaceILP; ++u) {
+        if (!have[u]) continue;
+        if (!FILL) aux[u] = atomicAdd(&qcount[cc[u]], 1u);
+        else aux[u] += __ldg(&qstart[cc[u]]);
+    }
+#pragma unroll
+    for (int u = 0; u < kPlaceILP; ++u) {
+        if (!have[u]) continue;
+        const long long i = i0 + (long long)u * blockDim.x;
+        if (!FILL) {
+            frank[i] = aux[u];
+        } else {
+            Vec4<AT> o;
+            o.x = v[u][0]; o.y = v[u][1]; o.z = v[u][2]; o.w = (AT)0;
+            qsorted[aux[u]] = o;
+        }
+    }
+    // (3) shifted images: none for almost every particle when the cutoff is short
+#pragma unroll
+    for (int u = 0; u < kPlaceILP; ++u) {
+        const long long i = i0 + (long long)u * blockDim.x;
+        if (have[u]) place_images_body<T, FILL>(fbase + i * 3, P, tcount, tstart, tsorted);
+    }
 }
 
 // Plain points (queries, or targets without periodic images).  S: storage
@@ -303,28 +341,47 @@ __global__ void __launch_bounds__(256) place_points_kernel(const T* __restrict__
     if (!plans[f].valid) return;
     __shared__ int s_words[kPlanHeadWords];
     const FramePlan& P = stage_plan_head(plans, f, s_words);
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const T* p = pts + ((long long)f * n + i) * 3;
-    S v[3];
-    int c[3];
-    bool keep = true;
+    const long long i0 = (long long)blockIdx.x * (blockDim.x * kPlaceILP) + threadIdx.x;
+    const T* fbase = pts + (long long)f * n * 3;
+    S v[kPlaceILP][3];
+    unsigned cc[kPlaceILP], slot[kPlaceILP];
+    bool keep[kPlaceILP];
 #pragma unroll
-    for (int d = 0; d < 3; ++d) {
-        v[d] = (S)p[d];
-        const double xd = (double)v[d];
-        if (DROP_OUTSIDE) keep = keep && (xd >= P.reg_lo[d]) && (xd <= P.reg_hi[d]);
-        c[d] = cell_index(xd, P.g0[d], P.inv_h[d], P.n[d]);
+    for (int u = 0; u < kPlaceILP; ++u) {
+        const long long i = i0 + (long long)u * blockDim.x;
+        keep[u] = i < n;
+        const T* p = fbase + (keep[u] ? i : 0) * 3;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) v[u][d] = (S)p[d];
     }
-    if (!keep) return;
-    const unsigned cc = P.cell_base + (unsigned)((c[2] * P.n[1] + c[1]) * P.n[0] + c[0]);
-    if (!FILL) {
-        atomicAdd(&count[cc], 1u);
-    } else {
-        const unsigned slot = start[cc] + atomicSub(&count[cc], 1u) - 1u;
-        Vec4<S> o;
-        o.x = v[0]; o.y = v[1]; o.z = v[2]; o.w = (S)0;
-        sorted[slot] = o;
+#pragma unroll
+    for (int u = 0; u < kPlaceILP; ++u) {
+        int c[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const double xd = (double)v[u][d];
+            if (DROP_OUTSIDE) keep[u] = keep[u] && (xd >= P.reg_lo[d]) && (xd <= P.reg_hi[d]);
+            c[d] = cell_index(xd, P.g0[d], P.inv_h[d], P.n[d]);
+        }
+        cc[u] = P.cell_base + (unsigned)((c[2] * P.n[1] + c[1]) * P.n[0] + c[0]);
+    }
+#pragma unroll
+    for (int u = 0; u < kPlaceILP; ++u) {
+        if (!keep[u]) continue;
+        if (!FILL) atomicAdd(&count[cc[u]], 1u);
+        else slot[u] = atomicSub(&count[cc[u]], 1u) - 1u;
+    }
+    if constexpr (FILL) {
+#pragma unroll
+        for (int u = 0; u < kPlaceILP; ++u)
+            if (keep[u]) slot[u] += __ldg(&start[cc[u]]);
+#pragma unroll
+        for (int u = 0; u < kPlaceILP; ++u) {
+            if (!keep[u]) continue;
+            Vec4<S> o;
+            o.x = v[u][0]; o.y = v[u][1]; o.z = v[u][2]; o.w = (S)0;
+            sorted[slot[u]] = o;
+        }
     }
 }
 
@@ -1450,8 +1507,8 @@ static void frame_stats_collect(amepb_ctx* ctx, int nframes, std::vector<FrameSt
     }
 }
 
-static int frame_stats(amepb_ctx* ctx, const void* pts, int dtype, int64_t n, int nframes,
-                       std::vector<FrameStats>& out, cudaStream_t stream, int slot) {
+int frame_stats(amepb_ctx* ctx, const void* pts, int dtype, int64_t n, int nframes,
+                std::vector<FrameStats>& out, cudaStream_t stream, int slot) {
     int rc = pinned_host_acquire(ctx);
     if (rc) return rc;
     rc = frame_stats_launch(ctx, pts, dtype, n, nframes, stream, slot);
@@ -1461,7 +1518,7 @@ static int frame_stats(amepb_ctx* ctx, const void* pts, int dtype, int64_t n, in
     return 0;
 }
 
-static int exclusive_scan(amepb_ctx* ctx, const unsigned* in, unsigned* out, long long len, cudaStream_t stream) {
+int exclusive_scan(amepb_ctx* ctx, const unsigned* in, unsigned* out, long long len, cudaStream_t stream) {
     const int nblocks = (int)((len + kScanTile - 1) / kScanTile);
     int rc = ensure_device(ctx, BUF_SCAN, sizeof(unsigned) * (size_t)(nblocks + 1));
     if (rc) return rc;
@@ -1744,7 +1801,8 @@ static int rdf_sub_batch(amepb_ctx* ctx, const RdfCall& c, int64_t f0, int nf, c
     AMEPB_CUDA(ctx, cudaMemsetAsync(ctx->bufs[BUF_MISC].p, 0, sizeof(unsigned long long), stream));
 
     // ---- cell build ------------------------------------------------------------
-    const dim3 tgrid((unsigned)((c.n + 255) / 256), nf), qgrid((unsigned)((m + 255) / 256), nf);
+    constexpr int kPlaceTile = 256 * kPlaceILP;
+    const dim3 tgrid((unsigned)((c.n + kPlaceTile - 1) / kPlaceTile), nf), qgrid((unsigned)((m + kPlaceTile - 1) / kPlaceTile), nf);
     auto place_targets = [&](bool fill) -> int {
         void* sorted = ctx->bufs[BUF_TSORTED].p;
         if (c.pbc) {

@@ -323,7 +323,9 @@ __global__ void __launch_bounds__(kC64Threads, 4) sf2d_c64_kernel(
     const T* __restrict__ coords, long long n, const double* __restrict__ qall, long long q_stride, int nq,
     long long chunksize, float2* __restrict__ rho, float4* __restrict__ chunk_out, long long nchunks) {
     extern __shared__ __align__(16) unsigned char smem_c64[];
-    constexpr size_t kBufBytes = sizeof(double2) * kC64Stage * (kC64RowA + kC64RowB);
+    // (one spare row per table: the operand prefetch of particle jj + 1 then needs no index clamp,
+    // which cost five uniform-datapath instructions per particle in the accumulation loop)
+    constexpr size_t kBufBytes = sizeof(double2) * (kC64Stage + 1) * (kC64RowA + kC64RowB);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tiles_a = (nq + kC64TileA - 1) / kC64TileA;
     const int tile_a = blockIdx.x % tiles_a, tile_b = blockIdx.x / tiles_a;
@@ -346,7 +348,7 @@ __global__ void __launch_bounds__(kC64Threads, 4) sf2d_c64_kernel(
     const int qa_idx = tile_a * kC64TileA + lane;
 
     auto buf_x = [&](int b) { return reinterpret_cast<double2*>(smem_c64 + b * kBufBytes); };
-    auto buf_y = [&](int b) { return reinterpret_cast<double2*>(smem_c64 + b * kBufBytes + sizeof(double2) * kC64Stage * kC64RowA); };
+    auto buf_y = [&](int b) { return reinterpret_cast<double2*>(smem_c64 + b * kBufBytes + sizeof(double2) * (kC64Stage + 1) * kC64RowA); };
     c64_build_stage<T>(base, q, j_lo, j_hi, tile_a * kC64TileA, tile_b * kC64TileB, nq, buf_x(0), buf_y(0));
     __syncthreads();
     int cur = 0;
@@ -367,8 +369,7 @@ __global__ void __launch_bounds__(kC64Threads, 4) sf2d_c64_kernel(
             double2 xa = sX[jj][lane], y0 = sY[jj][2 * warp], y1 = sY[jj][2 * warp + 1];
 #pragma unroll 2
             for (; jj < seg_end; ++jj) {
-                const int nx = jj + 1 < kC64Stage ? jj + 1 : jj;
-                const double2 xa_n = sX[nx][lane], y0_n = sY[nx][2 * warp], y1_n = sY[nx][2 * warp + 1];
+                const double2 xa_n = sX[jj + 1][lane], y0_n = sY[jj + 1][2 * warp], y1_n = sY[jj + 1][2 * warp + 1];
 #pragma unroll
                 for (int p = 0; p < 2; ++p) {
                     const double2 yb = p == 0 ? y0 : y1;
@@ -695,7 +696,7 @@ int amepb_sf2d_modes(amepb_ctx* ctx, const void* coords, int dtype, int space, i
     const double* d_q = reinterpret_cast<const double*>(ctx->bufs[BUF_SQ_A].p);
 
     const size_t smem_f64 = sizeof(double2) * kF64Stage * kF64Row * 2;
-    const size_t smem_c64 = 2 * sizeof(double2) * kC64Stage * (kC64RowA + kC64RowB);
+    const size_t smem_c64 = 2 * sizeof(double2) * (kC64Stage + 1) * (kC64RowA + kC64RowB);
     if (accum == AMEPB_ACCUM_C64_REFERENCE) {
         // frames per launch such that the chunk sums of the split kernel fit their buffer
         const size_t nchunks = (size_t)((n + chunksize - 1) / chunksize);

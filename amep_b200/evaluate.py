@@ -33,7 +33,7 @@ import numpy as np
 
 from . import _core, dist
 from .base import BaseEvaluation
-from .order import psi6_orientation, rotated_periodic_crop
+from .order import psi6_mean, psi6_orientation, rotated_periodic_crop
 from .spatialcor import pcf2d_frames, rdf_frames, sf2d_frames, sfiso_frames
 from .trajectory import TensorTrajectory
 from .utils import evaluated_indices
@@ -165,12 +165,23 @@ def _frame_batches(traj, indices, ptype, other, want_other):
 
 
 def _gather(traj, indices, ptype):
-    """Coordinates ``[F, n, 3]`` and boxes of the selected frames in one piece."""
-    parts = list(_frame_batches(traj, indices, ptype, None, False))
+    """Coordinates ``[F, n, 3]`` and boxes of the selected frames in one piece (copies: the blocks of
+    a streamed trajectory live in staging buffers that are reused)."""
+    parts = []
+    for coords, _, box in _frame_batches(traj, indices, ptype, None, False):
+        if isinstance(traj, TensorTrajectory) or _core._is_torch(coords):
+            parts.append((coords, box))
+        else:
+            parts.append((np.array(coords), box))
     if len(parts) == 1:
-        return parts[0][0].copy() if not isinstance(traj, TensorTrajectory) and not _core._is_torch(parts[0][0]) \
-            else parts[0][0], parts[0][2]
-    raise RuntimeError("unreachable: _gather is only used on single-block selections")
+        return parts[0]
+    if _core._is_torch(parts[0][0]):
+        import torch
+        stack = torch.cat([p[0] for p in parts])
+    else:
+        stack = np.concatenate([p[0] for p in parts])
+    boxes = [np.broadcast_to(p[1], (len(p[0]), 3, 2)) for p in parts]
+    return stack, np.concatenate(boxes)
 
 
 # =============================================================================
@@ -351,6 +362,10 @@ class SF2d(_FrameAverage):
     (``amep_b200.order.psi6_orientation``, sm_100a kernel), rotation of the periodic images about
     the box centre and crop to the box (``rotated_periodic_crop``).
 
+    Extension: ``orientation`` = array ``[len(traj)]`` of angles replaces the psi_6 angle (the
+    reference's angle carries the float32 noise of its own psi_6, and S(q) at large q is sensitive
+    to it: injecting the reference's angles is how the rotated path is compared to 1e-6).
+
     Memory: per-frame results are kept as float32 ``S`` rows (what ``sf2d`` returns) plus one pair
     of q grids; the reference's ``(nav, 3, ny, nx)`` float64 array is only materialised when
     ``frames`` is read.  Under ``torch.distributed`` only the frame *sum* is all-reduced for
@@ -358,7 +373,7 @@ class SF2d(_FrameAverage):
 
     def __init__(self, traj, skip: float = 0.0, nav: int = 10, ptype=None, other=None,
                  rotate: bool = True, ftype=None, max_workers=1, distributed=None, group=None,
-                 **kwargs) -> None:
+                 orientation=None, **kwargs) -> None:
         super().__init__()
         self.name = "sf2d"
         if ftype is not None or type(traj).__name__ == "FieldTrajectory":
@@ -367,7 +382,8 @@ class SF2d(_FrameAverage):
         kwargs.pop("verbose", None)
         idx = self._select(traj, skip, nav)
         sh = self._shard = _Shard(len(idx), distributed, group)
-        s_rows, qx_rows, qy_rows = [], [], []
+        s_rows, qx_rows, qy_rows, thetas = [], [], [], []
+        done = 0
         # the reference always passes other_coords, so rho is evaluated twice
         # (amep/evaluate.py:1380-1394); identical arrays give identical sums,
         # so one evaluation serves both when ptype == other
@@ -375,16 +391,19 @@ class SF2d(_FrameAverage):
         for coords, other_coords, box in _frame_batches(traj, idx[sh.lo:sh.hi], ptype, other, want_other):
             if rotate:
                 # the crop changes the particle number from frame to frame: one library call per frame
+                block = np.asarray(idx[sh.lo + done:sh.lo + done + coords.shape[0]])
+                allc = coords if ptype is None else _gather(traj, block, None)[0]   # psi_6 of *all* particles (:1352-1357)
                 for f in range(coords.shape[0]):
                     b = box[f] if np.ndim(box) == 3 else box
-                    c = _core.to_numpy(coords[f])
-                    theta = psi6_orientation(c, b)
-                    c = rotated_periodic_crop(c, b, theta)
+                    theta = psi6_orientation(allc[f], b) if orientation is None else float(orientation[block[f]])
+                    c = rotated_periodic_crop(coords[f], b, theta)
                     o = None
                     if want_other:
-                        o = rotated_periodic_crop(_core.to_numpy(other_coords[f]), b, theta)
+                        o = rotated_periodic_crop(other_coords[f], b, theta)
                     s, qx, qy = sf2d_frames(c[None], b, None if o is None else o[None], **kwargs)
                     s_rows.append(s), qx_rows.append(qx), qy_rows.append(qy)
+                    thetas.append(theta)
+                done += coords.shape[0]
             else:
                 s, qx, qy = sf2d_frames(coords, box, other_coords, compact_grids=True, **kwargs)
                 s_rows.append(s), qx_rows.append(qx), qy_rows.append(qy)
@@ -488,8 +507,7 @@ class PCF2d(_FrameAverage):
                     allc = coords
                 else:
                     allc = _gather(traj, block, None)[0]
-                from .order import psi6_mean
-                psi_rows = np.array([psi6_mean(_core.to_numpy(allc[f]), box[f] if np.ndim(box) == 3 else box)
+                psi_rows = np.array([psi6_mean(allc[f], box[f] if np.ndim(box) == 3 else box)
                                      for f in range(nf)], dtype=np.float64)
             elif callable(psi):
                 psi_rows = np.array([np.asarray(psi(f), dtype=np.float64) for f in traj[block]])

@@ -20,6 +20,10 @@
  *                             reached by sf2d/sfiso(mode='fft'), amep/spatialcor.py:1911-1940
  *   amepb_pcf2d_counts     <- amep/spatialcor.py:652-723    __dhist2d (difference vectors, rotation,
  *                             np.histogram2d) and the chunk fan-out + sum of pcf2d, :886-912
+ *   amepb_psi_k            <- amep/order.py:1183-1348       k_nearest_neighbors (periodic KD-tree query)
+ *                             amep/order.py:1361-1501       psi_k, the prologue of evaluate.SF2d(rotate=True)
+ *                             and evaluate.PCF2d (amep/evaluate.py:1352-1357, 730-735)
+ *   amepb_rotate_crop      <- amep/evaluate.py:1366-1377    in_box(rotate_coords(pbc_points(...)))
  *
  * Conventions
  *   - plain C types only; no exceptions cross the boundary;
@@ -224,6 +228,42 @@ int amepb_pcf2d_counts(amepb_ctx* ctx, const void* coords, int dtype, int64_t n,
                        const double* center, int center_f32, const double* rot, const double* xedges,
                        int32_t nxe, const double* yedges, int32_t nye, int64_t edge_stride,
                        uint64_t* counts, void* stream);
+
+/*
+ * k-atic bond order parameter of every particle of one 2D frame, psi_k of amep/order.py:1361-1501
+ * with its defaults (other_coords=None, pbc=True): the k nearest neighbours are ranks 2..k+1 of the
+ * float64 distances (x, y and z) to all nine float32 periodic images of all particles (pbc_points
+ * with enforce_nd=2 and no window, amep/pbc.py:296-326; rank 1 is the particle itself), image
+ * numbers folded back with % n; psi = 1/k sum_j exp(i k theta_j) with theta_j the angle of the bond
+ * to the UNSHIFTED position of neighbour j (amep/order.py:1488-1499), evaluated in the dtype of
+ * `coords` like NumPy does (float32 coordinates give a complex64 result).
+ *   coords        [n][3] of `dtype` in `space`;  1 <= k <= 8
+ *   psi_out       [n][2] (re, im) of `dtype` in `space`
+ *   neighbors_out [n][k] int32 in `space`, may be NULL: the neighbour ids in order of distance
+ *   bad_out       host, may be NULL: number of particles with an image of themselves (or nothing)
+ *                 among their neighbours -- the reference raises for such frames (ragged id array)
+ * Equal distances are ranked by image number (scipy's KD-tree leaves that order unspecified).
+ * The call returns after the work is complete (it synchronises `stream`).
+ */
+int amepb_psi_k(amepb_ctx* ctx, const void* coords, int dtype, int64_t n, int space,
+                const double* box_boundary, int box_dtype, int32_t k,
+                void* psi_out, int32_t* neighbors_out, int64_t* bad_out, void* stream);
+
+/*
+ * Rotated periodic crop of amep/evaluate.py:1366-1377:
+ *   in_box(rotate_coords(pbc_points(coords, box), angle, center), box)
+ * every periodic image (dim = 2: 9, dim = 3: 27 float32 copies in the order of amep/pbc.py:305-321,
+ * dim = dimension(coords)) minus the box centre (a float32 subtraction for a float32 box), rotated
+ * about z in float64 (amep/utils.py:547-652), plus the centre; the images inside the closed box are
+ * kept in the order of the image array (amep/utils.py:727-742).
+ *   rot       host [2]: cos and sin of the rotation angle as the caller's NumPy computed them
+ *   out       [capacity][3] float64 in `space`, or NULL to only count
+ *   count_out host: number of images kept (an error if it exceeds `capacity`)
+ * The call returns after the work is complete (it synchronises `stream`).
+ */
+int amepb_rotate_crop(amepb_ctx* ctx, const void* coords, int dtype, int64_t n, int space,
+                      const double* box_boundary, int box_dtype, int dim, const double* rot,
+                      double* out, int64_t capacity, int64_t* count_out, void* stream);
 
 /*
  * Density modes on the sf2d grid: rho[f][iy][ix] = sum_i exp(-i (qx[ix] x_i + qy[iy] y_i))

@@ -255,8 +255,6 @@ def test_evaluate_pcf2d(sc):
     for dev in ("numpy", "cuda"):
         data = c.copy() if dev == "numpy" else torch.from_numpy(c.copy()).cuda()
         traj = amep_b200.TensorTrajectory(data, box)
-        with pytest.raises(NotImplementedError):
-            amep_b200.evaluate.PCF2d(traj)
         ev = amep_b200.evaluate.PCF2d(traj, skip=0.2, nav=3, psi=psi, nxbins=24, nybins=24, rmax=5.0, njobs=4)
         want = [orc.pcf2d(c[i], box, None, 24, 24, 5.0, psi[i]) for i in ev.indices]
         np.testing.assert_array_equal(ev.avg, np.mean(np.array([w[0] for w in want]), axis=0))

@@ -267,8 +267,10 @@ def test_evaluate_sfiso_and_sf2d(sc):
     _close(ev2.avg, want[0])
     np.testing.assert_array_equal(ev2.qx, want[1])
     assert ev2.frames.shape[0] == 3 and ev2.frames.shape[1] == 3
-    with pytest.raises(NotImplementedError):
-        amep_b200.evaluate.SF2d(traj)  # the reference's default is rotate=True: loud, not silent
+    # the reference's default is rotate=True (psi_6 prologue, tests/test_order_gpu.py): runs, and the
+    # rotated structure factor has the grid of the unrotated one
+    ev_rot = amep_b200.evaluate.SF2d(traj, skip=0.0, nav=3, qmax=2.0)
+    assert ev_rot.avg.shape == ev2.avg.shape and np.array_equal(ev_rot.qx, ev2.qx)
     # mode='fft' through the evaluate classes (kwargs reach sf2d / sfiso unchanged)
     ev3 = amep_b200.evaluate.SF2d(traj, skip=0.0, nav=2, rotate=False, qmax=2.0, mode="fft", accuracy=0.2)
     idx = orc.frame_indices(nf, 0.0, 2)
