@@ -1664,6 +1664,9 @@ static int rdf_sub_batch(amepb_ctx* ctx, const RdfCall& c, int64_t f0, int nf, c
         in.n_queries = m;
         in.cells_per_cutoff = ctx->rdf_k_override;
         in.max_cells = std::max<int64_t>(4096, c.n * (c.pbc ? 2 : 1));
+        if (const char* kx = getenv("AMEPB_KX")) in.cells_per_cutoff_dim[0] = atoi(kx);   // experiments: anisotropic cells
+        if (const char* ky = getenv("AMEPB_KY")) in.cells_per_cutoff_dim[1] = atoi(ky);
+        if (const char* kz = getenv("AMEPB_KZ")) in.cells_per_cutoff_dim[2] = atoi(kz);
         if (const char* tp = getenv("AMEPB_TASK_PAIRS")) in.task_pairs = std::max(1024.0, atof(tp));
         if (const char* hm = getenv("AMEPB_HEAVY_RUN_MULT")) in.heavy_run_mult = std::max(0, atoi(hm));
         // edges must be usable: finite, non-decreasing

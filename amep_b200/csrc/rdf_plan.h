@@ -173,6 +173,7 @@ struct PlanInputs {
     int64_t n_targets;           // particles in coords
     int64_t n_queries;
     int cells_per_cutoff;        // 0 = automatic
+    int cells_per_cutoff_dim[3] = {0, 0, 0};   // per-dimension override (0 = follow cells_per_cutoff / automatic)
     int64_t max_cells;           // upper bound on cells for one frame
     double task_pairs = 262144.0;  // candidate pairs aimed at per block task
     int heavy_run_mult = 0;        // query cells per block task multiplier when warps share cells (0 = automatic)
@@ -267,7 +268,8 @@ inline bool plan_frame(const PlanInputs& in, int dim, const FrameStats& tgt, con
     auto cells_for = [&](int k, int* n) {
         double total = 1;
         for (int d = 0; d < 3; ++d) {
-            double want = floor(ext[d] * k / rcs);
+            const int kdim = in.cells_per_cutoff_dim[d] > 0 ? in.cells_per_cutoff_dim[d] : k;
+            double want = floor(ext[d] * kdim / rcs);
             n[d] = (int)std::min(std::max(want, 1.0), 1.0e6);
             total *= n[d];
         }
