@@ -1,5 +1,6 @@
-"""torchrun --nproc-per-node N tools/dist_check.py: evaluate.* sharded over N GPUs (NCCL) must equal
-the single-rank result bit for bit (RDF) / to rounding (S(q))."""
+"""torchrun --nproc-per-node N tools/dist_check.py: the evaluate classes sharded over N GPUs (NCCL)
+against the single-rank result -- bit for bit for RDF (integer counts) and for every per-frame row,
+to rounding for averages that are reduced as partial sums."""
 import os, sys
 import numpy as np, torch, torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -14,18 +15,37 @@ box = np.array([[0, L], [0, L], [-0.5, 0.5]], dtype=np.float32)
 coords = np.zeros((nf, n, 3), dtype=np.float32)
 coords[:, :, :2] = rng.uniform(0, L, (nf, n, 2))
 traj = amep_b200.TensorTrajectory(torch.from_numpy(coords).cuda(), box, times=np.arange(nf) * 1.0)
+host_traj = amep_b200.TensorTrajectory(coords, box, times=np.arange(nf) * 1.0)   # host arrays: every rank stages on its own GPU
 ok = True
-for name, make in (("RDF", lambda d: amep_b200.evaluate.RDF(traj, nav=nf, rmax=8.0, nbins=200, distributed=d)),
-                   ("SFiso", lambda d: amep_b200.evaluate.SFiso(traj, nav=nf, qmax=6.0, twod=True, num=8, distributed=d)),
-                   ("SF2d", lambda d: amep_b200.evaluate.SF2d(traj, nav=nf, rotate=False, qmax=3.0, distributed=d)),
-                   ("SF2d fft", lambda d: amep_b200.evaluate.SF2d(traj, nav=nf, rotate=False, qmax=3.0, mode="fft", accuracy=0.2, distributed=d))):
+ev = amep_b200.evaluate
+
+
+def report(name, same, close):
+    global ok
+    ok = ok and close
+    if rank == 0:
+        print(f"{name}: world {world}, bit-identical {same}, close {close}", flush=True)
+
+
+cases = (
+    ("RDF", lambda d: ev.RDF(traj, nav=nf, rmax=8.0, nbins=200, distributed=d), True),
+    ("RDF host arrays", lambda d: ev.RDF(host_traj, nav=nf, rmax=8.0, nbins=200, distributed=d), True),
+    ("RDF one frame (sharded inside the frame)", lambda d: ev.RDF(traj, nav=1, skip=0.5, rmax=8.0, nbins=200, distributed=d), True),
+    ("SFiso", lambda d: ev.SFiso(traj, nav=nf, qmax=6.0, twod=True, num=8, distributed=d), False),
+    ("SFiso one frame (idle ranks)", lambda d: ev.SFiso(traj, nav=1, qmax=6.0, twod=True, num=8, distributed=d), False),
+    ("SF2d", lambda d: ev.SF2d(traj, nav=nf, rotate=False, qmax=3.0, distributed=d), False),
+    ("SF2d rotate=True", lambda d: ev.SF2d(traj, nav=5, qmax=3.0, distributed=d), False),
+    ("SF2d fft", lambda d: ev.SF2d(traj, nav=nf, rotate=False, qmax=3.0, mode="fft", accuracy=0.2, distributed=d), False),
+    ("PCF2d (psi_6 orientation)", lambda d: ev.PCF2d(traj, nav=4, nxbins=50, nybins=50, rmax=6.0, distributed=d), False),
+)
+for name, make, exact in cases:
     sharded, alone = make(True), make(False)
     a, b = np.asarray(sharded.frames), np.asarray(alone.frames)
     same = np.array_equal(a, b)
-    close = np.allclose(a, b, rtol=1e-12, atol=1e-12 * np.abs(b).max())
-    ok = ok and (same if name == "RDF" else close)
-    if rank == 0:
-        print(f"{name}: world {world}, frames {a.shape}, bit-identical {same}, close {close}", flush=True)
+    avg_close = np.allclose(sharded.avg, alone.avg, rtol=1e-12, atol=1e-12 * np.abs(alone.avg).max())
+    if exact:
+        same = same and np.array_equal(sharded.avg, alone.avg) and np.array_equal(sharded.counts, alone.counts)
+    report(name, same, (same if exact else np.allclose(a, b, rtol=1e-12, atol=1e-12 * np.abs(b).max())) and avg_close)
 t = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(t, op=dist.ReduceOp.MIN)
 if rank == 0:
