@@ -486,3 +486,133 @@ def rotate_crop(coords, box_boundary, dim, cos_sin, device=None):
         rc = ctx.lib.amepb_rotate_crop(*args, ctypes.c_void_p(optr), m, ctypes.byref(count), stream)
         ctx.check(rc, "amepb_rotate_crop")
     return out
+
+
+def _single(p: Particles, what: str):
+    if p.nframes != 1:
+        raise ValueError(f"{what} takes one frame")
+    return p
+
+
+def pcf_angle_counts(coords, other, same, box_boundary, pbc, e, angle, dedges, aedges, device=None):
+    """Pair counts on the (distance, angle) grid of ``amep.spatialcor.pcf_angle``
+    (amepb_pcf_angle_counts) -> int64 ``[nd, na]`` NumPy array."""
+    pc = _single(coords if isinstance(coords, Particles) else Particles(coords), "pcf_angle")
+    po = pc if other is None else _single(other if isinstance(other, Particles) else Particles(other, "other_coords"), "pcf_angle")
+    if pc.on_device != po.on_device:
+        dev = (pc if pc.on_device else po).tensor.device
+        pc, po = pc.to_device(dev), po.to_device(dev)
+    box, box_code = box_array(box_boundary, 1)
+    de = np.ascontiguousarray(np.asarray(dedges), dtype=np.float64)
+    ae = np.ascontiguousarray(np.asarray(aedges), dtype=np.float64)
+    e = np.asarray(e, dtype=np.float64)
+    if e.ndim == 1:
+        e_arr, stride = np.ascontiguousarray(e), 0
+        e_norm = np.array([np.linalg.norm(e)], dtype=np.float64)
+    else:
+        e_arr, stride = np.ascontiguousarray(e), 3
+        if e_arr.shape != (po.n, 3):
+            raise ValueError("e must have shape (3,) or one direction per particle of other_coords")
+        e_norm = np.ascontiguousarray(np.sqrt((e_arr[:, 0] * e_arr[:, 0] + e_arr[:, 1] * e_arr[:, 1]) + e_arr[:, 2] * e_arr[:, 2]))
+    dev_index = _device_of(pc, device)
+    ctx = _lib.context(dev_index)
+    shape = (len(de) - 1, len(ae) - 1)
+    if pc.on_device:
+        import torch
+        out = torch.empty(shape, dtype=torch.int64, device=pc.tensor.device)
+        optr, space = out.data_ptr(), _lib.DEVICE
+    else:
+        out = np.empty(shape, dtype=np.int64)
+        optr, space = out.ctypes.data, _lib.HOST
+    dp = ctypes.POINTER(ctypes.c_double)
+    rc = ctx.lib.amepb_pcf_angle_counts(
+        ctx.handle, ctypes.c_void_p(pc.ptr()), pc.dtype, pc.n, ctypes.c_void_p(po.ptr()), po.dtype, po.n,
+        1 if same else 0, space, box.ctypes.data_as(dp), box_code, 1 if pbc else 0,
+        e_arr.ctypes.data_as(dp), stride, e_norm.ctypes.data_as(dp), float(angle),
+        de.ctypes.data_as(dp), len(de), ae.ctypes.data_as(dp), len(ae), ctypes.c_void_p(optr),
+        _stream_for(dev_index, pc.on_device))
+    ctx.check(rc, "amepb_pcf_angle_counts")
+    return to_numpy(out)
+
+
+_VALUE_KINDS = {np.dtype(np.float32): 0, np.dtype(np.float64): 1, np.dtype(np.complex64): 2, np.dtype(np.complex128): 3}
+
+
+def _values_array(values, n, on_device, device):
+    """Per-particle values ``[n]`` or ``[n, d]`` -> (contiguous array / tensor in the space of the
+    coordinates, kind code, components)."""
+    if _is_torch(values):
+        import torch
+        v = values
+        if v.dtype not in (torch.float32, torch.float64, torch.complex64, torch.complex128):
+            v = v.to(torch.float64)
+        v = v.contiguous()
+        if on_device and not v.is_cuda:
+            v = v.to(device)
+        if not on_device:
+            return _values_array(v.cpu().numpy(), n, False, device)
+        kind = {torch.float32: 0, torch.float64: 1, torch.complex64: 2, torch.complex128: 3}[v.dtype]
+        shape = tuple(v.shape)
+        holder, ptr = v, v.data_ptr()
+    else:
+        a = np.asarray(values)
+        if a.dtype not in _VALUE_KINDS:
+            a = a.astype(np.complex128 if np.iscomplexobj(a) else np.float64)
+        a = np.ascontiguousarray(a)
+        if on_device:
+            import torch
+            return _values_array(torch.from_numpy(a).to(device), n, True, device)
+        kind, shape, holder, ptr = _VALUE_KINDS[a.dtype], a.shape, a, a.ctypes.data
+    if len(shape) not in (1, 2) or shape[0] != n:
+        raise ValueError(f"amep.spatialcor.spatialcor: values have an invalid shape {shape}. The shape must be "
+                         "(N,) for scalar values and (N,d) for vector quantities.")
+    return holder, ptr, kind, (1 if len(shape) == 1 else shape[1])
+
+
+def spatialcor_sums(coords, values, other, other_values, box_boundary, pbc, edges, device=None):
+    """Pair counts and sums of ``conj(other_value) * value`` per distance bin of
+    ``amep.spatialcor.spatialcor`` (amepb_spatialcor_sums) -> (norm int64 ``[nb]``, cor complex128 ``[nb]``)."""
+    pc = _single(coords if isinstance(coords, Particles) else Particles(coords), "spatialcor")
+    po = None if other is None else _single(other if isinstance(other, Particles) else Particles(other, "other_coords"), "spatialcor")
+    if po is not None and pc.on_device != po.on_device:
+        dev = (pc if pc.on_device else po).tensor.device
+        pc, po = pc.to_device(dev), po.to_device(dev)
+    tdev = pc.tensor.device if pc.on_device else None
+    vh, vptr, kind, ncomp = _values_array(values, pc.n, pc.on_device, tdev)
+    wh = wptr = None
+    if po is not None:
+        wh, wptr, kind_o, ncomp_o = _values_array(other_values, po.n, pc.on_device, tdev)
+        if kind_o != kind or ncomp_o != ncomp:
+            # NumPy would promote the product: bring both to the wider kind
+            target = [np.float32, np.float64, np.complex64, np.complex128][max(kind, kind_o) if (kind < 2) == (kind_o < 2) else 3]
+            vh, vptr, kind, ncomp = _values_array(to_numpy(vh).astype(target), pc.n, pc.on_device, tdev)
+            wh, wptr, kind_o, ncomp_o = _values_array(to_numpy(wh).astype(target), po.n, pc.on_device, tdev)
+            if ncomp_o != ncomp:
+                raise ValueError("values and other_values must have the same number of components")
+    if ncomp > 4:
+        raise ValueError("amep_b200.spatialcor.spatialcor: at most 4 value components per particle")
+    box, box_code = box_array(box_boundary, 1)
+    e = np.ascontiguousarray(np.asarray(edges), dtype=np.float64)
+    nb = len(e) - 1
+    dev_index = _device_of(pc, device)
+    ctx = _lib.context(dev_index)
+    if pc.on_device:
+        import torch
+        norm = torch.empty(nb, dtype=torch.int64, device=pc.tensor.device)
+        cor = torch.empty((nb, 2), dtype=torch.float64, device=pc.tensor.device)
+        nptr, cptr, space = norm.data_ptr(), cor.data_ptr(), _lib.DEVICE
+    else:
+        norm = np.empty(nb, dtype=np.int64)
+        cor = np.empty((nb, 2), dtype=np.float64)
+        nptr, cptr, space = norm.ctypes.data, cor.ctypes.data, _lib.HOST
+    dp = ctypes.POINTER(ctypes.c_double)
+    rc = ctx.lib.amepb_spatialcor_sums(
+        ctx.handle, ctypes.c_void_p(pc.ptr()), pc.dtype, pc.n,
+        ctypes.c_void_p(po.ptr()) if po is not None else None, po.dtype if po is not None else 0,
+        po.n if po is not None else 0, space, box.ctypes.data_as(dp), box_code, 1 if pbc else 0,
+        ctypes.c_void_p(vptr), ctypes.c_void_p(wptr) if wptr else None, kind, ncomp,
+        e.ctypes.data_as(dp), len(e), ctypes.c_void_p(nptr), ctypes.c_void_p(cptr),
+        _stream_for(dev_index, pc.on_device))
+    ctx.check(rc, "amepb_spatialcor_sums")
+    c = to_numpy(cor)
+    return to_numpy(norm), c[:, 0] + 1j * c[:, 1], kind >= 2

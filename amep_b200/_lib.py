@@ -24,7 +24,7 @@ SYMBOLS = (
     "amepb_frame_dimension", "amepb_rdf_batch", "amepb_rdf_last_info",
     "amepb_rdf_set_cells_per_cutoff", "amepb_rdf_set_symmetric", "amepb_rdf_set_shard", "amepb_sq_harmonics", "amepb_sq_debye", "amepb_sf2d_modes",
     "amepb_density_counts",
-    "amepb_pcf2d_counts", "amepb_psi_k", "amepb_rotate_crop",
+    "amepb_pcf2d_counts", "amepb_psi_k", "amepb_rotate_crop", "amepb_pcf_angle_counts", "amepb_spatialcor_sums",
     "amepb_kernel_launches", "amepb_synchronize", "amepb_set_timing", "amepb_last_kernel_ms",
 )
 
@@ -120,6 +120,13 @@ def load():
         lib.amepb_pcf2d_counts.argtypes = [vp, vp, c.c_int, i64, vp, c.c_int, i64, c.c_int, c.c_int, i64,
                                            c.POINTER(c.c_double), c.c_int, c.POINTER(c.c_double),
                                            c.POINTER(c.c_double), i32, c.POINTER(c.c_double), i32, i64, vp, vp]
+        dp = c.POINTER(c.c_double)
+        lib.amepb_pcf_angle_counts.restype = c.c_int
+        lib.amepb_pcf_angle_counts.argtypes = [vp, vp, c.c_int, i64, vp, c.c_int, i64, c.c_int, c.c_int, dp, c.c_int, c.c_int,
+                                               dp, i64, dp, c.c_double, dp, i32, dp, i32, vp, vp]
+        lib.amepb_spatialcor_sums.restype = c.c_int
+        lib.amepb_spatialcor_sums.argtypes = [vp, vp, c.c_int, i64, vp, c.c_int, i64, c.c_int, dp, c.c_int, c.c_int,
+                                              vp, vp, c.c_int, i32, dp, i32, vp, vp, vp]
         lib.amepb_psi_k.restype = c.c_int
         lib.amepb_psi_k.argtypes = [vp, vp, c.c_int, i64, c.c_int, c.POINTER(c.c_double), c.c_int, i32, vp, vp,
                                     c.POINTER(i64), vp]

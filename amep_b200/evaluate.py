@@ -34,11 +34,12 @@ import numpy as np
 from . import _core, dist
 from .base import BaseEvaluation
 from .order import psi6_mean, psi6_orientation, rotated_periodic_crop
-from .spatialcor import pcf2d_frames, rdf_frames, sf2d_frames, sfiso_frames
+from .order import psi_k
+from .spatialcor import pcf2d_frames, pcf_angle, rdf_frames, sf2d_frames, sfiso_frames, spatialcor
 from .trajectory import TensorTrajectory
 from .utils import evaluated_indices
 
-__all__ = ["RDF", "SFiso", "SF2d", "PCF2d"]
+__all__ = ["RDF", "SFiso", "SF2d", "PCF2d", "PCFangle", "SpatialVelCor", "HexOrderCor"]
 
 # bytes of coordinates per streamed block (per species); three staging buffers are in flight
 STREAM_BLOCK_BYTES = 256 << 20
@@ -545,3 +546,121 @@ class PCF2d(_FrameAverage):
     @property
     def avg(self):
         return self._avg
+
+
+# =============================================================================
+# per-frame pair observables: PCFangle, SpatialVelCor, HexOrderCor
+# =============================================================================
+class _PerFrame(_FrameAverage):
+    """Evaluate classes whose kernels take one frame per call (all-pairs observables): the
+    selected frames are sharded over the ranks in contiguous blocks, every rank loops over its
+    frames, the rows are assembled with one all-reduce and averaged like average_func."""
+
+    def _run(self, traj, skip, nav, distributed, group, compute):
+        idx = self._select(traj, skip, nav)
+        sh = _Shard(len(idx), distributed, group)
+        rows = [np.array(compute(frame)) for frame in traj[np.asarray(idx[sh.lo:sh.hi])]]
+        local = np.stack(rows) if rows else None
+        self._frames = sh.assemble(local)
+        return np.mean(self._frames, axis=0)
+
+    @property
+    def frames(self):
+        return self._frames
+
+    @property
+    def avg(self):
+        return self._avg
+
+
+class PCFangle(_PerFrame):
+    """Angular pair correlation function g(r, theta), time-averaged (amep/evaluate.py:834-1196).
+    ``mode``: ``'psi6'`` (angles relative to the mean hexagonal orientation of the frame),
+    ``'orientations'`` (relative to every particle's own orientation) or ``'x'``."""
+
+    def __init__(self, traj, skip: float = 0.0, nav: int = 10, ptype=None, other=None, mode: str = "psi6",
+                 max_workers=1, distributed=None, group=None, **kwargs) -> None:
+        super().__init__()
+        self.name = "pcfa"
+        if mode not in ["psi6", "orientations", "x"]:
+            raise ValueError("Mode not recognized. Possible values are 'psi6', 'orientations', and 'x'.")
+        for ignored in ("verbose", "njobs", "chunksize"):
+            kwargs.pop(ignored, None)
+
+        def compute(frame):
+            # amep/evaluate.py:1046-1101
+            psi = None
+            e = np.array([1.0, 0.0, 0.0], dtype=float)
+            if mode == "orientations":
+                e = _core.to_numpy(frame.orientations(ptype=ptype if other is None else other))
+            elif mode == "psi6":
+                psi = psi6_mean(frame.coords(), frame.box)
+            c = frame.coords(ptype=ptype)
+            c = c.clone() if _core._is_torch(c) else np.array(c)       # pcf_angle zeroes z in place
+            if other is None:
+                return pcf_angle(c, frame.box, psi=psi, e=e, **kwargs)
+            o = frame.coords(ptype=other)
+            o = o.clone() if _core._is_torch(o) else np.array(o)
+            return pcf_angle(c, frame.box, other_coords=o, psi=psi, e=e, **kwargs)
+
+        res = self._run(traj, skip, nav, distributed, group, compute)
+        self._avg, self._r, self._theta = res[0], res[1], res[2]
+
+    @property
+    def r(self):
+        return self._r
+
+    @property
+    def theta(self):
+        return self._theta
+
+
+class SpatialVelCor(_PerFrame):
+    """Spatial velocity correlation function, time-averaged (amep/evaluate.py:219-403)."""
+
+    def __init__(self, traj, skip: float = 0.0, nav: int = 10, ptype=None, other=None, max_workers=1,
+                 distributed=None, group=None, **kwargs) -> None:
+        super().__init__()
+        self.name = "svc"
+        for ignored in ("verbose", "njobs", "chunksize"):
+            kwargs.pop(ignored, None)
+
+        def compute(frame):
+            # amep/evaluate.py:330-338: the second set is always passed
+            return spatialcor(frame.coords(ptype=ptype), frame.box, frame.velocities(ptype=ptype),
+                              other_coords=frame.coords(ptype=other), other_values=frame.velocities(ptype=other), **kwargs)
+
+        res = self._run(traj, skip, nav, distributed, group, compute)
+        self._avg, self._r = res[0], res[1]
+
+    @property
+    def r(self):
+        return self._r
+
+
+class HexOrderCor(_PerFrame):
+    """Spatial correlation function of the hexagonal order parameter, time-averaged
+    (amep/evaluate.py:2085-2330): psi_6 per particle (amepb_psi_k), then ``spatialcor``."""
+
+    def __init__(self, traj, skip: float = 0.0, nav: int = 10, ptype=None, other=None, max_workers=1,
+                 distributed=None, group=None, **kwargs) -> None:
+        super().__init__()
+        self.name = "hoc"
+        for ignored in ("verbose", "njobs", "chunksize"):
+            kwargs.pop(ignored, None)
+
+        def compute(frame):
+            # amep/evaluate.py:2219-2253
+            c = frame.coords(ptype=ptype)
+            hexorder = psi_k(c, frame.box, k=6)
+            if other is None:
+                return spatialcor(c, frame.box, hexorder, **kwargs)
+            o = frame.coords(ptype=other)
+            return spatialcor(c, frame.box, hexorder, other_coords=o, other_values=psi_k(o, frame.box, k=6), **kwargs)
+
+        res = self._run(traj, skip, nav, distributed, group, compute)
+        self._avg, self._r = res[0], res[1]
+
+    @property
+    def r(self):
+        return self._r

@@ -25,7 +25,8 @@ from .utils import (available_cpu_count, optimal_chunksize, runningmean, sq_from
 
 _log = logging.getLogger("amep_b200.spatialcor")
 
-__all__ = ["rdf", "sfiso", "sf2d", "pcf2d", "rdf_frames", "sfiso_frames", "sf2d_frames", "pcf2d_frames"]
+__all__ = ["rdf", "sfiso", "sf2d", "pcf2d", "pcf_angle", "spatialcor", "rdf_frames", "sfiso_frames", "sf2d_frames",
+           "pcf2d_frames"]
 
 
 def _box_numpy(box_boundary):
@@ -530,3 +531,109 @@ def pcf2d(coords, box_boundary, other_coords=None, nxbins=None, nybins=None, rma
     arrays set to zero in place (:846-848) and ``rmax = max(box)//(2*sqrt(2))`` by default (:861)."""
     g, X, Y = pcf2d_frames(coords, box_boundary, other_coords, nxbins=nxbins, nybins=nybins, rmax=rmax, psi=psi)
     return g[0], X[0], Y[0]
+
+
+# =============================================================================
+# PCF ANGLE
+# =============================================================================
+def pcf_angle(coords, box_boundary, other_coords=None, ndbins=500, nabins=100, rmax=None, psi=None, njobs=1,
+              pbc=True, verbose=False, chunksize=None, e=np.array([1.0, 0.0, 0.0])):
+    """Angle dependent radial pair correlation function g(r, theta) of one 2D frame; contract of
+    ``amep.spatialcor.pcf_angle`` (amep/spatialcor.py:1044-1318): minimum-image difference vectors,
+    angle to the direction ``e`` (one vector or one per particle), rotation by the ``psi`` angle;
+    the z column of the caller's arrays must be zero (ValueError otherwise) and is set to zero in
+    place like the reference does (:1197-1203).  Returns ``(g.T [na, nd], R, T)``.
+
+    ``e`` is evaluated in float64 (a float32 ``e``, e.g. trajectory orientations, makes the
+    reference compute the angles in float32: counts then agree except for pairs within float32
+    rounding of an angle edge)."""
+    same = other_coords is None
+
+    def host_view(c):
+        return c.detach().cpu().numpy() if _core._is_torch(c) else np.asarray(c)
+
+    for c in ((coords,) if same else (coords, other_coords)):
+        z = c[..., -1]
+        nonzero = bool((z != 0).any()) if _core._is_torch(c) else bool(np.any(np.asarray(z) != 0.0))
+        if nonzero:
+            raise ValueError("amep.spatialcor.pcf_angle: Input coordinates are not 2D. "
+                             "The z-coordinate must be zero for all particles.")
+        c[..., -1] = 0.0
+    bb = _box_numpy(box_boundary)
+    box = bb[:, 1] - bb[:, 0]
+    n = int(coords.shape[0])
+    n_other = n if same else int(other_coords.shape[0])
+    e = np.asarray(e)
+    if e.ndim == 1:
+        if e.shape[0] != 3:
+            raise ValueError("amep.spatialcor.pcf_angle: Invalid shape of e. "
+                             "If e is given as 1D array, it must have shape (3,).")
+    elif e.ndim == 2:
+        if e.shape != (n, 3):
+            raise ValueError("amep.spatialcor.pcf_angle: Invalid shape of e. "
+                             "If e is given as 2D array, it must have shape (N,3), "
+                             "where N is the number of particles.")
+    else:
+        raise ValueError("amep.spatialcor.pcf_angle: Invalid shape of e. e must be either 1D or 2D array.")
+    if ndbins is None:
+        ndbins = 500
+    if nabins is None:
+        nabins = 100
+    if rmax is None:
+        rmax = max(box) / 2
+    angle = _pcf2d_angle(psi)       # amep/spatialcor.py:1235-1241, the same expression as pcf2d's
+    dbins = np.linspace(0.0, rmax, ndbins + 1)
+    abins = np.linspace(0.0, 2 * np.pi, nabins + 1)
+    hist = _core.pcf_angle_counts(coords, None if same else other_coords, same, bb, pbc, e, angle, dbins, abins)
+    hist = hist.astype(float)
+    # normalization (amep/spatialcor.py:1306-1318)
+    area = 0.5 * (dbins[1:] ** 2 - dbins[:-1] ** 2)[:, None] * (abins[1:] - abins[:-1])
+    density = n / (box[0] * box[1])
+    res = hist / area / density / n_other
+    R, T = np.meshgrid(runningmean(dbins, 2), runningmean(abins, 2))
+    return res.T, R, T
+
+
+# =============================================================================
+# GENERAL SPATIAL CORRELATION FUNCTION
+# =============================================================================
+def spatialcor(coords, box_boundary, values, other_coords=None, other_values=None, dbin_edges=None, ndists=None,
+               chunksize=None, njobs=1, rmax=None, verbose=False, pbc=True):
+    """Spatial correlation function of per-particle values (scalars, vectors, complex numbers) of
+    one frame; contract of ``amep.spatialcor.spatialcor`` (amep/spatialcor.py:141-342): for every
+    distance bin the average of ``conj(other_value) * value`` over the pairs whose minimum-image
+    distance (the reference's periodic KD-tree, distances below ``max(box)/2``) falls into it,
+    normalised by the first bin.  The pair counts are exact; the sums are float64 (the reference
+    sums float32 values in float32)."""
+    bb = _box_numpy(box_boundary)
+    box = bb[:, 1] - bb[:, 0]
+    vshape = tuple(values.shape)
+    if len(vshape) != 1 and len(vshape) != 2:
+        raise ValueError(f"amep.spatialcor.spatialcor: values have an invalid shape {vshape}. The shape must be (N,) "
+                         "for scalar values and (N,d) for vector quantities.")
+    # amep/spatialcor.py:272-285: a missing partner defaults to the first set (the two error
+    # branches that follow in the reference are unreachable)
+    if other_coords is not None and other_values is None:
+        other_values = values
+    if other_coords is None and other_values is not None:
+        other_coords = coords
+    if other_coords is not None and int(other_values.shape[0]) != int(other_coords.shape[0]):
+        raise ValueError("amep.spatialcor.spatialcor: other_values must hold one row per particle of other_coords")
+    if rmax is None:
+        rmax = max(box) / 2.
+    if dbin_edges is None and ndists is not None:
+        dbin_edges = np.linspace(0.0, rmax, ndists)
+    elif dbin_edges is None and ndists is None:
+        dbin_edges = np.arange(0.0, rmax, 1.05)
+    dbin_edges = np.asarray(dbin_edges)
+    norm, cor, is_complex = _core.spatialcor_sums(coords, values, other_coords, other_values, bb, pbc, dbin_edges)
+    norm = norm.astype(float)
+    if is_complex:
+        cor = cor.astype(np.complex64)      # the reference accumulates complex values in complex64 (:72-73)
+    else:
+        cor = cor.real.copy()
+    norm[(norm == 0) & (cor == 0)] = 1
+    cor = cor / norm
+    if cor.dtype in [np.complex64, np.complex128, complex]:
+        cor = np.real(cor)
+    return cor / cor[0], runningmean(dbin_edges, 2)

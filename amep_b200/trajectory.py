@@ -57,6 +57,24 @@ class TensorFrame:
             return c[torch.from_numpy(mask).to(c.device)]
         return c[mask]
 
+    def _per_particle(self, data, what, ptype):
+        if data is None:
+            raise KeyError(f"The trajectory holds no {what}.")
+        d = data[self._index]
+        mask = self._mask(ptype)
+        if mask is None:
+            return d
+        if _core._is_torch(d):
+            import torch
+            return d[torch.from_numpy(mask).to(d.device)]
+        return d[mask]
+
+    def velocities(self, ptype=None, **kwargs):
+        return self._per_particle(self._traj._velocities, "velocities", ptype)
+
+    def orientations(self, ptype=None, **kwargs):
+        return self._per_particle(self._traj._orientations, "orientations", ptype)
+
     def n(self, ptype=None):
         mask = self._mask(ptype)
         return int(self._traj._coords.shape[1] if mask is None else mask.sum())
@@ -69,9 +87,11 @@ class TensorTrajectory:
     box    : ``(3,2)`` or ``(F,3,2)`` array (its dtype is kept: it decides the
              reference's arithmetic)
     times, steps : optional ``[F]``;  types : optional ``[N]`` or ``[F, N]`` particle types
+    velocities, orientations : optional ``[F, N, 3]`` (``frame.velocities()`` / ``frame.orientations()``,
+             read by SpatialVelCor and PCFangle(mode='orientations'))
     """
 
-    def __init__(self, coords, box, times=None, steps=None, types=None):
+    def __init__(self, coords, box, times=None, steps=None, types=None, velocities=None, orientations=None):
         if len(coords.shape) != 3 or coords.shape[-1] != 3:
             raise ValueError(f"coords must have shape (F, N, 3), got {tuple(coords.shape)}")
         self._coords = coords
@@ -82,6 +102,11 @@ class TensorTrajectory:
         self.steps = np.arange(nf) if steps is None else np.asarray(steps)
         self.times = self.steps.astype(float) if times is None else np.asarray(times)
         self._types = None if types is None else np.asarray(types)
+        for name, data in (("velocities", velocities), ("orientations", orientations)):
+            if data is not None and tuple(data.shape) != tuple(coords.shape):
+                raise ValueError(f"{name} must have the shape of coords, {tuple(coords.shape)}")
+        self._velocities = velocities
+        self._orientations = orientations
 
     def __len__(self):
         return int(self._coords.shape[0])

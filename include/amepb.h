@@ -20,6 +20,9 @@
  *                             reached by sf2d/sfiso(mode='fft'), amep/spatialcor.py:1911-1940
  *   amepb_pcf2d_counts     <- amep/spatialcor.py:652-723    __dhist2d (difference vectors, rotation,
  *                             np.histogram2d) and the chunk fan-out + sum of pcf2d, :886-912
+ *   amepb_pcf_angle_counts <- amep/spatialcor.py:929-1041   __dhist_angle and the chunk sum of pcf_angle, :1268-1304
+ *   amepb_spatialcor_sums  <- amep/spatialcor.py:47-135     __scor_chunk (periodic KD-tree query + value
+ *                             products per distance bin) and the chunk sum of spatialcor, :322-330
  *   amepb_psi_k            <- amep/order.py:1183-1348       k_nearest_neighbors (periodic KD-tree query)
  *                             amep/order.py:1361-1501       psi_k, the prologue of evaluate.SF2d(rotate=True)
  *                             and evaluate.PCF2d (amep/evaluate.py:1352-1357, 730-735)
@@ -228,6 +231,47 @@ int amepb_pcf2d_counts(amepb_ctx* ctx, const void* coords, int dtype, int64_t n,
                        const double* center, int center_f32, const double* rot, const double* xedges,
                        int32_t nxe, const double* yedges, int32_t nye, int64_t edge_stride,
                        uint64_t* counts, void* stream);
+
+/*
+ * Pair counts on the (distance, angle) grid of spatialcor.pcf_angle (amep/spatialcor.py:929-1041): for
+ * every row o of `other` and every row c of `coords` (skipping equal indices when same != 0) the
+ * difference c - o in the promoted dtype of the two arrays, folded to the minimum image when pbc != 0
+ * (amep.pbc.pbc_diff -> fold about the centred box, in the dtype NumPy promotes vector and box to,
+ * amep/pbc.py:155-163, 597-602); dist = norm in that dtype, pairs with dist == 0 dropped;
+ * theta = arccos(clip(dot(e, r) / (dist |e|), -1, 1)) in float64, 2 pi - theta where r_y < 0, minus
+ * `angle` (wrapped into [0, 2 pi)) when angle != 0; (dist, theta) binned like np.histogram2d.
+ * Both coordinate arrays must be flat (z == 0), as the reference enforces.
+ *   e, e_norm   host float64: one direction [3] and its norm [1] (e_stride == 0) or one per row of
+ *               `other`, [m][3] and [m] (e_stride == 3)
+ *   dedges, aedges  host float64, increasing (float32 edges widened exactly)
+ *   counts      [nde-1][nae-1] uint64 in `space`
+ * The call returns after the work is complete (it synchronises `stream`).
+ */
+int amepb_pcf_angle_counts(amepb_ctx* ctx, const void* coords, int dtype, int64_t n, const void* other,
+                           int other_dtype, int64_t m, int same, int space, const double* box_boundary,
+                           int box_dtype, int pbc, const double* e, int64_t e_stride, const double* e_norm,
+                           double angle, const double* dedges, int32_t nde, const double* aedges, int32_t nae,
+                           uint64_t* counts, void* stream);
+
+/*
+ * Pair counts and value-product sums per distance bin of spatialcor.spatialcor
+ * (amep/spatialcor.py:47-135): the periodic KD-tree of the reference restated -- `coords` shifted by
+ * box/2 - centre and folded into [0, L) (amep/pbc.py:632-655), the rows of `other` shifted, folded
+ * about the box centre (amep/spatialcor.py:315-319) and wrapped into [0, L) like scipy's periodic
+ * tree wraps query points; float64 minimum-image distances d; pairs with d < max(box)/2 only;
+ * bin i holds edges[i] <= d < edges[i+1] (no right-inclusive last bin, amep/spatialcor.py:112);
+ *   norm[i] += 1,  cor[i] += sum over the components of conj(other_value) * value  (float64).
+ * pbc == 0: plain float64 distances of the two arrays.
+ *   other, other_values  NULL: the same particles as coords / values
+ *   values      [n][ncomp], other_values [m][ncomp] in `space`; value_kind 0 float32, 1 float64,
+ *               2 complex64, 3 complex128 (interleaved re, im); 1 <= ncomp <= 4
+ *   norm        [nedges-1] uint64, cor [nedges-1][2] float64 (re, im), both in `space`
+ * The call returns after the work is complete (it synchronises `stream`).
+ */
+int amepb_spatialcor_sums(amepb_ctx* ctx, const void* coords, int dtype, int64_t n, const void* other,
+                          int other_dtype, int64_t m, int space, const double* box_boundary, int box_dtype,
+                          int pbc, const void* values, const void* other_values, int value_kind, int32_t ncomp,
+                          const double* edges, int32_t nedges, uint64_t* norm, double* cor, void* stream);
 
 /*
  * k-atic bond order parameter of every particle of one 2D frame, psi_k of amep/order.py:1361-1501

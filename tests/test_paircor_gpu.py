@@ -1,0 +1,193 @@
+"""pcf_angle / spatialcor (remaining functions) on the GPU against golden
+vectors of the unmodified reference (oracle/make_golden_paircor.py) and the CPU oracle.
+
+Parity bar: integer pair counts equal (distance bins are decided in the reference's own float
+arithmetic; angle bins in float64 through arccos, where a pair within an ulp of an angle edge could
+in principle differ -- none does in these fixtures); value sums of spatialcor in float64 against the
+reference's float32 dot products: 1e-5 relative (float32 inputs), 1e-10 (float64 inputs)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import amep_oracle as orc
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+PCFA = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "pcfa_*.npz")))
+SCOR = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "scor_*.npz")))
+
+
+@pytest.fixture(scope="module")
+def sc():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import amep_b200
+    return amep_b200.spatialcor
+
+
+def _dev(a, space):
+    return a if (a is None or space == "host") else torch.from_numpy(a).cuda()
+
+
+def _pcfa_kw(z):
+    kw = dict(ndbins=int(z["ndbins"]), nabins=int(z["nabins"]), pbc=bool(z["pbc"]), e=z["e"])
+    if not np.isnan(z["rmax"]):
+        kw["rmax"] = float(z["rmax"])
+    if "psi" in z.files:
+        kw["psi"] = z["psi"]
+    return kw
+
+
+@pytest.mark.parametrize("space", ["host", "device"])
+@pytest.mark.parametrize("name", PCFA)
+def test_pcf_angle_golden(sc, name, space):
+    z = np.load(os.path.join(GOLDEN, name))
+    coords = _dev(z["coords"].copy(), space)
+    other = _dev(z["other"].copy(), space) if "other" in z.files else None
+    g, R, T = sc.pcf_angle(coords, z["box"], other_coords=other, **_pcfa_kw(z))
+    assert g.dtype == z["g"].dtype and g.shape == z["g"].shape
+    np.testing.assert_array_equal(R, z["R"])
+    np.testing.assert_array_equal(T, z["T"])
+    np.testing.assert_array_equal(g, z["g"])       # counts equal => g bit-identical (same NumPy epilogue)
+    assert z["counts"].sum() > 0
+
+
+def test_pcf_angle_errors_and_side_effects(sc):
+    box = np.array([[0, 5], [0, 5], [-0.5, 0.5]])
+    c = np.random.default_rng(1).uniform(0, 5, (50, 3))
+    with pytest.raises(ValueError):            # not flat
+        sc.pcf_angle(c, box, ndbins=5, nabins=4)
+    c[:, 2] = 0
+    with pytest.raises(ValueError):
+        sc.pcf_angle(c, box, ndbins=5, nabins=4, e=np.array([1.0, 0.0]))
+    with pytest.raises(ValueError):
+        sc.pcf_angle(c, box, ndbins=5, nabins=4, e=np.ones((7, 3)))
+    g, R, T = sc.pcf_angle(c, box, ndbins=None, nabins=None, rmax=1.0)
+    assert g.shape == (100, 500)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_pcf_angle_larger_against_oracle(sc, dtype):
+    rng = np.random.default_rng(81)
+    n, m, L = 2500, 900, 30.0
+    box = np.array([[-L / 2, L / 2], [0, L], [-0.5, 0.5]], dtype=dtype)
+    c = np.zeros((n, 3), dtype=dtype)
+    c[:, 0] = rng.uniform(-L / 2 - 1, L / 2 + 1, n)        # a few particles outside the box
+    c[:, 1] = rng.uniform(0, L, n)
+    o = np.zeros((m, 3), dtype=dtype)
+    o[:, 0] = rng.uniform(-L / 2, L / 2, m)
+    o[:, 1] = rng.uniform(0, L, m)
+    o[:5] = c[:5]                                          # coincident pairs: dist == 0 is dropped
+    psi = np.array([-0.2, 0.7])
+    for other, kw in ((None, dict(ndbins=60, nabins=30, psi=psi)), (o, dict(ndbins=45, nabins=50, rmax=9.0))):
+        want = orc.pcf_angle(c.copy(), box, None if other is None else other.copy(), **kw)
+        got = sc.pcf_angle(torch.from_numpy(c.copy()).cuda(), box,
+                           other_coords=None if other is None else torch.from_numpy(other.copy()).cuda(), **kw)
+        for a, b in zip(got, want):
+            np.testing.assert_array_equal(a, b)
+
+
+def _scor_kw(z, name):
+    kw = dict(pbc=bool(z["pbc"]))
+    if not np.isnan(z["rmax"]):
+        kw["rmax"] = float(z["rmax"])
+    if int(z["ndists"]) >= 0:
+        kw["ndists"] = int(z["ndists"])
+    if "nopbc" in name:
+        kw["dbin_edges"] = z["edges"]
+    return kw
+
+
+@pytest.mark.parametrize("space", ["host", "device"])
+@pytest.mark.parametrize("name", SCOR)
+def test_spatialcor_golden(sc, name, space):
+    from amep_b200 import _core
+    z = np.load(os.path.join(GOLDEN, name))
+    coords, values = _dev(z["coords"], space), _dev(z["values"], space)
+    other = _dev(z["other"], space) if "other" in z.files else None
+    ovals = _dev(z["other_values"], space) if "other" in z.files else None
+    kw = _scor_kw(z, name)
+    c, r = sc.spatialcor(coords, z["box"], values, other_coords=other, other_values=ovals, **kw)
+    np.testing.assert_array_equal(r, z["r"])
+    assert c.dtype == z["c"].dtype and c.shape == z["c"].shape
+    f32 = z["coords"].dtype == np.float32
+    tol = 1e-5 if f32 else 1e-10
+    assert np.max(np.abs(c - z["c"])) < tol * max(1.0, float(np.max(np.abs(z["c"]))))
+    # the raw sums of the worker: pair counts exact
+    norm, cor, _ = _core.spatialcor_sums(coords, values, other, ovals, z["box"], bool(z["pbc"]), z["edges"])
+    np.testing.assert_array_equal(norm, z["norm"])
+    ref = z["cor"].astype(np.complex128)
+    assert np.max(np.abs(cor - ref)) < (2e-5 if f32 else 1e-10) * float(np.max(np.abs(ref)))
+
+
+def test_spatialcor_larger_against_oracle(sc):
+    from amep_b200 import _core
+    rng = np.random.default_rng(82)
+    n, m = 2600, 1100
+    box = np.array([[0, 22], [-5, 12], [0, 9]], dtype=np.float64)
+    lo, hi = box[:, 0], box[:, 1]
+    c = rng.uniform(lo - 1.0, hi + 1.0, (n, 3))          # unfolded coordinates
+    o = rng.uniform(lo, hi, (m, 3))
+    v = rng.normal(size=(n, 3))
+    w = rng.normal(size=(m, 3))
+    for pbc in (True, False):
+        edges = orc.spatialcor_edges(box, None, 40, 7.5)
+        cor_w, norm_w, _ = orc.spatialcor_sums(c, box, v, o, w, ndists=40, rmax=7.5, pbc=pbc)
+        norm, cor, _ = _core.spatialcor_sums(torch.from_numpy(c).cuda(), torch.from_numpy(v).cuda(), torch.from_numpy(o).cuda(),
+                                             torch.from_numpy(w).cuda(), box, pbc, edges)
+        np.testing.assert_array_equal(norm, norm_w)
+        assert np.max(np.abs(cor.real - cor_w)) < 1e-9 * np.max(np.abs(cor_w))
+        cg, rg = sc.spatialcor(c, box, v, other_coords=o, other_values=w, ndists=40, rmax=7.5, pbc=pbc)
+        cw, rw = orc.spatialcor(c, box, v, o, w, ndists=40, rmax=7.5, pbc=pbc)
+        np.testing.assert_array_equal(rg, rw)
+        assert np.max(np.abs(cg - cw)) < 1e-9 * np.max(np.abs(cw))
+
+
+def test_evaluate_pair_classes(sc):
+    """PCFangle (three modes), SpatialVelCor, HexOrderCor over a tensor trajectory against the oracle
+    composed the way the reference composes them (amep/evaluate.py:1046-1101, 330-338, 2219-2253)."""
+    import amep_b200
+    z = np.load(os.path.join(GOLDEN, "order_hex_f32.npz"))
+    rng = np.random.default_rng(83)
+    base = z["coords"]
+    nf, n = 3, len(base)
+    coords = np.stack([base, base[::-1].copy(), np.roll(base, 7, axis=0)])
+    vel = rng.normal(size=(nf, n, 3)).astype(np.float32)
+    ang = rng.uniform(0, 2 * np.pi, (nf, n))
+    ori = np.stack([np.cos(ang), np.sin(ang), np.zeros_like(ang)], axis=-1)       # float64 directions
+    box = z["box"]
+    traj = amep_b200.TensorTrajectory(torch.from_numpy(coords).cuda(), box, velocities=torch.from_numpy(vel).cuda(),
+                                      orientations=ori)
+    kw = dict(ndbins=30, nabins=18, rmax=4.0)
+    for mode in ("psi6", "orientations", "x"):
+        ev = amep_b200.evaluate.PCFangle(traj, skip=0.0, nav=3, mode=mode, **kw)
+        rows = []
+        for f in ev.indices:
+            psi, e = None, np.array([1.0, 0.0, 0.0])
+            if mode == "psi6":
+                p = np.mean(orc.psi_k(coords[f], box))
+                psi = np.array([p.real, p.imag])
+            elif mode == "orientations":
+                e = ori[f]
+            rows.append(np.array(orc.pcf_angle(coords[f].copy(), box, None, psi=psi, e=e, **kw)))
+        want = np.array(rows)
+        if mode == "psi6":      # the angle carries the last bits of psi_6: a pair on an angle edge may move
+            assert np.mean(ev.frames[:, 0] != want[:, 0]) < 0.02
+        else:
+            np.testing.assert_array_equal(ev.frames, want)
+            np.testing.assert_array_equal(ev.avg, np.mean(want, axis=0)[0])
+        np.testing.assert_array_equal(ev.r, np.mean(want, axis=0)[1])
+        np.testing.assert_array_equal(ev.theta, np.mean(want, axis=0)[2])
+    ev = amep_b200.evaluate.SpatialVelCor(traj, skip=0.0, nav=2, rmax=5.0)
+    rows = [np.array(orc.spatialcor(coords[f], box, vel[f], coords[f], vel[f], rmax=5.0)) for f in ev.indices]
+    assert np.max(np.abs(ev.frames - np.array(rows))) < 1e-5
+    np.testing.assert_array_equal(ev.r, rows[0][1])
+    ev = amep_b200.evaluate.HexOrderCor(traj, skip=0.0, nav=2, rmax=5.0)
+    rows = [np.array(orc.spatialcor(coords[f], box, orc.psi_k(coords[f], box), rmax=5.0)) for f in ev.indices]
+    assert np.max(np.abs(ev.frames - np.array(rows))) < 1e-5
+    assert ev.name == "hoc" and ev.avg.shape == rows[0][0].shape
