@@ -325,11 +325,27 @@ class SFiso(_FrameAverage):
             raise TypeError("amep_b200.evaluate.SFiso: field trajectories are not on the B200 hot path "
                             "(SURVEY.md section 8f)")
         idx = self._select(traj, skip, nav)
-        sh = _Shard(len(idx), distributed, group)
+        # fewer frames than ranks: the particle sums of 'fast' (and the Debye sums of 'std') are linear
+        # in the particles, so every rank takes a slice of them and the sums are all-reduced
+        sh = _Shard(len(idx), distributed, group, allow_intra=mode in ("fast", "std"))
         rows = []
         for coords, other_coords, box in _frame_batches(traj, idx[sh.lo:sh.hi], ptype, other, other is not None):
+            extra = {}
+            if sh.intra:
+                na = int(coords.shape[1])
+                nb_ = na if other_coords is None else int(other_coords.shape[1])
+                if min(na, nb_) < sh.ws:          # (every rank sees the same numbers: no rank is left waiting)
+                    raise ValueError("SFiso: more ranks than particles")
+                lo_a, hi_a = dist.shard_bounds(na, sh.rank, sh.ws)
+                if mode == "fast" and other_coords is not None:
+                    lo_b, hi_b = dist.shard_bounds(nb_, sh.rank, sh.ws)
+                    other_coords = other_coords[:, lo_b:hi_b]
+                elif mode == "std" and other_coords is None:
+                    other_coords = coords               # the slice pairs with all particles
+                coords = coords[:, lo_a:hi_a]
+                extra = dict(reduce=sh.all_sum, counts=(na, nb_))
             rows.append(sfiso_frames(coords, box, None, qmax=qmax, twod=twod, mode=mode,
-                                     other_coords=other_coords, accuracy=accuracy, num=num))
+                                     other_coords=other_coords, accuracy=accuracy, num=num, **extra))
         local = None
         if rows:
             s, q = (np.concatenate([p[k] for p in rows]) for k in range(2))

@@ -180,8 +180,13 @@ def _unique_directions(unit_vectors):
 
 
 def sfiso_frames(coords, box_boundary, N=None, qmax=20.0, twod=True, mode="std",
-                 other_coords=None, accuracy=0.5, num=64, reduce=None):
-    """``sfiso`` for a batch of frames -> ``(S [F, nq], q [F, nq])``."""
+                 other_coords=None, accuracy=0.5, num=64, reduce=None, counts=None):
+    """``sfiso`` for a batch of frames -> ``(S [F, nq], q [F, nq])``.
+
+    ``reduce`` / ``counts``: intra-frame sharding over ranks -- every rank passes its slice of the
+    particles, ``reduce`` sums the per-direction (cos, sin) sums (mode 'fast') or the Debye sums
+    of the slice of ``coords`` against all of ``other_coords`` (mode 'std') over the ranks, and
+    ``counts = (N_a, N_b)`` are the particle numbers of the whole frame for the normalisation."""
     modes = ["std", "fast", "fft"]
     pc = coords if isinstance(coords, _core.Particles) else _core.Particles(coords)
     po = pc if other_coords is None else (
@@ -233,7 +238,8 @@ def sfiso_frames(coords, box_boundary, N=None, qmax=20.0, twod=True, mode="std",
             sums = reduce(sums)
         if _core._is_torch(sums):
             sums = sums.cpu().numpy()
-        s = sums / np.sqrt(pc.n * po.n)
+        na, nb_ = (pc.n, po.n) if counts is None else counts
+        s = sums / np.sqrt(na * nb_)
         q = np.stack(q_rows) if per_frame_box else np.broadcast_to(q_rows[0], (nf, nq)).copy()
         return s, q
     unit_vectors = _sfiso_directions(twod, num)
@@ -254,7 +260,8 @@ def sfiso_frames(coords, box_boundary, N=None, qmax=20.0, twod=True, mode="std",
         hb = ha if po is pc else hb.cpu().numpy()
     # (C_a C_b + S_a S_b) / sqrt(N_a N_b), mean over directions
     # (amep/spatialcor.py:1440-1446, 1660-1664)
-    s_dir = (ha[..., 0] * hb[..., 0] + ha[..., 1] * hb[..., 1]) / np.sqrt(pc.n * po.n)
+    na, nb_ = (pc.n, po.n) if counts is None else counts
+    s_dir = (ha[..., 0] * hb[..., 0] + ha[..., 1] * hb[..., 1]) / np.sqrt(na * nb_)
     s = np.tensordot(weights, s_dir, axes=([0], [1])) / len(unit_vectors)
     q = np.stack(q_rows) if per_frame_box else np.broadcast_to(q_rows[0], (nf, nq)).copy()
     return s, q

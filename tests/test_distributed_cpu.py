@@ -57,11 +57,25 @@ def _oracle_rdf_frames(coords, box, other_coords=None, nbins=None, rmax=None, mo
 
 
 def _oracle_sfiso_frames(coords, box, N=None, qmax=20.0, twod=True, mode="fast", other_coords=None,
-                         accuracy=0.5, num=8, reduce=None):
+                         accuracy=0.5, num=8, reduce=None, counts=None):
+    """Stand-in for spatialcor.sfiso_frames(mode='fast') in NumPy: per direction the (cos, sin) sums
+    of the particles it is given, ``reduce`` over the ranks, the reference's normalisation
+    (amep/spatialcor.py:1440-1446, 1660-1664) with the particle numbers of the whole frame."""
     import amep_oracle as orc
     coords = np.asarray(coords)
-    rows = [orc.sfiso_fast(coords[f], box, qmax=qmax, twod=twod, num=num) for f in range(coords.shape[0])]
-    return np.array([r[0] for r in rows]), np.array([r[1] for r in rows])
+    q = orc.sf_qvalues(box, qmax)
+    dirs = orc.sfiso_directions(twod, num)
+    ha = np.zeros((coords.shape[0], len(dirs), len(q), 2))
+    for f in range(coords.shape[0]):
+        for d, u in enumerate(dirs):
+            proj = coords[f].astype(np.float64) @ u
+            ph = q[:, None] * proj[None, :]
+            ha[f, d, :, 0], ha[f, d, :, 1] = np.cos(ph).sum(axis=1), np.sin(ph).sum(axis=1)
+    if reduce is not None:
+        ha = reduce(ha)
+    na = coords.shape[1] if counts is None else counts[0]
+    s = ((ha[..., 0] ** 2 + ha[..., 1] ** 2) / np.sqrt(na * na)).mean(axis=1)
+    return s, np.broadcast_to(q, (coords.shape[0], len(q))).copy()
 
 
 def _oracle_sf2d_frames(coords, box, other_coords=None, qmax=20.0, compact_grids=False, **kw):
@@ -127,7 +141,10 @@ def _worker(rank, world, port, tmpdir):
         es = evaluate.SFiso(small, skip=0.0, nav=nav, qmax=2.0, num=4)
         rows = [_oracle_sfiso_frames(z["coords"][i:i + 1, :200], z["box"], qmax=2.0, num=4) for i in es.indices]
         want = np.array([(r[0][0], r[1][0]) for r in rows])
-        assert np.array_equal(es.frames, want) and np.array_equal(es.avg, np.mean(want, axis=0)[0])
+        if nav == 1:    # fewer frames than ranks: the particles of the frame are split, sums all-reduced
+            assert np.allclose(es.frames, want, rtol=1e-12, atol=1e-12) and np.array_equal(es.frames[:, 1], want[:, 1])
+        else:
+            assert np.array_equal(es.frames, want) and np.array_equal(es.avg, np.mean(want, axis=0)[0])
         e2 = evaluate.SF2d(small, skip=0.0, nav=nav, qmax=1.0, rotate=False)
         rows = [_oracle_sf2d_frames(z["coords"][i:i + 1, :200], z["box"], qmax=1.0) for i in e2.indices]
         want = np.array([(r[0][0], r[1][0], r[2][0]) for r in rows])

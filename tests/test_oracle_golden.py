@@ -207,3 +207,58 @@ def test_pcf2d_bit_exact(name):
     np.testing.assert_array_equal(g, z["g"])
     np.testing.assert_array_equal(X, z["X"])
     np.testing.assert_array_equal(Y, z["Y"])
+
+
+# ---- round 2: psi_6 prologue, pcf_angle, spatialcor (oracle pinned on reference goldens) -------------
+ORDER_CASES = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "order_*.npz")))
+PCFA_CASES = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "pcfa_*.npz")))
+SCOR_CASES = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "scor_*.npz")))
+
+
+@pytest.mark.parametrize("name", ORDER_CASES)
+def test_oracle_psi6_prologue(name):
+    """knn ids, psi_k, mean, angle bit for bit; the rotated crop to 1e-13 (the reference's np.dot may
+    fuse a multiply-add in the 3x3 rotation)."""
+    z = np.load(os.path.join(GOLDEN, name))
+    np.testing.assert_array_equal(orc.knn_ids(z["coords"], z["box"]), z["neighbors"])
+    psi = orc.psi_k(z["coords"], z["box"])
+    assert psi.dtype == z["psi"].dtype
+    np.testing.assert_array_equal(psi, z["psi"])
+    assert np.mean(psi) == z["psi_mean"][0]
+    assert orc.orientation_angle(np.mean(psi)) == float(z["theta"])
+    rc = orc.rotated_periodic_crop(z["coords"], z["box"], float(z["theta"]))
+    assert rc.shape == z["rotated"].shape and np.max(np.abs(rc - z["rotated"])) < 1e-13
+
+
+@pytest.mark.parametrize("name", PCFA_CASES)
+def test_oracle_pcf_angle(name):
+    z = np.load(os.path.join(GOLDEN, name))
+    kw = dict(ndbins=int(z["ndbins"]), nabins=int(z["nabins"]), rmax=None if np.isnan(z["rmax"]) else float(z["rmax"]),
+              psi=z["psi"] if "psi" in z.files else None, pbc=bool(z["pbc"]), e=z["e"])
+    other = z["other"] if "other" in z.files else None
+    counts, _, _ = orc.pcf_angle_counts(z["coords"], z["box"], other, **kw)
+    np.testing.assert_array_equal(counts, z["counts"])
+    g, R, T = orc.pcf_angle(z["coords"], z["box"], other, **kw)
+    np.testing.assert_array_equal(g, z["g"])
+    np.testing.assert_array_equal(R, z["R"])
+    np.testing.assert_array_equal(T, z["T"])
+
+
+@pytest.mark.parametrize("name", SCOR_CASES)
+def test_oracle_spatialcor(name):
+    """Pair counts per bin exact (the periodic KD-tree's distances restated); the value sums are
+    float64 here, float32 dot products in the reference: 1e-5 relative."""
+    z = np.load(os.path.join(GOLDEN, name))
+    kw = dict(rmax=None if np.isnan(z["rmax"]) else float(z["rmax"]), ndists=None if int(z["ndists"]) < 0 else int(z["ndists"]),
+              pbc=bool(z["pbc"]))
+    if "nopbc" in name:
+        kw["dbin_edges"] = z["edges"]
+    other = z["other"] if "other" in z.files else None
+    ovals = z["other_values"] if "other" in z.files else None
+    cor, norm, edges = orc.spatialcor_sums(z["coords"], z["box"], z["values"], other, ovals, **kw)
+    np.testing.assert_array_equal(norm, z["norm"])
+    np.testing.assert_array_equal(edges, z["edges"])
+    assert np.max(np.abs(cor - z["cor"])) < 1e-5 * np.max(np.abs(z["cor"]))
+    c, r = orc.spatialcor(z["coords"], z["box"], z["values"], other, ovals, **kw)
+    np.testing.assert_array_equal(r, z["r"])
+    assert np.max(np.abs(c - z["c"])) < 1e-5

@@ -513,3 +513,47 @@ def test_back_to_back_calls_do_not_clobber_the_parameter_block(sc, monkeypatch):
         torch.cuda.synchronize()
         assert torch.equal(ra.cpu(), ref["ra"]) and torch.equal(rb.cpu(), ref["rb"])
         assert torch.equal(ha.cpu(), ref["ha"]) and torch.equal(hb.cpu(), ref["hb"])
+
+
+def test_streamed_trajectory_on_the_gpu(sc, monkeypatch):
+    """A trajectory that is not tensor-backed (frame objects with coords() / box, like the
+    reference's HDF5 trajectory) is streamed through pinned staging buffers block by block; the
+    result equals the in-memory trajectory bit for bit, for RDF and SFiso."""
+    import amep_b200
+    from amep_b200 import evaluate
+    rng = np.random.default_rng(71)
+    nf, n, L = 13, 5000, 60.0
+    box = np.array([[0, L], [0, L], [-0.5, 0.5]], dtype=np.float32)
+    data = np.zeros((nf, n, 3), dtype=np.float32)
+    data[:, :, :2] = rng.uniform(0, L, (nf, n, 2))
+    types = np.array([1] * 3000 + [2] * 2000)
+
+    class Frame:
+        def __init__(self, i):
+            self.i = i
+            self.box = box
+
+        def coords(self, ptype=None, **kw):
+            c = np.array(data[self.i])
+            return c if ptype is None else c[types == ptype]
+
+    class Traj:
+        times = np.arange(nf) * 2.0
+
+        def __len__(self):
+            return nf
+
+        def __getitem__(self, item):
+            return [Frame(int(i)) for i in item] if isinstance(item, (list, np.ndarray)) else Frame(int(item))
+
+    monkeypatch.setattr(evaluate, "STREAM_BLOCK_BYTES", 3 * n * 12)      # three frames per block
+    mem = amep_b200.TensorTrajectory(data, box, times=Traj.times, types=types)
+    for kw in (dict(), dict(ptype=1, other=2)):
+        a = evaluate.RDF(Traj(), skip=0.0, nav=nf, rmax=6.0, nbins=120, **kw)
+        b = evaluate.RDF(mem, skip=0.0, nav=nf, rmax=6.0, nbins=120, **kw)
+        np.testing.assert_array_equal(a.frames, b.frames)
+        np.testing.assert_array_equal(a.counts, b.counts)
+        np.testing.assert_array_equal(a.times, b.times)
+    a = evaluate.SFiso(Traj(), skip=0.2, nav=5, qmax=3.0, num=8)
+    b = evaluate.SFiso(mem, skip=0.2, nav=5, qmax=3.0, num=8)
+    np.testing.assert_array_equal(a.frames, b.frames)
