@@ -70,6 +70,7 @@ struct amepb_ctx {
     void* last_stream = nullptr;
     bool sq_attr_harm = false;
     cudaStream_t copy_stream = nullptr;   // host-space staging
+    cudaStream_t stats_stream = nullptr;  // host-space staging: statistics of the next sub-batch (rdf.cu)
     cudaStream_t compute_stream = nullptr; // host-space calls made on the NULL stream
     static constexpr int kStageBuffers = 3;   // host-buffer path: staging buffers in flight
     cudaEvent_t ev_copied[kStageBuffers] = {nullptr, nullptr, nullptr};

@@ -165,6 +165,7 @@ void amepb_destroy(amepb_ctx* ctx) {
         if (ctx->ev_computed[b]) cudaEventDestroy(ctx->ev_computed[b]);
     }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->stats_stream) cudaStreamDestroy(ctx->stats_stream);
     if (ctx->compute_stream) cudaStreamDestroy(ctx->compute_stream);
     delete ctx;
 }

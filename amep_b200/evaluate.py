@@ -276,14 +276,21 @@ class RDF(_FrameAverage):
             extra = dict(shard=(sh.rank, sh.ws), reduce=sh.all_sum)
         for coords, other_coords, box in _frame_batches(traj, idx[sh.lo:sh.hi], ptype, other, other is not None):
             rows.append(rdf_frames(coords, box, other_coords, return_counts=True, **extra, **kwargs))
-        local = None
+        g = r = counts = None
         if rows:
-            g, r, counts = (np.concatenate([p[k] for p in rows]) for k in range(3))
-            local = np.stack([g, r, counts.astype(np.float64)], axis=1)   # counts < 2^53: exact
-        table = sh.assemble(local)
-        # np.array(results) of the reference: (nav, 2, nbins)
-        self._frames = np.ascontiguousarray(table[:, :2])
-        self._counts = table[:, 2].astype(np.int64)
+            g, r, counts = rows[0] if len(rows) == 1 else (np.concatenate([p[k] for p in rows]) for k in range(3))
+        if sh.ws == 1 or sh.intra:
+            # np.array(results) of the reference: (nav, 2, nbins)
+            self._frames = np.empty((len(g), 2, g.shape[1]))
+            self._frames[:, 0], self._frames[:, 1] = g, r
+            self._counts = counts
+        else:
+            local = None
+            if rows:
+                local = np.stack([g, r, counts.astype(np.float64)], axis=1)   # counts < 2^53: exact
+            table = sh.assemble(local)
+            self._frames = np.ascontiguousarray(table[:, :2])
+            self._counts = table[:, 2].astype(np.int64)
         avg = np.mean(self._frames, axis=0)   # amep/utils.py:186
         self._avg = avg[0]
         self._r = avg[1]

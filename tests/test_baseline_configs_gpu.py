@@ -192,8 +192,8 @@ def test_sf2d_reference_order_bit_identity(sc, capsys):
         with capsys.disabled():
             print(f"\n[sf2d c64 vs reference order] chunksize={cs_used}: identical components {frac:.6f}, "
                   f"max ulp distance {int(ulps.max())}, max |d rho|/|rho| {rel:.3e}")
-        assert frac >= 0.99, frac
+        assert frac >= 0.999, frac        # measured on B200: 1.000000, 0 ulp, all three chunk sizes
         assert rel < 1e-6
         # S itself (host epilogue = the reference's NumPy expression)
         s_want = np.real(want * want.conj()) / len(coords)
-        assert float(np.mean(s[0] == s_want)) >= 0.98
+        assert float(np.mean(s[0] == s_want)) >= 0.999

@@ -144,7 +144,8 @@ def test_sf2d_reference_order_multichunk_oracle(sc):
         np.testing.assert_array_equal(gx, qx)
         worst = _close(got.astype(np.float64), want.astype(np.float64))
         frac_equal = float(np.mean(got == want))
-        assert frac_equal > 0.5, (worst, frac_equal)
+        # measured: 1.0 (tests/test_baseline_configs_gpu.py prints the fraction for rho itself)
+        assert frac_equal >= 0.999, (worst, frac_equal)
 
 
 def test_sf2d_f64_accumulation(sc):
