@@ -785,6 +785,26 @@ __device__ __forceinline__ void query_loop_f32(const FastArgs& fa, unsigned sq_x
     if (u < np) packed(lds_v4(sq_xy + u * 16), ZMODE == 0 ? lds_b64(sq_z + u * 8) : 0ull);
 }
 
+#ifndef AMEPB_TWO_TARGETS
+#define AMEPB_TWO_TARGETS 0     // experiment: two staged targets per lane and query load
+#endif
+// Two targets per lane: every broadcast LDS.128 of a query pair feeds four packed pair evaluations.
+template <int ZMODE>
+__device__ __forceinline__ void query_loop_f32_two(const FastArgs& fa, unsigned sq_xy, unsigned sq_z, unsigned nq2,
+                                                   float ax, float ay, float az, unsigned ha, float bx, float by,
+                                                   float bz, unsigned hb, float dz2c) {
+    const unsigned np = nq2 >> 1;
+#pragma unroll 2
+    for (unsigned u = 0; u < np; ++u) {
+        const float4 xy = lds_v4(sq_xy + u * 16);
+        const f32x2 z = ZMODE == 0 ? lds_b64(sq_z + u * 8) : 0ull;
+        pair_update2<ZMODE>(pack2(xy.x, xy.y), pack2(xy.z, xy.w), z, ax, ay, az, fa.one, dz2c, fa.inv_w, fa.c_magic,
+                            fa.kclamp, fa.thr_addr, ha);
+        pair_update2<ZMODE>(pack2(xy.x, xy.y), pack2(xy.z, xy.w), z, bx, by, bz, fa.one, dz2c, fa.inv_w, fa.c_magic,
+                            fa.kclamp, fa.thr_addr, hb);
+    }
+}
+
 template <typename AT, typename NT, int ZMODE>
 __device__ __forceinline__ void warp_pairs_fast(const Vec4<AT>* __restrict__ qsorted, unsigned qa, unsigned qb,
                                                 const Vec4<NT>* __restrict__ tsorted, unsigned ta, unsigned tb,
@@ -1005,7 +1025,23 @@ __global__ void __launch_bounds__(kPairThreads, (sizeof(AT) == 4 ? kPairBlocksPe
                     unsigned fill = 0, lo_end = 0;
                     auto flush_stage = [&]() {
                         __syncwarp();
-                        for (unsigned g0 = 0; g0 < fill; g0 += 32) {
+                        unsigned g0 = 0;
+#if AMEPB_TWO_TARGETS
+                        for (; g0 + 32 < fill; g0 += 64) {
+                            const unsigned ga = g0 + lane, gb = ga + 32;
+                            const float ax = lds_f32(bx + 4 * ga), ay = lds_f32(by + 4 * ga);
+                            const float az = ZMODE == 0 ? lds_f32(bz + 4 * ga) : 0.f;
+                            float bx_ = __int_as_float(0x7fc00000), by_ = bx_, bz_ = bx_;
+                            if (gb < fill) {
+                                bx_ = lds_f32(bx + 4 * gb);
+                                by_ = lds_f32(by + 4 * gb);
+                                if (ZMODE == 0) bz_ = lds_f32(bz + 4 * gb);
+                            }
+                            query_loop_f32_two<ZMODE>(fa, sq_xy, sq_z, nq2, ax, ay, az, (!SYM || ga < lo_end) ? hist_addr : hist2_addr,
+                                                      bx_, by_, bz_, (!SYM || gb < lo_end) ? hist_addr : hist2_addr, dz2c);
+                        }
+#endif
+                        for (; g0 < fill; g0 += 32) {
                             const unsigned g = g0 + lane;
                             float nx = __int_as_float(0x7fc00000), ny = nx, nz = nx;
                             if (g < fill) {

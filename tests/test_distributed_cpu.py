@@ -166,6 +166,23 @@ def _worker(rank, world, port, tmpdir):
     assert np.array_equal(evp.avg, np.mean(np.array([w[0] for w in want]), axis=0))
     assert np.array_equal(evp.x, want[0][1]) and np.array_equal(evp.y, want[0][2])
     assert evp.frames.shape == (len(evp.indices), 3, 12, 12)
+    # (4) the per-frame pair observables (PCFangle, SpatialVelCor): frames sharded in blocks, rows assembled
+    import amep_oracle as orc
+    evaluate.pcf_angle = lambda c, box, other_coords=None, psi=None, e=None, **kw: orc.pcf_angle(
+        np.asarray(c), box, other_coords, psi=psi, e=e, **kw)
+    evaluate.spatialcor = lambda c, box, v, other_coords=None, other_values=None, **kw: orc.spatialcor(
+        np.asarray(c), box, np.asarray(v), other_coords, other_values, **kw)
+    flat = pc.copy()
+    flat[:, :, 2] = 0.0
+    vel = rng.normal(size=flat.shape).astype(np.float32)
+    vtraj = amep_b200.TensorTrajectory(flat, pbox, velocities=vel)
+    for nav in (5, 1):
+        eva = evaluate.PCFangle(vtraj, skip=0.0, nav=nav, mode="x", ndbins=10, nabins=8, rmax=3.0)
+        want = np.array([np.array(orc.pcf_angle(flat[i].copy(), pbox, None, ndbins=10, nabins=8, rmax=3.0)) for i in eva.indices])
+        assert np.array_equal(eva.frames, want) and np.array_equal(eva.avg, np.mean(want, axis=0)[0])
+        evv = evaluate.SpatialVelCor(vtraj, skip=0.0, nav=nav, rmax=4.0)
+        want = np.array([np.array(orc.spatialcor(flat[i], pbox, vel[i], flat[i], vel[i], rmax=4.0)) for i in evv.indices])
+        assert np.array_equal(evv.frames, want) and evv.r.shape == want[0][1].shape
     np.save(os.path.join(tmpdir, f"ok{rank}.npy"), np.array([1]))
     dist.destroy_process_group()
 
