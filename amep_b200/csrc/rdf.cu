@@ -574,12 +574,15 @@ struct PairArgs {
 
 // float32 regime: every warp gathers the neighbourhood of its query cell into a shared buffer
 // of kStageCapF32 targets (x[] | y[] (| z[])) and walks it in full 32-lane passes
-constexpr unsigned kStageCapF32 = 256;   // targets per warp and chunk (float32 regime; half of it in float64)
+#ifndef AMEPB_STAGE_CAP
+#define AMEPB_STAGE_CAP 256
+#endif
+constexpr unsigned kStageCapF32 = AMEPB_STAGE_CAP;   // targets per warp and chunk (float32 regime; half of it in float64)
 constexpr unsigned kQueryCapF32 = 64;    // queries per warp and chunk
 constexpr unsigned kUnitLimit = 1u << 21;                // flush after 2^31 counted pairs (units of 1024)
 constexpr int kPairThreads = 256;
 #ifndef AMEPB_PAIR_BLOCKS
-#define AMEPB_PAIR_BLOCKS 5
+#define AMEPB_PAIR_BLOCKS 4      // float32 kernels: 64 registers (four targets per lane need them)
 #endif
 constexpr int kPairBlocksPerSM = AMEPB_PAIR_BLOCKS;
 #ifndef AMEPB_PAIR_BLOCKS_F64
@@ -785,23 +788,36 @@ __device__ __forceinline__ void query_loop_f32(const FastArgs& fa, unsigned sq_x
     if (u < np) packed(lds_v4(sq_xy + u * 16), ZMODE == 0 ? lds_b64(sq_z + u * 8) : 0ull);
 }
 
-#ifndef AMEPB_TWO_TARGETS
-#define AMEPB_TWO_TARGETS 0     // experiment: two staged targets per lane and query load
+#ifndef AMEPB_TARGET_CASCADE
+#define AMEPB_TARGET_CASCADE 1   // passes left over by the groups of four: two of them together (-1.5 % in 2D)
 #endif
-// Two targets per lane: every broadcast LDS.128 of a query pair feeds four packed pair evaluations.
-template <int ZMODE>
-__device__ __forceinline__ void query_loop_f32_two(const FastArgs& fa, unsigned sq_xy, unsigned sq_z, unsigned nq2,
-                                                   float ax, float ay, float az, unsigned ha, float bx, float by,
-                                                   float bz, unsigned hb, float dz2c) {
+#ifndef AMEPB_QUERY_UNROLL
+#define AMEPB_QUERY_UNROLL 2
+#endif
+constexpr int kMultiQueryUnroll = AMEPB_QUERY_UNROLL;
+#ifndef AMEPB_TARGETS_PER_LANE
+#define AMEPB_TARGETS_PER_LANE 4     // staged targets a lane holds while it walks the staged queries
+#endif
+constexpr int kTargetsPerLane = AMEPB_TARGETS_PER_LANE;
+// Several targets per lane: every broadcast LDS.128 of a query pair feeds 2 * NT packed pair
+// evaluations instead of two, and the loop overhead is shared.  Round 2: two targets per lane are
+// 6-8 % faster than one on every configuration measured (2D uniform 6.07 -> 5.66 ms per 32 frames,
+// clustered 0.332 -> 0.306 ms per frame, 3D 6.21 -> 5.82 ms per 2M-particle frame); four per lane
+// at 64 registers and four blocks per SM another 3 % (5.53 / 0.295 / 5.60); 3, 6 or 8 per lane and
+// 3 or 5 blocks per SM were slower (profiles/r02_targets_per_lane_sweep.txt).
+template <int ZMODE, int NT>
+__device__ __forceinline__ void query_loop_f32_multi(const FastArgs& fa, unsigned sq_xy, unsigned sq_z, unsigned nq2,
+                                                     const float (&tx)[NT], const float (&ty)[NT], const float (&tz)[NT],
+                                                     const unsigned (&th)[NT], float dz2c) {
     const unsigned np = nq2 >> 1;
-#pragma unroll 2
+#pragma unroll kMultiQueryUnroll
     for (unsigned u = 0; u < np; ++u) {
         const float4 xy = lds_v4(sq_xy + u * 16);
         const f32x2 z = ZMODE == 0 ? lds_b64(sq_z + u * 8) : 0ull;
-        pair_update2<ZMODE>(pack2(xy.x, xy.y), pack2(xy.z, xy.w), z, ax, ay, az, fa.one, dz2c, fa.inv_w, fa.c_magic,
-                            fa.kclamp, fa.thr_addr, ha);
-        pair_update2<ZMODE>(pack2(xy.x, xy.y), pack2(xy.z, xy.w), z, bx, by, bz, fa.one, dz2c, fa.inv_w, fa.c_magic,
-                            fa.kclamp, fa.thr_addr, hb);
+#pragma unroll
+        for (int t = 0; t < NT; ++t)
+            pair_update2<ZMODE>(pack2(xy.x, xy.y), pack2(xy.z, xy.w), z, tx[t], ty[t], tz[t], fa.one, dz2c, fa.inv_w,
+                                fa.c_magic, fa.kclamp, fa.thr_addr, th[t]);
     }
 }
 
@@ -1026,21 +1042,44 @@ __global__ void __launch_bounds__(kPairThreads, (sizeof(AT) == 4 ? kPairBlocksPe
                     auto flush_stage = [&]() {
                         __syncwarp();
                         unsigned g0 = 0;
-#if AMEPB_TWO_TARGETS
-                        for (; g0 + 32 < fill; g0 += 64) {
-                            const unsigned ga = g0 + lane, gb = ga + 32;
-                            const float ax = lds_f32(bx + 4 * ga), ay = lds_f32(by + 4 * ga);
-                            const float az = ZMODE == 0 ? lds_f32(bz + 4 * ga) : 0.f;
-                            float bx_ = __int_as_float(0x7fc00000), by_ = bx_, bz_ = bx_;
-                            if (gb < fill) {
-                                bx_ = lds_f32(bx + 4 * gb);
-                                by_ = lds_f32(by + 4 * gb);
-                                if (ZMODE == 0) bz_ = lds_f32(bz + 4 * gb);
+                        if constexpr (kTargetsPerLane > 1) {
+                            // full groups of kTargetsPerLane passes (the last one may be ragged: NaN targets)
+                            for (; g0 + 32 * (kTargetsPerLane - 1) < fill; g0 += 32 * kTargetsPerLane) {
+                                float tx[kTargetsPerLane], ty[kTargetsPerLane], tz[kTargetsPerLane];
+                                unsigned th[kTargetsPerLane];
+#pragma unroll
+                                for (int t = 0; t < kTargetsPerLane; ++t) {
+                                    const unsigned g = g0 + 32 * t + lane;
+                                    tx[t] = ty[t] = tz[t] = __int_as_float(0x7fc00000);
+                                    if (g < fill) {
+                                        tx[t] = lds_f32(bx + 4 * g);
+                                        ty[t] = lds_f32(by + 4 * g);
+                                        if (ZMODE == 0) tz[t] = lds_f32(bz + 4 * g);
+                                    }
+                                    th[t] = (!SYM || g < lo_end) ? hist_addr : hist2_addr;
+                                }
+                                query_loop_f32_multi<ZMODE, kTargetsPerLane>(fa, sq_xy, sq_z, nq2, tx, ty, tz, th, dz2c);
                             }
-                            query_loop_f32_two<ZMODE>(fa, sq_xy, sq_z, nq2, ax, ay, az, (!SYM || ga < lo_end) ? hist_addr : hist2_addr,
-                                                      bx_, by_, bz_, (!SYM || gb < lo_end) ? hist_addr : hist2_addr, dz2c);
-                        }
+#if AMEPB_TARGET_CASCADE
+                            if (kTargetsPerLane > 2 && g0 + 32 < fill) {   // two of the passes that are left, together
+                                float tx[2], ty[2], tz[2];
+                                unsigned th[2];
+#pragma unroll
+                                for (int t = 0; t < 2; ++t) {
+                                    const unsigned g = g0 + 32 * t + lane;
+                                    tx[t] = ty[t] = tz[t] = __int_as_float(0x7fc00000);
+                                    if (g < fill) {
+                                        tx[t] = lds_f32(bx + 4 * g);
+                                        ty[t] = lds_f32(by + 4 * g);
+                                        if (ZMODE == 0) tz[t] = lds_f32(bz + 4 * g);
+                                    }
+                                    th[t] = (!SYM || g < lo_end) ? hist_addr : hist2_addr;
+                                }
+                                query_loop_f32_multi<ZMODE, 2>(fa, sq_xy, sq_z, nq2, tx, ty, tz, th, dz2c);
+                                g0 += 64;
+                            }
 #endif
+                        }
                         for (; g0 < fill; g0 += 32) {
                             const unsigned g = g0 + lane;
                             float nx = __int_as_float(0x7fc00000), ny = nx, nz = nx;
