@@ -281,6 +281,47 @@ def sq_debye(coords, other, q, twod, device=None):
     return out
 
 
+def sq_debye_ref(coords, other, q, twod, chunksize, device=None):
+    """The Debye sums of ``sq_debye`` in the reference's float32 arithmetic and summation order
+    (amepb_sq_debye_ref): float32 ``[F, nq]``, chunks of ``chunksize`` particles of ``other``."""
+    pc = coords if isinstance(coords, Particles) else Particles(coords)
+    po = None
+    if other is not None:
+        po = other if isinstance(other, Particles) else Particles(other)
+        if pc.on_device != po.on_device:
+            dev = (pc if pc.on_device else po).tensor.device
+            pc, po = pc.to_device(dev), po.to_device(dev)
+    nf = pc.nframes
+    qa = np.ascontiguousarray(np.asarray(q, dtype=np.float64))
+    if qa.ndim == 1:
+        nq, stride = qa.shape[0], 0
+    elif qa.ndim == 2 and qa.shape[0] == nf:
+        nq, stride = qa.shape[1], qa.shape[1]
+    else:
+        raise ValueError("q must have shape (nq,) or (F, nq)")
+    if int(chunksize) < 1:
+        raise ValueError("chunksize must be positive")
+    dev_index = _device_of(pc, device)
+    ctx = _lib.context(dev_index)
+    if pc.on_device:
+        import torch
+        out = torch.empty((nf, nq), dtype=torch.float32, device=pc.tensor.device)
+        optr, space = out.data_ptr(), _lib.DEVICE
+    else:
+        out = np.empty((nf, nq), dtype=np.float32)
+        optr, space = out.ctypes.data, _lib.HOST
+    if nq == 0:
+        return out
+    rc = ctx.lib.amepb_sq_debye_ref(
+        ctx.handle, ctypes.c_void_p(pc.ptr()), pc.dtype, pc.n,
+        ctypes.c_void_p(po.ptr()) if po is not None else None, po.dtype if po is not None else 0,
+        po.n if po is not None else 0, space, nf,
+        qa.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), stride, nq, 1 if twod else 0, int(chunksize),
+        ctypes.c_void_p(optr), _stream_for(dev_index, pc.on_device))
+    ctx.check(rc, "amepb_sq_debye_ref")
+    return out
+
+
 def density_counts(coords, box_boundary, xedges, yedges, pbc=True, device=None):
     """Particle counts on the grid of ``amep.continuum.hde`` (amepb_density_counts): int32
     ``[F, ny, nx]`` (a CUDA tensor if the coordinates live on the device, else NumPy).

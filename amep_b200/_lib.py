@@ -22,7 +22,7 @@ ABI_VERSION = 1
 SYMBOLS = (
     "amepb_abi_version", "amepb_create", "amepb_destroy", "amepb_last_error",
     "amepb_frame_dimension", "amepb_rdf_batch", "amepb_rdf_last_info",
-    "amepb_rdf_set_cells_per_cutoff", "amepb_rdf_set_symmetric", "amepb_rdf_set_shard", "amepb_sq_harmonics", "amepb_sq_debye", "amepb_sf2d_modes",
+    "amepb_rdf_set_cells_per_cutoff", "amepb_rdf_set_symmetric", "amepb_rdf_set_shard", "amepb_sq_harmonics", "amepb_sq_debye", "amepb_sq_debye_ref", "amepb_sf2d_modes",
     "amepb_density_counts",
     "amepb_pcf2d_counts", "amepb_psi_k", "amepb_rotate_crop", "amepb_pcf_angle_counts", "amepb_spatialcor_sums",
     "amepb_kernel_launches", "amepb_synchronize", "amepb_set_timing", "amepb_last_kernel_ms",
@@ -110,6 +110,9 @@ def load():
         lib.amepb_sq_debye.restype = c.c_int
         lib.amepb_sq_debye.argtypes = [vp, vp, c.c_int, i64, vp, c.c_int, i64, c.c_int, i64,
                                        c.POINTER(c.c_double), i64, i32, c.c_int, vp, vp]
+        lib.amepb_sq_debye_ref.restype = c.c_int
+        lib.amepb_sq_debye_ref.argtypes = [vp, vp, c.c_int, i64, vp, c.c_int, i64, c.c_int, i64,
+                                           c.POINTER(c.c_double), i64, i32, c.c_int, i64, vp, vp]
         lib.amepb_sf2d_modes.restype = c.c_int
         lib.amepb_sf2d_modes.argtypes = [vp, vp, c.c_int, c.c_int, i64, i64,
                                          c.POINTER(c.c_double), i64, i32, c.c_int, i64, vp, vp]

@@ -535,6 +535,148 @@ __global__ void debye_reduce_kernel(const double* __restrict__ partial, int nblo
     out[i] = s;
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Debye sum in the reference's own float32 order (amep/spatialcor.py:1363-1399), one chunk of
+// `other` at a time like compute_parallel hands them out:
+//   dists = cdist(coords32, other32[chunk]).flatten().astype(float32)      pair o = i * clen + j
+//   res   = float32(count(dists == 0));  dists = dists[dists != 0]
+//   res  += np.sum(K(dists[:, None] * q32[None, :]), axis=0)    if 4 n nq <= 1e9: row after row
+//   res[k] += np.sum(K(dists * q32[k]))                         else: NumPy's pairwise summation
+// with K = float32(j0(float64(x))) (scipy's float loop evaluates cephes j0 in double) or np.sinc in
+// float32.  The terms are evaluated in parallel; only the float32 additions follow the reference's
+// order: sequential over the rows (one thread per q over a buffer of terms), or the pairwise tree --
+// leaves of at most 128 consecutive elements summed with eight strided accumulators, one leaf and 32
+// q values per warp, then a host-built postfix program of the tree (PUSH leaf / ADD) run by one
+// thread per q.
+// ---------------------------------------------------------------------------------------
+constexpr int kRefLeaf = 128;   // NumPy's PW_BLOCKSIZE
+
+template <typename TA, typename TB>
+__device__ __forceinline__ float ref_pair_d32(const TA* __restrict__ a, const TB* __restrict__ b, long long i, long long j) {
+    // scipy cdist on float32 input: differences, squares and the root in float64, then .astype(float32)
+    const double dx = (double)(float)a[3 * i] - (double)(float)b[3 * j];
+    const double dy = (double)(float)a[3 * i + 1] - (double)(float)b[3 * j + 1];
+    const double dz = (double)(float)a[3 * i + 2] - (double)(float)b[3 * j + 2];
+    return (float)sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+}
+
+template <bool TWOD>
+__device__ __forceinline__ float ref_term(float d, float qk) {
+    if (TWOD) return (float)j0((double)__fmul_rn(d, qk));     // qk = float32(q)
+    // np.sinc: x = d * (q32 / pi) [qk], y = pi * where(x == 0, 1e-20, x), sin(y) / y -- all float32
+    float x = __fmul_rn(d, qk);
+    if (x == 0.f) x = 1.0e-20f;
+    const float y = __fmul_rn(3.14159274f, x);
+    return __fdiv_rn((float)sin((double)y), y);
+}
+
+// pairs of the chunk with distance zero (original pair indices, any order)
+template <typename TA, typename TB>
+__global__ void debye_ref_zero_kernel(const TA* __restrict__ a, long long na, const TB* __restrict__ b, long long clen,
+                                      unsigned long long* __restrict__ count, long long* __restrict__ list, long long cap) {
+    const long long total = na * clen;
+    for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (long long)gridDim.x * blockDim.x) {
+        const long long i = o / clen, j = o - i * clen;
+        if (ref_pair_d32(a, b, i, j) == 0.f) {
+            const unsigned long long at = atomicAdd(count, 1ull);
+            if ((long long)at < cap) list[at] = o;
+        }
+    }
+}
+
+// original pair index of the e-th non-zero distance: e + #{k : zp[k] <= e}, zp[k] = zero[k] - k (sorted)
+__device__ __forceinline__ long long ref_orig_index(long long e, const long long* __restrict__ zp, int nz) {
+    int lo = 0, hi = nz;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (zp[mid] <= e) lo = mid + 1;
+        else hi = mid;
+    }
+    return e + lo;
+}
+
+// One warp per group of <= 128 consecutive non-zero distances [start, start + len).
+// LEAF: out[g][k] = NumPy's block sum of the terms; else out[start + e][k] = term (row-major buffer).
+template <typename TA, typename TB, bool TWOD, bool LEAF>
+__global__ void __launch_bounds__(128) debye_ref_terms_kernel(const TA* __restrict__ a, const TB* __restrict__ b, long long clen,
+                                                              const long long* __restrict__ zp, int nz,
+                                                              const long long* __restrict__ gstart, const int* __restrict__ glen,
+                                                              long long ngroups, const float* __restrict__ qk, int q0, int nqt,
+                                                              float* __restrict__ out) {
+    __shared__ float s_d[4][kRefLeaf];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (long long g = (long long)blockIdx.x * 4 + warp; g < ngroups; g += (long long)gridDim.x * 4) {
+        const long long start = gstart[g];
+        const int len = glen[g];
+        __syncwarp();
+        for (int e = lane; e < len; e += 32) {
+            const long long o = ref_orig_index(start + e, zp, nz);
+            const long long i = o / clen;
+            s_d[warp][e] = ref_pair_d32(a, b, i, o - i * clen);
+        }
+        __syncwarp();
+        for (int kt = lane; kt < nqt; kt += 32) {
+            const float q = qk[q0 + kt];
+            if (!LEAF) {
+                for (int e = 0; e < len; ++e) out[(start + e) * nqt + kt] = ref_term<TWOD>(s_d[warp][e], q);
+                continue;
+            }
+            float res;
+            if (len < 8) {
+                res = 0.f;
+                for (int e = 0; e < len; ++e) res = __fadd_rn(res, ref_term<TWOD>(s_d[warp][e], q));
+            } else {
+                float r[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) r[u] = ref_term<TWOD>(s_d[warp][u], q);
+                int e = 8;
+                for (; e < len - (len % 8); e += 8) {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) r[u] = __fadd_rn(r[u], ref_term<TWOD>(s_d[warp][e + u], q));
+                }
+                res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                                __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+                for (; e < len; ++e) res = __fadd_rn(res, ref_term<TWOD>(s_d[warp][e], q));
+            }
+            out[g * nqt + kt] = res;
+        }
+    }
+}
+
+// np.sum(terms, axis=0): float32 rows added one after the other
+__global__ void debye_ref_rows_kernel(const float* __restrict__ terms, long long nrows, int nqt, float* __restrict__ sums) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nqt) return;
+    float acc = 0.f;
+    if (nrows > 0) acc = terms[k];
+    for (long long e = 1; e < nrows; ++e) acc = __fadd_rn(acc, terms[e * nqt + k]);
+    sums[k] = acc;
+}
+
+// NumPy's pairwise tree over the leaf sums: postfix program, op >= 0: push leaf op, op < 0: add
+__global__ void debye_ref_tree_kernel(const float* __restrict__ leaf, const int* __restrict__ prog, long long nops, int nqt,
+                                      float* __restrict__ sums) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nqt) return;
+    float st[64];
+    int sp = 0;
+    for (long long t = 0; t < nops; ++t) {
+        const int op = prog[t];
+        if (op >= 0) st[sp++] = leaf[(long long)op * nqt + k];
+        else { --sp; st[sp - 1] = __fadd_rn(st[sp - 1], st[sp]); }
+    }
+    sums[k] = sp > 0 ? st[0] : 0.f;
+}
+
+// res = float32(count0) + sums;  S = first ? res : S + res   (amep/spatialcor.py:1374-1375, 1631-1633)
+__global__ void debye_ref_accum_kernel(const float* __restrict__ sums, float count0, int q0, int nqt, int first, float* __restrict__ S) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nqt) return;
+    const float res = __fadd_rn(count0, sums[k]);
+    S[q0 + k] = first ? res : __fadd_rn(S[q0 + k], res);
+}
+
 }  // namespace amepb
 
 using namespace amepb;
@@ -895,6 +1037,195 @@ int amepb_sq_debye(amepb_ctx* ctx, const void* coords, int dtype, int64_t n, con
         AMEPB_CUDA(ctx, cudaMemcpyAsync(out, d_out, sizeof(double) * (size_t)nframes * nq, cudaMemcpyDeviceToHost, stream));
         AMEPB_CUDA(ctx, cudaStreamSynchronize(stream));
     }
+    return 0;
+}
+
+namespace {
+// NumPy's pairwise summation tree over n elements (numpy/_core/src/umath/loops_utils.h.src,
+// @TYPE@_pairwise_sum): blocks of <= 128 elements are leaves, larger ranges split at
+// n2 = n/2 - (n/2) % 8.  Emits the leaves in order and the postfix program that combines them.
+void pairwise_tree(long long start, long long n, std::vector<long long>& gstart, std::vector<int>& glen, std::vector<int>& prog) {
+    if (n <= kRefLeaf) {
+        prog.push_back((int)gstart.size());
+        gstart.push_back(start);
+        glen.push_back((int)n);
+        return;
+    }
+    long long n2 = n / 2;
+    n2 -= n2 % 8;
+    pairwise_tree(start, n2, gstart, glen, prog);
+    pairwise_tree(start + n2, n - n2, gstart, glen, prog);
+    prog.push_back(-1);
+}
+}  // namespace
+
+int amepb_sq_debye_ref(amepb_ctx* ctx, const void* coords, int dtype, int64_t n, const void* other, int other_dtype,
+                       int64_t m, int space, int64_t nframes, const double* q, int64_t q_stride, int32_t nq, int twod,
+                       int64_t chunksize, float* out, void* stream_) {
+    if (!ctx) return AMEPB_E_INVAL;
+    auto ok_dtype = [](int d) { return d == AMEPB_F32 || d == AMEPB_F64; };
+    if (!coords || !q || !out || nframes < 0 || n <= 0 || nq <= 0 || nq > 65536 || chunksize <= 0 || !ok_dtype(dtype) ||
+        (other && (!ok_dtype(other_dtype) || m <= 0)) || (space != AMEPB_DEVICE && space != AMEPB_HOST) ||
+        (q_stride != 0 && q_stride < nq))
+        return fail(ctx, AMEPB_E_INVAL, "amepb_sq_debye_ref: invalid argument");
+    if (nframes == 0) return 0;
+    DeviceGuard guard(ctx->device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    ctx->last_stream = stream_;
+    timing_reset(ctx);
+    if (!other) {
+        other = coords;
+        other_dtype = dtype;
+        m = n;
+    }
+    if ((double)n * (double)std::min<int64_t>(chunksize, m) >= 9.0e18)
+        return fail(ctx, AMEPB_E_INVAL, "amepb_sq_debye_ref: chunk too large");
+    const size_t abytes = (size_t)n * 3 * elem_bytes(dtype) * nframes;
+    const size_t bbytes = (size_t)m * 3 * elem_bytes(other_dtype) * nframes;
+    const char* d_a = reinterpret_cast<const char*>(coords);
+    const char* d_b = reinterpret_cast<const char*>(other);
+    int rc;
+    if (space == AMEPB_HOST) {
+        if ((rc = ensure_device(ctx, BUF_STAGE_A, abytes))) return rc;
+        AMEPB_CUDA(ctx, cudaMemcpyAsync(ctx->bufs[BUF_STAGE_A].p, coords, abytes, cudaMemcpyHostToDevice, stream));
+        d_a = reinterpret_cast<const char*>(ctx->bufs[BUF_STAGE_A].p);
+        if (other == coords) {
+            d_b = d_a;
+        } else {
+            if ((rc = ensure_device(ctx, BUF_STAGE_B, bbytes))) return rc;
+            AMEPB_CUDA(ctx, cudaMemcpyAsync(ctx->bufs[BUF_STAGE_B].p, other, bbytes, cudaMemcpyHostToDevice, stream));
+            d_b = reinterpret_cast<const char*>(ctx->bufs[BUF_STAGE_B].p);
+        }
+    }
+    // device blocks: [S: nq floats][sums: nq floats][qk: nq floats][zero count: 8 bytes][zero list / zp]
+    constexpr long long kZeroCap = 1ll << 22;
+    const size_t head_bytes = ((size_t)3 * nq * sizeof(float) + 15) & ~(size_t)15;
+    if ((rc = ensure_device(ctx, BUF_SQ_A, head_bytes + 16 + sizeof(long long) * (size_t)kZeroCap))) return rc;
+    char* blk = reinterpret_cast<char*>(ctx->bufs[BUF_SQ_A].p);
+    float* d_S = reinterpret_cast<float*>(blk);
+    float* d_sums = d_S + nq;
+    float* d_qk = d_sums + nq;
+    unsigned long long* d_zcount = reinterpret_cast<unsigned long long*>(blk + head_bytes);
+    long long* d_zlist = reinterpret_cast<long long*>(blk + head_bytes + 16);
+    std::vector<float> qk(nq);
+    std::vector<long long> zhost, gstart;
+    std::vector<int> glen, prog;
+    std::vector<float> s_host(nq);
+    const int blocks = ctx->sm_count * 8;
+    cudaEvent_t ev0 = timing_event(ctx, stream);
+    for (int64_t f = 0; f < nframes; ++f) {
+        const double* qf = q + (q_stride ? f * q_stride : 0);
+        for (int k = 0; k < nq; ++k) {
+            // float32(q), in 3D divided by pi in float32 (amep/spatialcor.py:1366, 1395)
+            const volatile float q32 = (float)qf[k];
+            const volatile float qpi = q32 / 3.14159274f;
+            qk[k] = twod ? q32 : qpi;
+        }
+        // (small synchronous upload; this entry point synchronises once per chunk anyway)
+        AMEPB_CUDA(ctx, cudaMemcpyAsync(d_qk, qk.data(), sizeof(float) * nq, cudaMemcpyHostToDevice, stream));
+        AMEPB_CUDA(ctx, cudaStreamSynchronize(stream));
+        const char* fa = d_a + (size_t)f * n * 3 * elem_bytes(dtype);
+        const char* fbase = d_b + (size_t)f * m * 3 * elem_bytes(other_dtype);
+        int first = 1;
+        for (int64_t c0 = 0; c0 < m; c0 += chunksize) {
+            const long long clen = std::min<int64_t>(chunksize, m - c0);
+            const char* fb = fbase + (size_t)c0 * 3 * elem_bytes(other_dtype);
+            const long long total = (long long)n * clen;
+            // ---- zero distances -> compaction table ----
+            AMEPB_CUDA(ctx, cudaMemsetAsync(d_zcount, 0, 8, stream));
+#define AMEPB_REF_ZERO(TA, TB) debye_ref_zero_kernel<TA, TB><<<blocks, 256, 0, stream>>>((const TA*)fa, n, (const TB*)fb, clen, d_zcount, d_zlist, kZeroCap)
+            if (dtype == AMEPB_F32 && other_dtype == AMEPB_F32) AMEPB_REF_ZERO(float, float);
+            else if (dtype == AMEPB_F32) AMEPB_REF_ZERO(float, double);
+            else if (other_dtype == AMEPB_F32) AMEPB_REF_ZERO(double, float);
+            else AMEPB_REF_ZERO(double, double);
+#undef AMEPB_REF_ZERO
+            AMEPB_LAUNCH_CHECK(ctx);
+            unsigned long long nz64 = 0;
+            AMEPB_CUDA(ctx, cudaMemcpyAsync(&nz64, d_zcount, 8, cudaMemcpyDeviceToHost, stream));
+            AMEPB_CUDA(ctx, cudaStreamSynchronize(stream));
+            if ((long long)nz64 > kZeroCap)
+                return fail(ctx, AMEPB_E_INVAL, "amepb_sq_debye_ref: more than 2^22 coincident pairs in one chunk");
+            const int nz = (int)nz64;
+            zhost.resize(nz);
+            if (nz) {
+                AMEPB_CUDA(ctx, cudaMemcpyAsync(zhost.data(), d_zlist, sizeof(long long) * nz, cudaMemcpyDeviceToHost, stream));
+                AMEPB_CUDA(ctx, cudaStreamSynchronize(stream));
+                std::sort(zhost.begin(), zhost.end());
+                for (int k = 0; k < nz; ++k) zhost[k] -= k;
+                AMEPB_CUDA(ctx, cudaMemcpyAsync(d_zlist, zhost.data(), sizeof(long long) * nz, cudaMemcpyHostToDevice, stream));
+                AMEPB_CUDA(ctx, cudaStreamSynchronize(stream));   // zhost is reused by the next chunk
+            }
+            const long long nn = total - nz;   // non-zero distances
+            // ---- the reference's branch: one 2D array of terms, or one pairwise sum per q ----
+            const bool rows = !((double)(4 * nn) * (double)nq / 1e9 > 1.0);
+            gstart.clear();
+            glen.clear();
+            prog.clear();
+            if (rows) {
+                for (long long st = 0; st < nn; st += kRefLeaf) {
+                    gstart.push_back(st);
+                    glen.push_back((int)std::min<long long>(kRefLeaf, nn - st));
+                }
+            } else {
+                pairwise_tree(0, nn, gstart, glen, prog);
+            }
+            const long long ngroups = (long long)gstart.size();
+            const size_t tab_bytes = (sizeof(long long) + sizeof(int)) * (size_t)ngroups + sizeof(int) * prog.size() + 64;
+            if ((rc = ensure_device(ctx, BUF_SQ_B, tab_bytes))) return rc;
+            char* tab = reinterpret_cast<char*>(ctx->bufs[BUF_SQ_B].p);
+            long long* d_gstart = reinterpret_cast<long long*>(tab);
+            int* d_glen = reinterpret_cast<int*>(tab + sizeof(long long) * (size_t)ngroups);
+            int* d_prog = d_glen + ngroups;
+            if (ngroups) {
+                AMEPB_CUDA(ctx, cudaMemcpyAsync(d_gstart, gstart.data(), sizeof(long long) * ngroups, cudaMemcpyHostToDevice, stream));
+                AMEPB_CUDA(ctx, cudaMemcpyAsync(d_glen, glen.data(), sizeof(int) * ngroups, cudaMemcpyHostToDevice, stream));
+            }
+            if (!prog.empty())
+                AMEPB_CUDA(ctx, cudaMemcpyAsync(d_prog, prog.data(), sizeof(int) * prog.size(), cudaMemcpyHostToDevice, stream));
+            // q tiles so that the buffer of terms / leaf sums stays below 2 GB
+            const long long rows_out = rows ? nn : ngroups;
+            int qt = nq;
+            while (qt > 32 && (double)rows_out * qt * 4.0 > 2.0e9) qt = (qt + 1) / 2;
+            if ((rc = ensure_device(ctx, BUF_ORD_C, std::max<size_t>(16, sizeof(float) * (size_t)rows_out * qt)))) return rc;
+            float* d_buf = reinterpret_cast<float*>(ctx->bufs[BUF_ORD_C].p);
+            for (int q0 = 0; q0 < nq; q0 += qt) {
+                const int nqt = std::min(qt, nq - q0);
+                if (ngroups) {
+                    const unsigned tb = (unsigned)std::min<long long>((ngroups + 3) / 4, (long long)ctx->sm_count * 16);
+#define AMEPB_REF_TERMS(TA, TB)                                                                                                   \
+    do {                                                                                                                          \
+        if (twod && rows) debye_ref_terms_kernel<TA, TB, true, false><<<tb, 128, 0, stream>>>((const TA*)fa, (const TB*)fb, clen, d_zlist, nz, d_gstart, d_glen, ngroups, d_qk, q0, nqt, d_buf); \
+        else if (twod) debye_ref_terms_kernel<TA, TB, true, true><<<tb, 128, 0, stream>>>((const TA*)fa, (const TB*)fb, clen, d_zlist, nz, d_gstart, d_glen, ngroups, d_qk, q0, nqt, d_buf); \
+        else if (rows) debye_ref_terms_kernel<TA, TB, false, false><<<tb, 128, 0, stream>>>((const TA*)fa, (const TB*)fb, clen, d_zlist, nz, d_gstart, d_glen, ngroups, d_qk, q0, nqt, d_buf); \
+        else debye_ref_terms_kernel<TA, TB, false, true><<<tb, 128, 0, stream>>>((const TA*)fa, (const TB*)fb, clen, d_zlist, nz, d_gstart, d_glen, ngroups, d_qk, q0, nqt, d_buf); \
+    } while (0)
+                    if (dtype == AMEPB_F32 && other_dtype == AMEPB_F32) AMEPB_REF_TERMS(float, float);
+                    else if (dtype == AMEPB_F32) AMEPB_REF_TERMS(float, double);
+                    else if (other_dtype == AMEPB_F32) AMEPB_REF_TERMS(double, float);
+                    else AMEPB_REF_TERMS(double, double);
+#undef AMEPB_REF_TERMS
+                    AMEPB_LAUNCH_CHECK(ctx);
+                }
+                const unsigned qb = (unsigned)((nqt + 63) / 64);
+                if (rows) debye_ref_rows_kernel<<<qb, 64, 0, stream>>>(d_buf, nn, nqt, d_sums);
+                else debye_ref_tree_kernel<<<qb, 64, 0, stream>>>(d_buf, d_prog, (long long)prog.size(), nqt, d_sums);
+                AMEPB_LAUNCH_CHECK(ctx);
+                debye_ref_accum_kernel<<<qb, 64, 0, stream>>>(d_sums, (float)nz, q0, nqt, first, d_S);
+                AMEPB_LAUNCH_CHECK(ctx);
+            }
+            // (the host tables of this chunk are rebuilt for the next one: wait for their uploads)
+            AMEPB_CUDA(ctx, cudaStreamSynchronize(stream));
+            first = 0;
+        }
+        if (space == AMEPB_HOST) {
+            AMEPB_CUDA(ctx, cudaMemcpyAsync(out + (size_t)f * nq, d_S, sizeof(float) * nq, cudaMemcpyDeviceToHost, stream));
+        } else {
+            AMEPB_CUDA(ctx, cudaMemcpyAsync(out + (size_t)f * nq, d_S, sizeof(float) * nq, cudaMemcpyDeviceToDevice, stream));
+        }
+        AMEPB_CUDA(ctx, cudaStreamSynchronize(stream));
+    }
+    cudaEvent_t ev1 = timing_event(ctx, stream);
+    if (ev0 && ev1) ctx->ev_sq.emplace_back(ev0, ev1);
     return 0;
 }
 

@@ -351,8 +351,11 @@ class SFiso(_FrameAverage):
                     other_coords = coords               # the slice pairs with all particles
                 coords = coords[:, lo_a:hi_a]
                 extra = dict(reduce=sh.all_sum, counts=(na, nb_))
+            # (mode 'std': the reference's float32 sums per chunk of `chunksize` particles,
+            # amep/evaluate.py:1699-1724 -- unless the frame is split over the ranks)
             rows.append(sfiso_frames(coords, box, None, qmax=qmax, twod=twod, mode=mode,
-                                     other_coords=other_coords, accuracy=accuracy, num=num, **extra))
+                                     other_coords=other_coords, accuracy=accuracy, num=num,
+                                     chunksize=chunksize, njobs=njobs, **extra))
         local = None
         if rows:
             s, q = (np.concatenate([p[k] for p in rows]) for k in range(2))

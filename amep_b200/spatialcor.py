@@ -179,9 +179,29 @@ def _unique_directions(unit_vectors):
     return np.array(reps), np.array(weights, dtype=np.float64)
 
 
+def _sfiso_chunksize(n_other, chunksize, njobs):
+    """amep/spatialcor.py:1583-1590: part of the result in mode 'std' with ``accum='f32'`` -- every
+    chunk of ``other_coords`` is summed on its own in float32."""
+    if njobs > available_cpu_count():
+        njobs = available_cpu_count()
+    if chunksize is None:
+        chunksize = optimal_chunksize(n_other, 2 * n_other)
+    if chunksize > n_other:
+        chunksize = int(n_other / njobs)
+    return chunksize
+
+
 def sfiso_frames(coords, box_boundary, N=None, qmax=20.0, twod=True, mode="std",
-                 other_coords=None, accuracy=0.5, num=64, reduce=None, counts=None):
+                 other_coords=None, accuracy=0.5, num=64, reduce=None, counts=None,
+                 accum="f32", chunksize=None, njobs=1):
     """``sfiso`` for a batch of frames -> ``(S [F, nq], q [F, nq])``.
+
+    Mode 'std': ``accum='f32'`` (default) follows the reference's float32 arithmetic *and* summation
+    order (row after row or NumPy's pairwise sum, per chunk of ``chunksize`` particles of
+    ``other_coords``; ``chunksize`` / ``njobs`` have the reference's meaning and defaults);
+    ``accum='f64'`` rounds distances and arguments like the reference but evaluates and adds the
+    terms in float64 (one pass over all pairs: closer to the exact sum than the reference itself,
+    SURVEY.md section 0 fact 5, and the only form that can be sharded over ranks).
 
     ``reduce`` / ``counts``: intra-frame sharding over ranks -- every rank passes its slice of the
     particles, ``reduce`` sums the per-direction (cos, sin) sums (mode 'fast') or the Debye sums
@@ -233,7 +253,16 @@ def sfiso_frames(coords, box_boundary, N=None, qmax=20.0, twod=True, mode="std",
         if nq == 0:
             return np.zeros((nf, 0)), np.zeros((nf, 0))
         qarr = np.stack(q_rows) if per_frame_box else q_rows[0]
-        sums = _core.sq_debye(pc, None if po is pc else po, qarr, twod)
+        if accum not in ("f32", "f64"):
+            raise ValueError("accum must be 'f32' (the reference's order) or 'f64'")
+        if accum == "f32" and reduce is None:
+            cs = _sfiso_chunksize(po.n, chunksize, njobs)
+            if cs < 1:
+                raise ValueError("sfiso: chunksize must be positive")
+            sums = _core.sq_debye_ref(pc, None if po is pc else po, qarr, twod, cs)
+        else:
+            # (a sum split over ranks cannot follow the reference's order)
+            sums = _core.sq_debye(pc, None if po is pc else po, qarr, twod)
         if reduce is not None:
             sums = reduce(sums)
         if _core._is_torch(sums):
@@ -268,12 +297,13 @@ def sfiso_frames(coords, box_boundary, N=None, qmax=20.0, twod=True, mode="std",
 
 
 def sfiso(coords, box_boundary, N, qmax=20.0, twod=True, njobs=1, chunksize=None, mode="std",
-          other_coords=None, accuracy=0.5, num=64, verbose=False):
+          other_coords=None, accuracy=0.5, num=64, verbose=False, accum="f32"):
     """Isotropic static structure factor of one frame; contract of
     ``amep.spatialcor.sfiso`` (amep/spatialcor.py:1451-1687).  ``N`` is ignored
-    exactly as in the reference (:1579-1581)."""
+    exactly as in the reference (:1579-1581).  ``accum``: see ``sfiso_frames``."""
     s, q = sfiso_frames(coords, box_boundary, N, qmax=qmax, twod=twod, mode=mode,
-                        other_coords=other_coords, accuracy=accuracy, num=num)
+                        other_coords=other_coords, accuracy=accuracy, num=num,
+                        accum=accum, chunksize=chunksize, njobs=njobs)
     return s[0], q[0]
 
 

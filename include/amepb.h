@@ -14,6 +14,7 @@
  *                             amep/spatialcor.py:566-600    chunk fan-out + sum
  *   amepb_sq_harmonics     <- amep/spatialcor.py:1402-1448  __sf_iso_chunk_fast
  *   amepb_sq_debye         <- amep/spatialcor.py:1324-1399  __sf_iso_chunk_std
+ *   amepb_sq_debye_ref     <- the same, in the reference's float32 summation order
  *   amepb_sf2d_modes       <- amep/spatialcor.py:1690-1719  __sf2d_chunk_std
  *                             amep/spatialcor.py:1876-1907  chunk fan-out + sum
  *   amepb_density_counts   <- amep/continuum.py:300-407     hde (np.histogram2d of the images),
@@ -191,6 +192,24 @@ int amepb_sq_debye(amepb_ctx* ctx, const void* coords, int dtype, int64_t n,
                    int space, int64_t nframes,
                    const double* q, int64_t q_stride, int32_t nq, int twod,
                    double* out, void* stream);
+
+/*
+ * The same Debye sum in the reference's own float32 arithmetic AND summation order
+ * (amep/spatialcor.py:1363-1399 per chunk, :1617-1633 over the chunks): per chunk of `chunksize`
+ * particles of `other` (the reference's compute_parallel tasks, amep/spatialcor.py:1583-1590),
+ *   res = float32(#{d == 0}) + sum over the non-zero distances, pair order i * chunk_len + j,
+ * the sum taken like NumPy takes it -- row after row (np.sum(axis=0) of the [pairs, nq] array) while
+ * 4 * pairs * nq <= 1e9 bytes, else NumPy's pairwise summation per q -- and the chunk results added
+ * in chunk order in float32.  J0 is evaluated in float64 and rounded (scipy's float32 loop), sin(x)/x
+ * in float32 (np.sinc).  out[f][k] is the float32 sum S before the division by sqrt(N_a N_b).
+ * Synchronous: the call returns when out is complete (it synchronises `stream` once per chunk).
+ *   q  host float64 [nq] (q_stride 0) or [nframes][q_stride];  out [nframes][nq] float32 in `space`
+ */
+int amepb_sq_debye_ref(amepb_ctx* ctx, const void* coords, int dtype, int64_t n,
+                       const void* other, int other_dtype, int64_t m,
+                       int space, int64_t nframes,
+                       const double* q, int64_t q_stride, int32_t nq, int twod,
+                       int64_t chunksize, float* out, void* stream);
 
 /*
  * Particle counts on the grid of the histogram density estimate used by sf2d(mode='fft')

@@ -57,7 +57,7 @@ def _oracle_rdf_frames(coords, box, other_coords=None, nbins=None, rmax=None, mo
 
 
 def _oracle_sfiso_frames(coords, box, N=None, qmax=20.0, twod=True, mode="fast", other_coords=None,
-                         accuracy=0.5, num=8, reduce=None, counts=None):
+                         accuracy=0.5, num=8, reduce=None, counts=None, chunksize=None, njobs=1):
     """Stand-in for spatialcor.sfiso_frames(mode='fast') in NumPy: per direction the (cos, sin) sums
     of the particles it is given, ``reduce`` over the ranks, the reference's normalisation
     (amep/spatialcor.py:1440-1446, 1660-1664) with the particle numbers of the whole frame."""

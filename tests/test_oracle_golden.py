@@ -91,7 +91,8 @@ def test_fft_mode_bit_exact(name):
     np.testing.assert_array_equal(qi, z["q_iso"])
 
 
-@pytest.mark.parametrize("name", ["sfiso_std_2d_f64.npz", "sfiso_std_3d_cross_f32.npz"])
+@pytest.mark.parametrize("name", ["sfiso_std_2d_f64.npz", "sfiso_std_3d_cross_f32.npz", "sfiso_std_2d_pairwise.npz",
+                                  "sfiso_std_2d_chunks1000.npz", "sfiso_std_3d_pairwise.npz"])
 def test_sfiso_std_debye_bit_exact(name):
     z = _load(name)
     other = z["other"] if "other" in z.files else None
@@ -103,7 +104,8 @@ def test_sfiso_std_debye_bit_exact(name):
     # the reference's float32 evaluation sits ~1e-5 from the float64 evaluation of the same sum
     s64, _ = orc.sfiso_std_f64(z["coords"], z["box"], qmax=float(z["qmax"]), twod=bool(z["twod"]),
                                other_coords=other)
-    assert np.max(np.abs(s64 - s) / np.maximum(np.abs(s64), 1e-2)) < 2e-4
+    # (2.2e-4 for the 2600-particle frame summed row after row in chunks of 1000)
+    assert np.max(np.abs(s64 - s) / np.maximum(np.abs(s64), 1e-2)) < 5e-4
 
 
 @pytest.mark.parametrize("name", ["sf2d_f64_onechunk.npz", "sf2d_f32_chunks.npz", "sf2d_f64_cross.npz"])
