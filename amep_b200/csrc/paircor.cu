@@ -16,6 +16,7 @@
 // staged through shared memory as broadcasts.  No fused multiply-add in any value that is
 // compared against a bin edge.
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -78,6 +79,8 @@ struct PcfaArgs {
     int pbc, same;
     int nde, nae;              // number of distance / angle edges
     int uniform_d, uniform_a;
+    float cert_margin;         // > 0: angle bins may be decided in float32 (in units of a bin), see the kernel
+    float pre_r2;              // > 0: squared distance beyond which the float32 pre-test drops a pair
 };
 
 constexpr int kPcfaThreads = 128;
@@ -85,8 +88,13 @@ constexpr int kPcfaTile = 512;
 
 // TC / TO: dtypes of coords / other; P: dtype the difference vector ends up in -- float only if
 // both arrays and (with pbc) the box are float32.
-template <typename TC, typename TO, typename P>
-__global__ void __launch_bounds__(kPcfaThreads) pcf_angle_kernel(
+// PRIV: the (r, theta) grid fits into shared memory as 32-bit counters (the default 500 x 100 grid:
+// 200 KB): one block of 1024 queries per SM counts there and adds its non-zero bins to the global grid
+// once.  With the default rmax = L/2 three pairs in four are binned, and one 64-bit global atomic per
+// binned pair bounded the first version of this kernel (5.8e10 pairs/s at N = 100k).
+constexpr int kPcfaThreadsPriv = 1024;
+template <typename TC, typename TO, typename P, int THREADS, bool PRIV>
+__global__ void __launch_bounds__(THREADS) pcf_angle_kernel(
     const TC* __restrict__ coords, long long n, const TO* __restrict__ other, long long m, PcfaArgs A,
     const double* __restrict__ edges /* distance edges, then angle edges */, const double* __restrict__ e_all,
     const double* __restrict__ e_norm_all, unsigned long long* __restrict__ counts) {
@@ -96,7 +104,11 @@ __global__ void __launch_bounds__(kPcfaThreads) pcf_angle_kernel(
     double* s_ed = reinterpret_cast<double*>(smem_pcfa);
     double* s_ea = s_ed + A.nde;
     TC* s_t = reinterpret_cast<TC*>(s_ea + A.nae);   // [tile][2]
+    unsigned* s_hist = reinterpret_cast<unsigned*>(s_t + 2 * kPcfaTile);   // PRIV: [nde - 1][nae - 1]
+    const int nbins_total = (A.nde - 1) * (A.nae - 1);
     for (int k = threadIdx.x; k < A.nde + A.nae; k += blockDim.x) s_ed[k] = edges[k];
+    if (PRIV)
+        for (int k = threadIdx.x; k < nbins_total; k += blockDim.x) s_hist[k] = 0u;
     const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool have_q = q < m;
     D ox = 0, oy = 0;
@@ -118,6 +130,9 @@ __global__ void __launch_bounds__(kPcfaThreads) pcf_angle_kernel(
         vz = Rn<P>::add(Rn<P>::mul(fb, Rn<P>::sub(s, Rn<P>::nearest(s))), fc);
     }
     const P vz2 = Rn<P>::mul(vz, vz);
+    const float fox = (float)ox, foy = (float)oy;
+    const float plx = (float)A.fbox[0], ply = (float)A.fbox[1], pcx = (float)A.fcen[0], pcy = (float)A.fcen[1];
+    const float pix = 1.0f / plx, piy = 1.0f / ply;
     const double two_pi = 6.283185307179586;   // 2*np.pi
     const long long tile0 = (long long)blockIdx.y * ((n + gridDim.y - 1) / gridDim.y);
     const long long tile1 = min(n, tile0 + (n + gridDim.y - 1) / gridDim.y);
@@ -132,6 +147,21 @@ __global__ void __launch_bounds__(kPcfaThreads) pcf_angle_kernel(
         if (!have_q) continue;
         for (int k = 0; k < cnt; ++k) {
             if (A.same && t0 + k == q) continue;   // coords[particlerange != n]
+            if (A.pre_r2 > 0.f) {
+                // Cheap float32 look at the pair first: minimum image by multiply / magic-number rounding /
+                // fma (no division, no conversion -- the exact fold below keeps the XU pipe 71 % busy),
+                // and a pair farther than the last distance edge by more than pre_r2's tolerance (8e-6 of
+                // the box, far above the float32 rounding of either fold) cannot be counted.
+                float ax = (float)s_t[2 * k] - fox, ay = (float)s_t[2 * k + 1] - foy;
+                if (A.pbc) {
+                    const float ux = ax - pcx, uy = ay - pcy;
+                    const float rx = __fadd_rn(__fmaf_rn(ux, pix, 12582912.f), -12582912.f);
+                    const float ry = __fadd_rn(__fmaf_rn(uy, piy, 12582912.f), -12582912.f);
+                    ax = __fmaf_rn(-rx, plx, ux) + pcx;
+                    ay = __fmaf_rn(-ry, ply, uy) + pcy;
+                }
+                if (ax * ax + ay * ay > A.pre_r2) continue;   // (NaN and huge values fall through to the exact test)
+            }
             P vx = (P)Rn<D>::sub((D)s_t[2 * k], ox);
             P vy = (P)Rn<D>::sub((D)s_t[2 * k + 1], oy);
             if (A.pbc) {
@@ -148,6 +178,39 @@ __global__ void __launch_bounds__(kPcfaThreads) pcf_angle_kernel(
             const double dd = (double)dist;
             const int bd = edge_bin(dd, s_ed, A.nde, A.inv_wd, A.uniform_d != 0);
             if (bd < 0) continue;
+            // Angle bin decided in float32 where that is certain (uniform angle edges from 0 to 2 pi).
+            // theta~ = atan2(|e x r|, e.r), mirrored and rotated like the float64 value below, is within
+            // 3e-6 rad of the *true* angle (products and sums 5e-7, atan2f 2 ulp = 5e-7, the float32
+            // constants and the three additions 2.4e-7 each, the scaling 7.5e-7).  The reference's own
+            // angle is arccos of a ratio that carries the float32 rounding of dist (2e-7 relative), so it
+            // sits up to 2e-7 / sin(theta) from the true angle -- 3.5e-4 rad at the poles, where it
+            // returns exactly 0 or pi for a whole cone of directions.  Hence: only pairs with
+            // sin(theta~) >= 4e-3 (all but 0.25 %), and only a value farther than cert_margin = 6e-5 rad
+            // (>= 3e-6 + 2e-7 / 4e-3) from both edges of its bin, are decided here; the rest -- one pair
+            // in 250 for 100 angle bins -- takes the float64 arccos like the reference.
+            if (A.cert_margin > 0.f) {
+                const float fx = (float)vx, fy = (float)vy, fz = (float)vz;
+                const float f0 = (float)e0, f1 = (float)e1, f2 = (float)e2;
+                const float dotf = f0 * fx + f1 * fy + f2 * fz;
+                const float cx = f1 * fz - f2 * fy, cy = f2 * fx - f0 * fz, cz = f0 * fy - f1 * fx;
+                const float cr2 = cx * cx + cy * cy + cz * cz;
+                float th = atan2f(sqrtf(cr2), dotf);
+                if (vy < (P)0) th = 6.2831855f - th;
+                if (A.angle != 0.0) {
+                    th -= (float)A.angle;
+                    if (th < 0.f) th += 6.2831855f;
+                    if (th >= 6.2831855f) th -= 6.2831855f;
+                }
+                const float fb = th * (float)A.inv_wa;
+                const float fl = floorf(fb);
+                if (cr2 >= 1.6e-5f * (cr2 + dotf * dotf) && fb - fl > A.cert_margin && (fl + 1.0f) - fb > A.cert_margin &&
+                    fl >= 0.f && fl < (float)(A.nae - 1)) {
+                    const int bc = (int)fl;
+                    if (PRIV) atomicAdd(&s_hist[bd * (A.nae - 1) + bc], 1u);
+                    else atomicAdd(&counts[(long long)bd * (A.nae - 1) + bc], 1ull);
+                    continue;
+                }
+            }
             // ratio = clip(dot(e, r) / (dist * |e|), -1, 1); theta = arccos(ratio) in float64
             const double dot = __dadd_rn(__dadd_rn(__dmul_rn(e0, (double)vx), __dmul_rn(e1, (double)vy)), __dmul_rn(e2, (double)vz));
             double ratio = __ddiv_rn(dot, __dmul_rn(dd, en));
@@ -161,7 +224,15 @@ __global__ void __launch_bounds__(kPcfaThreads) pcf_angle_kernel(
             }
             const int ba = edge_bin(theta, s_ea, A.nae, A.inv_wa, A.uniform_a != 0);
             if (ba < 0) continue;
-            atomicAdd(&counts[(long long)bd * (A.nae - 1) + ba], 1ull);
+            if (PRIV) atomicAdd(&s_hist[bd * (A.nae - 1) + ba], 1u);
+            else atomicAdd(&counts[(long long)bd * (A.nae - 1) + ba], 1ull);
+        }
+    }
+    if (PRIV) {
+        __syncthreads();
+        for (int k = threadIdx.x; k < nbins_total; k += blockDim.x) {
+            const unsigned v = s_hist[k];
+            if (v) atomicAdd(&counts[k], (unsigned long long)v);
         }
     }
 }
@@ -378,6 +449,23 @@ int amepb_pcf_angle_counts(amepb_ctx* ctx, const void* coords, int dtype, int64_
     A.angle = angle;
     A.uniform_d = edges_uniform(dedges, nde, &A.inv_wd) ? 1 : 0;
     A.uniform_a = edges_uniform(aedges, nae, &A.inv_wa) ? 1 : 0;
+    // float32-certified angle bins: uniform edges from 0 to 2 pi (what pcf_angle always passes), margin 6e-5 rad
+    const bool no_cert = getenv("AMEPB_PCFA_NO_F32_ANGLE") != nullptr;   // A/B switch for measurements and tests
+    A.cert_margin = 0.f;
+    if (A.uniform_a && !no_cert && aedges[0] == 0.0 && fabs(aedges[nae - 1] - 6.283185307179586) < 1e-9 &&
+        6e-5 * A.inv_wa < 0.25)
+        A.cert_margin = (float)(6e-5 * A.inv_wa);
+    // float32 pre-test of the distance (see the kernel): last edge plus 8e-6 of the largest coordinate scale
+    A.pre_r2 = 0.f;
+    {
+        const double scale = fabs(A.fbox[0]) + fabs(A.fbox[1]) + fabs(A.fcen[0]) + fabs(A.fcen[1]) + fabs(dedges[nde - 1]);
+        const double r = dedges[nde - 1] + 8e-6 * scale;
+        const bool no_pre = getenv("AMEPB_PCFA_NO_PRETEST") != nullptr;   // A/B switch for measurements and tests
+        // (not worth its instructions when most pairs are in range, e.g. the default rmax = L/2 with periodic images)
+        const bool mostly_in = pbc && 3.2 * r * r > 0.5 * fabs(A.fbox[0] * A.fbox[1]);
+        if (!no_pre && !mostly_in && r > 0 && r < 1e15 && (!pbc || (A.fbox[0] > 0 && A.fbox[1] > 0 && scale < 1e15)))
+            A.pre_r2 = (float)(r * r * (1.0 + 1e-6));
+    }
     A.e[0] = e[0]; A.e[1] = e[1]; A.e[2] = e[2];
     A.e_norm = e_norm[0];
     A.e_stride = (int)e_stride;
@@ -408,16 +496,34 @@ int amepb_pcf_angle_counts(amepb_ctx* ctx, const void* coords, int dtype, int64_
     AMEPB_CUDA(ctx, cudaMemsetAsync(d_counts, 0, gbytes, stream));
     const bool all_f32 = dtype == AMEPB_F32 && other_dtype == AMEPB_F32;
     const bool p_f32 = all_f32 && (!pbc || box_dtype == AMEPB_F32);
-    const unsigned qblocks = (unsigned)((m + kPcfaThreads - 1) / kPcfaThreads);
-    // split the targets so that a few thousand blocks are in flight
+    // shared-memory grid (see pcf_angle_kernel) when it fits next to the edges and the target tile
+    const size_t base_smem = ebytes + (size_t)kPcfaTile * 2 * (dtype == AMEPB_F32 ? 4 : 8);
+    const size_t priv_smem = base_smem + sizeof(unsigned) * (size_t)(nde - 1) * (nae - 1);
+    const bool no_priv = getenv("AMEPB_PCFA_GLOBAL_ATOMICS") != nullptr;   // A/B switch for measurements and tests
+    const bool priv = priv_smem <= 225 * 1024 && !no_priv;
+    const int threads = priv ? kPcfaThreadsPriv : kPcfaThreads;
+    const unsigned qblocks = (unsigned)((m + threads - 1) / threads);
+    // split the targets so that a few thousand blocks are in flight (shared grid: two waves of one
+    // block per SM, and at most 2^32 pairs per block for its 32-bit counters)
+    const long long want_blocks = priv ? 2LL * ctx->sm_count : 8LL * ctx->sm_count;
     unsigned ysplit = (unsigned)std::max<long long>(1, std::min<long long>((n + kPcfaTile - 1) / kPcfaTile,
-                                                                            (8LL * ctx->sm_count + qblocks - 1) / qblocks));
+                                                                            (want_blocks + qblocks - 1) / qblocks));
+    if (priv) ysplit = (unsigned)std::max<long long>(ysplit, ((long long)threads * n >> 31) + 1);
     ysplit = std::min(ysplit, 65535u);
     const dim3 grid(qblocks, ysplit);
-    const size_t smem = ebytes + (size_t)kPcfaTile * 2 * (dtype == AMEPB_F32 ? 4 : 8);
-#define AMEPB_PCFA(TC, TO, P) \
-    pcf_angle_kernel<TC, TO, P><<<grid, kPcfaThreads, smem, stream>>>((const TC*)d_c, n, (const TO*)d_o, m, A, d_edges, d_e, d_en, \
-                                                                       reinterpret_cast<unsigned long long*>(d_counts))
+    const size_t smem = priv ? priv_smem : base_smem;
+#define AMEPB_PCFA(TC, TO, P)                                                                                                    \
+    do {                                                                                                                         \
+        if (priv) {                                                                                                              \
+            AMEPB_CUDA(ctx, cudaFuncSetAttribute(pcf_angle_kernel<TC, TO, P, kPcfaThreadsPriv, true>,                            \
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                       \
+            pcf_angle_kernel<TC, TO, P, kPcfaThreadsPriv, true><<<grid, kPcfaThreadsPriv, smem, stream>>>(                       \
+                (const TC*)d_c, n, (const TO*)d_o, m, A, d_edges, d_e, d_en, reinterpret_cast<unsigned long long*>(d_counts));   \
+        } else {                                                                                                                 \
+            pcf_angle_kernel<TC, TO, P, kPcfaThreads, false><<<grid, kPcfaThreads, smem, stream>>>(                              \
+                (const TC*)d_c, n, (const TO*)d_o, m, A, d_edges, d_e, d_en, reinterpret_cast<unsigned long long*>(d_counts));   \
+        }                                                                                                                        \
+    } while (0)
     if (p_f32) AMEPB_PCFA(float, float, float);
     else if (all_f32) AMEPB_PCFA(float, float, double);
     else if (dtype == AMEPB_F32) AMEPB_PCFA(float, double, double);

@@ -92,6 +92,34 @@ def test_pcf_angle_larger_against_oracle(sc, dtype):
             np.testing.assert_array_equal(a, b)
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_pcf_angle_float32_angle_decisions_equal_float64(sc, monkeypatch, dtype):
+    """4e8 pairs: deciding the angle bin in float32 where the 6e-5 rad margin allows it, counting in the
+    shared-memory grid, gives the same integers as the float64 arccos of every pair with global atomics
+    (AMEPB_PCFA_NO_F32_ANGLE, AMEPB_PCFA_GLOBAL_ATOMICS, AMEPB_PCFA_NO_PRETEST) -- with and without the psi rotation, with a
+    reference direction off the x axis, 100 and 2000 angle bins (the margin is 2 % of a bin there)."""
+    rng = np.random.default_rng(83)
+    n, L = 20000, 100.0
+    box = np.array([[0, L], [0, L], [-0.5, 0.5]], dtype=dtype)
+    c = np.zeros((n, 3), dtype=dtype)
+    c[:, :2] = rng.uniform(0, L, (n, 2))
+    ct = torch.from_numpy(c).cuda()
+    cases = (dict(), dict(psi=np.array([0.8, 0.3])), dict(e=np.array([0.3, -0.9, 0.0]), nabins=2000, ndbins=20),
+             dict(rmax=7.5, ndbins=750))
+    for kw in cases:
+        out = {}
+        for mode in ("fast", "f64"):
+            for var in ("AMEPB_PCFA_NO_F32_ANGLE", "AMEPB_PCFA_GLOBAL_ATOMICS", "AMEPB_PCFA_NO_PRETEST"):
+                if mode == "f64":
+                    monkeypatch.setenv(var, "1")
+                else:
+                    monkeypatch.delenv(var, raising=False)
+            out[mode] = sc.pcf_angle(ct.clone(), box, **kw)
+        assert np.isfinite(out["fast"][0]).all() and out["fast"][0].sum() > 0
+        for a, b in zip(out["fast"], out["f64"]):
+            np.testing.assert_array_equal(a, b)
+
+
 def _scor_kw(z, name):
     kw = dict(pbc=bool(z["pbc"]))
     if not np.isnan(z["rmax"]):
