@@ -55,6 +55,25 @@ __device__ __forceinline__ Vec4<double> load_vec4(const Vec4<double>* p) {
     return r;
 }
 
+// One record of a cell-sorted array.  compact (FramePlan::compact): float32 arrays of flat frames
+// hold (x, y) pairs only -- half the bytes of the scattered stores of the fill pass, which are what
+// bounds it (tools/place_probe.cu: 8-byte records 123 G/s, 16-byte records 75 G/s), and half the
+// bytes the pair kernel gathers.
+__device__ __forceinline__ void store_record(Vec4<float>* arr, unsigned slot, float x, float y, float z, bool compact) {
+    if (compact) {
+        reinterpret_cast<float2*>(arr)[slot] = make_float2(x, y);
+    } else {
+        Vec4<float> o;
+        o.x = x; o.y = y; o.z = z; o.w = 0.0f;
+        arr[slot] = o;
+    }
+}
+__device__ __forceinline__ void store_record(Vec4<double>* arr, unsigned slot, double x, double y, double z, bool) {
+    Vec4<double> o;
+    o.x = x; o.y = y; o.z = z; o.w = 0.0;
+    arr[slot] = o;
+}
+
 struct StatsOut {  // mirrors FrameStats, device side
     double lo[3];
     double hi[3];
@@ -66,6 +85,13 @@ struct StatsOut {  // mirrors FrameStats, device side
 // ---------------------------------------------------------------------------
 // stats kernel: per frame min / max / "column differs from particle 0"
 // ---------------------------------------------------------------------------
+// (minima and maxima are taken in the element type -- exact, and for float32 input free of the six
+// float->double conversions per particle that kept this HBM-bound pass on the conversion pipe)
+__device__ __forceinline__ float stat_min(float a, float b) { return fminf(a, b); }
+__device__ __forceinline__ float stat_max(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ double stat_min(double a, double b) { return fmin(a, b); }
+__device__ __forceinline__ double stat_max(double a, double b) { return fmax(a, b); }
+
 template <typename T>
 __global__ void __launch_bounds__(256) stats_partial_kernel(const T* __restrict__ pts, long long n,
                                                             StatsOut* __restrict__ partial) {
@@ -73,7 +99,8 @@ __global__ void __launch_bounds__(256) stats_partial_kernel(const T* __restrict_
     const T* base = pts + (long long)f * n * 3;
     const T f0 = base[0], f1 = base[1], f2 = base[2];
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
-    double lo0 = inf, lo1 = inf, lo2 = inf, hi0 = -inf, hi1 = -inf, hi2 = -inf;
+    const T tinf = (T)inf;
+    T lo0 = tinf, lo1 = tinf, lo2 = tinf, hi0 = -tinf, hi1 = -tinf, hi2 = -tinf;
     int v0 = 0, v1 = 0, v2 = 0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (long long)gridDim.x * blockDim.x) {
@@ -81,17 +108,17 @@ __global__ void __launch_bounds__(256) stats_partial_kernel(const T* __restrict_
         v0 |= !(x == f0);
         v1 |= !(y == f1);
         v2 |= !(z == f2);
-        lo0 = fmin(lo0, (double)x); hi0 = fmax(hi0, (double)x);
-        lo1 = fmin(lo1, (double)y); hi1 = fmax(hi1, (double)y);
-        lo2 = fmin(lo2, (double)z); hi2 = fmax(hi2, (double)z);
+        lo0 = stat_min(lo0, x); hi0 = stat_max(hi0, x);
+        lo1 = stat_min(lo1, y); hi1 = stat_max(hi1, y);
+        lo2 = stat_min(lo2, z); hi2 = stat_max(hi2, z);
     }
     for (int o = 16; o > 0; o >>= 1) {
-        lo0 = fmin(lo0, __shfl_xor_sync(0xffffffffu, lo0, o));
-        lo1 = fmin(lo1, __shfl_xor_sync(0xffffffffu, lo1, o));
-        lo2 = fmin(lo2, __shfl_xor_sync(0xffffffffu, lo2, o));
-        hi0 = fmax(hi0, __shfl_xor_sync(0xffffffffu, hi0, o));
-        hi1 = fmax(hi1, __shfl_xor_sync(0xffffffffu, hi1, o));
-        hi2 = fmax(hi2, __shfl_xor_sync(0xffffffffu, hi2, o));
+        lo0 = stat_min(lo0, __shfl_xor_sync(0xffffffffu, lo0, o));
+        lo1 = stat_min(lo1, __shfl_xor_sync(0xffffffffu, lo1, o));
+        lo2 = stat_min(lo2, __shfl_xor_sync(0xffffffffu, lo2, o));
+        hi0 = stat_max(hi0, __shfl_xor_sync(0xffffffffu, hi0, o));
+        hi1 = stat_max(hi1, __shfl_xor_sync(0xffffffffu, hi1, o));
+        hi2 = stat_max(hi2, __shfl_xor_sync(0xffffffffu, hi2, o));
         v0 |= __shfl_xor_sync(0xffffffffu, v0, o);
         v1 |= __shfl_xor_sync(0xffffffffu, v1, o);
         v2 |= __shfl_xor_sync(0xffffffffu, v2, o);
@@ -100,8 +127,8 @@ __global__ void __launch_bounds__(256) stats_partial_kernel(const T* __restrict_
     __shared__ int s_var[8][3];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (lane == 0) {
-        s_red[warp][0] = lo0; s_red[warp][1] = lo1; s_red[warp][2] = lo2;
-        s_red[warp][3] = hi0; s_red[warp][4] = hi1; s_red[warp][5] = hi2;
+        s_red[warp][0] = (double)lo0; s_red[warp][1] = (double)lo1; s_red[warp][2] = (double)lo2;
+        s_red[warp][3] = (double)hi0; s_red[warp][4] = (double)hi1; s_red[warp][5] = (double)hi2;
         s_var[warp][0] = v0; s_var[warp][1] = v1; s_var[warp][2] = v2;
     }
     __syncthreads();
@@ -184,6 +211,35 @@ __device__ __forceinline__ void place_images_body(const T* __restrict__ p, const
                                                   unsigned* __restrict__ count,
                                                   const unsigned* __restrict__ start,
                                                   Vec4<float>* __restrict__ sorted) {
+    // Shortcut for the interior: almost every particle is farther than the cutoff from all box
+    // faces and cannot have a kept shifted image (near_lo / near_hi, conservative bounds from the
+    // host); it then needs no image arithmetic at all -- 70 of the 190 instructions per particle.
+    {
+        bool maybe = false;
+        float b0[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            b0[d] = (float)p[d];
+            if (P.nshift[d] == 3) maybe = maybe || !(b0[d] > P.near_lo[d] && b0[d] < P.near_hi[d]);   // (NaN: full test)
+        }
+        if (!maybe) {
+            if (P.sym) return;   // the unshifted image is the query itself
+            if (!(b0[0] >= P.keep_lo[0] && b0[0] <= P.keep_hi[0] && b0[1] >= P.keep_lo[1] && b0[1] <= P.keep_hi[1] &&
+                  b0[2] >= P.keep_lo[2] && b0[2] <= P.keep_hi[2]))
+                return;
+            const int cx = cell_index((double)b0[0], P.g0[0], P.inv_h[0], P.n[0]);
+            const int cy = cell_index((double)b0[1], P.g0[1], P.inv_h[1], P.n[1]);
+            const int cz = cell_index((double)b0[2], P.g0[2], P.inv_h[2], P.n[2]);
+            const unsigned c = P.cell_base + (unsigned)((cz * P.n[1] + cy) * P.n[0] + cx);
+            if (!FILL) {
+                atomicAdd(&count[c], 1u);
+            } else {
+                const unsigned slot = start[c] + atomicSub(&count[c], 1u) - 1u;
+                store_record(sorted, slot, b0[0], b0[1], b0[2], P.compact != 0);
+            }
+            return;
+        }
+    }
     float img[3][3];
     bool ok[3][3];
     bool any_shift = false;
@@ -212,9 +268,7 @@ __device__ __forceinline__ void place_images_body(const T* __restrict__ p, const
             atomicAdd(&count[c], 1u);
         } else {
             const unsigned slot = start[c] + atomicSub(&count[c], 1u) - 1u;
-            Vec4<float> o;
-            o.x = img[0][vx]; o.y = img[1][vy]; o.z = img[2][vz]; o.w = 0.0f;
-            sorted[slot] = o;
+            store_record(sorted, slot, img[0][vx], img[1][vy], img[2][vz], P.compact != 0);
         }
     };
     if (!any_shift) {
@@ -315,9 +369,7 @@ __global__ void __launch_bounds__(256) place_self_kernel(const T* __restrict__ p
         if (!FILL) {
             frank[i] = aux[u];
         } else {
-            Vec4<AT> o;
-            o.x = v[u][0]; o.y = v[u][1]; o.z = v[u][2]; o.w = (AT)0;
-            qsorted[aux[u]] = o;
+            store_record(qsorted, aux[u], v[u][0], v[u][1], v[u][2], P.compact != 0);
         }
     }
     // (3) shifted images: none for almost every particle when the cutoff is short
@@ -378,9 +430,7 @@ __global__ void __launch_bounds__(256) place_points_kernel(const T* __restrict__
 #pragma unroll
         for (int u = 0; u < kPlaceILP; ++u) {
             if (!keep[u]) continue;
-            Vec4<S> o;
-            o.x = v[u][0]; o.y = v[u][1]; o.z = v[u][2]; o.w = (S)0;
-            sorted[slot[u]] = o;
+            store_record(sorted, slot[u], v[u][0], v[u][1], v[u][2], P.compact != 0);
         }
     }
 }
@@ -628,12 +678,22 @@ __device__ __forceinline__ Vec4<double> load_query<double, false>(const Vec4<dou
 // One warp: all queries of one cell against one neighbour row (contiguous in the
 // sorted image array).  Lanes hold images in registers, queries are broadcast loads.
 // General version: threshold table anywhere, search loops, shared or global histogram.
+// record j of a sorted array (compact: (x, y) pairs, see store_record; float32 arrays only)
+__device__ __forceinline__ Vec4<float> load_record(const Vec4<float>* arr, unsigned j, bool compact) {
+    if (!compact) return load_vec4(arr + j);
+    const float2 v = __ldg(reinterpret_cast<const float2*>(arr) + j);
+    Vec4<float> r;
+    r.x = v.x; r.y = v.y; r.z = 0.0f; r.w = 0.0f;
+    return r;
+}
+__device__ __forceinline__ Vec4<double> load_record(const Vec4<double>* arr, unsigned j, bool) { return load_vec4(arr + j); }
+
 template <typename AT, typename NT, int ZMODE, bool DIRECT>
 __device__ __noinline__ void warp_pairs_general(const Vec4<AT>* __restrict__ qsorted, unsigned qa, unsigned qb,
                                                 const Vec4<NT>* __restrict__ tsorted, unsigned ta, unsigned tb,
                                                 const AT* __restrict__ thr, int nbins, AT dz2c, float inv_w,
                                                 float c_magic, unsigned weight, unsigned* __restrict__ s_hist,
-                                                unsigned long long* __restrict__ g_hist) {
+                                                unsigned long long* __restrict__ g_hist, bool compact = false) {
     const int lane = threadIdx.x & 31;
     const AT nan = (AT)__int_as_float(0x7fc00000);
     const AT thr_lo = thr[0], thr_hi = thr[nbins];
@@ -641,11 +701,11 @@ __device__ __noinline__ void warp_pairs_general(const Vec4<AT>* __restrict__ qso
         const unsigned j = base + lane;
         AT nx = nan, ny = nan, nz = nan;
         if (j < tb) {
-            const Vec4<NT> nb = load_vec4(tsorted + j);
+            const Vec4<NT> nb = load_record(tsorted, j, compact);
             nx = (AT)nb.x; ny = (AT)nb.y; nz = (AT)nb.z;
         }
         for (unsigned q = qa; q < qb; ++q) {
-            const Vec4<AT> qv = load_vec4(qsorted + q);
+            const Vec4<AT> qv = load_record(qsorted, q, compact);
             const AT s = pair_s<AT, ZMODE>(qv, nx, ny, nz, dz2c);
             if (s >= thr_lo && s < thr_hi) {
                 int g = max((int)bin_guess(Arith<AT>::approx(s), inv_w, c_magic, (unsigned)nbins) - 1, 0);
@@ -995,6 +1055,8 @@ __global__ void __launch_bounds__(kPairThreads, (sizeof(AT) == 4 ? kPairBlocksPe
                 const unsigned sq_z = sq_xy + 8 * kQueryCap;        // ZMODE == 0 only
                 const Vec4<float>* qarr = reinterpret_cast<const Vec4<float>*>(qsorted);
                 const Vec4<float>* tarr = reinterpret_cast<const Vec4<float>*>(tsorted);
+                const bool compact = P.compact != 0;            // flat frames: (x, y) records, see store_record
+                const unsigned rec2 = compact ? 1u : 2u;        // record size in float2 units
                 // entries: [0] own cell (SYM), [1, G] ghost rows (SYM, if any can be near),
                 // then the real rows (SYM: upper half shell) -- weight-1 entries first
                 int G = 0;
@@ -1021,7 +1083,7 @@ __global__ void __launch_bounds__(kPairThreads, (sizeof(AT) == 4 ? kPairBlocksPe
                                 const Vec4<float> v = load_vec4(qarr + qc + i);
                                 x = v.x; y = v.y; z = v.z;
                             } else {
-                                const float2 v = __ldg(reinterpret_cast<const float2*>(qarr + qc + i));
+                                const float2 v = __ldg(reinterpret_cast<const float2*>(qarr) + (size_t)(qc + i) * rec2);
                                 x = v.x; y = v.y;
                             }
                             if (x == x) { lo[0] = fminf(lo[0], x); hi[0] = fmaxf(hi[0], x); }
@@ -1101,7 +1163,7 @@ __global__ void __launch_bounds__(kPairThreads, (sizeof(AT) == 4 ? kPairBlocksPe
                     // farther than the cutoff from the box around the staged queries: no query of this
                     // round can reach them (cull_r2 carries a 1e-4 relative margin, far above the
                     // float32 rounding of either side).  Returns the new fill level.
-                    auto copy_targets = [&](const Vec4<float>* src, unsigned n, unsigned at, bool cull) -> unsigned {
+                    auto copy_targets = [&](const Vec4<float>* src0, unsigned first, unsigned n, unsigned at, bool cull) -> unsigned {
 #pragma unroll 1
                         for (unsigned base = 0; base < n; base += 32) {
                             const unsigned i = base + lane;
@@ -1109,10 +1171,10 @@ __global__ void __launch_bounds__(kPairThreads, (sizeof(AT) == 4 ? kPairBlocksPe
                             bool keep = i < n;
                             if (keep) {
                                 if (ZMODE == 0) {
-                                    const Vec4<float> v = load_vec4(src + i);
+                                    const Vec4<float> v = load_vec4(src0 + first + i);
                                     x = v.x; y = v.y; z = v.z;
                                 } else {
-                                    const float2 v = __ldg(reinterpret_cast<const float2*>(src + i));
+                                    const float2 v = __ldg(reinterpret_cast<const float2*>(src0) + (size_t)(first + i) * rec2);
                                     x = v.x; y = v.y;
                                 }
                                 if (cull) {
@@ -1183,11 +1245,11 @@ __global__ void __launch_bounds__(kPairThreads, (sizeof(AT) == 4 ? kPairBlocksPe
                             todo &= todo - 1;
                             const unsigned st = __shfl_sync(0xffffffffu, start, src), ln = __shfl_sync(0xffffffffu, len, src);
                             const unsigned fl = __shfl_sync(0xffffffffu, flags, src);
-                            const Vec4<float>* arr = ((fl & 2) ? qarr : tarr) + st;
+                            const Vec4<float>* arr0 = (fl & 2) ? qarr : tarr;
                             const bool cull = fl != 2;   // the own cell holds the queries themselves
                             if (fill + ln <= kStageCap && small_ok) {  // the usual case: the row fits
                                 const unsigned before = fill;
-                                fill = copy_targets(arr, ln, fill, cull);
+                                fill = copy_targets(arr0, st, ln, fill, cull);
                                 if (!(fl & 1)) lo_end = fill;
                                 staged += nqc * (fill - before);   // at most kQueryCap * kStageCap
                                 continue;
@@ -1196,15 +1258,15 @@ __global__ void __launch_bounds__(kPairThreads, (sizeof(AT) == 4 ? kPairBlocksPe
                             if (npairs > direct_pairs) {  // giant cells: straight to the global histogram
                                 oversize += npairs;
                                 warp_pairs_general<float, float, ZMODE == 0 ? 0 : 1, true>(
-                                    qarr, qc, qc + nqc, arr, 0u, ln, reinterpret_cast<const float*>(thr), nbins,
-                                    (float)dz2c, inv_w, c_magic, (fl & 1) ? 2u : 1u, s_hist, g_hist);
+                                    qarr, qc, qc + nqc, arr0, st, st + ln, reinterpret_cast<const float*>(thr), nbins,
+                                    (float)dz2c, inv_w, c_magic, (fl & 1) ? 2u : 1u, s_hist, g_hist, ZMODE != 0 && compact);
                                 continue;
                             }
                             unsigned off = 0;
                             while (off < ln) {
                                 const unsigned n = min(ln - off, kStageCap - fill);
                                 const unsigned before = fill;
-                                fill = copy_targets(arr + off, n, fill, cull);
+                                fill = copy_targets(arr0, st + off, n, fill, cull);
                                 staged += (unsigned long long)nqc * (fill - before);
                                 off += n;
                                 if (!(fl & 1)) lo_end = fill;
@@ -1821,7 +1883,6 @@ static int rdf_sub_batch(amepb_ctx* ctx, const RdfCall& c, int64_t f0, int nf, c
     // this stream had run; a read queued by another call on another stream is waited for here)
     if ((rc = pinned_host_acquire(ctx))) return rc;
     char* hp = reinterpret_cast<char*>(ctx->pinned);
-    memcpy(hp, plans.data(), plan_bytes);
     char* hthr = hp + ((plan_bytes + 15) & ~(size_t)15);
     bool uniform = true;
     for (int tb = 0; tb < ntables; ++tb) {
@@ -1847,6 +1908,18 @@ static int rdf_sub_batch(amepb_ctx* ctx, const RdfCall& c, int64_t f0, int nf, c
             ctx->thr_cache_f64 = arith_f64 ? 1 : 0;
         }
     }
+    // z mode of the pair kernel (all frames flat: dz*dz is a per-frame constant, or zero)
+    int zmode = all_zconst ? 2 : 0;
+    for (int f = 0; f < nf && zmode == 2; ++f)
+        if (plans[f].valid && plans[f].dz2c != 0.0) zmode = 1;
+    // compact (x, y) records: flat frames in the float32 regime on the staged walk (the same test as launch_pairs)
+    {
+        const size_t tab = pair_thr_bytes(nbins, sizeof(float)) + (size_t)(nbins + 2) * sizeof(unsigned) * (sym ? 2 : 1);
+        static const bool no_compact = getenv("AMEPB_NO_COMPACT_RECORDS") != nullptr;   // A/B switch for measurements
+        const bool compact = !arith_f64 && !targets_f64 && zmode != 0 && tab <= 40 * 1024 && uniform && nbins <= (1 << 17) && !no_compact;
+        for (int f = 0; f < nf; ++f) plans[f].compact = compact ? 1 : 0;
+    }
+    memcpy(hp, plans.data(), plan_bytes);
     {
         const long long pw = (long long)(plan_bytes / sizeof(int)), tw = (long long)((thr_bytes + 3) / sizeof(int));
         upload_kernel<<<(unsigned)std::min<long long>(64, (pw + 255) / 256), 256, 0, stream>>>(
@@ -1995,9 +2068,6 @@ static int rdf_sub_batch(amepb_ctx* ctx, const RdfCall& c, int64_t f0, int nf, c
     args.one = 1.0f;
     args.shard_index = ctx->rdf_shard_index;
     args.shard_count = ctx->rdf_shard_count;
-    int zmode = all_zconst ? 2 : 0;
-    for (int f = 0; f < nf && zmode == 2; ++f)
-        if (plans[f].valid && plans[f].dz2c != 0.0) zmode = 1;
     if (sym) {
         if (!arith_f64) rc = launch_pairs<float, float, true>(ctx, args, zmode, stream);
         else rc = launch_pairs<double, double, true>(ctx, args, zmode, stream);

@@ -112,6 +112,8 @@ struct FramePlan {
     double reg_hi[3];
     float keep_lo[3];  // window and region as one closed float32 interval: a float32 image x is
     float keep_hi[3];  // kept iff keep_lo <= x <= keep_hi (same decisions as the four tests above)
+    float near_lo[3];  // a particle with near_lo < x < near_hi in every shifted dimension cannot have a
+    float near_hi[3];  // kept *shifted* image (conservative: only a shortcut, never a decision)
     double dz2c;       // constant dz*dz term of the z-constant kernels
     double bin_e0;     // first edge and 1/width for the bin guess
     double bin_inv_w;
@@ -135,6 +137,7 @@ struct FramePlan {
     unsigned direct_pairs; // warp tasks with more pairs than this bypass the 32-bit shared histogram
     int row0;              // index of the (oy, oz) = (0, 0) row; rows after it are the "upper" half shell
     int sym;               // symmetric mode: real-real pairs once (weight 2), ghosts separately
+    int compact;           // the float32 sorted arrays hold (x, y) records (flat frames, staged float32 walk)
     int kd[3];             // neighbourhood half-widths in cells
     int gfree_lo[3];       // cells [gfree_lo, gfree_hi] (all dims) cannot hold ghost images
     int gfree_hi[3];
@@ -254,6 +257,17 @@ inline bool plan_frame(const PlanInputs& in, int dim, const FrameStats& tgt, con
         ext[d] = hi - lo;
         P.keep_lo[d] = std::max(float_above(P.win_lo[d], true), float_above(lo, false));
         P.keep_hi[d] = std::min(float_below(P.win_hi[d], true), float_below(hi, false));
+        // x + L <= keep_hi needs x <= keep_hi - L (+ rounding), x - L >= keep_lo needs x >= keep_lo + L (- rounding)
+        P.near_lo[d] = std::numeric_limits<float>::infinity();     // default: every particle takes the full test
+        P.near_hi[d] = -std::numeric_limits<float>::infinity();
+        if (in.pbc && P.nshift[d] == 3) {
+            const double L = (double)P.shift[d];
+            const double slack = 1e-5 * (fabs((double)P.keep_lo[d]) + fabs((double)P.keep_hi[d]) + fabs(L) + 1.0);
+            if (L > 0 && P.keep_lo[d] <= P.keep_hi[d]) {
+                P.near_lo[d] = float_above((double)P.keep_hi[d] - L + slack, false);
+                P.near_hi[d] = float_below((double)P.keep_lo[d] + L - slack, false);
+            }
+        }
     }
 
     // expected number of images in the region (uniform-density estimate)
