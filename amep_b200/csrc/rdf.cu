@@ -295,7 +295,10 @@ __device__ __forceinline__ void place_images_body(const T* __restrict__ p, const
 // its cell-counter atomics / offset gathers back to back, so that several L2 round trips are in
 // flight per thread: with one particle per thread the kernels were latency bound (long-scoreboard
 // stalls of 10-12 per issue, 21-27 % of the HBM rate; profiles/r01_place_v8_ncu_summary.txt).
-constexpr int kPlaceILP = 4;
+#ifndef AMEPB_PLACE_ILP
+#define AMEPB_PLACE_ILP 2
+#endif
+constexpr int kPlaceILP = AMEPB_PLACE_ILP;
 
 template <typename T, bool FILL>
 __global__ void __launch_bounds__(256) place_images_kernel(const T* __restrict__ pts, long long n,
@@ -331,14 +334,18 @@ __global__ void __launch_bounds__(256) place_self_kernel(const T* __restrict__ p
     const int f = blockIdx.y;
     if (!plans[f].valid) return;
     __shared__ int s_words[kPlanHeadWords];
-    const FramePlan& P = stage_plan_head(plans, f, s_words);
     const long long i0 = (long long)blockIdx.x * (blockDim.x * kPlaceILP) + threadIdx.x;
     const T* fbase = pts + (long long)f * n * 3;
     unsigned* frank = qrank + (long long)f * n;
     AT v[kPlaceILP][3];
     unsigned cc[kPlaceILP], aux[kPlaceILP];
     bool have[kPlaceILP];
-    // (1) all loads of the thread's particles (consecutive threads read consecutive records)
+    // (1) all loads of the thread's particles (consecutive threads read consecutive records),
+    // issued before the plan is staged so that they are in flight across its barrier.
+    // Measured alternatives (profiles/r02_place_variants.txt): 1 / 2 / 4 / 8 records per thread;
+    // the block's span loaded element by element (one 128-byte line per warp load) into shared
+    // memory and picked apart there -- slower (40 us per frame against 30): the extra barrier in
+    // front of the dependent chain costs more than the three-lines-per-load pattern.
 #pragma unroll
     for (int u = 0; u < kPlaceILP; ++u) {
         const long long i = i0 + (long long)u * blockDim.x;
@@ -348,6 +355,7 @@ __global__ void __launch_bounds__(256) place_self_kernel(const T* __restrict__ p
         for (int d = 0; d < 3; ++d) v[u][d] = (AT)p[d];
         if (FILL) aux[u] = have[u] ? frank[i] : 0u;
     }
+    const FramePlan& P = stage_plan_head(plans, f, s_words);
     // (2) cells, then the dependent L2 accesses back to back
 #pragma unroll
     for (int u = 0; u < kPlaceILP; ++u) {
@@ -372,11 +380,22 @@ __global__ void __launch_bounds__(256) place_self_kernel(const T* __restrict__ p
             store_record(qsorted, aux[u], v[u][0], v[u][1], v[u][2], P.compact != 0);
         }
     }
-    // (3) shifted images: none for almost every particle when the cutoff is short
+    // (3) shifted images: none for almost every particle when the cutoff is short.  In the symmetric
+    // mode the test of place_images_body's shortcut is made here, on the values the thread already holds.
 #pragma unroll
     for (int u = 0; u < kPlaceILP; ++u) {
         const long long i = i0 + (long long)u * blockDim.x;
-        if (have[u]) place_images_body<T, FILL>(fbase + i * 3, P, tcount, tstart, tsorted);
+        if (!have[u]) continue;
+        if (P.sym) {
+            bool maybe = false;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                const float b = (float)v[u][d];
+                if (P.nshift[d] == 3) maybe = maybe || !(b > P.near_lo[d] && b < P.near_hi[d]);
+            }
+            if (!maybe) continue;
+        }
+        place_images_body<T, FILL>(fbase + i * 3, P, tcount, tstart, tsorted);
     }
 }
 
