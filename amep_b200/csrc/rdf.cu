@@ -330,11 +330,17 @@ __global__ void __launch_bounds__(256) place_self_kernel(const T* __restrict__ p
                                                          unsigned* __restrict__ qcount,
                                                          const unsigned* __restrict__ qstart,
                                                          Vec4<AT>* __restrict__ qsorted,
-                                                         unsigned* __restrict__ qrank) {
-    const int f = blockIdx.y;
+                                                         unsigned* __restrict__ qrank, int frame_fast) {
+    // frame_fast (count pass): consecutive blocks belong to different frames, so the cell-counter
+    // atomics in flight spread over the counters of the whole sub-batch (random L2 atomics run at
+    // 126 G/s over >= 1M counters, at 100 G/s over the 62 500 of one configs[1] frame,
+    // tools/place_probe.cu).  The fill pass keeps all blocks inside one frame: its scattered stores
+    // must complete their sectors while the frame's 8-16 MB of sorted output are still in L2.
+    const int f = frame_fast ? blockIdx.x : blockIdx.y;
+    const unsigned tile = frame_fast ? blockIdx.y : blockIdx.x;
     if (!plans[f].valid) return;
     __shared__ int s_words[kPlanHeadWords];
-    const long long i0 = (long long)blockIdx.x * (blockDim.x * kPlaceILP) + threadIdx.x;
+    const long long i0 = (long long)tile * (blockDim.x * kPlaceILP) + threadIdx.x;
     const T* fbase = pts + (long long)f * n * 3;
     unsigned* frank = qrank + (long long)f * n;
     AT v[kPlaceILP][3];
@@ -2015,15 +2021,19 @@ static int rdf_sub_batch(amepb_ctx* ctx, const RdfCall& c, int64_t f0, int nf, c
         if ((rc = ensure_device(ctx, BUF_QRANK, sizeof(unsigned) * (size_t)m * nf))) return rc;
         qrank = reinterpret_cast<unsigned*>(ctx->bufs[BUF_QRANK].p);
     }
+    // count pass: frames as the fast block index (see place_self_kernel) when the tile count fits gridDim.y
+    static const bool no_frame_fast = getenv("AMEPB_NO_FRAME_FAST") != nullptr;   // A/B switch for measurements
+    const int frame_fast = (nf > 1 && tgrid.x <= 65535u && !no_frame_fast) ? 1 : 0;
+    const dim3 cgrid = frame_fast ? dim3((unsigned)nf, tgrid.x) : tgrid;
     auto place_self = [&](bool fill) -> int {
         Vec4<float>* ts = reinterpret_cast<Vec4<float>*>(ctx->bufs[BUF_TSORTED].p);
         void* qs = ctx->bufs[BUF_QSORTED].p;
         if (c.coords_dtype == AMEPB_F32) {
-            if (fill) place_self_kernel<float, float, true><<<tgrid, 256, 0, stream>>>((const float*)d_coords, c.n, d_plans, tcount, tstart, ts, qcount, qstart, (Vec4<float>*)qs, qrank);
-            else place_self_kernel<float, float, false><<<tgrid, 256, 0, stream>>>((const float*)d_coords, c.n, d_plans, tcount, tstart, ts, qcount, qstart, (Vec4<float>*)qs, qrank);
+            if (fill) place_self_kernel<float, float, true><<<tgrid, 256, 0, stream>>>((const float*)d_coords, c.n, d_plans, tcount, tstart, ts, qcount, qstart, (Vec4<float>*)qs, qrank, 0);
+            else place_self_kernel<float, float, false><<<cgrid, 256, 0, stream>>>((const float*)d_coords, c.n, d_plans, tcount, tstart, ts, qcount, qstart, (Vec4<float>*)qs, qrank, frame_fast);
         } else {
-            if (fill) place_self_kernel<double, double, true><<<tgrid, 256, 0, stream>>>((const double*)d_coords, c.n, d_plans, tcount, tstart, ts, qcount, qstart, (Vec4<double>*)qs, qrank);
-            else place_self_kernel<double, double, false><<<tgrid, 256, 0, stream>>>((const double*)d_coords, c.n, d_plans, tcount, tstart, ts, qcount, qstart, (Vec4<double>*)qs, qrank);
+            if (fill) place_self_kernel<double, double, true><<<tgrid, 256, 0, stream>>>((const double*)d_coords, c.n, d_plans, tcount, tstart, ts, qcount, qstart, (Vec4<double>*)qs, qrank, 0);
+            else place_self_kernel<double, double, false><<<cgrid, 256, 0, stream>>>((const double*)d_coords, c.n, d_plans, tcount, tstart, ts, qcount, qstart, (Vec4<double>*)qs, qrank, frame_fast);
         }
         AMEPB_LAUNCH_CHECK(ctx);
         return 0;
