@@ -26,6 +26,8 @@ enum {
     BUF_TSORTED,       // images in cell order
     BUF_QSORTED,       // queries in cell order
     BUF_QRANK,         // rank of each query inside its cell (fused self placement)
+    BUF_STRIPS,        // partitioned build: strip counts | cursors | starts
+    BUF_MID,           // partitioned build: records in strip order
     BUF_SCAN,          // scan block sums
     BUF_MISC,          // task counter, candidate counter
     BUF_STAGE_A,       // host-space staging: coords

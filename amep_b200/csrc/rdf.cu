@@ -405,6 +405,246 @@ __global__ void __launch_bounds__(256) place_self_kernel(const T* __restrict__ p
     }
 }
 
+// ---------------------------------------------------------------------------
+// Partitioned build of the query array (self RDF with images, symmetric walk; round 2).
+// place_self_kernel pays one returning L2 atomic per particle (count pass, 100-126 G/s) and one
+// scattered store per particle that has to reach DRAM (fill pass, 75-123 G/s): 8-10 us + 8-13 us per
+// 1M-particle frame whatever else the kernels do (tools/place_probe.cu).  Here no particle touches a
+// global atomic and no store is scattered farther than its own strip:
+//   strip_count_kernel    strips = runs of cell rows.  Counters of a tile of particles in shared memory,
+//                         one global atomic per (tile, strip).  Shifted images of the few particles
+//                         near a box face are counted as before (place_images_body).
+//   strip_scan_kernel     exclusive scan of the strip counts of every frame
+//   strip_scatter_kernel  ranks inside the tile from shared-memory atomics, one returning global atomic
+//                         per (tile, strip) reserves a run of the strip's region, records go there;
+//                         shifted images are filled
+//   strip_sort_kernel     one block per (strip, frame): cell counters in shared memory -- count, scan,
+//                         cursors --, the cell offsets of the strip written coalesced, the records
+//                         scattered inside the strip's own few hundred kilobytes
+// Prototype on 32 frames of 1M particles (tools/partition_probe.cu, profiles/r02_partition_probe.json):
+// 2.5 + 0.5 + 7.4 + 6.1 = 16.5 us per frame against 24 us of count + scans + fill.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned block_exclusive_scan(unsigned v, unsigned* s_warp, unsigned* total);
+
+constexpr int kStripThreads = 256;
+#ifndef AMEPB_STRIP_PER
+#define AMEPB_STRIP_PER 8
+#endif
+constexpr int kStripPer = AMEPB_STRIP_PER;         // particles per thread of the two tile kernels
+constexpr int kStripTile = kStripThreads * kStripPer;
+constexpr int kMaxStrips = 512;
+constexpr int kSortThreads = 256;
+constexpr int kSortCache = 8;                      // records a thread keeps in registers between the sweeps
+
+// row / strip_rows by a multiply (strip_magic = 2^32 / strip_rows + 1; exact while rows * strip_rows < 2^31,
+// which the host checks): an integer division per particle would cost as much as the rest of the tile kernel
+__device__ __forceinline__ int strip_of(const FramePlan& P, int cy, int cz) {
+    const unsigned row = (unsigned)(cz * P.n[1] + cy);
+    const unsigned q = __umulhi(row, P.strip_magic);
+    return (int)(P.strip_magic ? q : row);   // (a select, not a branch; magic 0 stands for strip_rows == 1)
+}
+// (not inlined: the image arithmetic would otherwise set the register count of the tile kernels)
+template <typename T, bool FILL>
+__device__ __noinline__ void place_images_listed(const T* p, const FramePlan* P, unsigned* count, const unsigned* start,
+                                                 Vec4<float>* sorted) {
+    place_images_body<T, FILL>(p, *P, count, start, sorted);
+}
+
+// record type of the intermediate (strip-ordered) and the sorted array: (x, y) pairs or four components
+template <typename AT, bool XY>
+struct StripRec;
+template <>
+struct StripRec<float, true> {
+    typedef float2 type;
+    static __device__ __forceinline__ float2 make(float x, float y, float) { return make_float2(x, y); }
+    static __device__ __forceinline__ float z(const float2&) { return 0.f; }
+};
+template <>
+struct StripRec<float, false> {
+    typedef float4 type;
+    static __device__ __forceinline__ float4 make(float x, float y, float z) { return make_float4(x, y, z, 0.f); }
+    static __device__ __forceinline__ float z(const float4& v) { return v.z; }
+};
+template <>
+struct StripRec<double, false> {
+    typedef double4 type;
+    static __device__ __forceinline__ double4 make(double x, double y, double z) { return make_double4(x, y, z, 0.0); }
+    static __device__ __forceinline__ double z(const double4& v) { return v.z; }
+};
+
+// SCATTER = false: strip counts (+ count of the shifted images); true: records to their strips (+ fill of the images)
+// FLAT: every frame of the launch has a single layer of cells (no cell arithmetic for z)
+template <typename T, typename AT, bool XY, bool SCATTER, bool FLAT>
+__global__ void __launch_bounds__(kStripThreads) strip_tile_kernel(const T* __restrict__ pts, long long n,
+                                                                   const FramePlan* __restrict__ plans,
+                                                                   unsigned* __restrict__ strip_count,
+                                                                   unsigned* __restrict__ strip_cursor,
+                                                                   typename StripRec<AT, XY>::type* __restrict__ mid,
+                                                                   unsigned* __restrict__ tcount,
+                                                                   const unsigned* __restrict__ tstart,
+                                                                   Vec4<float>* __restrict__ tsorted) {
+    const int f = blockIdx.y;
+    if (!plans[f].valid) return;
+    __shared__ int s_words[kPlanHeadWords];
+    __shared__ unsigned s_h[kMaxStrips], s_base[kMaxStrips];
+    __shared__ unsigned short s_list[kStripTile];   // particles of the tile that may have a kept shifted image
+    __shared__ unsigned s_nlist;
+    if (threadIdx.x == 0) s_nlist = 0;
+    const long long i0 = (long long)blockIdx.x * kStripTile + threadIdx.x;
+    const T* fbase = pts + (long long)f * n * 3;
+    AT v[kStripPer][3];
+    unsigned st[kStripPer], rk[kStripPer];
+#pragma unroll
+    for (int u = 0; u < kStripPer; ++u) {
+        const long long i = i0 + (long long)u * kStripThreads;
+        const T* p = fbase + (i < n ? i : 0) * 3;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) v[u][d] = (AT)p[d];
+    }
+    for (int k = threadIdx.x; k < kMaxStrips; k += kStripThreads) s_h[k] = 0;
+    const FramePlan& P = stage_plan_head(plans, f, s_words);
+#pragma unroll
+    for (int u = 0; u < kStripPer; ++u) {
+        const long long i = i0 + (long long)u * kStripThreads;
+        const int cy = cell_index((double)v[u][1], P.g0[1], P.inv_h[1], P.n[1]);
+        const int cz = FLAT ? 0 : cell_index((double)v[u][2], P.g0[2], P.inv_h[2], P.n[2]);
+        st[u] = (unsigned)strip_of(P, cy, cz);
+        rk[u] = 0;
+        if (i < n) {
+            rk[u] = atomicAdd(&s_h[st[u]], 1u);
+            // Shifted images (symmetric walk: the unshifted image is the query itself) exist for the few
+            // particles near a box face only.  They are listed and handled by consecutive threads below:
+            // called in place, the image arithmetic ran for one or two lanes of most warps -- two thirds
+            // of all warp instructions of this kernel.
+            bool maybe = false;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                const float b = (float)v[u][d];
+                if (P.nshift[d] == 3) maybe = maybe || !(b > P.near_lo[d] && b < P.near_hi[d]);
+            }
+            if (maybe) s_list[atomicAdd(&s_nlist, 1u)] = (unsigned short)(threadIdx.x + u * kStripThreads);
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < P.nstrips; k += kStripThreads) {
+        const unsigned c = s_h[k];
+        if (!c) continue;
+        if (!SCATTER) atomicAdd(&strip_count[P.strip_base + k], c);
+        else s_base[k] = atomicAdd(&strip_cursor[P.strip_base + k], c);
+    }
+    if (SCATTER) {
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < kStripPer; ++u) {
+            const long long i = i0 + (long long)u * kStripThreads;
+            if (i < n) mid[s_base[st[u]] + rk[u]] = StripRec<AT, XY>::make(v[u][0], v[u][1], v[u][2]);
+        }
+    }
+    const unsigned nl = s_nlist;   // (complete since the barrier after the ranks)
+    for (unsigned e = threadIdx.x; e < nl; e += kStripThreads)
+        place_images_listed<T, SCATTER>(fbase + ((long long)blockIdx.x * kStripTile + s_list[e]) * 3, &P, tcount, tstart, tsorted);
+}
+
+// one warp per frame: exclusive scan of its strip counts from the frame's first query slot
+__global__ void __launch_bounds__(32) strip_scan_kernel(const FramePlan* __restrict__ plans, const unsigned* __restrict__ strip_count,
+                                                        unsigned* __restrict__ strip_cursor, unsigned* __restrict__ strip_start) {
+    const FramePlan& P = plans[blockIdx.x];
+    if (!P.valid || !P.strip_rows) return;
+    const int lane = threadIdx.x;
+    unsigned carry = P.qbase;
+    for (int k0 = 0; k0 < P.nstrips; k0 += 32) {
+        const int k = k0 + lane;
+        const unsigned c = k < P.nstrips ? strip_count[P.strip_base + k] : 0u;
+        unsigned inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (k < P.nstrips) {
+            strip_start[P.strip_base + blockIdx.x + k] = carry + inc - c;     // (nstrips + 1 entries per frame)
+            strip_cursor[P.strip_base + k] = carry + inc - c;
+        }
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) strip_start[P.strip_base + blockIdx.x + P.nstrips] = carry;
+}
+
+template <typename AT, bool XY, bool FLAT>
+__global__ void __launch_bounds__(kSortThreads) strip_sort_kernel(const typename StripRec<AT, XY>::type* __restrict__ mid,
+                                                                  const FramePlan* __restrict__ plans,
+                                                                  const unsigned* __restrict__ strip_start, long long n,
+                                                                  unsigned* __restrict__ qstart,
+                                                                  typename StripRec<AT, XY>::type* __restrict__ sorted) {
+    typedef typename StripRec<AT, XY>::type Rec;
+    extern __shared__ unsigned s_cnt[];   // [cells of the strip]: counts, then cursors
+    __shared__ unsigned s_warp[33];
+    __shared__ int s_words[kPlanHeadWords];
+    const int f = blockIdx.y, s = blockIdx.x;
+    if (!plans[f].valid || s >= plans[f].nstrips) return;
+    const FramePlan& P = stage_plan_head(plans, f, s_words);
+    const int nrows_total = P.n[1] * P.n[2];
+    const int row0 = s * P.strip_rows;
+    const int nrows = min(P.strip_rows, nrows_total - row0);
+    const int nx = P.n[0];
+    const int ncell = nrows * nx;
+    const unsigned a = strip_start[P.strip_base + f + s], b = strip_start[P.strip_base + f + s + 1];
+    for (int k = threadIdx.x; k < ncell; k += kSortThreads) s_cnt[k] = 0;
+    auto local_cell = [&](const Rec& r) {
+        const int cx = cell_index((double)r.x, P.g0[0], P.inv_h[0], P.n[0]);
+        const int cy = cell_index((double)r.y, P.g0[1], P.inv_h[1], P.n[1]);
+        const int cz = FLAT ? 0 : cell_index((double)StripRec<AT, XY>::z(r), P.g0[2], P.inv_h[2], P.n[2]);
+        return (cz * P.n[1] + cy - row0) * nx + cx;
+    };
+    // the first kSortCache * kSortThreads records of the strip stay in registers for the second sweep
+    Rec cv[kSortCache];
+    int cc[kSortCache];
+#pragma unroll
+    for (int u = 0; u < kSortCache; ++u) {
+        const unsigned i = a + threadIdx.x + u * kSortThreads;
+        if (i < b) cv[u] = mid[i];
+        else cv[u] = StripRec<AT, XY>::make((AT)0, (AT)0, (AT)0);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < kSortCache; ++u) {
+        const unsigned i = a + threadIdx.x + u * kSortThreads;
+        cc[u] = 0;
+        if (i < b) {
+            cc[u] = local_cell(cv[u]);
+            atomicAdd(&s_cnt[cc[u]], 1u);
+        }
+    }
+    for (unsigned i = a + threadIdx.x + kSortCache * kSortThreads; i < b; i += kSortThreads) atomicAdd(&s_cnt[local_cell(mid[i])], 1u);
+    __syncthreads();
+    // exclusive scan of the counters (a contiguous chunk per thread), offsets from the strip's first slot
+    const int per = (ncell + kSortThreads - 1) / kSortThreads;
+    const int k0 = min(ncell, (int)threadIdx.x * per), k1 = min(ncell, k0 + per);
+    unsigned sum = 0;
+    for (int k = k0; k < k1; ++k) sum += s_cnt[k];
+    unsigned total;
+    unsigned off = a + block_exclusive_scan(sum, s_warp, &total);
+    unsigned* cs = qstart + P.cell_base + (unsigned)row0 * (unsigned)nx;
+    for (int k = k0; k < k1; ++k) {
+        const unsigned c = s_cnt[k];
+        cs[k] = off;
+        s_cnt[k] = off;   // cursor
+        off += c;
+    }
+    // the entry behind the frame's last cell (the first one of the next frame, or the end of the array)
+    if (s == P.nstrips - 1 && threadIdx.x == 0) qstart[P.cell_base + P.ncells] = b;
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < kSortCache; ++u) {
+        const unsigned i = a + threadIdx.x + u * kSortThreads;
+        if (i < b) sorted[atomicAdd(&s_cnt[cc[u]], 1u)] = cv[u];
+    }
+    for (unsigned i = a + threadIdx.x + kSortCache * kSortThreads; i < b; i += kSortThreads) {
+        const Rec r = mid[i];
+        sorted[atomicAdd(&s_cnt[local_cell(r)], 1u)] = r;
+    }
+}
+
 // Plain points (queries, or targets without periodic images).  S: storage
 // type.  DROP_OUTSIDE: skip points outside the grid region (targets); queries
 // are clamped into the boundary cells instead.
@@ -1944,6 +2184,41 @@ static int rdf_sub_batch(amepb_ctx* ctx, const RdfCall& c, int64_t f0, int nf, c
         const bool compact = !arith_f64 && !targets_f64 && zmode != 0 && tab <= 40 * 1024 && uniform && nbins <= (1 << 17) && !no_compact;
         for (int f = 0; f < nf; ++f) plans[f].compact = compact ? 1 : 0;
     }
+    // partitioned build of the query array (strip_* kernels): self RDF with images on the symmetric walk,
+    // enough (strip, frame) blocks to fill the machine, the cell counters of a strip in shared memory
+    long long total_strips = 0;
+    int max_strips = 0;
+    size_t sort_smem = 0;
+    bool partitioned = false;
+    {
+        static const bool no_part = getenv("AMEPB_NO_PARTITIONED_BUILD") != nullptr;   // A/B switch for measurements and tests
+        bool ok = self && c.pbc && sym && !no_part;
+        unsigned qbase = 0;
+        for (int f = 0; f < nf; ++f) {
+            FramePlan& P = plans[f];
+            P.strip_rows = 0;
+            P.nstrips = 0;
+            P.strip_base = (unsigned)total_strips;
+            P.qbase = qbase;
+            if (!P.valid) continue;
+            qbase += (unsigned)m;
+            const long long rows = (long long)P.n[1] * P.n[2];
+            const long long rps = std::max<long long>(1, (rows + kMaxStrips - 1) / kMaxStrips);
+            const long long ns = (rows + rps - 1) / rps;
+            const size_t smem = sizeof(unsigned) * (size_t)rps * (size_t)P.n[0];
+            if (smem > 160 * 1024 || rows <= 0) ok = false;
+            if (rows * rps >= (1ll << 31)) ok = false;
+            P.strip_rows = (int)rps;
+            P.strip_magic = rps == 1 ? 0u : (unsigned)((1ull << 32) / (unsigned long long)rps + 1ull);
+            P.nstrips = (int)ns;
+            total_strips += ns;
+            max_strips = std::max<int>(max_strips, (int)ns);
+            sort_smem = std::max(sort_smem, smem);
+        }
+        partitioned = ok && total_strips >= 2LL * ctx->sm_count;
+        if (!partitioned)
+            for (int f = 0; f < nf; ++f) plans[f].strip_rows = 0;
+    }
     memcpy(hp, plans.data(), plan_bytes);
     {
         const long long pw = (long long)(plan_bytes / sizeof(int)), tw = (long long)((thr_bytes + 3) / sizeof(int));
@@ -2038,15 +2313,86 @@ static int rdf_sub_batch(amepb_ctx* ctx, const RdfCall& c, int64_t f0, int nf, c
         AMEPB_LAUNCH_CHECK(ctx);
         return 0;
     };
-    if (fused) {
+    // partitioned build: records in strip order, strip counters
+    const bool xy_records = !arith_f64 && plans[0].compact != 0;
+    bool flat_cells = true;   // every valid frame has one layer of cells
+    for (int f = 0; f < nf; ++f)
+        if (plans[f].valid && plans[f].n[2] != 1) flat_cells = false;
+    unsigned *strip_count = nullptr, *strip_cursor = nullptr, *strip_start = nullptr;
+    const dim3 sgrid((unsigned)((c.n + kStripTile - 1) / kStripTile), nf);
+    if (partitioned) {
+        const size_t rec = xy_records ? sizeof(float2) : (arith_f64 ? sizeof(Vec4<double>) : sizeof(Vec4<float>));
+        if ((rc = ensure_device(ctx, BUF_MID, rec * (size_t)m * nf))) return rc;
+        if ((rc = ensure_device(ctx, BUF_STRIPS, sizeof(unsigned) * (size_t)(3 * total_strips + nf + 8)))) return rc;
+        strip_count = reinterpret_cast<unsigned*>(ctx->bufs[BUF_STRIPS].p);
+        strip_cursor = strip_count + total_strips;
+        strip_start = strip_cursor + total_strips;
+        AMEPB_CUDA(ctx, cudaMemsetAsync(strip_count, 0, sizeof(unsigned) * (size_t)total_strips, stream));
+    }
+    auto strip_tiles = [&](bool scatter) -> int {
+        Vec4<float>* ts = reinterpret_cast<Vec4<float>*>(ctx->bufs[BUF_TSORTED].p);
+        void* mid = ctx->bufs[BUF_MID].p;
+#define AMEPB_STRIP_TILE2(T, AT, XY, FL)                                                                                         \
+    do {                                                                                                                         \
+        if (scatter) strip_tile_kernel<T, AT, XY, true, FL><<<sgrid, kStripThreads, 0, stream>>>((const T*)d_coords, c.n, d_plans, strip_count, strip_cursor, (typename StripRec<AT, XY>::type*)mid, tcount, tstart, ts); \
+        else strip_tile_kernel<T, AT, XY, false, FL><<<sgrid, kStripThreads, 0, stream>>>((const T*)d_coords, c.n, d_plans, strip_count, strip_cursor, (typename StripRec<AT, XY>::type*)mid, tcount, tstart, ts); \
+    } while (0)
+#define AMEPB_STRIP_TILE(T, AT, XY)                                                                                              \
+    do {                                                                                                                         \
+        if (flat_cells) AMEPB_STRIP_TILE2(T, AT, XY, true);                                                                      \
+        else AMEPB_STRIP_TILE2(T, AT, XY, false);                                                                                \
+    } while (0)
+        if (c.coords_dtype == AMEPB_F32 && xy_records) AMEPB_STRIP_TILE(float, float, true);
+        else if (c.coords_dtype == AMEPB_F32) AMEPB_STRIP_TILE(float, float, false);
+        else AMEPB_STRIP_TILE(double, double, false);
+#undef AMEPB_STRIP_TILE2
+#undef AMEPB_STRIP_TILE
+        AMEPB_LAUNCH_CHECK(ctx);
+        return 0;
+    };
+    auto strip_sort = [&]() -> int {
+        const dim3 grid((unsigned)max_strips, nf);
+        void* mid = ctx->bufs[BUF_MID].p;
+        void* qs = ctx->bufs[BUF_QSORTED].p;
+#define AMEPB_STRIP_SORT2(AT, XY, FL)                                                                                            \
+    do {                                                                                                                         \
+        if (sort_smem > 48 * 1024)                                                                                               \
+            AMEPB_CUDA(ctx, cudaFuncSetAttribute(strip_sort_kernel<AT, XY, FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem)); \
+        strip_sort_kernel<AT, XY, FL><<<grid, kSortThreads, sort_smem, stream>>>((const typename StripRec<AT, XY>::type*)mid, d_plans, strip_start, c.n, qstart, (typename StripRec<AT, XY>::type*)qs); \
+    } while (0)
+#define AMEPB_STRIP_SORT(AT, XY)                                                                                                 \
+    do {                                                                                                                         \
+        if (flat_cells) AMEPB_STRIP_SORT2(AT, XY, true);                                                                         \
+        else AMEPB_STRIP_SORT2(AT, XY, false);                                                                                   \
+    } while (0)
+        if (c.coords_dtype == AMEPB_F32 && xy_records) AMEPB_STRIP_SORT(float, true);
+        else if (c.coords_dtype == AMEPB_F32) AMEPB_STRIP_SORT(float, false);
+        else AMEPB_STRIP_SORT(double, false);
+#undef AMEPB_STRIP_SORT2
+#undef AMEPB_STRIP_SORT
+        AMEPB_LAUNCH_CHECK(ctx);
+        return 0;
+    };
+    if (partitioned) {
+        if ((rc = strip_tiles(false))) return rc;
+    } else if (fused) {
         if ((rc = place_self(false))) return rc;
     } else {
         if (have_targets && (rc = place_targets(false))) return rc;
         if ((rc = place_queries(false))) return rc;
     }
     if ((rc = exclusive_scan(ctx, tcount, tstart, total_cells + 1, stream))) return rc;
-    if ((rc = exclusive_scan(ctx, qcount, qstart, total_cells + 1, stream))) return rc;
-    if (fused) {
+    if (partitioned) {
+        strip_scan_kernel<<<nf, 32, 0, stream>>>(d_plans, strip_count, strip_cursor, strip_start);
+        AMEPB_LAUNCH_CHECK(ctx);
+        if ((rc = strip_tiles(true))) return rc;
+        if ((rc = strip_sort())) return rc;
+    } else if ((rc = exclusive_scan(ctx, qcount, qstart, total_cells + 1, stream))) {
+        return rc;
+    }
+    if (partitioned) {
+        // (queries and shifted images are in place)
+    } else if (fused) {
         if ((rc = place_self(true))) return rc;
     } else {
         if (have_targets && (rc = place_targets(true))) return rc;
