@@ -498,8 +498,10 @@ __global__ void __launch_bounds__(kStripThreads) strip_tile_kernel(const T* __re
     for (int u = 0; u < kStripPer; ++u) {
         const long long i = i0 + (long long)u * kStripThreads;
         const T* p = fbase + (i < n ? i : 0) * 3;
+        // (x, y) records belong to flat frames without images along z: z is neither stored nor tested
 #pragma unroll
-        for (int d = 0; d < 3; ++d) v[u][d] = (AT)p[d];
+        for (int d = 0; d < (XY ? 2 : 3); ++d) v[u][d] = (AT)p[d];
+        if (XY) v[u][2] = (AT)0;
     }
     for (int k = threadIdx.x; k < kMaxStrips; k += kStripThreads) s_h[k] = 0;
     const FramePlan& P = stage_plan_head(plans, f, s_words);
@@ -518,7 +520,7 @@ __global__ void __launch_bounds__(kStripThreads) strip_tile_kernel(const T* __re
             // of all warp instructions of this kernel.
             bool maybe = false;
 #pragma unroll
-            for (int d = 0; d < 3; ++d) {
+            for (int d = 0; d < (XY ? 2 : 3); ++d) {
                 const float b = (float)v[u][d];
                 if (P.nshift[d] == 3) maybe = maybe || !(b > P.near_lo[d] && b < P.near_hi[d]);
             }
@@ -2318,6 +2320,10 @@ static int rdf_sub_batch(amepb_ctx* ctx, const RdfCall& c, int64_t f0, int nf, c
     bool flat_cells = true;   // every valid frame has one layer of cells
     for (int f = 0; f < nf; ++f)
         if (plans[f].valid && plans[f].n[2] != 1) flat_cells = false;
+    // ((x, y) records: z is constant in every frame; a frame that still shifts images along z -- a single
+    // particle counts as three-dimensional -- keeps the old build)
+    for (int f = 0; f < nf; ++f)
+        if (partitioned && xy_records && plans[f].valid && (plans[f].nshift[2] == 3 || plans[f].n[2] != 1)) partitioned = false;
     unsigned *strip_count = nullptr, *strip_cursor = nullptr, *strip_start = nullptr;
     const dim3 sgrid((unsigned)((c.n + kStripTile - 1) / kStripTile), nf);
     if (partitioned) {
