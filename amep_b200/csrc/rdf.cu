@@ -2182,7 +2182,7 @@ static int rdf_sub_batch(amepb_ctx* ctx, const RdfCall& c, int64_t f0, int nf, c
     // compact (x, y) records: flat frames in the float32 regime on the staged walk (the same test as launch_pairs)
     {
         const size_t tab = pair_thr_bytes(nbins, sizeof(float)) + (size_t)(nbins + 2) * sizeof(unsigned) * (sym ? 2 : 1);
-        static const bool no_compact = getenv("AMEPB_NO_COMPACT_RECORDS") != nullptr;   // A/B switch for measurements
+        const bool no_compact = getenv("AMEPB_NO_COMPACT_RECORDS") != nullptr;   // A/B switch for measurements and tests
         const bool compact = !arith_f64 && !targets_f64 && zmode != 0 && tab <= 40 * 1024 && uniform && nbins <= (1 << 17) && !no_compact;
         for (int f = 0; f < nf; ++f) plans[f].compact = compact ? 1 : 0;
     }
@@ -2193,7 +2193,7 @@ static int rdf_sub_batch(amepb_ctx* ctx, const RdfCall& c, int64_t f0, int nf, c
     size_t sort_smem = 0;
     bool partitioned = false;
     {
-        static const bool no_part = getenv("AMEPB_NO_PARTITIONED_BUILD") != nullptr;   // A/B switch for measurements and tests
+        const bool no_part = getenv("AMEPB_NO_PARTITIONED_BUILD") != nullptr;   // A/B switch for measurements and tests
         bool ok = self && c.pbc && sym && !no_part;
         unsigned qbase = 0;
         for (int f = 0; f < nf; ++f) {
@@ -2217,7 +2217,8 @@ static int rdf_sub_batch(amepb_ctx* ctx, const RdfCall& c, int64_t f0, int nf, c
             max_strips = std::max<int>(max_strips, (int)ns);
             sort_smem = std::max(sort_smem, smem);
         }
-        partitioned = ok && total_strips >= 2LL * ctx->sm_count;
+        const bool force_part = getenv("AMEPB_FORCE_PARTITIONED_BUILD") != nullptr;   // tests: also for tiny batches
+        partitioned = ok && (total_strips >= 2LL * ctx->sm_count || force_part);
         if (!partitioned)
             for (int f = 0; f < nf; ++f) plans[f].strip_rows = 0;
     }

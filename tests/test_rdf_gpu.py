@@ -229,6 +229,64 @@ def test_symmetric_and_ordered_evaluation_agree(sc, case):
     assert out[True][1] < 0.9 * out[False][1]
 
 
+@pytest.mark.parametrize("case", [c for c in CASES if c[4] is None and c[2] is np.float32 and c[6].get("pbc", True)],
+                         ids=lambda c: c[0])
+def test_partitioned_build_equals_placement_kernels(sc, monkeypatch, case):
+    """The partitioned build of the query array (strip kernels) and the placement kernels feed the
+    pair kernel the same cells: equal integer counts, with 16-byte and with (x, y) records, also for
+    particles outside the box, clustered frames and three dimensions (forced for these small
+    frames; large batches take it by themselves)."""
+    name, dim, dtype, n, m, box, kw, gen, spill = case
+    rng = np.random.default_rng(zlib.crc32(name.encode()) + 1)
+    box = np.array(box, dtype=dtype)
+    make = _clustered if gen == "clustered" else (lambda r, k, b, d: _uniform(r, k, b, d, spill))
+    coords = np.stack([make(rng, n, box.astype(np.float64), dtype) for _ in range(3)])
+    if dim == 2:
+        coords[:, :, 2] = 0
+    out = {}
+    for mode in ("strips", "strips-vec4", "placement"):
+        for var in ("AMEPB_FORCE_PARTITIONED_BUILD", "AMEPB_NO_PARTITIONED_BUILD", "AMEPB_NO_COMPACT_RECORDS"):
+            monkeypatch.delenv(var, raising=False)
+        if mode == "placement":
+            monkeypatch.setenv("AMEPB_NO_PARTITIONED_BUILD", "1")
+        else:
+            monkeypatch.setenv("AMEPB_FORCE_PARTITIONED_BUILD", "1")
+        if mode == "strips-vec4":
+            monkeypatch.setenv("AMEPB_NO_COMPACT_RECORDS", "1")
+        _, _, counts = sc.rdf_frames(torch.from_numpy(coords).cuda(), box, return_counts=True, **kw)
+        out[mode] = counts
+    assert out["placement"].sum() > 0
+    np.testing.assert_array_equal(out["strips"], out["placement"])
+    np.testing.assert_array_equal(out["strips-vec4"], out["placement"])
+    want, _ = corc.rdf_counts(coords[1], box, **{k: v for k, v in kw.items() if k in ("nbins", "rmax", "pbc")})
+    np.testing.assert_array_equal(out["strips"][1], want)
+
+
+def test_partitioned_build_with_per_frame_boxes(sc, monkeypatch):
+    """Frames with their own boxes (every frame has its own grid, strips and query offset) and a few
+    particles outside the box in x: the partitioned build, forced, equals the placement kernels and
+    the oracle."""
+    rng = np.random.default_rng(12)
+    nf, n = 7, 1800
+    boxes = np.zeros((nf, 3, 2), dtype=np.float32)
+    coords = np.zeros((nf, n, 3), dtype=np.float32)
+    for f in range(nf):
+        L = 28 + 3 * f
+        boxes[f] = [[0, L], [-L / 2, L / 2], [-0.5, 0.5]]
+        coords[f, :, 0] = rng.uniform(-1, L + 1, n)
+        coords[f, :, 1] = rng.uniform(-L / 2, L / 2, n)
+    monkeypatch.setenv("AMEPB_FORCE_PARTITIONED_BUILD", "1")
+    g, r, counts = sc.rdf_frames(torch.from_numpy(coords).cuda(), boxes, nbins=150, rmax=9.0, return_counts=True)
+    monkeypatch.delenv("AMEPB_FORCE_PARTITIONED_BUILD")
+    monkeypatch.setenv("AMEPB_NO_PARTITIONED_BUILD", "1")
+    g2, r2, counts2 = sc.rdf_frames(torch.from_numpy(coords).cuda(), boxes, nbins=150, rmax=9.0, return_counts=True)
+    np.testing.assert_array_equal(counts, counts2)
+    np.testing.assert_array_equal(g, g2)
+    for f in (0, 3, 6):
+        want, _ = corc.rdf_counts(coords[f], boxes[f], nbins=150, rmax=9.0)
+        np.testing.assert_array_equal(counts[f], want)
+
+
 def test_batch_of_frames_with_per_frame_boxes(sc):
     rng = np.random.default_rng(11)
     nf, n = 9, 1500
