@@ -430,6 +430,9 @@ constexpr int kStripThreads = 256;
 #ifndef AMEPB_STRIP_PER
 #define AMEPB_STRIP_PER 8
 #endif
+#ifndef AMEPB_STRIP_BLOCKS
+#define AMEPB_STRIP_BLOCKS 5      // resident blocks per SM the tile kernels are compiled for (48 registers; 4 and 6 measured slower)
+#endif
 constexpr int kStripPer = AMEPB_STRIP_PER;         // particles per thread of the two tile kernels
 constexpr int kStripTile = kStripThreads * kStripPer;
 constexpr int kMaxStrips = 512;
@@ -475,7 +478,7 @@ struct StripRec<double, false> {
 // SCATTER = false: strip counts (+ count of the shifted images); true: records to their strips (+ fill of the images)
 // FLAT: every frame of the launch has a single layer of cells (no cell arithmetic for z)
 template <typename T, typename AT, bool XY, bool SCATTER, bool FLAT>
-__global__ void __launch_bounds__(kStripThreads) strip_tile_kernel(const T* __restrict__ pts, long long n,
+__global__ void __launch_bounds__(kStripThreads, AMEPB_STRIP_BLOCKS) strip_tile_kernel(const T* __restrict__ pts, long long n,
                                                                    const FramePlan* __restrict__ plans,
                                                                    unsigned* __restrict__ strip_count,
                                                                    unsigned* __restrict__ strip_cursor,
@@ -505,27 +508,48 @@ __global__ void __launch_bounds__(kStripThreads) strip_tile_kernel(const T* __re
     }
     for (int k = threadIdx.x; k < kMaxStrips; k += kStripThreads) s_h[k] = 0;
     const FramePlan& P = stage_plan_head(plans, f, s_words);
+    // (the plan values of the loop in registers: read through P, they were re-loaded from shared memory
+    // for every particle)
+    const double g0y = P.g0[1], ihy = P.inv_h[1], g0z = P.g0[2], ihz = P.inv_h[2];
+    const int ny = P.n[1], nz = P.n[2];
+    const unsigned magic = P.strip_magic;
+    float nlo[3], nhi[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        // a dimension without shifted images never makes a particle a candidate
+        const bool sh = P.nshift[d] == 3;
+        nlo[d] = sh ? P.near_lo[d] : -__int_as_float(0x7f800000);
+        nhi[d] = sh ? P.near_hi[d] : __int_as_float(0x7f800000);
+    }
+    unsigned near_mask = 0;   // bit u: particle u of this thread may have a kept shifted image
 #pragma unroll
     for (int u = 0; u < kStripPer; ++u) {
         const long long i = i0 + (long long)u * kStripThreads;
-        const int cy = cell_index((double)v[u][1], P.g0[1], P.inv_h[1], P.n[1]);
-        const int cz = FLAT ? 0 : cell_index((double)v[u][2], P.g0[2], P.inv_h[2], P.n[2]);
-        st[u] = (unsigned)strip_of(P, cy, cz);
+        const int cy = cell_index((double)v[u][1], g0y, ihy, ny);
+        const int cz = FLAT ? 0 : cell_index((double)v[u][2], g0z, ihz, nz);
+        const unsigned row = (unsigned)(cz * ny + cy);
+        st[u] = magic ? __umulhi(row, magic) : row;
         rk[u] = 0;
         if (i < n) {
             rk[u] = atomicAdd(&s_h[st[u]], 1u);
-            // Shifted images (symmetric walk: the unshifted image is the query itself) exist for the few
-            // particles near a box face only.  They are listed and handled by consecutive threads below:
-            // called in place, the image arithmetic ran for one or two lanes of most warps -- two thirds
-            // of all warp instructions of this kernel.
             bool maybe = false;
 #pragma unroll
             for (int d = 0; d < (XY ? 2 : 3); ++d) {
                 const float b = (float)v[u][d];
-                if (P.nshift[d] == 3) maybe = maybe || !(b > P.near_lo[d] && b < P.near_hi[d]);
+                maybe = maybe || !(b > nlo[d] && b < nhi[d]);   // (NaN: candidate)
             }
-            if (maybe) s_list[atomicAdd(&s_nlist, 1u)] = (unsigned short)(threadIdx.x + u * kStripThreads);
+            if (maybe) near_mask |= 1u << u;
         }
+    }
+    // Shifted images (symmetric walk: the unshifted image is the query itself) exist for the few
+    // particles near a box face only.  They are listed -- one shared atomic per thread that has any --
+    // and handled by consecutive threads below: called in place, the image arithmetic ran for one or
+    // two lanes of most warps, two thirds of all warp instructions of this kernel.
+    if (near_mask) {
+        unsigned at = atomicAdd(&s_nlist, (unsigned)__popc(near_mask));
+#pragma unroll
+        for (int u = 0; u < kStripPer; ++u)
+            if (near_mask & (1u << u)) s_list[at++] = (unsigned short)(threadIdx.x + u * kStripThreads);
     }
     __syncthreads();
     for (int k = threadIdx.x; k < P.nstrips; k += kStripThreads) {
