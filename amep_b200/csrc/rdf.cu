@@ -487,7 +487,6 @@ __global__ void __launch_bounds__(kStripThreads, AMEPB_STRIP_BLOCKS) strip_tile_
                                                                    const unsigned* __restrict__ tstart,
                                                                    Vec4<float>* __restrict__ tsorted) {
     const int f = blockIdx.y;
-    if (!plans[f].valid) return;
     __shared__ int s_words[kPlanHeadWords];
     __shared__ unsigned s_h[kMaxStrips], s_base[kMaxStrips];
     __shared__ unsigned short s_list[kStripTile];   // particles of the tile that may have a kept shifted image
@@ -508,6 +507,7 @@ __global__ void __launch_bounds__(kStripThreads, AMEPB_STRIP_BLOCKS) strip_tile_
     }
     for (int k = threadIdx.x; k < kMaxStrips; k += kStripThreads) s_h[k] = 0;
     const FramePlan& P = stage_plan_head(plans, f, s_words);
+    if (!P.valid) return;   // (block-uniform; asked only now so that the loads above are not behind a round trip)
     // (the plan values of the loop in registers: read through P, they were re-loaded from shared memory
     // for every particle)
     const double g0y = P.g0[1], ihy = P.inv_h[1], g0z = P.g0[2], ihz = P.inv_h[2];
@@ -555,8 +555,8 @@ __global__ void __launch_bounds__(kStripThreads, AMEPB_STRIP_BLOCKS) strip_tile_
     for (int k = threadIdx.x; k < P.nstrips; k += kStripThreads) {
         const unsigned c = s_h[k];
         if (!c) continue;
-        if (!SCATTER) atomicAdd(&strip_count[P.strip_base + k], c);
-        else s_base[k] = atomicAdd(&strip_cursor[P.strip_base + k], c);
+        if (!SCATTER) atomicAdd(&strip_count[f * kMaxStrips + k], c);
+        else s_base[k] = atomicAdd(&strip_cursor[f * kMaxStrips + k], c);
     }
     if (SCATTER) {
         __syncthreads();
@@ -571,29 +571,32 @@ __global__ void __launch_bounds__(kStripThreads, AMEPB_STRIP_BLOCKS) strip_tile_
         place_images_listed<T, SCATTER>(fbase + ((long long)blockIdx.x * kStripTile + s_list[e]) * 3, &P, tcount, tstart, tsorted);
 }
 
-// one warp per frame: exclusive scan of its strip counts from the frame's first query slot
+// one warp per frame: exclusive scan of its strip counts from the frame's first query slot.  The strip
+// arrays have a fixed stride per frame (kMaxStrips counters, kMaxStrips + 1 starts), so that the sort
+// kernel can read its range before it knows the plan; unused entries hold the end of the frame's range
+// (an invalid frame: zeros), i.e. empty strips.
 __global__ void __launch_bounds__(32) strip_scan_kernel(const FramePlan* __restrict__ plans, const unsigned* __restrict__ strip_count,
                                                         unsigned* __restrict__ strip_cursor, unsigned* __restrict__ strip_start) {
-    const FramePlan& P = plans[blockIdx.x];
-    if (!P.valid || !P.strip_rows) return;
+    const int f = blockIdx.x;
+    const FramePlan& P = plans[f];
     const int lane = threadIdx.x;
-    unsigned carry = P.qbase;
-    for (int k0 = 0; k0 < P.nstrips; k0 += 32) {
+    const bool live = P.valid && P.strip_rows;
+    const int ns = live ? P.nstrips : 0;
+    unsigned carry = live ? P.qbase : 0u;
+    for (int k0 = 0; k0 < kMaxStrips; k0 += 32) {
         const int k = k0 + lane;
-        const unsigned c = k < P.nstrips ? strip_count[P.strip_base + k] : 0u;
+        const unsigned c = k < ns ? strip_count[f * kMaxStrips + k] : 0u;
         unsigned inc = c;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
             if (lane >= o) inc += t;
         }
-        if (k < P.nstrips) {
-            strip_start[P.strip_base + blockIdx.x + k] = carry + inc - c;     // (nstrips + 1 entries per frame)
-            strip_cursor[P.strip_base + k] = carry + inc - c;
-        }
+        strip_start[f * (kMaxStrips + 1) + k] = carry + inc - c;
+        strip_cursor[f * kMaxStrips + k] = carry + inc - c;
         carry += __shfl_sync(0xffffffffu, inc, 31);
     }
-    if (lane == 0) strip_start[P.strip_base + blockIdx.x + P.nstrips] = carry;
+    if (lane == 0) strip_start[f * (kMaxStrips + 1) + kMaxStrips] = carry;
 }
 
 template <typename AT, bool XY, bool FLAT>
@@ -607,22 +610,9 @@ __global__ void __launch_bounds__(kSortThreads) strip_sort_kernel(const typename
     __shared__ unsigned s_warp[33];
     __shared__ int s_words[kPlanHeadWords];
     const int f = blockIdx.y, s = blockIdx.x;
-    if (!plans[f].valid || s >= plans[f].nstrips) return;
-    const FramePlan& P = stage_plan_head(plans, f, s_words);
-    const int nrows_total = P.n[1] * P.n[2];
-    const int row0 = s * P.strip_rows;
-    const int nrows = min(P.strip_rows, nrows_total - row0);
-    const int nx = P.n[0];
-    const int ncell = nrows * nx;
-    const unsigned a = strip_start[P.strip_base + f + s], b = strip_start[P.strip_base + f + s + 1];
-    for (int k = threadIdx.x; k < ncell; k += kSortThreads) s_cnt[k] = 0;
-    auto local_cell = [&](const Rec& r) {
-        const int cx = cell_index((double)r.x, P.g0[0], P.inv_h[0], P.n[0]);
-        const int cy = cell_index((double)r.y, P.g0[1], P.inv_h[1], P.n[1]);
-        const int cz = FLAT ? 0 : cell_index((double)StripRec<AT, XY>::z(r), P.g0[2], P.inv_h[2], P.n[2]);
-        return (cz * P.n[1] + cy - row0) * nx + cx;
-    };
-    // the first kSortCache * kSortThreads records of the strip stay in registers for the second sweep
+    // the strip's range and its first records are requested before the plan is staged (fixed-stride strip
+    // arrays, see strip_scan_kernel): two dependent round trips per block instead of four
+    const unsigned a = strip_start[f * (kMaxStrips + 1) + s], b = strip_start[f * (kMaxStrips + 1) + s + 1];
     Rec cv[kSortCache];
     int cc[kSortCache];
 #pragma unroll
@@ -631,6 +621,21 @@ __global__ void __launch_bounds__(kSortThreads) strip_sort_kernel(const typename
         if (i < b) cv[u] = mid[i];
         else cv[u] = StripRec<AT, XY>::make((AT)0, (AT)0, (AT)0);
     }
+    const FramePlan& P = stage_plan_head(plans, f, s_words);
+    if (!P.valid || s >= P.nstrips) return;   // (block-uniform)
+    const int nrows_total = P.n[1] * P.n[2];
+    const int row0 = s * P.strip_rows;
+    const int nrows = min(P.strip_rows, nrows_total - row0);
+    const int nx = P.n[0];
+    const int ncell = nrows * nx;
+    for (int k = threadIdx.x; k < ncell; k += kSortThreads) s_cnt[k] = 0;
+    auto local_cell = [&](const Rec& r) {
+        const int cx = cell_index((double)r.x, P.g0[0], P.inv_h[0], P.n[0]);
+        const int cy = cell_index((double)r.y, P.g0[1], P.inv_h[1], P.n[1]);
+        const int cz = FLAT ? 0 : cell_index((double)StripRec<AT, XY>::z(r), P.g0[2], P.inv_h[2], P.n[2]);
+        return (cz * P.n[1] + cy - row0) * nx + cx;
+    };
+    // (the first kSortCache * kSortThreads records of the strip stay in registers for the second sweep)
     __syncthreads();
 #pragma unroll
     for (int u = 0; u < kSortCache; ++u) {
@@ -2224,7 +2229,6 @@ static int rdf_sub_batch(amepb_ctx* ctx, const RdfCall& c, int64_t f0, int nf, c
             FramePlan& P = plans[f];
             P.strip_rows = 0;
             P.nstrips = 0;
-            P.strip_base = (unsigned)total_strips;
             P.qbase = qbase;
             if (!P.valid) continue;
             qbase += (unsigned)m;
@@ -2354,11 +2358,12 @@ static int rdf_sub_batch(amepb_ctx* ctx, const RdfCall& c, int64_t f0, int nf, c
     if (partitioned) {
         const size_t rec = xy_records ? sizeof(float2) : (arith_f64 ? sizeof(Vec4<double>) : sizeof(Vec4<float>));
         if ((rc = ensure_device(ctx, BUF_MID, rec * (size_t)m * nf))) return rc;
-        if ((rc = ensure_device(ctx, BUF_STRIPS, sizeof(unsigned) * (size_t)(3 * total_strips + nf + 8)))) return rc;
+        const size_t per_frame = (size_t)kMaxStrips;   // fixed stride per frame, see strip_scan_kernel
+        if ((rc = ensure_device(ctx, BUF_STRIPS, sizeof(unsigned) * ((size_t)nf * (3 * per_frame + 1) + 8)))) return rc;
         strip_count = reinterpret_cast<unsigned*>(ctx->bufs[BUF_STRIPS].p);
-        strip_cursor = strip_count + total_strips;
-        strip_start = strip_cursor + total_strips;
-        AMEPB_CUDA(ctx, cudaMemsetAsync(strip_count, 0, sizeof(unsigned) * (size_t)total_strips, stream));
+        strip_cursor = strip_count + (size_t)nf * per_frame;
+        strip_start = strip_cursor + (size_t)nf * per_frame;
+        AMEPB_CUDA(ctx, cudaMemsetAsync(strip_count, 0, sizeof(unsigned) * (size_t)nf * per_frame, stream));
     }
     auto strip_tiles = [&](bool scatter) -> int {
         Vec4<float>* ts = reinterpret_cast<Vec4<float>*>(ctx->bufs[BUF_TSORTED].p);

@@ -142,7 +142,6 @@ struct FramePlan {
     int strip_rows;        // cell rows (fixed y, z; all x) per strip; 0: this frame is not partitioned
     int nstrips;
     unsigned strip_magic;  // row / strip_rows == umulhi(row, strip_magic) (0: strip_rows == 1)
-    unsigned strip_base;   // offset of the frame's strips in the flat strip arrays
     unsigned qbase;        // first slot of the frame's queries in the sorted query array
     int kd[3];             // neighbourhood half-widths in cells
     int gfree_lo[3];       // cells [gfree_lo, gfree_hi] (all dims) cannot hold ghost images
