@@ -287,6 +287,51 @@ def test_partitioned_build_with_per_frame_boxes(sc, monkeypatch):
         np.testing.assert_array_equal(counts[f], want)
 
 
+@pytest.mark.parametrize("seed", range(12))
+def test_random_configurations_all_build_paths(sc, monkeypatch, seed):
+    """Randomly drawn frames -- dimension, particle number, box shape and offset, cutoff from a few per
+    cent of the box to L/2, bin number, batch size, a few particles outside the box -- through every
+    build of the cell arrays (partitioned, partitioned with 16-byte records, placement kernels with and
+    without (x, y) records): all equal, and equal to the brute-force oracle."""
+    rng = np.random.default_rng(9000 + seed)
+    dim = 2 if rng.random() < 0.6 else 3
+    n = int(rng.integers(300, 5000))
+    nf = int(rng.integers(1, 5))
+    lens = rng.uniform(8.0, 40.0, 3)
+    if dim == 2:
+        lens[2] = 1.0
+    lo = rng.uniform(-20.0, 20.0, 3)
+    if dim == 2:
+        lo[2] = -0.5
+    box = np.stack([lo, lo + lens], axis=1).astype(np.float32)
+    lmin = float(min(lens[:dim]))
+    rmax = float(rng.choice([0.07, 0.15, 0.3, 0.5]) * lmin)
+    nbins = int(rng.choice([17, 100, 500, 1021]))
+    coords = np.zeros((nf, n, 3), dtype=np.float32)
+    for d in range(dim):
+        coords[:, :, d] = rng.uniform(box[d, 0], box[d, 1], (nf, n))
+    if dim == 2:
+        coords[:, :, 2] = 0.0
+    if rng.random() < 0.3:   # a few particles just outside the box: the ordered walk takes over
+        coords[0, :5, 0] = box[0, 1] + rng.uniform(0.0, 0.2, 5)
+    out = {}
+    for mode, env in (("strips", {"AMEPB_FORCE_PARTITIONED_BUILD": "1"}),
+                      ("strips-vec4", {"AMEPB_FORCE_PARTITIONED_BUILD": "1", "AMEPB_NO_COMPACT_RECORDS": "1"}),
+                      ("placement", {"AMEPB_NO_PARTITIONED_BUILD": "1"}),
+                      ("placement-vec4", {"AMEPB_NO_PARTITIONED_BUILD": "1", "AMEPB_NO_COMPACT_RECORDS": "1"})):
+        for var in ("AMEPB_FORCE_PARTITIONED_BUILD", "AMEPB_NO_PARTITIONED_BUILD", "AMEPB_NO_COMPACT_RECORDS"):
+            monkeypatch.delenv(var, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        _, _, counts = sc.rdf_frames(torch.from_numpy(coords).cuda(), box, rmax=rmax, nbins=nbins, return_counts=True)
+        out[mode] = counts
+    for mode in ("strips-vec4", "placement", "placement-vec4"):
+        np.testing.assert_array_equal(out[mode], out["strips"], err_msg=f"{mode} seed {seed}")
+    f = int(rng.integers(0, nf))
+    want, _ = corc.rdf_counts(coords[f], box, nbins=nbins, rmax=rmax)
+    np.testing.assert_array_equal(out["strips"][f], want, err_msg=f"oracle seed {seed} dim {dim} n {n} rmax {rmax} nbins {nbins}")
+
+
 def test_batch_of_frames_with_per_frame_boxes(sc):
     rng = np.random.default_rng(11)
     nf, n = 9, 1500

@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, GPU call AJ: partitioned build against the placement kernels (new tests), full RDF suite
+# round 2, GPU call AJ: partitioned build against the placement kernels (new tests), random configurations, full RDF suite
 set -x
 cd "$GRAFT_REPO_ROOT" || exit 1
 mkdir -p gpurun_out
