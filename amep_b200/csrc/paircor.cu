@@ -21,6 +21,7 @@
 #include <algorithm>
 
 #include "amepb_internal.cuh"
+#include "rdf_plan.h"
 
 namespace amepb {
 
@@ -285,8 +286,10 @@ __global__ void scor_prep_kernel(const T* __restrict__ pts, long long n, ScorPre
 struct ScorArgs {
     double L[3], hb[3];    // box lengths and half lengths (float64 of the box dtype values)
     double ub;             // distance_upper_bound = max(box) / 2
-    double inv_w;
+    double inv_w, e0;
+    double s_lo, s_hi;     // squared-distance window of a counted pair, see scor_pair_kernel
     int pbc, ne, uniform, ncomp, cplx, same;
+    int copies;            // copies of the shared bins per block: one per warp, or 1
 };
 
 constexpr int kScorThreads = 128;
@@ -309,22 +312,29 @@ __global__ void scor_values_kernel(const V* __restrict__ v, long long count, int
 
 __global__ void __launch_bounds__(kScorThreads) scor_pair_kernel(
     const double* __restrict__ tpos, long long n, const double* __restrict__ qpos, long long m,
-    const double* __restrict__ tval, const double* __restrict__ qval, ScorArgs A, const double* __restrict__ edges,
+    const double* __restrict__ tval, const double* __restrict__ qval, ScorArgs A, const double* __restrict__ thr,
     unsigned long long* __restrict__ norm, double* __restrict__ cor) {
+    // thr[k]: smallest squared distance whose float64 root reaches edges[k] (host, sq_threshold): the bin of
+    // a pair is decided on s = dx^2 + dy^2 + dz^2 without the IEEE square root; A.s_hi: below it the pair
+    // is inside the tree's distance_upper_bound and below the last edge.
+    constexpr int kWarps = kScorThreads / 32;
     extern __shared__ __align__(16) unsigned char smem_scor[];
-    double* s_e = reinterpret_cast<double*>(smem_scor);
-    double* s_re = s_e + A.ne;
-    double* s_im = s_re + (A.ne - 1);
-    unsigned* s_n = reinterpret_cast<unsigned*>(s_im + (A.ne - 1));
-    double* s_pos = reinterpret_cast<double*>(s_n + ((A.ne + 1) & ~1));  // [tile][3]   (even count: 8-byte alignment)
-    double* s_val = s_pos + 3 * kScorTile;                               // [tile][ncomp][2]
+    double* s_t = reinterpret_cast<double*>(smem_scor);        // thresholds [ne]
     const int nb = A.ne - 1;
-    for (int k = threadIdx.x; k < A.ne; k += blockDim.x) s_e[k] = edges[k];
-    for (int k = threadIdx.x; k < nb; k += blockDim.x) {
+    // [copies][nb]: one copy per warp when that fits (the float64 adds are compare-and-swap loops), else one
+    const int ncopy = A.copies;
+    double* s_re = s_t + A.ne;
+    double* s_im = s_re + ncopy * nb;
+    unsigned* s_n = reinterpret_cast<unsigned*>(s_im + ncopy * nb);
+    double* s_pos = reinterpret_cast<double*>(s_n + ((ncopy * nb + 1) & ~1));  // [tile][3]   (even count: 8-byte alignment)
+    double* s_val = s_pos + 3 * kScorTile;                                      // [tile][ncomp][2]
+    for (int k = threadIdx.x; k < A.ne; k += blockDim.x) s_t[k] = thr[k];
+    for (int k = threadIdx.x; k < ncopy * nb; k += blockDim.x) {
         s_re[k] = 0.0;
         s_im[k] = 0.0;
         s_n[k] = 0u;
     }
+    const int wofs = (ncopy == kWarps ? (int)(threadIdx.x >> 5) : 0) * nb;
     const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool have_q = q < m;
     double qx = 0, qy = 0, qz = 0, qv[kScorMaxComp][2];
@@ -339,6 +349,12 @@ __global__ void __launch_bounds__(kScorThreads) scor_pair_kernel(
                 qv[c][1] = qval[(q * A.ncomp + c) * 2 + 1];
             }
     }
+    // (box values in registers; without pbc the half lengths are infinite and no wrap happens)
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    const double Lx = A.L[0], Ly = A.L[1], Lz = A.L[2];
+    const double hx = A.pbc ? A.hb[0] : inf, hy = A.pbc ? A.hb[1] : inf, hz = A.pbc ? A.hb[2] : inf;
+    const double s_lo = A.s_lo, s_hi = A.s_hi;
+    const float e0 = (float)A.e0, inv_w = (float)A.inv_w;
     const long long per = (n + gridDim.y - 1) / gridDim.y;
     const long long tile0 = (long long)blockIdx.y * per, tile1 = min(n, tile0 + per);
     for (long long t0 = tile0; t0 < tile1; t0 += kScorTile) {
@@ -350,38 +366,65 @@ __global__ void __launch_bounds__(kScorThreads) scor_pair_kernel(
         if (!have_q) continue;
         for (int k = 0; k < cnt; ++k) {
             double dx = __dsub_rn(qx, s_pos[3 * k]), dy = __dsub_rn(qy, s_pos[3 * k + 1]), dz = __dsub_rn(qz, s_pos[3 * k + 2]);
-            if (A.pbc) {
-                // scipy BoxDist1D: one wrap by the box length where |d| exceeds half of it
-                dx = dx < -A.hb[0] ? __dadd_rn(dx, A.L[0]) : (dx > A.hb[0] ? __dsub_rn(dx, A.L[0]) : dx);
-                dy = dy < -A.hb[1] ? __dadd_rn(dy, A.L[1]) : (dy > A.hb[1] ? __dsub_rn(dy, A.L[1]) : dy);
-                dz = dz < -A.hb[2] ? __dadd_rn(dz, A.L[2]) : (dz > A.hb[2] ? __dsub_rn(dz, A.L[2]) : dz);
+            // scipy BoxDist1D: one wrap by the box length where |d| exceeds half of it (selects, no branches)
+            const double dxm = __dadd_rn(dx, Lx), dxp = __dsub_rn(dx, Lx);
+            const double dym = __dadd_rn(dy, Ly), dyp = __dsub_rn(dy, Ly);
+            const double dzm = __dadd_rn(dz, Lz), dzp = __dsub_rn(dz, Lz);
+            dx = dx < -hx ? dxm : (dx > hx ? dxp : dx);
+            dy = dy < -hy ? dym : (dy > hy ? dyp : dy);
+            dz = dz < -hz ? dzm : (dz > hz ? dzp : dz);
+            const double s = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+            // d < distance_upper_bound, d < edges[-1] (no right-inclusive last bin here), d >= edges[0]
+            if (!(s < s_hi) || !(s >= s_lo)) continue;
+            int b;
+            if (A.uniform) {
+                float r;
+                asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"((float)s));
+                b = min(max((int)((r - e0) * inv_w), 0), nb - 1);
+                while (b > 0 && s < s_t[b]) --b;
+                while (b < nb - 1 && s >= s_t[b + 1]) ++b;
+            } else {
+                int lo = 0, hi = nb;   // s_t[lo] <= s < s_t[hi]
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (s >= s_t[mid]) lo = mid;
+                    else hi = mid;
+                }
+                b = lo;
             }
-            const double d = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
-            if (!(d < A.ub)) continue;     // the tree query returns neighbours below distance_upper_bound only
-            // mask = (dists >= edges[i]) & (dists < edges[i+1]): no right-inclusive last bin here
-            if (!(d < s_e[nb])) continue;
-            const int b = edge_bin(d, s_e, A.ne, A.inv_w, A.uniform != 0);
-            if (b < 0) continue;
             // conj(other_value) * value, summed over the components
             double re = 0.0, im = 0.0;
+            if (A.cplx) {
 #pragma unroll
-            for (int c = 0; c < kScorMaxComp; ++c)
-                if (c < A.ncomp) {
-                    const double vr = s_val[(k * A.ncomp + c) * 2], vi = s_val[(k * A.ncomp + c) * 2 + 1];
-                    re += qv[c][0] * vr + qv[c][1] * vi;
-                    im += qv[c][0] * vi - qv[c][1] * vr;
-                }
-            atomicAdd(&s_n[b], 1u);
-            atomicAdd(&s_re[b], re);
-            if (A.cplx) atomicAdd(&s_im[b], im);
+                for (int c = 0; c < kScorMaxComp; ++c)
+                    if (c < A.ncomp) {
+                        const double vr = s_val[(k * A.ncomp + c) * 2], vi = s_val[(k * A.ncomp + c) * 2 + 1];
+                        re += qv[c][0] * vr + qv[c][1] * vi;
+                        im += qv[c][0] * vi - qv[c][1] * vr;
+                    }
+            } else {   // real values: the imaginary parts are zero
+#pragma unroll
+                for (int c = 0; c < kScorMaxComp; ++c)
+                    if (c < A.ncomp) re += qv[c][0] * s_val[(k * A.ncomp + c) * 2];
+            }
+            atomicAdd(&s_n[wofs + b], 1u);
+            atomicAdd(&s_re[wofs + b], re);
+            if (A.cplx) atomicAdd(&s_im[wofs + b], im);
         }
     }
     __syncthreads();
     for (int k = threadIdx.x; k < nb; k += blockDim.x) {
-        if (s_n[k]) {
-            atomicAdd(&norm[k], (unsigned long long)s_n[k]);
-            atomicAdd(&cor[2 * k], s_re[k]);
-            if (A.cplx) atomicAdd(&cor[2 * k + 1], s_im[k]);
+        unsigned cn = 0;
+        double re = 0.0, im = 0.0;
+        for (int w = 0; w < ncopy; ++w) {
+            cn += s_n[w * nb + k];
+            re += s_re[w * nb + k];
+            im += s_im[w * nb + k];
+        }
+        if (cn) {
+            atomicAdd(&norm[k], (unsigned long long)cn);
+            atomicAdd(&cor[2 * k], re);
+            if (A.cplx) atomicAdd(&cor[2 * k + 1], im);
         }
     }
 }
@@ -597,7 +640,11 @@ int amepb_spatialcor_sums(amepb_ctx* ctx, const void* coords, int dtype, int64_t
     double* d_cor = reinterpret_cast<double*>(d_norm + nb);
     if ((rc = ensure_pinned(ctx, sizeof(double) * nedges))) return rc;
     if ((rc = pinned_host_acquire(ctx))) return rc;
-    memcpy(ctx->pinned, edges, sizeof(double) * nedges);
+    // squared-distance thresholds of the edges: thr[k] = smallest s with sqrt(s) >= edges[k] (float64, IEEE root)
+    {
+        double* thr = reinterpret_cast<double*>(ctx->pinned);
+        for (int k = 0; k < nedges; ++k) thr[k] = sq_threshold<double>(edges[k], false);
+    }
     AMEPB_CUDA(ctx, cudaMemcpyAsync(d_edges, ctx->pinned, sizeof(double) * nedges, cudaMemcpyHostToDevice, stream));
     AMEPB_CUDA(ctx, cudaMemsetAsync(d_norm, 0, (sizeof(uint64_t) + 2 * sizeof(double)) * nb, stream));
     ScorPrep S;
@@ -614,6 +661,9 @@ int amepb_spatialcor_sums(amepb_ctx* ctx, const void* coords, int dtype, int64_t
     }
     S.pbc = pbc ? 1 : 0;
     A.ub = in_box_dtype(maxbox / 2.0, box_dtype);
+    A.e0 = edges[0];
+    A.s_lo = sq_threshold<double>(edges[0], false);
+    A.s_hi = std::min(sq_threshold<double>(A.ub, false), sq_threshold<double>(edges[nedges - 1], false));
     A.pbc = S.pbc;
     A.ne = nedges;
     A.uniform = edges_uniform(edges, nedges, &A.inv_w) ? 1 : 0;
@@ -645,7 +695,10 @@ int amepb_spatialcor_sums(amepb_ctx* ctx, const void* coords, int dtype, int64_t
     unsigned ysplit = (unsigned)std::max<long long>(1, std::min<long long>((n + kScorTile - 1) / kScorTile,
                                                                             (8LL * ctx->sm_count + qblocks - 1) / qblocks));
     ysplit = std::min(ysplit, 65535u);
-    const size_t smem = sizeof(double) * nedges + 2 * sizeof(double) * nb + sizeof(unsigned) * ((nedges + 1) & ~1) +
+    int kw = kScorThreads / 32;
+    if ((2 * sizeof(double) + sizeof(unsigned)) * (size_t)kw * nb > 96 * 1024) kw = 1;
+    A.copies = kw;
+    const size_t smem = sizeof(double) * nedges + 2 * sizeof(double) * kw * nb + sizeof(unsigned) * ((kw * nb + 1) & ~1) +
                         sizeof(double) * 3 * kScorTile + sizeof(double) * 2 * kScorTile * ncomp + 16;
     if (smem > 48 * 1024)
         AMEPB_CUDA(ctx, cudaFuncSetAttribute(scor_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
