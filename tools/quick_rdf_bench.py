@@ -92,6 +92,10 @@ if __name__ == "__main__":
                               ms_per_frame=round(best / nf, 4), pair_ms=round(info["pair_kernel_ms"] / nf, 4),
                               build_ms=round(info["build_ms"] / nf, 4), pair_evals_per_s=pairs / best * 1e3,
                               candidates=info["candidate_pairs"])), flush=True)
+    if "cfg5fast" in which:
+        n = 2_000_000
+        L = float((n / 0.8) ** (1 / 3))
+        run("cfg5like_3d_2M_rmax10", n, 1, 3, L, 10.0, 500, ks=(0,), reps=3)
     if "cfg5" in which:
         n = 2_000_000
         L = float((n / 0.8) ** (1 / 3))
