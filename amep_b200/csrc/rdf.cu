@@ -2216,7 +2216,7 @@ static int rdf_sub_batch(amepb_ctx* ctx, const RdfCall& c, int64_t f0, int nf, c
         for (int f = 0; f < nf; ++f) plans[f].compact = compact ? 1 : 0;
     }
     // partitioned build of the query array (strip_* kernels): self RDF with images on the symmetric walk,
-    // enough (strip, frame) blocks to fill the machine, the cell counters of a strip in shared memory
+    // enough (strip, frame) blocks to be worth it, the cell counters of a strip in shared memory
     long long total_strips = 0;
     int max_strips = 0;
     size_t sort_smem = 0;
@@ -2246,7 +2246,8 @@ static int rdf_sub_batch(amepb_ctx* ctx, const RdfCall& c, int64_t f0, int nf, c
             sort_smem = std::max(sort_smem, smem);
         }
         const bool force_part = getenv("AMEPB_FORCE_PARTITIONED_BUILD") != nullptr;   // tests: also for tiny batches
-        partitioned = ok && (total_strips >= 2LL * ctx->sm_count || force_part);
+        // (measured down to one 1M-particle frame, 254 strips: never slower than the placement kernels)
+        partitioned = ok && (total_strips >= 128 || force_part);
         if (!partitioned)
             for (int f = 0; f < nf; ++f) plans[f].strip_rows = 0;
     }
