@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, GPU call AE (8 GPUs): sharded evaluate classes vs single rank, bench line at N=8
+# round 2, GPU call AE (8 GPUs; rerun with the final code as call AR): sharded evaluate classes vs single rank, bench line at N=8
 set -x
 cd "$GRAFT_REPO_ROOT" || exit 1
 mkdir -p gpurun_out
