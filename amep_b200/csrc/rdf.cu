@@ -437,7 +437,13 @@ constexpr int kStripPer = AMEPB_STRIP_PER;         // particles per thread of th
 constexpr int kStripTile = kStripThreads * kStripPer;
 constexpr int kMaxStrips = 512;
 constexpr int kSortThreads = 256;
-constexpr int kSortCache = 8;                      // records a thread keeps in registers between the sweeps
+// records a thread keeps in registers between the two sweeps of strip_sort_kernel: 128 bytes' worth
+// (16 (x, y) records cover a configs[1] strip of 4 k particles; measured 256 x 16: 20.6 us per frame for the
+// whole build, 256 x 8: 21.1, 512 x 8: 21.0, 512 x 4: 20.8, 128 x 16: 21.7)
+template <typename Rec>
+struct SortCache {
+    static constexpr int value = sizeof(Rec) <= 8 ? 16 : (sizeof(Rec) <= 16 ? 8 : 4);
+};
 
 // row / strip_rows by a multiply (strip_magic = 2^32 / strip_rows + 1; exact while rows * strip_rows < 2^31,
 // which the host checks): an integer division per particle would cost as much as the rest of the tile kernel
@@ -606,6 +612,7 @@ __global__ void __launch_bounds__(kSortThreads) strip_sort_kernel(const typename
                                                                   unsigned* __restrict__ qstart,
                                                                   typename StripRec<AT, XY>::type* __restrict__ sorted) {
     typedef typename StripRec<AT, XY>::type Rec;
+    constexpr int kSortCache = SortCache<Rec>::value;
     extern __shared__ unsigned s_cnt[];   // [cells of the strip]: counts, then cursors
     __shared__ unsigned s_warp[33];
     __shared__ int s_words[kPlanHeadWords];
