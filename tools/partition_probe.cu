@@ -110,6 +110,76 @@ __global__ void __launch_bounds__(kThreads) p2_strip_scatter(const float* __rest
     }
 }
 
+// variant: the tile's records are first ordered by strip in shared memory (with their destinations), then
+// written by consecutive threads -- runs of ~8 consecutive records per strip instead of 32 scattered 8-byte stores
+template <int PER>
+__global__ void __launch_bounds__(kThreads) p2_strip_scatter_sorted(const float* __restrict__ pts, long long n, Grid G, unsigned* __restrict__ cursor,
+                                                                   float2* __restrict__ mid) {
+    __shared__ unsigned s_h[512], s_base[512], s_off[512];
+    __shared__ unsigned s_warp[33];
+    __shared__ float2 s_rec[kThreads * PER];
+    __shared__ unsigned s_dst[kThreads * PER];
+    const int f = blockIdx.y;
+    for (int k = threadIdx.x; k < 512; k += kThreads) s_h[k] = 0;
+    __syncthreads();
+    const float* base = pts + (long long)f * n * 3;
+    const long long i0 = (long long)blockIdx.x * (kThreads * PER) + threadIdx.x;
+    float x[PER], y[PER];
+    unsigned st[PER], rk[PER];
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+        const long long i = i0 + (long long)u * kThreads;
+        x[u] = i < n ? base[3 * i] : 0.f;
+        y[u] = i < n ? base[3 * i + 1] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+        const long long i = i0 + (long long)u * kThreads;
+        st[u] = cell_of((double)y[u], G.g0y, G.inv_h, G.ny) / G.rows_per_strip;
+        if (i < n) rk[u] = atomicAdd(&s_h[st[u]], 1u);
+    }
+    __syncthreads();
+    // exclusive scan of the tile's strip counts (two strips per thread) + reservation
+    const unsigned c0 = s_h[2 * threadIdx.x], c1 = s_h[2 * threadIdx.x + 1];
+    unsigned inc = c0 + c1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    if (c0) s_base[2 * threadIdx.x] = atomicAdd(&cursor[f * G.nstrips + 2 * threadIdx.x], c0);
+    if (c1) s_base[2 * threadIdx.x + 1] = atomicAdd(&cursor[f * G.nstrips + 2 * threadIdx.x + 1], c1);
+    __syncthreads();
+    if (warp == 0) {
+        unsigned w = lane < kThreads / 32 ? s_warp[lane] : 0u, winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
+        }
+        s_warp[lane] = winc - w;
+    }
+    __syncthreads();
+    const unsigned e0 = s_warp[warp] + inc - (c0 + c1);
+    s_off[2 * threadIdx.x] = e0;
+    s_off[2 * threadIdx.x + 1] = e0 + c0;
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+        const long long i = i0 + (long long)u * kThreads;
+        if (i < n) {
+            const unsigned pos = s_off[st[u]] + rk[u];
+            s_rec[pos] = make_float2(x[u], y[u]);
+            s_dst[pos] = s_base[st[u]] + rk[u];
+        }
+    }
+    __syncthreads();
+    const int cnt = (int)min((long long)(kThreads * PER), n - (long long)blockIdx.x * (kThreads * PER));
+    for (int j = threadIdx.x; j < cnt; j += kThreads) mid[s_dst[j]] = s_rec[j];
+}
+
 constexpr int kP3Threads = 256;
 constexpr int kP3Cache = 8;
 __global__ void __launch_bounds__(kP3Threads) p3_strip_sort(const float2* __restrict__ mid, const unsigned* __restrict__ strip_start, Grid G,
@@ -210,7 +280,9 @@ int main(int argc, char** argv) {
     cudaEvent_t ev[6];
     for (auto& e : ev) cudaEventCreate(&e);
     printf("{\n");
-    for (int rps : {1, 2, 4}) {
+    for (int variant = 0; variant < 2; ++variant)
+    for (int rps : {1, 2}) {
+        const bool sorted_scatter = variant == 1;
         G.rows_per_strip = rps;
         G.nstrips = (G.ny + rps - 1) / rps;
         const size_t smem3 = sizeof(unsigned) * (size_t)rps * G.nx;
@@ -225,7 +297,8 @@ int main(int argc, char** argv) {
             cudaEventRecord(ev[1]);
             strip_scan<<<F, 32>>>(scnt, sstart, scur, G.nstrips, n);
             cudaEventRecord(ev[2]);
-            p2_strip_scatter<PER><<<tg, kThreads>>>(pts, n, G, scur, mid);
+            if (sorted_scatter) p2_strip_scatter_sorted<PER><<<tg, kThreads>>>(pts, n, G, scur, mid);
+            else p2_strip_scatter<PER><<<tg, kThreads>>>(pts, n, G, scur, mid);
             cudaEventRecord(ev[3]);
             p3_strip_sort<<<dim3(G.nstrips, F), kP3Threads, smem3>>>(mid, sstart, G, n, cstart, sorted);
             cudaEventRecord(ev[4]);
@@ -250,8 +323,8 @@ int main(int argc, char** argv) {
             }
         }
         if (hs[G.nx * G.ny] != n) ++bad;
-        printf(" \"rows_per_strip_%d\": {\"nstrips\": %d, \"p1_us_per_frame\": %.2f, \"scan_us\": %.2f, \"p2_us_per_frame\": %.2f, \"p3_us_per_frame\": %.2f, \"total_us_per_frame\": %.2f, \"check_errors\": %lld},\n",
-               rps, G.nstrips, best[0] * 1e3 / F, best[1] * 1e3 / F, best[2] * 1e3 / F, best[3] * 1e3 / F,
+        printf(" \"%srows_per_strip_%d\": {\"nstrips\": %d, \"p1_us_per_frame\": %.2f, \"scan_us\": %.2f, \"p2_us_per_frame\": %.2f, \"p3_us_per_frame\": %.2f, \"total_us_per_frame\": %.2f, \"check_errors\": %lld},\n",
+               sorted_scatter ? "sorted_scatter_" : "", rps, G.nstrips, best[0] * 1e3 / F, best[1] * 1e3 / F, best[2] * 1e3 / F, best[3] * 1e3 / F,
                (best[0] + best[1] + best[2] + best[3]) * 1e3 / F, bad);
     }
     printf(" \"frames\": %d, \"n\": %lld\n}\n", F, n);
