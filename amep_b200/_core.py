@@ -422,10 +422,12 @@ def pcf2d_counts(coords, other, center, center_f32, rot, xedges, yedges, device=
     return out
 
 
-def sf2d_modes(coords, qpos, nq, accum="c64", chunksize=0, device=None):
+def sf2d_modes(coords, qpos, nq, accum="c64", chunksize=0, device=None, shard=None):
     """rho(q) on the sf2d grid (amepb_sf2d_modes) -> complex array ``[F, 2nq, 2nq]``.
 
-    ``qpos``: the positive half of the q axis, float64 ``[nq]`` (shared) or ``[F, nq]``."""
+    ``qpos``: the positive half of the q axis, float64 ``[nq]`` (shared) or ``[F, nq]``.
+    ``shard=(index, count)``: only this share of the rows of q tiles, zeros elsewhere
+    (amepb_sf2d_set_shard); the arrays of all shares add up to the full one exactly."""
     pc = coords if isinstance(coords, Particles) else Particles(coords)
     nf = pc.nframes
     q = np.ascontiguousarray(np.asarray(qpos, dtype=np.float64))
@@ -449,11 +451,17 @@ def sf2d_modes(coords, qpos, nq, accum="c64", chunksize=0, device=None):
         optr, space = out.ctypes.data, _lib.HOST
     if nq == 0:
         return out
-    rc = ctx.lib.amepb_sf2d_modes(
-        ctx.handle, ctypes.c_void_p(pc.ptr()), pc.dtype, space, nf, pc.n,
-        q.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), stride, int(nq), mode, int(chunksize),
-        ctypes.c_void_p(optr), _stream_for(dev_index, pc.on_device))
-    ctx.check(rc, "amepb_sf2d_modes")
+    if shard is not None:
+        ctx.set_sf2d_shard(*shard)
+    try:
+        rc = ctx.lib.amepb_sf2d_modes(
+            ctx.handle, ctypes.c_void_p(pc.ptr()), pc.dtype, space, nf, pc.n,
+            q.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), stride, int(nq), mode, int(chunksize),
+            ctypes.c_void_p(optr), _stream_for(dev_index, pc.on_device))
+        ctx.check(rc, "amepb_sf2d_modes")
+    finally:
+        if shard is not None:
+            ctx.set_sf2d_shard(0, 1)
     return out
 
 

@@ -22,7 +22,7 @@ ABI_VERSION = 1
 SYMBOLS = (
     "amepb_abi_version", "amepb_create", "amepb_destroy", "amepb_last_error",
     "amepb_frame_dimension", "amepb_rdf_batch", "amepb_rdf_last_info",
-    "amepb_rdf_set_cells_per_cutoff", "amepb_rdf_set_symmetric", "amepb_rdf_set_shard", "amepb_sq_harmonics", "amepb_sq_debye", "amepb_sq_debye_ref", "amepb_sf2d_modes",
+    "amepb_rdf_set_cells_per_cutoff", "amepb_rdf_set_symmetric", "amepb_rdf_set_shard", "amepb_sq_harmonics", "amepb_sq_debye", "amepb_sq_debye_ref", "amepb_sf2d_modes", "amepb_sf2d_set_shard",
     "amepb_density_counts",
     "amepb_pcf2d_counts", "amepb_psi_k", "amepb_rotate_crop", "amepb_pcf_angle_counts", "amepb_spatialcor_sums",
     "amepb_kernel_launches", "amepb_synchronize", "amepb_set_timing", "amepb_last_kernel_ms",
@@ -104,6 +104,8 @@ def load():
         lib.amepb_rdf_set_symmetric.argtypes = [vp, c.c_int]
         lib.amepb_rdf_set_shard.restype = c.c_int
         lib.amepb_rdf_set_shard.argtypes = [vp, c.c_int, c.c_int]
+        lib.amepb_sf2d_set_shard.restype = c.c_int
+        lib.amepb_sf2d_set_shard.argtypes = [vp, c.c_int, c.c_int]
         lib.amepb_sq_harmonics.restype = c.c_int
         lib.amepb_sq_harmonics.argtypes = [vp, vp, c.c_int, c.c_int, i64, i64,
                                            c.POINTER(c.c_double), i64, i32, i32, vp, vp]
@@ -190,6 +192,10 @@ class Context:
     def set_shard(self, index: int, count: int):
         """Intra-frame sharding of amepb_rdf_batch (amepb_rdf_set_shard)."""
         self.check(self.lib.amepb_rdf_set_shard(self.handle, int(index), int(count)), "amepb_rdf_set_shard")
+
+    def set_sf2d_shard(self, index: int, count: int):
+        """Intra-frame sharding of amepb_sf2d_modes over rows of q tiles (amepb_sf2d_set_shard)."""
+        self.check(self.lib.amepb_sf2d_set_shard(self.handle, int(index), int(count)), "amepb_sf2d_set_shard")
 
     def set_cells_per_cutoff(self, k: int):
         self.check(self.lib.amepb_rdf_set_cells_per_cutoff(self.handle, int(k)),

@@ -69,6 +69,7 @@ struct amepb_ctx {
     int rdf_k_override = 0;
     bool rdf_symmetric = true;
     int rdf_shard_index = 0, rdf_shard_count = 1;   // amepb_rdf_set_shard
+    int sf2d_shard_index = 0, sf2d_shard_count = 1; // amepb_sf2d_set_shard
     void* last_stream = nullptr;
     bool sq_attr_harm = false;
     cudaStream_t copy_stream = nullptr;   // host-space staging

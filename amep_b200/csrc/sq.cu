@@ -168,7 +168,9 @@ constexpr int kF64Row = 65;        // 64 table entries per particle and axis + 1
 template <typename T, int UNROLL>
 __global__ void __launch_bounds__(kF64Threads, 1) sf2d_f64_kernel(
     const T* __restrict__ coords, long long n, const double* __restrict__ qall, long long q_stride, int nq,
-    int ksplit, double* __restrict__ partial) {
+    int ksplit, double* __restrict__ partial, int shard_index, int shard_count) {
+    // (intra-frame sharding, amepb_sf2d_set_shard: a block whose row of tiles belongs to another share has nothing to do)
+    if ((int)(blockIdx.x / ((nq + 63) / 64)) % shard_count != shard_index) return;
     // shared: X[stage][64 + 1], Y[stage][64 + 1] as double2 (65 KB, dynamic)
     extern __shared__ __align__(16) unsigned char smem_f64[];
     // (rows padded by one entry: the builder's lanes hold different particles, a row apart, and
@@ -248,16 +250,17 @@ __global__ void __launch_bounds__(kF64Threads, 1) sf2d_f64_kernel(
 
 // combine the splits and expand the four quadrants: rho[f][iy][ix] complex128
 __global__ void sf2d_f64_finish_kernel(const double* __restrict__ partial, int ksplit, int nq, long long nframes,
-                                       double2* __restrict__ rho) {
+                                       double2* __restrict__ rho, int shard_index, int shard_count) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long per = (long long)nq * nq;
     if (i >= nframes * per) return;
     const long long f = i / per;
     const int b = (int)((i % per) / nq), a = (int)(i % nq);
     double s[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int k = 0; k < ksplit; ++k)
+    if ((b / 64) % shard_count == shard_index)   // (rows of other shares stay zero: their partial sums were never written)
+        for (int k = 0; k < ksplit; ++k)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) s[c] += partial[(((f * ksplit + k) * 4 + c) * (long long)nq + b) * nq + a];
+            for (int c = 0; c < 4; ++c) s[c] += partial[(((f * ksplit + k) * 4 + c) * (long long)nq + b) * nq + a];
     const double cc = s[0], ss = s[1], cs = s[2], sc = s[3];
     const double2 pp = make_double2(cc - ss, -(sc + cs));  // (+qa, +qb)
     const double2 mp = make_double2(cc + ss, sc - cs);     // (-qa, +qb)
@@ -321,7 +324,10 @@ __device__ __noinline__ void c64_build_stage(const T* __restrict__ base, const d
 template <typename T, bool SPLIT>
 __global__ void __launch_bounds__(kC64Threads, 4) sf2d_c64_kernel(
     const T* __restrict__ coords, long long n, const double* __restrict__ qall, long long q_stride, int nq,
-    long long chunksize, float2* __restrict__ rho, float4* __restrict__ chunk_out, long long nchunks) {
+    long long chunksize, float2* __restrict__ rho, float4* __restrict__ chunk_out, long long nchunks, int shard_index,
+    int shard_count) {
+    // (intra-frame sharding, amepb_sf2d_set_shard: rows of tiles of other shares are left to them; rho is zeroed beforehand)
+    if ((int)(blockIdx.x / ((nq + kC64TileA - 1) / kC64TileA)) % shard_count != shard_index) return;
     extern __shared__ __align__(16) unsigned char smem_c64[];
     // (one spare row per table: the operand prefetch of particle jj + 1 then needs no index clamp,
     // which cost five uniform-datapath instructions per particle in the accumulation loop)
@@ -423,14 +429,15 @@ __global__ void __launch_bounds__(kC64Threads, 4) sf2d_c64_kernel(
 
 // Sequential float32 sum of the chunk sums of the SPLIT kernel, in chunk order.
 __global__ void sf2d_c64_combine_kernel(const float4* __restrict__ chunk_out, long long nchunks, int nq, long long nframes,
-                                        float2* __restrict__ rho) {
+                                        float2* __restrict__ rho, int shard_index, int shard_count) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nframes * nq * nq) return;
     const int a = (int)(i % nq), b = (int)((i / nq) % nq);
     const long long frame = i / ((long long)nq * nq);
     float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
     const float4* src = chunk_out + (frame * nchunks * nq + b) * nq + a;
-    for (long long c = 0; c < nchunks; ++c) {
+    const bool mine = (b / kC64TileB) % shard_count == shard_index;   // (other shares' rows: zeros)
+    for (long long c = 0; mine && c < nchunks; ++c) {
         const float4 v = src[c * nq * nq];
         t0 = __fadd_rn(t0, v.x); t1 = __fadd_rn(t1, v.y); t2 = __fadd_rn(t2, v.z); t3 = __fadd_rn(t3, v.w);
     }
@@ -904,20 +911,20 @@ int amepb_sf2d_modes(amepb_ctx* ctx, const void* coords, int dtype, int space, i
             const char* un = getenv("AMEPB_SF2D_UNROLL");
             const int unroll = un ? atoi(un) : 2;
             if (dtype == AMEPB_F32 && unroll == 1)
-                sf2d_f64_kernel<float, 1><<<grid, kF64Threads, smem_f64, stream>>>((const float*)d_coords, n, qf, q_stride, nq, ksplit, d_part);
+                sf2d_f64_kernel<float, 1><<<grid, kF64Threads, smem_f64, stream>>>((const float*)d_coords, n, qf, q_stride, nq, ksplit, d_part, ctx->sf2d_shard_index, ctx->sf2d_shard_count);
             else if (dtype == AMEPB_F32 && unroll == 4)
-                sf2d_f64_kernel<float, 4><<<grid, kF64Threads, smem_f64, stream>>>((const float*)d_coords, n, qf, q_stride, nq, ksplit, d_part);
+                sf2d_f64_kernel<float, 4><<<grid, kF64Threads, smem_f64, stream>>>((const float*)d_coords, n, qf, q_stride, nq, ksplit, d_part, ctx->sf2d_shard_index, ctx->sf2d_shard_count);
             else if (dtype == AMEPB_F32)
-                sf2d_f64_kernel<float, 2><<<grid, kF64Threads, smem_f64, stream>>>((const float*)d_coords, n, qf, q_stride, nq, ksplit, d_part);
+                sf2d_f64_kernel<float, 2><<<grid, kF64Threads, smem_f64, stream>>>((const float*)d_coords, n, qf, q_stride, nq, ksplit, d_part, ctx->sf2d_shard_index, ctx->sf2d_shard_count);
             else
-                sf2d_f64_kernel<double, 2><<<grid, kF64Threads, smem_f64, stream>>>((const double*)d_coords, n, qf, q_stride, nq, ksplit, d_part);
+                sf2d_f64_kernel<double, 2><<<grid, kF64Threads, smem_f64, stream>>>((const double*)d_coords, n, qf, q_stride, nq, ksplit, d_part, ctx->sf2d_shard_index, ctx->sf2d_shard_count);
             AMEPB_LAUNCH_CHECK(ctx);
             {
                 cudaEvent_t ev1 = timing_event(ctx, stream);
                 if (ev0 && ev1) ctx->ev_sq.emplace_back(ev0, ev1);
             }
             const long long total = (long long)nf * nq * nq;
-            sf2d_f64_finish_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(d_part, ksplit, nq, nf, reinterpret_cast<double2*>(d_out));
+            sf2d_f64_finish_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(d_part, ksplit, nq, nf, reinterpret_cast<double2*>(d_out), ctx->sf2d_shard_index, ctx->sf2d_shard_count);
             AMEPB_LAUNCH_CHECK(ctx);
         } else {
             const int tiles_a = (nq + kC64TileA - 1) / kC64TileA, tiles_b = (nq + kC64TileB - 1) / kC64TileB;
@@ -935,18 +942,20 @@ int amepb_sf2d_modes(amepb_ctx* ctx, const void* coords, int dtype, int space, i
                 float4* d_chunks = reinterpret_cast<float4*>(ctx->bufs[BUF_SQ_B].p);
                 dim3 grid((unsigned)(tiles_a * tiles_b), (unsigned)nf, (unsigned)ksplit_c);
                 if (dtype == AMEPB_F32)
-                    sf2d_c64_kernel<float, true><<<grid, kC64Threads, smem_c64, stream>>>((const float*)d_coords, n, qf, q_stride, nq, chunksize, reinterpret_cast<float2*>(d_out), d_chunks, nchunks);
+                    sf2d_c64_kernel<float, true><<<grid, kC64Threads, smem_c64, stream>>>((const float*)d_coords, n, qf, q_stride, nq, chunksize, reinterpret_cast<float2*>(d_out), d_chunks, nchunks, ctx->sf2d_shard_index, ctx->sf2d_shard_count);
                 else
-                    sf2d_c64_kernel<double, true><<<grid, kC64Threads, smem_c64, stream>>>((const double*)d_coords, n, qf, q_stride, nq, chunksize, reinterpret_cast<float2*>(d_out), d_chunks, nchunks);
+                    sf2d_c64_kernel<double, true><<<grid, kC64Threads, smem_c64, stream>>>((const double*)d_coords, n, qf, q_stride, nq, chunksize, reinterpret_cast<float2*>(d_out), d_chunks, nchunks, ctx->sf2d_shard_index, ctx->sf2d_shard_count);
                 AMEPB_LAUNCH_CHECK(ctx);
                 const long long total = (long long)nf * nq * nq;
-                sf2d_c64_combine_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(d_chunks, nchunks, nq, nf, reinterpret_cast<float2*>(d_out));
+                sf2d_c64_combine_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(d_chunks, nchunks, nq, nf, reinterpret_cast<float2*>(d_out), ctx->sf2d_shard_index, ctx->sf2d_shard_count);
             } else {
                 dim3 grid((unsigned)(tiles_a * tiles_b), (unsigned)nf);
+                if (ctx->sf2d_shard_count > 1)   // rows of other shares stay zero
+                    AMEPB_CUDA(ctx, cudaMemsetAsync(d_out, 0, sizeof(float2) * (size_t)nf * 4 * nq * nq, stream));
                 if (dtype == AMEPB_F32)
-                    sf2d_c64_kernel<float, false><<<grid, kC64Threads, smem_c64, stream>>>((const float*)d_coords, n, qf, q_stride, nq, chunksize, reinterpret_cast<float2*>(d_out), nullptr, nchunks);
+                    sf2d_c64_kernel<float, false><<<grid, kC64Threads, smem_c64, stream>>>((const float*)d_coords, n, qf, q_stride, nq, chunksize, reinterpret_cast<float2*>(d_out), nullptr, nchunks, ctx->sf2d_shard_index, ctx->sf2d_shard_count);
                 else
-                    sf2d_c64_kernel<double, false><<<grid, kC64Threads, smem_c64, stream>>>((const double*)d_coords, n, qf, q_stride, nq, chunksize, reinterpret_cast<float2*>(d_out), nullptr, nchunks);
+                    sf2d_c64_kernel<double, false><<<grid, kC64Threads, smem_c64, stream>>>((const double*)d_coords, n, qf, q_stride, nq, chunksize, reinterpret_cast<float2*>(d_out), nullptr, nchunks, ctx->sf2d_shard_index, ctx->sf2d_shard_count);
             }
             AMEPB_LAUNCH_CHECK(ctx);
             cudaEvent_t ev1 = timing_event(ctx, stream);
@@ -1037,6 +1046,13 @@ int amepb_sq_debye(amepb_ctx* ctx, const void* coords, int dtype, int64_t n, con
         AMEPB_CUDA(ctx, cudaMemcpyAsync(out, d_out, sizeof(double) * (size_t)nframes * nq, cudaMemcpyDeviceToHost, stream));
         AMEPB_CUDA(ctx, cudaStreamSynchronize(stream));
     }
+    return 0;
+}
+
+int amepb_sf2d_set_shard(amepb_ctx* ctx, int index, int count) {
+    if (!ctx || count < 1 || index < 0 || index >= count) return AMEPB_E_INVAL;
+    ctx->sf2d_shard_index = index;
+    ctx->sf2d_shard_count = count;
     return 0;
 }
 

@@ -408,7 +408,12 @@ class SF2d(_FrameAverage):
                             "(SURVEY.md section 8f)")
         kwargs.pop("verbose", None)
         idx = self._select(traj, skip, nav)
-        sh = self._shard = _Shard(len(idx), distributed, group)
+        # fewer frames than ranks (mode 'std'): every rank takes all selected frames and a share of the rows
+        # of q tiles of each (amepb_sf2d_set_shard); the rho arrays are summed over the ranks -- exact
+        sh = self._shard = _Shard(len(idx), distributed, group, allow_intra=kwargs.get("mode", "std") == "std")
+        if sh.intra:
+            kwargs = dict(kwargs, shard=(sh.rank, sh.ws), reduce=sh.all_sum)
+        multi = sh.ws > 1 and not sh.intra   # frames spread over the ranks
         s_rows, qx_rows, qy_rows, thetas = [], [], [], []
         done = 0
         # the reference always passes other_coords, so rho is evaluated twice
@@ -445,16 +450,16 @@ class SF2d(_FrameAverage):
         nsel = len(idx)
         # ---- average (np.mean(np.array(results), axis=0): sequential float64 sums over the frames)
         shared_grid = qx is None or len(qx) == 1
-        if sh.ws > 1:
+        if multi:
             shared_grid = bool(dist.all_true(shared_grid, group))
-        if sh.ws == 1:
+        if not multi:
             self._avg = np.mean(self._s, axis=0, dtype=np.float64)
         else:
             tail = sh.tail_shape(self._s)
             part = np.zeros(tail) if self._s is None or len(self._s) == 0 else np.sum(self._s, axis=0, dtype=np.float64)
             self._avg = sh.all_sum(part) / nsel
         if shared_grid:
-            if sh.ws > 1:   # ranks without frames take the grids from rank 0's block
+            if multi:   # ranks without frames take the grids from rank 0's block
                 tail = sh.tail_shape(qx)
                 gx = qx[0] if (qx is not None and sh.lo == 0 and sh.hi > 0) else np.zeros(tail)
                 gy = qy[0] if (qy is not None and sh.lo == 0 and sh.hi > 0) else np.zeros(tail)

@@ -403,8 +403,13 @@ def _sf2d_fft_frames(pc, po, same, bb, qmax, Ntot, accuracy):
 
 def sf2d_frames(coords, box_boundary, other_coords=None, qmax=20.0, njobs=1, mode="std", Ntot=None,
                 accuracy=0.1, chunksize=None, accum="c64", reduce=None, return_modes=False,
-                compact_grids=False, verbose=False):
+                compact_grids=False, verbose=False, shard=None):
     """``sf2d`` for a batch of frames -> ``(S [F, ny, nx], Qx [F, ny, nx], Qy [F, ny, nx])``.
+
+    ``shard=(index, count)`` with ``reduce`` (a sum over the ranks): intra-frame sharding of mode
+    'std' -- every rank holds the frames and computes its share of the rows of q tiles in the
+    reference's order over all particles, ``reduce`` adds the shares (exact: every element of rho
+    comes from one rank).
 
     ``accum='c64'`` reproduces the reference's complex64 running sums (order and
     chunking included); ``accum='f64'`` sums in float64 (closer to the exact
@@ -437,8 +442,8 @@ def sf2d_frames(coords, box_boundary, other_coords=None, qmax=20.0, njobs=1, mod
         raise ValueError("sf2d_frames: the box changes the number of q values between frames")
     cs = _sf2d_chunksize(pc.n, po.n, chunksize, njobs)
     qpos = np.stack(q_rows) if per_frame_box else q_rows[0]
-    rho = _core.sf2d_modes(pc, qpos, nq, accum=accum, chunksize=cs)
-    rho_other = rho if same else _core.sf2d_modes(po, qpos, nq, accum=accum, chunksize=cs)
+    rho = _core.sf2d_modes(pc, qpos, nq, accum=accum, chunksize=cs, shard=shard)
+    rho_other = rho if same else _core.sf2d_modes(po, qpos, nq, accum=accum, chunksize=cs, shard=shard)
     if reduce is not None:
         rho = reduce(rho)
         rho_other = rho if same else reduce(rho_other)

@@ -211,6 +211,15 @@ int amepb_sq_debye_ref(amepb_ctx* ctx, const void* coords, int dtype, int64_t n,
                        const double* q, int64_t q_stride, int32_t nq, int twod,
                        int64_t chunksize, float* out, void* stream);
 
+/* Intra-frame sharding of amepb_sf2d_modes (default 0 of 1): later calls on this context compute only the
+ * rows of q tiles t (16 q_b values each in the reference-order mode, 64 in the float64 mode) with
+ * t % count == index and return zeros elsewhere, so the rho arrays of the `count` shares of the same call
+ * -- one per GPU, each holding a copy of the frame -- add up to the full array exactly (every element is
+ * computed by one share, in the reference's order over all particles).  The split the reference makes
+ * over particle chunks (amep/spatialcor.py:1876-1907) cannot be spread over devices without changing its
+ * complex64 rounding sequence; a split over q can.  Used when there are fewer frames than GPUs. */
+int amepb_sf2d_set_shard(amepb_ctx* ctx, int index, int count);
+
 /*
  * Particle counts on the grid of the histogram density estimate used by sf2d(mode='fft')
  * (amep/continuum.py:300-407 hde, called through coords_to_density by amep/spatialcor.py:1918-1920):

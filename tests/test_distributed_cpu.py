@@ -78,11 +78,27 @@ def _oracle_sfiso_frames(coords, box, N=None, qmax=20.0, twod=True, mode="fast",
     return s, np.broadcast_to(q, (coords.shape[0], len(q))).copy()
 
 
-def _oracle_sf2d_frames(coords, box, other_coords=None, qmax=20.0, compact_grids=False, **kw):
+def _oracle_sf2d_frames(coords, box, other_coords=None, qmax=20.0, compact_grids=False, shard=None, reduce=None, **kw):
+    """Stand-in for spatialcor.sf2d_frames(mode='std').  With ``shard`` / ``reduce`` (fewer frames than
+    ranks) it does what amepb_sf2d_set_shard does: this rank's rows of q tiles of rho, zeros elsewhere,
+    summed over the ranks."""
     import amep_oracle as orc
     coords = np.asarray(coords)
     rows = [orc.sf2d_std(coords[f], box, qmax=qmax) for f in range(coords.shape[0])]
     s = np.array([r[0] for r in rows])
+    if shard is not None:
+        index, count = shard
+        qx, qy = orc.sf2d_grid(box, qmax)
+        cs = orc.sf2d_chunksize(coords.shape[1], coords.shape[1])
+        rho = np.array([getattr(orc, "_density_modes_c64")(coords[f], qx, qy, cs) for f in range(coords.shape[0])])
+        nq = rho.shape[1] // 2
+        mine = np.zeros(2 * nq, dtype=bool)
+        for b in range(nq):                       # row b of the positive quadrant and its mirror row
+            if (b // 16) % count == index:
+                mine[nq + b] = mine[nq - 1 - b] = True
+        rho = np.where(mine[None, :, None], rho, 0).astype(np.complex64)
+        rho = reduce(rho)
+        s = np.real(rho * rho.conj()) / coords.shape[1]
     if compact_grids:
         return s, rows[0][1][None], rows[0][2][None]
     return s, np.array([r[1] for r in rows]), np.array([r[2] for r in rows])

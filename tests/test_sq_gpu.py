@@ -313,3 +313,33 @@ def test_evaluate_sfiso_and_sf2d(sc):
     ev4 = amep_b200.evaluate.SFiso(traj, skip=0.0, nav=2, qmax=2.0, twod=True, mode="fft", accuracy=0.2)
     rows = [orc.sfiso_fft(coords[i], box, n, qmax=2.0, accuracy=0.2) for i in idx]
     _close(ev4.avg, np.mean(np.array([r[0] for r in rows]), axis=0), rtol=1e-6, atol_scale=1e-9)
+
+
+@pytest.mark.parametrize("accum", ["c64", "f64"])
+@pytest.mark.parametrize("n,chunksize", [(3000, 3000), (20000, 300)])
+def test_sf2d_shards_over_q_add_up(sc, accum, n, chunksize):
+    """amepb_sf2d_set_shard: the rho arrays of the shares (rows of q tiles, zeros elsewhere) add up to
+    the unsharded array bit for bit -- reference order with and without the chunk split over blocks,
+    float64 mode; 1, 3 and 8 shares (more shares than rows of tiles in the float64 mode)."""
+    from amep_b200 import _core
+    rng = np.random.default_rng(77)
+    L = 60.0
+    c = np.zeros((2, n, 3), dtype=np.float32)
+    c[:, :, :2] = rng.uniform(0, L, (2, n, 2))
+    ct = torch.from_numpy(c).cuda()
+    q = np.arange(1, 71) * (2 * np.pi / L)            # 70 positive q values: 140 x 140 grid
+    full = _core.sf2d_modes(ct, q, len(q), accum=accum, chunksize=chunksize).cpu().numpy()
+    assert np.abs(full).max() > 0
+    for count in (1, 3, 8):
+        total = np.zeros_like(full)
+        nonzero_shares = 0
+        for index in range(count):
+            part = _core.sf2d_modes(ct, q, len(q), accum=accum, chunksize=chunksize, shard=(index, count)).cpu().numpy()
+            assert np.all((part == 0) | (part == full))   # every element: this share's or zero
+            nonzero_shares += bool(np.any(part != 0))
+            total += part
+        np.testing.assert_array_equal(total, full)
+        assert nonzero_shares >= min(count, 2)
+    # the context is back to "everything"
+    again = _core.sf2d_modes(ct, q, len(q), accum=accum, chunksize=chunksize).cpu().numpy()
+    np.testing.assert_array_equal(again, full)

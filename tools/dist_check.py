@@ -35,6 +35,8 @@ cases = (
     ("SFiso one frame (idle ranks)", lambda d: ev.SFiso(traj, nav=1, qmax=6.0, twod=True, num=8, distributed=d), False),
     ("SF2d", lambda d: ev.SF2d(traj, nav=nf, rotate=False, qmax=3.0, distributed=d), False),
     ("SF2d rotate=True", lambda d: ev.SF2d(traj, nav=5, qmax=3.0, distributed=d), False),
+    ("SF2d one frame (rows of q tiles sharded over the ranks)", lambda d: ev.SF2d(traj, nav=1, rotate=False, qmax=6.0, distributed=d), False),
+    ("SF2d rotate=True, one frame (sharded over q)", lambda d: ev.SF2d(traj, nav=1, qmax=6.0, distributed=d), False),
     ("SF2d fft", lambda d: ev.SF2d(traj, nav=nf, rotate=False, qmax=3.0, mode="fft", accuracy=0.2, distributed=d), False),
     ("PCF2d (psi_6 orientation)", lambda d: ev.PCF2d(traj, nav=4, nxbins=50, nybins=50, rmax=6.0, distributed=d), False),
 )
