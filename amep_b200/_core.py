@@ -361,7 +361,7 @@ def density_counts(coords, box_boundary, xedges, yedges, pbc=True, device=None):
     return out
 
 
-def pcf2d_counts(coords, other, center, center_f32, rot, xedges, yedges, device=None):
+def pcf2d_counts(coords, other, center, center_f32, rot, xedges, yedges, device=None, query_offset=None):
     """Pair counts on the (dx, dy) grid of ``amep.spatialcor.pcf2d`` (amepb_pcf2d_counts): int64
     ``[F, nx, ny]`` (a CUDA tensor if the coordinates live on the device, else NumPy).
 
@@ -412,13 +412,21 @@ def pcf2d_counts(coords, other, center, center_f32, rot, xedges, yedges, device=
         else:
             out[...] = 0
         return out
-    rc = ctx.lib.amepb_pcf2d_counts(
-        ctx.handle, ctypes.c_void_p(pc.ptr()), pc.dtype, pc.n, ctypes.c_void_p(po.ptr()), po.dtype, po.n,
-        1 if same else 0, space, nf, cen.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), 1 if center_f32 else 0,
-        rot_ptr, xe.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), nxe,
-        ye.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), nye, stride,
-        ctypes.c_void_p(optr), _stream_for(dev_index, pc.on_device))
-    ctx.check(rc, "amepb_pcf2d_counts")
+    # query_offset: ``other`` is the slice of ``coords`` from that particle on (intra-frame sharding,
+    # amepb_pcf2d_set_query_offset): equal global indices are skipped like for other=None
+    if query_offset is not None:
+        ctx.set_pcf2d_query_offset(query_offset)
+    try:
+        rc = ctx.lib.amepb_pcf2d_counts(
+            ctx.handle, ctypes.c_void_p(pc.ptr()), pc.dtype, pc.n, ctypes.c_void_p(po.ptr()), po.dtype, po.n,
+            1 if same else 0, space, nf, cen.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), 1 if center_f32 else 0,
+            rot_ptr, xe.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), nxe,
+            ye.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), nye, stride,
+            ctypes.c_void_p(optr), _stream_for(dev_index, pc.on_device))
+        ctx.check(rc, "amepb_pcf2d_counts")
+    finally:
+        if query_offset is not None:
+            ctx.set_pcf2d_query_offset(-1)
     return out
 
 

@@ -227,7 +227,10 @@ __global__ void __launch_bounds__(kPcfThreads) pcf2d_kernel(const TC* __restrict
         }
         __syncthreads();
         if (!live) continue;
-        const int skip = (same && qi >= t0 && qi < t0 + cnt) ? (int)(qi - t0) : -1;
+        // same: 1 = identical arrays (index i pairs with index i), >= 2: the queries are the slice of the
+        // targets that starts at index same - 2 (amepb_pcf2d_set_query_offset), 0 = unrelated arrays
+        const long long self = same == 1 ? qi : (same >= 2 ? qi + (long long)(same - 2) : -1);
+        const int skip = (self >= t0 && self < t0 + cnt) ? (int)(self - t0) : -1;
         for (int i = 0; i < cnt; ++i) {
             int bx, by;
             if (!B.bins(pcf_sub<D>(qx, sx[i]), pcf_sub<D>(qy, sy[i]), bx, by)) continue;
@@ -417,7 +420,7 @@ __global__ void __launch_bounds__(kPcfThreads) pcf2d_cells_kernel(
             __syncthreads();
             for (int q = threadIdx.x; q < nqc; q += kPcfThreads) {
                 const typename PcfVec2<D>::type qv = qs[q0 + q];
-                const int skip = same ? qidx[q0 + q] : -2;
+                const int skip = same == 1 ? qidx[q0 + q] : (same >= 2 ? qidx[q0 + q] + (same - 2) : -2);
                 for (int i = 0; i < cnt; ++i) {
                     const typename PcfVec2<D>::type tv = s_tv[i];
                     int bx, by;
@@ -571,7 +574,7 @@ static int pcf2d_cells_frame(amepb_ctx* ctx, cudaStream_t stream, const TC* coor
     }
     const bool rot = hF.rotate != 0;
 #define AMEPB_PCF_CELLS(DT, CF, RT, THR) \
-    pcf2d_cells_kernel<DT, CF, RT><<<grid, kPcfThreads, smem, stream>>>(qs, qidx, qstart, ts, tidx, tstart, P, same, d_frame, d_xe, nxe, d_ye, nye, THR, stage, d_grid)
+    pcf2d_cells_kernel<DT, CF, RT><<<grid, kPcfThreads, smem, stream>>>(qs, qidx, qstart, ts, tidx, tstart, P, (same ? 1 : ctx->pcf2d_self_code), d_frame, d_xe, nxe, d_ye, nye, THR, stage, d_grid)
     if constexpr (sizeof(D) == 4) {
         if (center_f32) { if (rot) AMEPB_PCF_CELLS(float, true, true, thr); else AMEPB_PCF_CELLS(float, true, false, thr); }
         else { if (rot) AMEPB_PCF_CELLS(float, false, true, thr); else AMEPB_PCF_CELLS(float, false, false, thr); }
@@ -737,13 +740,13 @@ extern "C" int amepb_pcf2d_counts(amepb_ctx* ctx, const void* coords, int dtype,
         const float* th0 = d_thr ? d_thr + f0 * (nxe + nye) : nullptr;
         unsigned long long* g0 = d_counts + (size_t)f0 * (nxe - 1) * (nye - 1);
         if (dtype == AMEPB_F32 && other_dtype == AMEPB_F32)
-            launch_pcf2d<float, float>(rot_run, grid, stream, cf32, c0, n, o0, m, same, fr, xe0, nxe, ye0, nye, dev_stride, per_split, th0, stage, smem, g0);
+            launch_pcf2d<float, float>(rot_run, grid, stream, cf32, c0, n, o0, m, (same ? 1 : ctx->pcf2d_self_code), fr, xe0, nxe, ye0, nye, dev_stride, per_split, th0, stage, smem, g0);
         else if (dtype == AMEPB_F32)
-            launch_pcf2d<float, double>(rot_run, grid, stream, cf32, c0, n, o0, m, same, fr, xe0, nxe, ye0, nye, dev_stride, per_split, th0, stage, smem, g0);
+            launch_pcf2d<float, double>(rot_run, grid, stream, cf32, c0, n, o0, m, (same ? 1 : ctx->pcf2d_self_code), fr, xe0, nxe, ye0, nye, dev_stride, per_split, th0, stage, smem, g0);
         else if (other_dtype == AMEPB_F32)
-            launch_pcf2d<double, float>(rot_run, grid, stream, cf32, c0, n, o0, m, same, fr, xe0, nxe, ye0, nye, dev_stride, per_split, th0, stage, smem, g0);
+            launch_pcf2d<double, float>(rot_run, grid, stream, cf32, c0, n, o0, m, (same ? 1 : ctx->pcf2d_self_code), fr, xe0, nxe, ye0, nye, dev_stride, per_split, th0, stage, smem, g0);
         else
-            launch_pcf2d<double, double>(rot_run, grid, stream, cf32, c0, n, o0, m, same, fr, xe0, nxe, ye0, nye, dev_stride, per_split, th0, stage, smem, g0);
+            launch_pcf2d<double, double>(rot_run, grid, stream, cf32, c0, n, o0, m, (same ? 1 : ctx->pcf2d_self_code), fr, xe0, nxe, ye0, nye, dev_stride, per_split, th0, stage, smem, g0);
     };
     // consecutive frames with the same `angle != 0` share a launch
     auto launch_direct = [&](int64_t f0, int64_t nf) {
@@ -792,5 +795,11 @@ extern "C" int amepb_pcf2d_counts(amepb_ctx* ctx, const void* coords, int dtype,
     }
     // the pinned parameter block is reused by the next call
     AMEPB_CUDA(ctx, cudaStreamSynchronize(stream));
+    return 0;
+}
+
+extern "C" int amepb_pcf2d_set_query_offset(amepb_ctx* ctx, int64_t offset) {
+    if (!ctx || offset >= (1LL << 31) - 2) return AMEPB_E_INVAL;
+    ctx->pcf2d_self_code = offset < 0 ? 0 : (int)offset + 2;
     return 0;
 }

@@ -524,7 +524,11 @@ class PCF2d(_FrameAverage):
         for ignored in ("verbose", "njobs", "chunksize", "pbc"):
             kwargs.pop(ignored, None)
         idx = self._select(traj, skip, nav)
-        sh = _Shard(len(idx), distributed, group)
+        # fewer frames than ranks: every rank takes all selected frames and a slice of the query particles
+        # of each (amepb_pcf2d_set_query_offset); the integer grids are summed before the normalisation
+        sh = _Shard(len(idx), distributed, group, allow_intra=True)
+        if sh.intra:
+            kwargs = dict(kwargs, shard=(sh.rank, sh.ws), reduce=sh.all_sum)
         rows = []
         done = 0
         for coords, other_coords, box in _frame_batches(traj, idx[sh.lo:sh.hi], ptype, other, other is not None):

@@ -504,8 +504,12 @@ def _zero_last_column(data):
 
 
 def pcf2d_frames(coords, box_boundary, other_coords=None, nxbins=None, nybins=None, rmax=None,
-                 psi=None, zero_last_column=True):
+                 psi=None, zero_last_column=True, shard=None, reduce=None):
     """``pcf2d`` for a batch of frames ``[F, N, 3]`` in one library call.
+
+    ``shard=(index, count)`` with ``reduce`` (a sum over the ranks): intra-frame sharding -- this rank
+    pairs its slice of the query particles with all targets, ``reduce`` adds the integer grids of the
+    ranks before the normalisation (exact).
 
     ``box_boundary``: ``(3,2)`` or ``(F,3,2)``; ``psi``: ``None``, ``(2,)`` or ``(F,2)``.  Returns
     ``(g [F, nx, ny], X [F, ny, nx], Y [F, ny, nx])``: per frame what ``amep.spatialcor.pcf2d``
@@ -543,11 +547,23 @@ def pcf2d_frames(coords, box_boundary, other_coords=None, nxbins=None, nybins=No
         rots.append((1.0 if angle != 0.0 else 0.0, np.cos(theta), np.sin(theta)))
         boxes.append(box)
     center_f32 = nf > 0 and centers[0].dtype == np.float32
-    counts = _core.pcf2d_counts(
-        pc, None if same else po, np.array(centers, dtype=np.float64).reshape(nf, 3), center_f32,
-        np.array(rots, dtype=np.float64).reshape(nf, 3) if any(r[0] for r in rots) else None,
-        np.array(xbins_all, dtype=np.float64).reshape(nf, nxbins + 1),
-        np.array(ybins_all, dtype=np.float64).reshape(nf, nybins + 1))
+    queries, query_offset = (None if same else po), None
+    if shard is not None:
+        from .dist import shard_bounds
+        lo, hi = shard_bounds(po.n, shard[0], shard[1])
+        src = po.tensor if po.on_device else po.array
+        queries = _core.Particles(src[:, lo:hi].contiguous() if po.on_device else np.ascontiguousarray(src[:, lo:hi]))
+        query_offset = lo if same else None     # (a slice of the targets themselves: equal global indices are skipped)
+    if shard is not None and queries.n == 0:
+        counts = np.zeros((nf, nxbins, nybins), dtype=np.int64)
+    else:
+        counts = _core.pcf2d_counts(
+            pc, queries, np.array(centers, dtype=np.float64).reshape(nf, 3), center_f32,
+            np.array(rots, dtype=np.float64).reshape(nf, 3) if any(r[0] for r in rots) else None,
+            np.array(xbins_all, dtype=np.float64).reshape(nf, nxbins + 1),
+            np.array(ybins_all, dtype=np.float64).reshape(nf, nybins + 1), query_offset=query_offset)
+    if reduce is not None:
+        counts = reduce(counts)
     if _core._is_torch(counts):
         counts = counts.cpu().numpy()
     g, xs, ys = [], [], []

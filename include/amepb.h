@@ -260,6 +260,13 @@ int amepb_pcf2d_counts(amepb_ctx* ctx, const void* coords, int dtype, int64_t n,
                        int32_t nxe, const double* yedges, int32_t nye, int64_t edge_stride,
                        uint64_t* counts, void* stream);
 
+/* Intra-frame sharding of amepb_pcf2d_counts (default: off, offset < 0): in later calls on this context
+ * with `same == 0` the query array `other` is the slice of the target array `coords` that starts at particle
+ * `offset`, and a query is not paired with the target of the same *global* index -- what the reference does
+ * for other_coords=None (amep/spatialcor.py:700-703).  The uint64 grids of the slices of one frame -- one
+ * per GPU -- add up to the grid of the whole frame exactly. */
+int amepb_pcf2d_set_query_offset(amepb_ctx* ctx, int64_t offset);
+
 /*
  * Pair counts on the (distance, angle) grid of spatialcor.pcf_angle (amep/spatialcor.py:929-1041): for
  * every row o of `other` and every row c of `coords` (skipping equal indices when same != 0) the

@@ -105,7 +105,9 @@ def _oracle_sf2d_frames(coords, box, other_coords=None, qmax=20.0, compact_grids
 
 
 def _oracle_pcf2d_frames(coords, box, other_coords=None, nxbins=None, nybins=None, rmax=None, psi=None,
-                         zero_last_column=True):
+                         zero_last_column=True, shard=None, reduce=None):
+    """(``shard`` / ``reduce`` -- fewer frames than ranks -- are accepted and not emulated: every rank
+    computes the whole frame here; the slicing itself is tested on the GPU, tests/test_pcf2d_gpu.py)"""
     import amep_oracle as orc
     coords = np.asarray(coords)
     out = []

@@ -270,3 +270,42 @@ def test_evaluate_pcf2d(sc):
         np.testing.assert_array_equal(ev3.avg, np.mean(np.array([w[0] for w in want3]), axis=0))
         z = data[:, :, 2].cpu().numpy() if dev == "cuda" else data[:, :, 2]
         assert np.all(z == 0.125)
+
+
+@pytest.mark.parametrize("walk", ["direct", "cells"])
+def test_pcf2d_query_slices_add_up(sc, monkeypatch, walk):
+    """Intra-frame sharding (amepb_pcf2d_set_query_offset): the grids of the query slices of a frame --
+    every slice paired with all targets, equal global indices skipped -- add up to the grid of the whole
+    frame, with and without the rotation, through both pair walks; pcf2d_frames(shard=..., reduce=...)
+    then normalises like the unsharded call."""
+    from amep_b200 import _core, spatialcor
+    monkeypatch.setenv("AMEPB_PCF2D_CELLS", "1" if walk == "cells" else "0")
+    rng = np.random.default_rng(91)
+    n, L = 30000, 120.0
+    c = np.zeros((1, n, 3), dtype=np.float32)
+    c[0, :, :2] = rng.uniform(0, L, (n, 2))
+    c[0, 17] = c[0, 5]                      # a coincident pair: counted (different indices), unlike a self pair
+    ct = torch.from_numpy(c).cuda()
+    edges = np.linspace(-30.0, 30.0, 201)[None]
+    cen = np.array([[L / 2, L / 2, 0.0]])
+    for rot in (None, np.array([[1.0, np.cos(-0.7), np.sin(-0.7)]])):
+        full = _core.pcf2d_counts(ct, None, cen, True, rot, edges, edges).cpu().numpy()
+        total = np.zeros_like(full)
+        for lo, hi in ((0, 9000), (9000, 9001), (9001, 30000)):
+            total += _core.pcf2d_counts(ct, ct[:, lo:hi].contiguous(), cen, True, rot, edges, edges, query_offset=lo).cpu().numpy()
+        np.testing.assert_array_equal(total, full)
+        assert full.sum() > 1e6
+    box = np.array([[0, L], [0, L], [-0.5, 0.5]], dtype=np.float32)
+    want = spatialcor.pcf2d_frames(ct.clone(), box, nxbins=100, nybins=100, rmax=25.0, psi=np.array([0.6, 0.8]), zero_last_column=False)
+    parts = []
+    got = None
+    for index in range(3):
+        acc = []
+        g = spatialcor.pcf2d_frames(ct.clone(), box, nxbins=100, nybins=100, rmax=25.0, psi=np.array([0.6, 0.8]),
+                                    zero_last_column=False, shard=(index, 3), reduce=lambda a: (acc.append(np.asarray(a.cpu() if hasattr(a, "cpu") else a)), acc[-1])[1])
+        parts.append(acc[0])
+    total = sum(parts)
+    g = spatialcor.pcf2d_frames(ct.clone(), box, nxbins=100, nybins=100, rmax=25.0, psi=np.array([0.6, 0.8]),
+                                zero_last_column=False, shard=(0, 3), reduce=lambda a: total)
+    for a, b in zip(g, want):
+        np.testing.assert_array_equal(a, b)

@@ -32,13 +32,14 @@ cases = (
     ("RDF host arrays", lambda d: ev.RDF(host_traj, nav=nf, rmax=8.0, nbins=200, distributed=d), True),
     ("RDF one frame (sharded inside the frame)", lambda d: ev.RDF(traj, nav=1, skip=0.5, rmax=8.0, nbins=200, distributed=d), True),
     ("SFiso", lambda d: ev.SFiso(traj, nav=nf, qmax=6.0, twod=True, num=8, distributed=d), False),
-    ("SFiso one frame (idle ranks)", lambda d: ev.SFiso(traj, nav=1, qmax=6.0, twod=True, num=8, distributed=d), False),
+    ("SFiso one frame (particles split over the ranks)", lambda d: ev.SFiso(traj, nav=1, qmax=6.0, twod=True, num=8, distributed=d), False),
     ("SF2d", lambda d: ev.SF2d(traj, nav=nf, rotate=False, qmax=3.0, distributed=d), False),
     ("SF2d rotate=True", lambda d: ev.SF2d(traj, nav=5, qmax=3.0, distributed=d), False),
     ("SF2d one frame (rows of q tiles sharded over the ranks)", lambda d: ev.SF2d(traj, nav=1, rotate=False, qmax=6.0, distributed=d), False),
     ("SF2d rotate=True, one frame (sharded over q)", lambda d: ev.SF2d(traj, nav=1, qmax=6.0, distributed=d), False),
     ("SF2d fft", lambda d: ev.SF2d(traj, nav=nf, rotate=False, qmax=3.0, mode="fft", accuracy=0.2, distributed=d), False),
     ("PCF2d (psi_6 orientation)", lambda d: ev.PCF2d(traj, nav=4, nxbins=50, nybins=50, rmax=6.0, distributed=d), False),
+    ("PCF2d one frame (query particles sharded over the ranks)", lambda d: ev.PCF2d(traj, nav=1, nxbins=50, nybins=50, rmax=6.0, distributed=d), False),
 )
 for name, make, exact in cases:
     sharded, alone = make(True), make(False)
