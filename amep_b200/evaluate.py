@@ -591,10 +591,14 @@ class _PerFrame(_FrameAverage):
     selected frames are sharded over the ranks in contiguous blocks, every rank loops over its
     frames, the rows are assembled with one all-reduce and averaged like average_func."""
 
-    def _run(self, traj, skip, nav, distributed, group, compute):
+    def _run(self, traj, skip, nav, distributed, group, compute, allow_intra=False):
         idx = self._select(traj, skip, nav)
-        sh = _Shard(len(idx), distributed, group)
-        rows = [np.array(compute(frame)) for frame in traj[np.asarray(idx[sh.lo:sh.hi])]]
+        # allow_intra (the spatialcor classes): with fewer frames than ranks every rank takes all selected
+        # frames and a slice of the query particles of each; counts and sums are all-reduced before the
+        # normalisation (compute(frame, shard=..., reduce=...))
+        sh = _Shard(len(idx), distributed, group, allow_intra=allow_intra)
+        extra = dict(shard=(sh.rank, sh.ws), reduce=sh.all_sum) if sh.intra else {}
+        rows = [np.array(compute(frame, **extra)) for frame in traj[np.asarray(idx[sh.lo:sh.hi])]]
         local = np.stack(rows) if rows else None
         self._frames = sh.assemble(local)
         return np.mean(self._frames, axis=0)
@@ -660,12 +664,13 @@ class SpatialVelCor(_PerFrame):
         for ignored in ("verbose", "njobs", "chunksize"):
             kwargs.pop(ignored, None)
 
-        def compute(frame):
+        def compute(frame, **extra):
             # amep/evaluate.py:330-338: the second set is always passed
             return spatialcor(frame.coords(ptype=ptype), frame.box, frame.velocities(ptype=ptype),
-                              other_coords=frame.coords(ptype=other), other_values=frame.velocities(ptype=other), **kwargs)
+                              other_coords=frame.coords(ptype=other), other_values=frame.velocities(ptype=other),
+                              **kwargs, **extra)
 
-        res = self._run(traj, skip, nav, distributed, group, compute)
+        res = self._run(traj, skip, nav, distributed, group, compute, allow_intra=True)
         self._avg, self._r = res[0], res[1]
 
     @property
@@ -684,16 +689,17 @@ class HexOrderCor(_PerFrame):
         for ignored in ("verbose", "njobs", "chunksize"):
             kwargs.pop(ignored, None)
 
-        def compute(frame):
+        def compute(frame, **extra):
             # amep/evaluate.py:2219-2253
             c = frame.coords(ptype=ptype)
             hexorder = psi_k(c, frame.box, k=6)
             if other is None:
-                return spatialcor(c, frame.box, hexorder, **kwargs)
+                return spatialcor(c, frame.box, hexorder, **kwargs, **extra)
             o = frame.coords(ptype=other)
-            return spatialcor(c, frame.box, hexorder, other_coords=o, other_values=psi_k(o, frame.box, k=6), **kwargs)
+            return spatialcor(c, frame.box, hexorder, other_coords=o, other_values=psi_k(o, frame.box, k=6),
+                              **kwargs, **extra)
 
-        res = self._run(traj, skip, nav, distributed, group, compute)
+        res = self._run(traj, skip, nav, distributed, group, compute, allow_intra=True)
         self._avg, self._r = res[0], res[1]
 
     @property

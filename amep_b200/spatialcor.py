@@ -656,13 +656,17 @@ def pcf_angle(coords, box_boundary, other_coords=None, ndbins=500, nabins=100, r
 # GENERAL SPATIAL CORRELATION FUNCTION
 # =============================================================================
 def spatialcor(coords, box_boundary, values, other_coords=None, other_values=None, dbin_edges=None, ndists=None,
-               chunksize=None, njobs=1, rmax=None, verbose=False, pbc=True):
+               chunksize=None, njobs=1, rmax=None, verbose=False, pbc=True, shard=None, reduce=None):
     """Spatial correlation function of per-particle values (scalars, vectors, complex numbers) of
     one frame; contract of ``amep.spatialcor.spatialcor`` (amep/spatialcor.py:141-342): for every
     distance bin the average of ``conj(other_value) * value`` over the pairs whose minimum-image
     distance (the reference's periodic KD-tree, distances below ``max(box)/2``) falls into it,
     normalised by the first bin.  The pair counts are exact; the sums are float64 (the reference
-    sums float32 values in float32)."""
+    sums float32 values in float32).
+
+    ``shard=(index, count)`` with ``reduce`` (a sum over the ranks): intra-frame sharding -- this rank
+    takes its slice of the second set (the query particles of the periodic tree), ``reduce`` adds pair
+    counts and sums of the ranks before the normalisation (counts exact, sums to float64 rounding)."""
     bb = _box_numpy(box_boundary)
     box = bb[:, 1] - bb[:, 0]
     vshape = tuple(values.shape)
@@ -684,7 +688,17 @@ def spatialcor(coords, box_boundary, values, other_coords=None, other_values=Non
     elif dbin_edges is None and ndists is None:
         dbin_edges = np.arange(0.0, rmax, 1.05)
     dbin_edges = np.asarray(dbin_edges)
+    if shard is not None:
+        from .dist import shard_bounds
+        oc = coords if other_coords is None else other_coords
+        ov = values if other_values is None else other_values
+        if int(oc.shape[0]) < shard[1]:     # (every rank sees the same numbers: no rank is left waiting)
+            raise ValueError("amep_b200.spatialcor.spatialcor: more ranks than particles")
+        lo, hi = shard_bounds(int(oc.shape[0]), shard[0], shard[1])
+        other_coords, other_values = oc[lo:hi], ov[lo:hi]
     norm, cor, is_complex = _core.spatialcor_sums(coords, values, other_coords, other_values, bb, pbc, dbin_edges)
+    if reduce is not None:
+        norm, cor = reduce(norm), reduce(cor)
     norm = norm.astype(float)
     if is_complex:
         cor = cor.astype(np.complex64)      # the reference accumulates complex values in complex64 (:72-73)

@@ -14,7 +14,9 @@ nf, n, L = 11, 3000, 40.0
 box = np.array([[0, L], [0, L], [-0.5, 0.5]], dtype=np.float32)
 coords = np.zeros((nf, n, 3), dtype=np.float32)
 coords[:, :, :2] = rng.uniform(0, L, (nf, n, 2))
-traj = amep_b200.TensorTrajectory(torch.from_numpy(coords).cuda(), box, times=np.arange(nf) * 1.0)
+vel = rng.normal(size=(nf, n, 3)).astype(np.float32)
+traj = amep_b200.TensorTrajectory(torch.from_numpy(coords).cuda(), box, times=np.arange(nf) * 1.0,
+                                  velocities=torch.from_numpy(vel).cuda())
 host_traj = amep_b200.TensorTrajectory(coords, box, times=np.arange(nf) * 1.0)   # host arrays: every rank stages on its own GPU
 ok = True
 ev = amep_b200.evaluate
@@ -39,6 +41,9 @@ cases = (
     ("SF2d rotate=True, one frame (sharded over q)", lambda d: ev.SF2d(traj, nav=1, qmax=6.0, distributed=d), False),
     ("SF2d fft", lambda d: ev.SF2d(traj, nav=nf, rotate=False, qmax=3.0, mode="fft", accuracy=0.2, distributed=d), False),
     ("PCF2d (psi_6 orientation)", lambda d: ev.PCF2d(traj, nav=4, nxbins=50, nybins=50, rmax=6.0, distributed=d), False),
+    ("SpatialVelCor", lambda d: ev.SpatialVelCor(traj, nav=4, distributed=d), False),
+    ("SpatialVelCor one frame (query particles sharded over the ranks)", lambda d: ev.SpatialVelCor(traj, nav=1, distributed=d), False),
+    ("HexOrderCor one frame (query particles sharded over the ranks)", lambda d: ev.HexOrderCor(traj, nav=1, distributed=d), False),
     ("PCF2d one frame (query particles sharded over the ranks)", lambda d: ev.PCF2d(traj, nav=1, nxbins=50, nybins=50, rmax=6.0, distributed=d), False),
 )
 for name, make, exact in cases:
