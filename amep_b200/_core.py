@@ -551,7 +551,7 @@ def _single(p: Particles, what: str):
     return p
 
 
-def pcf_angle_counts(coords, other, same, box_boundary, pbc, e, angle, dedges, aedges, device=None):
+def pcf_angle_counts(coords, other, same, box_boundary, pbc, e, angle, dedges, aedges, device=None, query_offset=None):
     """Pair counts on the (distance, angle) grid of ``amep.spatialcor.pcf_angle``
     (amepb_pcf_angle_counts) -> int64 ``[nd, na]`` NumPy array."""
     pc = _single(coords if isinstance(coords, Particles) else Particles(coords), "pcf_angle")
@@ -582,13 +582,20 @@ def pcf_angle_counts(coords, other, same, box_boundary, pbc, e, angle, dedges, a
         out = np.empty(shape, dtype=np.int64)
         optr, space = out.ctypes.data, _lib.HOST
     dp = ctypes.POINTER(ctypes.c_double)
-    rc = ctx.lib.amepb_pcf_angle_counts(
-        ctx.handle, ctypes.c_void_p(pc.ptr()), pc.dtype, pc.n, ctypes.c_void_p(po.ptr()), po.dtype, po.n,
-        1 if same else 0, space, box.ctypes.data_as(dp), box_code, 1 if pbc else 0,
-        e_arr.ctypes.data_as(dp), stride, e_norm.ctypes.data_as(dp), float(angle),
-        de.ctypes.data_as(dp), len(de), ae.ctypes.data_as(dp), len(ae), ctypes.c_void_p(optr),
-        _stream_for(dev_index, pc.on_device))
-    ctx.check(rc, "amepb_pcf_angle_counts")
+    # query_offset: ``other`` (and ``e``) is the slice of ``coords`` from that particle on (intra-frame sharding)
+    if query_offset is not None:
+        ctx.set_pcf_angle_query_offset(query_offset)
+    try:
+        rc = ctx.lib.amepb_pcf_angle_counts(
+            ctx.handle, ctypes.c_void_p(pc.ptr()), pc.dtype, pc.n, ctypes.c_void_p(po.ptr()), po.dtype, po.n,
+            1 if same else 0, space, box.ctypes.data_as(dp), box_code, 1 if pbc else 0,
+            e_arr.ctypes.data_as(dp), stride, e_norm.ctypes.data_as(dp), float(angle),
+            de.ctypes.data_as(dp), len(de), ae.ctypes.data_as(dp), len(ae), ctypes.c_void_p(optr),
+            _stream_for(dev_index, pc.on_device))
+        ctx.check(rc, "amepb_pcf_angle_counts")
+    finally:
+        if query_offset is not None:
+            ctx.set_pcf_angle_query_offset(-1)
     return to_numpy(out)
 
 

@@ -24,7 +24,7 @@ SYMBOLS = (
     "amepb_frame_dimension", "amepb_rdf_batch", "amepb_rdf_last_info",
     "amepb_rdf_set_cells_per_cutoff", "amepb_rdf_set_symmetric", "amepb_rdf_set_shard", "amepb_sq_harmonics", "amepb_sq_debye", "amepb_sq_debye_ref", "amepb_sf2d_modes", "amepb_sf2d_set_shard",
     "amepb_density_counts",
-    "amepb_pcf2d_counts", "amepb_pcf2d_set_query_offset", "amepb_psi_k", "amepb_rotate_crop", "amepb_pcf_angle_counts", "amepb_spatialcor_sums",
+    "amepb_pcf2d_counts", "amepb_pcf2d_set_query_offset", "amepb_psi_k", "amepb_rotate_crop", "amepb_pcf_angle_counts", "amepb_pcf_angle_set_query_offset", "amepb_spatialcor_sums",
     "amepb_kernel_launches", "amepb_synchronize", "amepb_set_timing", "amepb_last_kernel_ms",
 )
 
@@ -104,6 +104,8 @@ def load():
         lib.amepb_rdf_set_symmetric.argtypes = [vp, c.c_int]
         lib.amepb_rdf_set_shard.restype = c.c_int
         lib.amepb_rdf_set_shard.argtypes = [vp, c.c_int, c.c_int]
+        lib.amepb_pcf_angle_set_query_offset.restype = c.c_int
+        lib.amepb_pcf_angle_set_query_offset.argtypes = [vp, i64]
         lib.amepb_pcf2d_set_query_offset.restype = c.c_int
         lib.amepb_pcf2d_set_query_offset.argtypes = [vp, i64]
         lib.amepb_sf2d_set_shard.restype = c.c_int
@@ -194,6 +196,10 @@ class Context:
     def set_shard(self, index: int, count: int):
         """Intra-frame sharding of amepb_rdf_batch (amepb_rdf_set_shard)."""
         self.check(self.lib.amepb_rdf_set_shard(self.handle, int(index), int(count)), "amepb_rdf_set_shard")
+
+    def set_pcf_angle_query_offset(self, offset: int):
+        """The queries of amepb_pcf_angle_counts are the slice of the targets from ``offset`` on (< 0: off)."""
+        self.check(self.lib.amepb_pcf_angle_set_query_offset(self.handle, int(offset)), "amepb_pcf_angle_set_query_offset")
 
     def set_pcf2d_query_offset(self, offset: int):
         """The queries of amepb_pcf2d_counts are the slice of the targets from ``offset`` on (< 0: off)."""

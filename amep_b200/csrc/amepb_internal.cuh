@@ -71,6 +71,7 @@ struct amepb_ctx {
     int rdf_shard_index = 0, rdf_shard_count = 1;   // amepb_rdf_set_shard
     int sf2d_shard_index = 0, sf2d_shard_count = 1; // amepb_sf2d_set_shard
     int pcf2d_self_code = 0;                         // amepb_pcf2d_set_query_offset: 0 = off, else offset + 2
+    long long pcfa_query_offset = -1;                // amepb_pcf_angle_set_query_offset
     void* last_stream = nullptr;
     bool sq_attr_harm = false;
     cudaStream_t copy_stream = nullptr;   // host-space staging

@@ -78,6 +78,7 @@ struct PcfaArgs {
     double e[3], e_norm;       // one reference direction (e_stride == 0)
     int e_stride;              // 3: one direction per query particle
     int pbc, same;
+    long long self_off;        // >= 0: query q is particle q + self_off of the targets and is not paired with it
     int nde, nae;              // number of distance / angle edges
     int uniform_d, uniform_a;
     float cert_margin;         // > 0: angle bins may be decided in float32 (in units of a bin), see the kernel
@@ -147,7 +148,7 @@ __global__ void __launch_bounds__(THREADS) pcf_angle_kernel(
         __syncthreads();
         if (!have_q) continue;
         for (int k = 0; k < cnt; ++k) {
-            if (A.same && t0 + k == q) continue;   // coords[particlerange != n]
+            if (A.self_off >= 0 && t0 + k == q + A.self_off) continue;   // coords[particlerange != n]
             if (A.pre_r2 > 0.f) {
                 // Cheap float32 look at the pair first: minimum image by multiply / magic-number rounding /
                 // fma (no division, no conversion -- the exact fold below keeps the XU pipe 71 % busy),
@@ -514,6 +515,8 @@ int amepb_pcf_angle_counts(amepb_ctx* ctx, const void* coords, int dtype, int64_
     A.e_stride = (int)e_stride;
     A.pbc = pbc ? 1 : 0;
     A.same = same ? 1 : 0;
+    // same arrays: query q is target q; a slice of the targets passed as `other` (amepb_pcf_angle_set_query_offset)
+    A.self_off = same ? 0 : (ctx->pcfa_query_offset >= 0 ? ctx->pcfa_query_offset : -1);
     A.nde = nde;
     A.nae = nae;
     // edge arrays (and per-particle directions) to the device
@@ -577,6 +580,12 @@ int amepb_pcf_angle_counts(amepb_ctx* ctx, const void* coords, int dtype, int64_
     if (space == AMEPB_HOST) AMEPB_CUDA(ctx, cudaMemcpyAsync(counts, d_counts, gbytes, cudaMemcpyDeviceToHost, stream));
     // the pinned block and the direction arrays of the caller are reused after the call
     AMEPB_CUDA(ctx, cudaStreamSynchronize(stream));
+    return 0;
+}
+
+int amepb_pcf_angle_set_query_offset(amepb_ctx* ctx, int64_t offset) {
+    if (!ctx) return AMEPB_E_INVAL;
+    ctx->pcfa_query_offset = offset < 0 ? -1 : (long long)offset;
     return 0;
 }
 

@@ -593,7 +593,7 @@ class _PerFrame(_FrameAverage):
 
     def _run(self, traj, skip, nav, distributed, group, compute, allow_intra=False):
         idx = self._select(traj, skip, nav)
-        # allow_intra (the spatialcor classes): with fewer frames than ranks every rank takes all selected
+        # allow_intra: with fewer frames than ranks every rank takes all selected
         # frames and a slice of the query particles of each; counts and sums are all-reduced before the
         # normalisation (compute(frame, shard=..., reduce=...))
         sh = _Shard(len(idx), distributed, group, allow_intra=allow_intra)
@@ -626,7 +626,7 @@ class PCFangle(_PerFrame):
         for ignored in ("verbose", "njobs", "chunksize"):
             kwargs.pop(ignored, None)
 
-        def compute(frame):
+        def compute(frame, **extra):
             # amep/evaluate.py:1046-1101
             psi = None
             e = np.array([1.0, 0.0, 0.0], dtype=float)
@@ -637,12 +637,12 @@ class PCFangle(_PerFrame):
             c = frame.coords(ptype=ptype)
             c = c.clone() if _core._is_torch(c) else np.array(c)       # pcf_angle zeroes z in place
             if other is None:
-                return pcf_angle(c, frame.box, psi=psi, e=e, **kwargs)
+                return pcf_angle(c, frame.box, psi=psi, e=e, **kwargs, **extra)
             o = frame.coords(ptype=other)
             o = o.clone() if _core._is_torch(o) else np.array(o)
-            return pcf_angle(c, frame.box, other_coords=o, psi=psi, e=e, **kwargs)
+            return pcf_angle(c, frame.box, other_coords=o, psi=psi, e=e, **kwargs, **extra)
 
-        res = self._run(traj, skip, nav, distributed, group, compute)
+        res = self._run(traj, skip, nav, distributed, group, compute, allow_intra=True)
         self._avg, self._r, self._theta = res[0], res[1], res[2]
 
     @property

@@ -595,7 +595,7 @@ def pcf2d(coords, box_boundary, other_coords=None, nxbins=None, nybins=None, rma
 # PCF ANGLE
 # =============================================================================
 def pcf_angle(coords, box_boundary, other_coords=None, ndbins=500, nabins=100, rmax=None, psi=None, njobs=1,
-              pbc=True, verbose=False, chunksize=None, e=np.array([1.0, 0.0, 0.0])):
+              pbc=True, verbose=False, chunksize=None, e=np.array([1.0, 0.0, 0.0]), shard=None, reduce=None):
     """Angle dependent radial pair correlation function g(r, theta) of one 2D frame; contract of
     ``amep.spatialcor.pcf_angle`` (amep/spatialcor.py:1044-1318): minimum-image difference vectors,
     angle to the direction ``e`` (one vector or one per particle), rotation by the ``psi`` angle;
@@ -604,7 +604,11 @@ def pcf_angle(coords, box_boundary, other_coords=None, ndbins=500, nabins=100, r
 
     ``e`` is evaluated in float64 (a float32 ``e``, e.g. trajectory orientations, makes the
     reference compute the angles in float32: counts then agree except for pairs within float32
-    rounding of an angle edge)."""
+    rounding of an angle edge).
+
+    ``shard=(index, count)`` with ``reduce`` (a sum over the ranks): intra-frame sharding -- this rank
+    pairs its slice of the query particles (and of a per-particle ``e``) with all targets, ``reduce``
+    adds the integer grids before the normalisation (exact)."""
     same = other_coords is None
 
     def host_view(c):
@@ -642,7 +646,18 @@ def pcf_angle(coords, box_boundary, other_coords=None, ndbins=500, nabins=100, r
     angle = _pcf2d_angle(psi)       # amep/spatialcor.py:1235-1241, the same expression as pcf2d's
     dbins = np.linspace(0.0, rmax, ndbins + 1)
     abins = np.linspace(0.0, 2 * np.pi, nabins + 1)
-    hist = _core.pcf_angle_counts(coords, None if same else other_coords, same, bb, pbc, e, angle, dbins, abins)
+    if shard is None:
+        hist = _core.pcf_angle_counts(coords, None if same else other_coords, same, bb, pbc, e, angle, dbins, abins)
+    else:
+        from .dist import shard_bounds
+        if n_other < shard[1]:     # (every rank sees the same numbers: no rank is left waiting)
+            raise ValueError("amep_b200.spatialcor.pcf_angle: more ranks than particles")
+        lo, hi = shard_bounds(n_other, shard[0], shard[1])
+        q = (coords if same else other_coords)[lo:hi]
+        hist = _core.pcf_angle_counts(coords, q, False, bb, pbc, e[lo:hi] if e.ndim == 2 else e, angle, dbins, abins,
+                                      query_offset=lo if same else None)
+    if reduce is not None:
+        hist = reduce(hist)
     hist = hist.astype(float)
     # normalization (amep/spatialcor.py:1306-1318)
     area = 0.5 * (dbins[1:] ** 2 - dbins[:-1] ** 2)[:, None] * (abins[1:] - abins[:-1])

@@ -288,6 +288,13 @@ int amepb_pcf_angle_counts(amepb_ctx* ctx, const void* coords, int dtype, int64_
                            double angle, const double* dedges, int32_t nde, const double* aedges, int32_t nae,
                            uint64_t* counts, void* stream);
 
+/* Intra-frame sharding of amepb_pcf_angle_counts (default: off, offset < 0): in later calls on this context
+ * with `same == 0` the query array `other` (and the per-particle directions `e`) is the slice of the target
+ * array `coords` that starts at particle `offset`; a query is not paired with the target of the same global
+ * index (amep/spatialcor.py:1003: coords[particlerange != n]).  The uint64 grids of the slices add up to the
+ * grid of the whole frame exactly. */
+int amepb_pcf_angle_set_query_offset(amepb_ctx* ctx, int64_t offset);
+
 /*
  * Pair counts and value-product sums per distance bin of spatialcor.spatialcor
  * (amep/spatialcor.py:47-135): the periodic KD-tree of the reference restated -- `coords` shifted by

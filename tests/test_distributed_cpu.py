@@ -186,8 +186,22 @@ def _worker(rank, world, port, tmpdir):
     assert evp.frames.shape == (len(evp.indices), 3, 12, 12)
     # (4) the per-frame pair observables (PCFangle, SpatialVelCor): frames sharded in blocks, rows assembled
     import amep_oracle as orc
-    evaluate.pcf_angle = lambda c, box, other_coords=None, psi=None, e=None, **kw: orc.pcf_angle(
-        np.asarray(c), box, other_coords, psi=psi, e=e, **kw)
+    def _oracle_pcf_angle(c, box, other_coords=None, psi=None, e=None, shard=None, reduce=None, **kw):
+        """Stand-in for spatialcor.pcf_angle.  With ``shard`` / ``reduce`` (fewer frames than ranks) the
+        integer grids go through the all-reduce before the normalisation (rank 0 contributes the counts of
+        the frame, the others zeros: the slicing of the queries itself is tested on the GPU)."""
+        c = np.asarray(c)
+        if shard is None:
+            return orc.pcf_angle(c, box, other_coords, psi=psi, e=e, **kw)
+        hist, dbins, abins = orc.pcf_angle_counts(c, box, other_coords, psi=psi, e=e, **kw)
+        hist = reduce(hist if shard[0] == 0 else np.zeros_like(hist))
+        bl = np.asarray(box)[:, 1] - np.asarray(box)[:, 0]
+        n_other = len(c) if other_coords is None else len(other_coords)
+        area = 0.5 * (dbins[1:] ** 2 - dbins[:-1] ** 2)[:, None] * (abins[1:] - abins[:-1])
+        res = hist.astype(float) / area / (len(c) / (bl[0] * bl[1])) / n_other
+        R, T = np.meshgrid(orc.bin_centres(dbins), orc.bin_centres(abins))
+        return res.T, R, T
+    evaluate.pcf_angle = _oracle_pcf_angle
     def _oracle_spatialcor(c, box, v, other_coords=None, other_values=None, shard=None, reduce=None, **kw):
         """Stand-in for spatialcor.spatialcor; with ``shard`` / ``reduce`` (fewer frames than ranks) this
         rank's slice of the second set, pair counts and sums added over the ranks before the normalisation."""

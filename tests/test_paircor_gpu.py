@@ -261,3 +261,31 @@ def test_spatialcor_query_slices_add_up(sc):
         got_c, got_r = sc.spatialcor(ct, box, values, shard=(0, 3), reduce=lambda a: next(it))
         np.testing.assert_allclose(got_c, want_c, rtol=1e-9, atol=1e-12)
         np.testing.assert_array_equal(got_r, want_r)
+
+
+def test_pcf_angle_query_slices_add_up(sc):
+    """Intra-frame sharding of pcf_angle (amepb_pcf_angle_set_query_offset): the grids of the query
+    slices -- every slice paired with all targets, equal global indices skipped, per-particle
+    directions sliced along -- add up to the grid of the whole frame; pcf_angle(shard=..., reduce=...)
+    normalises like the unsharded call."""
+    from amep_b200 import _core
+    rng = np.random.default_rng(87)
+    n, L = 5000, 60.0
+    box = np.array([[0, L], [0, L], [-0.5, 0.5]], dtype=np.float32)
+    c = np.zeros((n, 3), dtype=np.float32)
+    c[:, :2] = rng.uniform(0, L, (n, 2))
+    c[11] = c[3]                                  # a coincident pair (dist == 0 is dropped either way)
+    ct = torch.from_numpy(c).cuda()
+    ang = rng.uniform(0, 2 * np.pi, n)
+    e_pp = np.stack([np.cos(ang), np.sin(ang), np.zeros(n)], axis=1)
+    for e in (np.array([1.0, 0.0, 0.0]), e_pp):
+        kw = dict(ndbins=80, nabins=36, rmax=12.0, psi=np.array([0.3, 0.9]), e=e)
+        want = sc.pcf_angle(ct.clone(), box, **kw)
+        grids = []
+        for index in range(3):
+            sc.pcf_angle(ct.clone(), box, shard=(index, 3), reduce=lambda a: (grids.append(np.asarray(a)), a)[1], **kw)
+        total = sum(grids)
+        assert total.sum() > 1e5
+        got = sc.pcf_angle(ct.clone(), box, shard=(1, 3), reduce=lambda a: total, **kw)
+        for a, b in zip(got, want):
+            np.testing.assert_array_equal(a, b)

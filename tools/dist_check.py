@@ -41,6 +41,7 @@ cases = (
     ("SF2d rotate=True, one frame (sharded over q)", lambda d: ev.SF2d(traj, nav=1, qmax=6.0, distributed=d), False),
     ("SF2d fft", lambda d: ev.SF2d(traj, nav=nf, rotate=False, qmax=3.0, mode="fft", accuracy=0.2, distributed=d), False),
     ("PCF2d (psi_6 orientation)", lambda d: ev.PCF2d(traj, nav=4, nxbins=50, nybins=50, rmax=6.0, distributed=d), False),
+    ("PCFangle one frame (query particles sharded over the ranks)", lambda d: ev.PCFangle(traj, nav=1, mode="psi6", ndbins=60, nabins=24, rmax=8.0, distributed=d), False),
     ("SpatialVelCor", lambda d: ev.SpatialVelCor(traj, nav=4, distributed=d), False),
     ("SpatialVelCor one frame (query particles sharded over the ranks)", lambda d: ev.SpatialVelCor(traj, nav=1, distributed=d), False),
     ("HexOrderCor one frame (query particles sharded over the ranks)", lambda d: ev.HexOrderCor(traj, nav=1, distributed=d), False),
