@@ -16,13 +16,16 @@ current one (``_streamed_batches``), so wall time is max(read, compute) rather t
 sum and host memory stays at a few staging buffers instead of the whole selection.
 
 Multi-GPU.  Frames are the unit of sharding (contiguous blocks per rank, one
-all-reduce).  With fewer selected frames than ranks the RDF is sharded *inside* the
-frame instead (every rank holds the frame, ``amepb_rdf_set_shard`` deals out the query
-cell runs, the integer histograms add up exactly) -- the split the reference makes over
-query chunks (amep/spatialcor.py:587-600).
+all-reduce).  With fewer selected frames than ranks the work is sharded *inside* the
+frame instead, every rank holding the frame: the RDF by query cell runs
+(``amepb_rdf_set_shard``; integer histograms, exact) -- the split the reference makes over
+query chunks (amep/spatialcor.py:587-600) --, SF2d by rows of q tiles (``amepb_sf2d_set_shard``,
+exact), SFiso by particles (sums to float64 rounding), PCF2d / PCFangle / SpatialVelCor /
+HexOrderCor by query particles (integer grids and pair counts exact).
 
-``max_workers``, ``njobs`` and ``chunksize`` (except sf2d's, which is part of
-the result) are accepted for compatibility and have no effect.
+``max_workers`` and ``njobs`` are accepted for compatibility and have no effect; ``chunksize``
+matters where it is part of the reference's result (sf2d's complex64 and sfiso('std')'s float32
+partial sums).
 """
 from __future__ import annotations
 
